@@ -1,0 +1,163 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the VisionLLMv2 forward hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+One JSON line on rank 0.  See DESIGN.md "Measurement" for what each field means.
+Workloads live in bench_workloads.py; the default is the most complete
+native path available (see DEFAULT_WORKLOAD there).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
+                              ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else max(args.warmup, 1)
+
+    import bench_workloads as benchlib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name = args.workload or benchlib.DEFAULT_WORKLOAD
+
+    if args.impl == "reference":
+        # The reference's CPU implementation of the path, on the host cores; rank 0 only.
+        if rank != 0:
+            return
+        line = benchlib.run_reference_arm(name, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup)
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = benchlib.WORKLOADS[name](rank=rank, world=world, device=torch.device("cuda", local_rank))
+    wl.setup()
+
+    from visionllm_b200 import _lib
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """EXACTLY `steps` calls, barrier+sync on both sides, CUDA events, max over ranks -> ms total."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        launches = _lib.launch_count() - l0
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(wl.step_device, args.steps, args.warmup)
+    kern = wl.dominant_kernel_ms(args.steps)            # live CUDA-event time of the dominant kernel
+    ms_e2e, _ = timed(wl.step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    units = wl.units_per_step() * world
+    peaks = benchlib.measured_peaks()
+    roof = wl.roofline(kern, peaks)
+    line = {
+        "metric": wl.metric, "value": units / (ms_dev / args.steps / 1e3), "unit": wl.unit,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+        "data": "synthetic", "config": wl.config(),
+        "e2e": {"value": units / (ms_e2e / args.steps / 1e3), "unit": wl.unit,
+                "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+    }
+    line.update(wl.extra())
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = benchlib.cpu_baseline(name)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

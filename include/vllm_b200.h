@@ -1,0 +1,73 @@
+/* libvllm_b200.so -- C-ABI of the B200-native VisionLLMv2 forward hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  All pointers are DEVICE
+ * pointers unless the parameter name says `host`.  Every function is
+ * re-entrant, keeps no global state (except the tuning knob marked below),
+ * enqueues on the caller's `stream` (a cudaStream_t passed as void*) and never
+ * allocates or synchronises.  Outputs are caller-allocated and fully written.
+ *
+ * Return value: 0 = ok; < 0 = argument error (VLLM_E*); > 0 = the cudaError_t
+ * of a failed launch.  The reference only printf()s launch errors
+ * (mmcv/ops/csrc/pytorch/cuda/ms_deform_attn_cuda.cu:41-44) and its Python
+ * caller silently falls back to grid_sample (grounding_dino/
+ * modeling_ov_grounding_dino_mask_dn.py:777-779); this boundary reports them.
+ *
+ * Paths below are relative to /root/reference/VisionLLMv2/.
+ */
+#ifndef VLLM_B200_H
+#define VLLM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLLM_OK 0
+#define VLLM_EINVAL (-1)       /* null pointer / negative size / inconsistent shapes */
+#define VLLM_EUNSUPPORTED (-2) /* shape outside what the kernels implement */
+#define VLLM_EALIGN (-3)       /* pointer alignment the vector path needs is missing */
+
+/* Library identity / build info: "vllm_b200 <git-less version> sm_100a". */
+const char* vllm_version(void);
+
+/* ---- Multi-scale deformable attention --------------------------------------
+ * Replaces `ms_deform_attn_forward` of the reference extension module
+ * `MultiScaleDeformableAttention`:
+ *   visionllmv2/model/unipose/ops/src/ms_deform_attn.h:21-40 (pybind vision.cpp:13-16)
+ *   mmcv/mmcv/ops/csrc/pytorch/ms_deform_attn.cpp:38-60 (pybind.cpp:788-798)
+ *   kernel: mmcv/mmcv/ops/csrc/common/cuda/ms_deform_attn_cuda_kernel.cuh:17-64,200-254
+ * value [batch, spatial_size, num_heads, channels]; spatial_shapes [num_levels,2]
+ * int64 (H,W) on device; level_start_index [num_levels] int64 on device;
+ * sampling_loc [batch, num_query, num_heads, num_levels, num_point, 2] (x,y);
+ * attn_weight [batch, num_query, num_heads, num_levels, num_point];
+ * out [batch, num_query, num_heads*channels].
+ * host_shapes_hint: optional HOST copy of spatial_shapes (may be NULL); only
+ * used to order the work (2-D pixel patches when num_query == spatial_size);
+ * results never depend on it.
+ * flags bit0 (VLLM_MSDA_STRICT): reference thread mapping and summation order
+ * with no FMA contraction -- bit-exact against oracle/msda_oracle.c.
+ */
+#define VLLM_MSDA_STRICT 1
+int vllm_msda_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const float* sampling_loc, const float* attn_weight, float* out, int batch,
+                          int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                          int num_point, const int64_t* host_shapes_hint, int flags, void* stream);
+/* fp64 instance of the same operator (AT_DISPATCH_FLOATING_TYPES,
+ * ms_deform_attn_cuda.cu:258); always the strict kernel. */
+int vllm_msda_forward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const double* sampling_loc, const double* attn_weight, double* out, int batch,
+                          int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                          int num_point, void* stream);
+/* Parity instrumentation: for each of n_samples = batch*num_query*num_heads*
+ * num_levels*num_point samples writes (h_low, w_low, mask) int32 triples using
+ * the SAME device function the forward kernels use.  mask bit0 = sample in
+ * range (kernel.cuh:241), bits1..4 = corner in bounds (kernel.cuh:39-57).
+ * h_low/w_low are 0 when bit0 is clear. */
+int vllm_msda_sample_indices_f32(const int64_t* spatial_shapes, const float* sampling_loc, int32_t* out_hwm,
+                                 long long n_samples, int num_levels, int num_point, void* stream);
+/* Tuning knob for bench sweeps (process-global, not part of the drop-in API). */
+int vllm_msda_set_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,76 @@
+"""ctypes binding of libvllm_b200.so (the C-ABI in include/vllm_b200.h).
+
+The library is built in-tree by ``make`` / ``__graft_entry__.build()`` and is
+the ONLY compute path of this package: a missing library is an ImportError at
+first use, never a silent fallback (the reference silently falls back to
+grid_sample, grounding_dino/modeling_ov_grounding_dino_mask_dn.py:777-779).
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvllm_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+_launches = 0  # number of C-ABI compute calls issued (bench.py's gpu_launches)
+
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+vp = ctypes.c_void_p
+ci = ctypes.c_int
+cll = ctypes.c_longlong
+cf = ctypes.c_float
+
+_SIGNATURES = {
+    "vllm_version": (ctypes.c_char_p, []),
+    "vllm_msda_forward_f32": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
+    "vllm_msda_forward_f64": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
+    "vllm_msda_sample_indices_f32": (ci, [vp, vp, vp, cll, ci, ci, vp]),
+    "vllm_msda_set_variant": (ci, [ci]),
+}
+
+
+class VllmB200Error(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_PATH} is missing: build it with `make` or "
+                        "`python -c 'import __graft_entry__ as g; g.build()'`. "
+                        "visionllm_b200 has no CPU/eager fallback.")
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = L
+    return _lib
+
+
+_ERR = {-1: "invalid argument", -2: "unsupported shape", -3: "misaligned pointer"}
+
+
+def check(rc, what):
+    """Raise on a non-zero C-ABI return code."""
+    global _launches
+    _launches += 1
+    if rc == 0:
+        return
+    if rc < 0:
+        raise VllmB200Error(f"{what}: {_ERR.get(rc, 'error')} (rc={rc})")
+    raise VllmB200Error(f"{what}: CUDA error {rc} at launch")
+
+
+def launch_count():
+    return _launches

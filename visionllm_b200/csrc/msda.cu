@@ -1,0 +1,422 @@
+// Multi-scale deformable attention (MSDA) forward for sm_100a.
+//
+// Replaces the reference operator
+//   mmcv/ops/csrc/common/cuda/ms_deform_attn_cuda_kernel.cuh:17-64,200-254
+//   (== visionllmv2/model/unipose/ops/src/cuda/ms_deform_im2col_cuda.cuh:33-85,237-300)
+// behind the C-ABI declared in include/vllm_b200.h.
+//
+// Data layout (all contiguous, identical to the reference extension):
+//   value  [N, S, M, D]          S = sum_l H_l*W_l, level-major, row-major
+//   shapes [L, 2] int64 (H, W)   on the DEVICE, like the reference
+//   lsi    [L]    int64          level start index, on the DEVICE
+//   loc    [N, Lq, M, L, P, 2]   (x, y) normalised
+//   attw   [N, Lq, M, L, P]
+//   out    [N, Lq, M*D]
+//
+// Two kernels:
+//  * msda_fwd_strict_kernel<T>: one thread per output scalar, the reference's
+//    arithmetic and summation order with every product/sum individually
+//    rounded (no FMA contraction).  Any D / L / P, fp32 and fp64.  Bit-exact
+//    against oracle/msda_oracle.c.
+//  * msda_fwd_warp_kernel: the fast fp32 path for D == 32.  One warp owns a
+//    (query, head) pair.  Phase 1: one lane per (level, point) sample does the
+//    index arithmetic ONCE (the reference repeats it in all D threads) and
+//    writes {element offset, bilinear*attention weight} per corner to a
+//    warp-private shared-memory slab.  Phase 2: lane = (corner, channel quad):
+//    one predicated LDG.128 per lane fetches the four 128-byte corner rows of
+//    a sample in a single instruction; each lane FMAs into a float4
+//    accumulator; two shuffle rounds fold the four corner groups at the end.
+//    Queries are visited in 2-D pixel patches per level when the queries are
+//    the pixels themselves (encoder self-attention), so the overlapping
+//    sampling neighbourhoods of a CTA hit in L1.
+//
+// Sampling-index arithmetic (bit-exact contract): the
+// reference computes `loc * spatial - 0.5` with a double literal, so the
+// product is rounded to fp32 BEFORE the subtraction; nvcc must not contract it
+// into an FMA.  msda_geom() uses __fmul_rn/__fsub_rn and is shared by both
+// kernels and by the index-dump entry point the parity tests use.
+#include "common.cuh"
+#include <limits.h>
+
+#define MSDA_MAX_LEVELS 8
+
+struct MsdaTiling {
+  int mode;                          // 0: tiles of consecutive queries; 1: 2-D pixel patches
+  int n_tiles;                       // tiles per (batch, head)
+  int tile_start[MSDA_MAX_LEVELS + 1];
+  int H[MSDA_MAX_LEVELS], W[MSDA_MAX_LEVELS];
+  int q_start[MSDA_MAX_LEVELS];
+  int tiles_w[MSDA_MAX_LEVELS];
+};
+
+// ---------------------------------------------------------------------------
+// Index arithmetic shared by every path (reference .cuh:238-241 and :22-29).
+// ---------------------------------------------------------------------------
+template <typename T> struct MsdaGeom {
+  int h_low, w_low;
+  T lh, lw;
+  int mask;  // bit0: sample in range; bits1..4: corner (ll, lh, hl, hh) in bounds
+};
+
+__device__ __forceinline__ float msda_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float msda_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float msda_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double msda_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double msda_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double msda_add(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename T>
+__device__ __forceinline__ MsdaGeom<T> msda_geom(T loc_w, T loc_h, int H, int W) {
+  MsdaGeom<T> g;
+  const T h_im = msda_sub(msda_mul(loc_h, (T)H), (T)0.5);
+  const T w_im = msda_sub(msda_mul(loc_w, (T)W), (T)0.5);
+  g.mask = 0; g.h_low = 0; g.w_low = 0; g.lh = 0; g.lw = 0;
+  if (h_im > (T)-1 && w_im > (T)-1 && h_im < (T)H && w_im < (T)W) {
+    // The reference calls floorf() for every scalar type (kernel.cuh:22-23).
+    const int h_low = (int)floorf((float)h_im);
+    const int w_low = (int)floorf((float)w_im);
+    g.h_low = h_low; g.w_low = w_low;
+    g.lh = msda_sub(h_im, (T)h_low);
+    g.lw = msda_sub(w_im, (T)w_low);
+    const int h_high = h_low + 1, w_high = w_low + 1;
+    int m = 1;
+    if (h_low >= 0 && w_low >= 0) m |= 2;
+    if (h_low >= 0 && w_high <= W - 1) m |= 4;
+    if (h_high <= H - 1 && w_low >= 0) m |= 8;
+    if (h_high <= H - 1 && w_high <= W - 1) m |= 16;
+    g.mask = m;
+  }
+  return g;
+}
+
+// ---------------------------------------------------------------------------
+// Strict kernel: reference mapping, reference order, no contraction.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_fwd_strict_kernel(const long long n, const T* __restrict__ value,
+                       const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+                       const T* __restrict__ loc, const T* __restrict__ attw, T* __restrict__ out,
+                       int S, int M, int D, int L, int Lq, int P) {
+  __shared__ int s_h[MSDA_MAX_LEVELS], s_w[MSDA_MAX_LEVELS], s_start[MSDA_MAX_LEVELS];
+  if (threadIdx.x < L) {
+    s_h[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    s_w[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    s_start[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x; index < n; index += stride) {
+    const int c = (int)(index % D);
+    const long long pair = index / D;  // (b*Lq + q)*M + m
+    const int m = (int)(pair % M);
+    const long long b = pair / M / Lq;
+    long long wptr = pair * L * P;
+    const int qid_stride = M * D;
+    const T* vb = value + b * (long long)S * qid_stride;
+    T col = 0;
+    for (int l = 0; l < L; ++l) {
+      const int H = s_h[l], W = s_w[l];
+      const T* vl = vb + (long long)s_start[l] * qid_stride + m * D + c;
+      for (int p = 0; p < P; ++p, ++wptr) {
+        const T lw_ = loc[2 * wptr], lh_ = loc[2 * wptr + 1];
+        const T weight = attw[wptr];
+        const MsdaGeom<T> g = msda_geom<T>(lw_, lh_, H, W);
+        if (g.mask & 1) {
+          const T hh = msda_sub((T)1, g.lh), hw = msda_sub((T)1, g.lw);
+          const int w_stride = qid_stride, h_stride = W * qid_stride;
+          const int o_hl = g.h_low * h_stride, o_wl = g.w_low * w_stride;
+          T v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+          if (g.mask & 2) v1 = vl[o_hl + o_wl];
+          if (g.mask & 4) v2 = vl[o_hl + o_wl + w_stride];
+          if (g.mask & 8) v3 = vl[o_hl + h_stride + o_wl];
+          if (g.mask & 16) v4 = vl[o_hl + h_stride + o_wl + w_stride];
+          const T w1 = msda_mul(hh, hw), w2 = msda_mul(hh, g.lw);
+          const T w3 = msda_mul(g.lh, hw), w4 = msda_mul(g.lh, g.lw);
+          T val = msda_mul(w1, v1);
+          val = msda_add(val, msda_mul(w2, v2));
+          val = msda_add(val, msda_mul(w3, v3));
+          val = msda_add(val, msda_mul(w4, v4));
+          col = msda_add(col, msda_mul(val, weight));
+        }
+      }
+    }
+    out[index] = col;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Index dump (parity instrumentation): (h_low, w_low, mask) per sample.
+// ---------------------------------------------------------------------------
+__global__ void msda_index_dump_kernel(long long n_samples, const int64_t* __restrict__ shapes,
+                                       const float* __restrict__ loc, int32_t* __restrict__ out,
+                                       int L, int P) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += stride) {
+    const int l = (int)((i / P) % L);
+    const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+    const MsdaGeom<float> g = msda_geom<float>(loc[2 * i], loc[2 * i + 1], H, W);
+    out[3 * i] = g.h_low; out[3 * i + 1] = g.w_low; out[3 * i + 2] = g.mask;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fast warp kernel (fp32, D == 32, L*P <= 32).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 ld_stream_f2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// TH x TW query tile per CTA, NW warps; each warp owns TH*TW/NW queries.
+template <int TH, int TW, int NW, typename OutT>
+__global__ void __launch_bounds__(NW * 32)
+msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                     const float* __restrict__ attw, OutT* __restrict__ out,
+                     int S, int M, int L, int Lq, int P, const __grid_constant__ MsdaTiling tl) {
+  constexpr int D = 32;
+  constexpr int TQ = TH * TW;
+  constexpr int QPW = TQ / NW;  // queries per warp
+  static_assert(TQ % NW == 0, "tile must split evenly over warps");
+  __shared__ int s_h[MSDA_MAX_LEVELS], s_w[MSDA_MAX_LEVELS], s_start[MSDA_MAX_LEVELS];
+  __shared__ int2 s_meta[NW][32][4];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < L) {
+    s_h[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    s_w[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    s_start[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  __syncthreads();
+
+  const int m = blockIdx.x % M;
+  const int tile = blockIdx.x / M;
+  const int b = blockIdx.y;
+  const int K = L * P;
+  const int G = (32 / K) < QPW ? (32 / K) : QPW;  // (query, head) pairs per phase-1 pass
+  const int MD = M * D;
+
+  // tile -> query mapping
+  int lvl = 0, ty = 0, tx = 0;
+  if (tl.mode == 1) {
+    while (lvl + 1 < L && tile >= tl.tile_start[lvl + 1]) ++lvl;
+    const int lt = tile - tl.tile_start[lvl];
+    ty = lt / tl.tiles_w[lvl]; tx = lt % tl.tiles_w[lvl];
+  }
+  auto query_of = [&](int t) -> int {  // t: tile-local index; -1 if outside
+    if (tl.mode == 0) { const int q = tile * TQ + t; return q < Lq ? q : -1; }
+    const int py = ty * TH + t / TW, px = tx * TW + t % TW;
+    if (py >= tl.H[lvl] || px >= tl.W[lvl]) return -1;
+    return tl.q_start[lvl] + py * tl.W[lvl] + px;
+  };
+
+  const float* vb = value + (size_t)b * S * MD + m * D;
+  const int corner = lane >> 3, cq = lane & 7;
+
+  for (int t0 = 0; t0 < QPW; t0 += G) {
+    // ---- phase 1: one lane per sample ---------------------------------
+    {
+      const int g = lane / K, s = lane - g * K;
+      int q = -1;
+      if (g < G && t0 + g < QPW) q = query_of(warp * QPW + t0 + g);
+      int2 meta[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) meta[c] = make_int2(-1, 0);
+      if (q >= 0) {
+        const size_t pair = ((size_t)b * Lq + q) * M + m;
+        const size_t si = pair * K + s;
+        const float2 xy = ld_stream_f2(loc + 2 * si);
+        const float aw = ld_stream_f1(attw + si);
+        const int l = s / P;
+        const int H = s_h[l], W = s_w[l];
+        const MsdaGeom<float> ge = msda_geom<float>(xy.x, xy.y, H, W);
+        if (ge.mask & 1) {
+          const float hh = 1.f - ge.lh, hw = 1.f - ge.lw;
+          const int base = (s_start[l] + ge.h_low * W + ge.w_low) * MD;
+          const float w1 = hh * hw, w2 = hh * ge.lw, w3 = ge.lh * hw, w4 = ge.lh * ge.lw;
+          if (ge.mask & 2) meta[0] = make_int2(base, __float_as_int(w1 * aw));
+          if (ge.mask & 4) meta[1] = make_int2(base + MD, __float_as_int(w2 * aw));
+          if (ge.mask & 8) meta[2] = make_int2(base + W * MD, __float_as_int(w3 * aw));
+          if (ge.mask & 16) meta[3] = make_int2(base + W * MD + MD, __float_as_int(w4 * aw));
+        }
+      }
+      int4* dst = reinterpret_cast<int4*>(&s_meta[warp][lane][0]);
+      dst[0] = make_int4(meta[0].x, meta[0].y, meta[1].x, meta[1].y);
+      dst[1] = make_int4(meta[2].x, meta[2].y, meta[3].x, meta[3].y);
+    }
+    __syncwarp();
+    // ---- phase 2: lane = (corner, channel quad) -------------------------
+    for (int g = 0; g < G && t0 + g < QPW; ++g) {
+      const int q = query_of(warp * QPW + t0 + g);
+      if (q < 0) continue;  // warp-uniform
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int2* mp = &s_meta[warp][g * K][corner];
+#pragma unroll 4
+      for (int s = 0; s < K; ++s) {
+        const int2 me = mp[s * 4];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (me.x >= 0) v = __ldg(reinterpret_cast<const float4*>(vb + me.x) + cq);
+        const float w = __int_as_float(me.y);
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+      if (corner == 0) {
+        OutT* op = out + (((size_t)b * Lq + q) * M + m) * D + cq * 4;
+        if constexpr (sizeof(OutT) == 4) {
+          __stcs(reinterpret_cast<float4*>(op), acc);
+        } else {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(op) = pk;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+static int g_msda_variant = 0;  // bench/tuning knob, see vllm_msda_set_variant
+
+static bool build_tiling(MsdaTiling& tl, const int64_t* host_shapes, int L, int Lq, int S, int TH, int TW) {
+  tl.mode = 0;
+  tl.n_tiles = (Lq + TH * TW - 1) / (TH * TW);
+  if (!host_shapes || Lq != S) return false;
+  long long tot = 0; int tiles = 0;
+  for (int l = 0; l < L; ++l) {
+    const long long H = host_shapes[2 * l], W = host_shapes[2 * l + 1];
+    if (H <= 0 || W <= 0 || H > INT_MAX || W > INT_MAX) return false;
+    tl.H[l] = (int)H; tl.W[l] = (int)W; tl.q_start[l] = (int)tot;
+    tl.tile_start[l] = tiles;
+    tl.tiles_w[l] = (int)((W + TW - 1) / TW);
+    tiles += tl.tiles_w[l] * (int)((H + TH - 1) / TH);
+    tot += H * W;
+  }
+  tl.tile_start[L] = tiles;
+  if (tot != Lq) return false;  // hint inconsistent with the query count: keep linear tiles
+  tl.mode = 1; tl.n_tiles = tiles;
+  return true;
+}
+
+template <int TH, int TW, int NW, typename OutT>
+static int launch_warp(const float* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
+                       const float* attw, OutT* out, int N, int S, int M, int L, int Lq, int P,
+                       const int64_t* host_shapes, cudaStream_t st) {
+  MsdaTiling tl; memset(&tl, 0, sizeof(tl));
+  build_tiling(tl, host_shapes, L, Lq, S, TH, TW);
+  dim3 grid((unsigned)(tl.n_tiles * M), (unsigned)N);
+  if (N > 65535) return VLLM_EUNSUPPORTED;
+  msda_fwd_warp_kernel<TH, TW, NW, OutT><<<grid, NW * 32, 0, st>>>(value, shapes, lsi, loc, attw, out, S, M, L,
+                                                                   Lq, P, tl);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+template <typename T>
+static int launch_strict(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* attw,
+                         T* out, int N, int S, int M, int D, int L, int Lq, int P, cudaStream_t st) {
+  const long long n = (long long)N * Lq * M * D;
+  if (n == 0) return VLLM_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)vllm_num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  msda_fwd_strict_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(n, value, shapes, lsi, loc, attw, out, S, M, D, L,
+                                                               Lq, P);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+static int check_common(const void* value, const void* shapes, const void* lsi, const void* loc, const void* attw,
+                        const void* out, int N, int S, int M, int D, int L, int Lq, int P) {
+  if (N < 0 || S < 0 || M <= 0 || D <= 0 || L <= 0 || Lq < 0 || P <= 0) return VLLM_EINVAL;
+  if (L > MSDA_MAX_LEVELS) return VLLM_EUNSUPPORTED;
+  if ((long long)N * Lq == 0) return VLLM_OK + 1000;  // empty: nothing to do
+  if (!value || !shapes || !lsi || !loc || !attw || !out) return VLLM_EINVAL;
+  if ((long long)S * M * D > INT_MAX) return VLLM_EUNSUPPORTED;  // per-image offsets are int32
+  return VLLM_OK;
+}
+
+extern "C" {
+
+int vllm_msda_set_variant(int v) { g_msda_variant = v; return VLLM_OK; }
+
+int vllm_msda_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const float* sampling_loc, const float* attn_weight, float* out, int batch,
+                          int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                          int num_point, const int64_t* host_shapes_hint, int flags, void* stream) {
+  int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, batch,
+                        spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (rc == 1000) return VLLM_OK;
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool strict = flags & 1;
+  const int K = num_levels * num_point;
+  if (!strict && channels == 32 && K <= 32 && vllm_aligned(value, 16) && vllm_aligned(out, 16) &&
+      vllm_aligned(sampling_loc, 8)) {
+    switch (g_msda_variant) {
+      case 1: return launch_warp<8, 8, 8, float>(value, spatial_shapes, level_start_index, sampling_loc,
+                                                 attn_weight, out, batch, spatial_size, num_heads, num_levels,
+                                                 num_query, num_point, host_shapes_hint, st);
+      case 2: return launch_warp<16, 16, 16, float>(value, spatial_shapes, level_start_index, sampling_loc,
+                                                    attn_weight, out, batch, spatial_size, num_heads, num_levels,
+                                                    num_query, num_point, host_shapes_hint, st);
+      case 3: return launch_warp<16, 16, 32, float>(value, spatial_shapes, level_start_index, sampling_loc,
+                                                    attn_weight, out, batch, spatial_size, num_heads, num_levels,
+                                                    num_query, num_point, host_shapes_hint, st);
+      case 4: return launch_warp<8, 8, 8, float>(value, spatial_shapes, level_start_index, sampling_loc,
+                                                 attn_weight, out, batch, spatial_size, num_heads, num_levels,
+                                                 num_query, num_point, nullptr, st);
+      default: return launch_warp<8, 16, 16, float>(value, spatial_shapes, level_start_index, sampling_loc,
+                                                    attn_weight, out, batch, spatial_size, num_heads, num_levels,
+                                                    num_query, num_point, host_shapes_hint, st);
+    }
+  }
+  return launch_strict<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, batch,
+                              spatial_size, num_heads, channels, num_levels, num_query, num_point, st);
+}
+
+int vllm_msda_forward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const double* sampling_loc, const double* attn_weight, double* out, int batch,
+                          int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                          int num_point, void* stream) {
+  int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, batch,
+                        spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (rc == 1000) return VLLM_OK;
+  if (rc) return rc;
+  return launch_strict<double>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, batch,
+                               spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                               (cudaStream_t)stream);
+}
+
+int vllm_msda_sample_indices_f32(const int64_t* spatial_shapes, const float* sampling_loc, int32_t* out_hwm,
+                                 long long n_samples, int num_levels, int num_point, void* stream) {
+  if (n_samples < 0 || num_levels <= 0 || num_point <= 0) return VLLM_EINVAL;
+  if (n_samples == 0) return VLLM_OK;
+  if (!spatial_shapes || !sampling_loc || !out_hwm) return VLLM_EINVAL;
+  long long blocks = (n_samples + 255) / 256;
+  const long long cap = (long long)vllm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  msda_index_dump_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n_samples, spatial_shapes,
+                                                                             sampling_loc, out_hwm, num_levels,
+                                                                             num_point);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+"""Drop-in for the reference extension module ``MultiScaleDeformableAttention``.
+
+Same surface as the pybind module built from
+``visionllmv2/model/unipose/ops/src/vision.cpp:13-16`` (positional
+``im2col_step``) and as ``mmcv._ext`` (keyword ``im2col_step``,
+``mmcv/ops/multi_scale_deform_attn.py:54-94``):
+
+    ms_deform_attn_forward(value, spatial_shapes, level_start_index,
+                           sampling_loc, attn_weight, im2col_step) -> Tensor[N, Lq, M*D]
+
+Install it where the reference looks it up::
+
+    import visionllm_b200.msda as ext
+    gd.MultiScaleDeformableAttention = ext          # grounding_dino/...mask_dn.py:110,147
+    sys.modules["MultiScaleDeformableAttention"] = ext   # unipose/ops/functions/ms_deform_attn_func.py:19
+    mmcv.ops.multi_scale_deform_attn.ext_module = ext    # mmcv/ops/multi_scale_deform_attn.py:19-20
+
+Errors follow the reference's convention (RuntimeError for non-contiguous /
+non-CUDA / wrong-dtype inputs and for ``batch % min(batch, im2col_step) != 0``,
+ms_deform_attn_cuda.cu:215-245) -- and, unlike the reference, launch errors
+raise too.  ``im2col_step`` is validated and otherwise ignored (one launch).
+"""
+import torch
+
+from . import _lib
+
+STRICT = 1
+
+_shape_cache = {}
+
+
+def _host_shapes(spatial_shapes):
+    """Cached host copy of the (tiny) spatial_shapes tensor: work-ordering hint only."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.device.index)
+    hit = _shape_cache.get(key)
+    if hit is None:
+        if len(_shape_cache) > 64:
+            _shape_cache.clear()
+        hit = spatial_shapes.detach().to("cpu", torch.int64).contiguous()
+        _shape_cache[key] = hit
+    return hit
+
+
+def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    names = ("value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight")
+    for n, t in zip(names, (value, spatial_shapes, level_start_index, sampling_loc, attn_weight)):
+        if not t.is_contiguous():
+            raise RuntimeError(f"{n} tensor has to be contiguous")
+        if not t.is_cuda:
+            raise RuntimeError(f"{n} must be a CUDA tensor")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes / level_start_index must be int64")
+    if value.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError(f"ms_deform_attn_forward not implemented for '{value.dtype}'")
+    if sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
+        raise RuntimeError("expected sampling_loc / attn_weight to have the dtype of value")
+    if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5:
+        raise RuntimeError("expected value[N,S,M,D], sampling_loc[N,Lq,M,L,P,2], attn_weight[N,Lq,M,L,P]")
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    _, Lq, M2, L2, P, two = sampling_loc.shape
+    if (M2, L2, two) != (M, L, 2) or tuple(attn_weight.shape) != (N, Lq, M, L, P) or sampling_loc.shape[0] != N:
+        raise RuntimeError("inconsistent MSDA shapes")
+    step = min(N, int(im2col_step)) if N > 0 else 1
+    if step <= 0 or (N > 0 and N % step != 0):
+        raise RuntimeError(f"batch({N}) must divide im2col_step({step})")
+    return N, S, M, D, L, Lq, P
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                           im2col_step=64, *, flags=0, host_shapes=None):
+    N, S, M, D, L, Lq, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                         im2col_step)
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    if out.numel() == 0:
+        return out
+    L_ = _lib.lib()
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if value.dtype == torch.float32:
+            hs = host_shapes if host_shapes is not None else _host_shapes(spatial_shapes)
+            rc = L_.vllm_msda_forward_f32(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                          sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
+                                          N, S, M, D, L, Lq, P, hs.data_ptr(), int(flags), stream)
+        else:
+            rc = L_.vllm_msda_forward_f64(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                          sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
+                                          N, S, M, D, L, Lq, P, stream)
+    _lib.check(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_sample_indices(spatial_shapes, sampling_loc):
+    """(h_low, w_low, mask) int32 per sample, from the device function the kernels use."""
+    if sampling_loc.dtype != torch.float32 or not sampling_loc.is_cuda or not sampling_loc.is_contiguous():
+        raise RuntimeError("sampling_loc must be a contiguous CUDA float32 tensor")
+    L, P = sampling_loc.shape[-3], sampling_loc.shape[-2]
+    n = sampling_loc.numel() // 2
+    out = torch.empty(tuple(sampling_loc.shape[:-1]) + (3,), dtype=torch.int32, device=sampling_loc.device)
+    with torch.cuda.device(sampling_loc.device):
+        rc = _lib.lib().vllm_msda_sample_indices_f32(spatial_shapes.data_ptr(), sampling_loc.data_ptr(),
+                                                     out.data_ptr(), n, L, P,
+                                                     torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_sample_indices")
+    return out
+
+
+def ms_deform_attn_backward(*args, **kwargs):
+    raise NotImplementedError(
+        "ms_deform_attn_backward is a SURVEY 8(f) 'next' row (forward-only hot path this round)")
