@@ -67,6 +67,47 @@ int vllm_msda_sample_indices_f32(const int64_t* spatial_shapes, const float* sam
 /* Tuning knob for bench sweeps (process-global, not part of the drop-in API). */
 int vllm_msda_set_variant(int variant);
 
+/* ---- bf16 tensor-core GEMM with fused epilogue (tcgen05 / TMEM / TMA) ----------
+ * C[M, n_out] = epi(A[M,K] . B[N,K]^T): every nn.Linear on the hot path
+ * (internvit/modeling_intern_vit.py:112,124,172-173; modeling_visionllmv2.py:162-184;
+ * HF LlamaDecoderLayer / internlm2/modeling_internlm2.py:235-360;
+ * grounding_dino/modeling_ov_grounding_dino_mask_dn.py:674-677,1116-1117), replacing
+ * torch's cuBLAS calls plus the separate bias / activation / LayerScale / residual
+ * elementwise kernels.  A, B bf16 row-major with row pitches lda, ldb (elements,
+ * multiples of 8, 16-byte aligned bases).  epilogue order: +bias[N] (bf16, may be
+ * NULL) -> act -> *colscale[N] (bf16, may be NULL) -> +residual[M, ldr] (bf16, may be
+ * NULL) -> store bf16 (out_f32 = 0) or fp32 (out_f32 = 1) with row pitch ldc.
+ * act: 0 none, 1 GELU(erf), 2 ReLU, 3 SiLU, 4 SwiGLU (columns (2j,2j+1) = (gate_j,
+ * up_j) -> n_out = N/2 = silu(gate)*up), 5 quick-GELU (CLIP). */
+#define VLLM_ACT_NONE 0
+#define VLLM_ACT_GELU 1
+#define VLLM_ACT_RELU 2
+#define VLLM_ACT_SILU 3
+#define VLLM_ACT_SWIGLU 4
+#define VLLM_ACT_QUICKGELU 5
+int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                   const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
+                   void* stream);
+/* Tuning knob (process-global): 1 = cta_group::1 tiles 128x256, 2 = CTA-pair tiles 256x256. */
+int vllm_gemm_set_variant(int variant);
+
+/* ---- row-wise norms and RoPE (bf16 in/out, fp32 statistics) ----------------------
+ * vllm_rmsnorm_bf16 replaces apex.normalization.FusedRMSNorm forward
+ * (apex/csrc/layer_norm_cuda.cpp:436-441 rms_forward_affine; kernel
+ * layer_norm_cuda_kernel.cu:353-437) and the python fallbacks InternRMSNorm
+ * (internvit/modeling_intern_vit.py:33-44) / InternLM2RMSNorm / LlamaRMSNorm.
+ * Rows may be strided (ldx, ldy in elements) so q/k slices of a packed qkv tensor are
+ * normalised in place.  cols % 8 == 0, cols <= 16384. */
+int vllm_rmsnorm_bf16(const void* x, long long ldx, const void* weight, void* y, long long ldy, long long rows,
+                      int cols, float eps, void* stream);
+int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const void* bias, void* y, long long ldy,
+                        long long rows, int cols, float eps, void* stream);
+/* In-place rotate-half RoPE on x[tokens, heads, head_dim] rows with pitch ld; cos/sin
+ * [tokens, head_dim] bf16 gathered per position (HF Llama apply_rotary_pos_emb;
+ * internlm2/modeling_internlm2.py:218-232). */
+int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long long tokens, int heads,
+                   int head_dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

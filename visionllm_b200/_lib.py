@@ -28,6 +28,11 @@ _SIGNATURES = {
     "vllm_msda_forward_f64": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
     "vllm_msda_sample_indices_f32": (ci, [vp, vp, vp, cll, ci, ci, vp]),
     "vllm_msda_set_variant": (ci, [ci]),
+    "vllm_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp]),
+    "vllm_gemm_set_variant": (ci, [ci]),
+    "vllm_rmsnorm_bf16": (ci, [vp, cll, vp, vp, cll, cll, ci, cf, vp]),
+    "vllm_layernorm_bf16": (ci, [vp, cll, vp, vp, vp, cll, cll, ci, cf, vp]),
+    "vllm_rope_bf16": (ci, [vp, cll, vp, vp, cll, ci, ci, vp]),
 }
 
 

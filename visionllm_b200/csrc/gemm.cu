@@ -1,0 +1,365 @@
+// bf16 GEMM with fused epilogue on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+//   C[M, N] = epilogue( A[M, K] . B[N, K]^T )      A, B bf16 K-major (B is an nn.Linear weight [out, in])
+//   epilogue: (+bias[N]) -> act -> (*colscale[N]) -> (+residual[M, N]) -> bf16 | fp32
+//   act = SWIGLU pairs columns (2j, 2j+1) = (gate_j, up_j) and writes N/2 columns.
+//
+// This one kernel carries every dense projection on the hot path:
+//   InternViT  qkv / proj(+bias, *ls1, +x) / fc1(+bias, GELU) / fc2(+bias, *ls2, +x)
+//              (internvit/modeling_intern_vit.py:112,124,172-173,206-208), patch-embed as im2col GEMM (:73-85)
+//   vl_bridge  Linear+GELU+Linear (modeling_visionllmv2.py:162-184)
+//   LLM        q/k/v/o, gate|up (SwiGLU), down(+residual)  (HF LlamaDecoderLayer; internlm2/modeling_internlm2.py:235-360)
+//   GDINO      value/offset/weight/output projections, FFN (ReLU)  (grounding_dino/...mask_dn.py:674-677,1116-1117)
+//
+// Structure (persistent, warp-specialised, one CTA or one CTA pair per SM):
+//   warp 0   TMA producer: A tile 128x64 and B tile (256|128)x64 bf16, 128B swizzle, STAGES-deep mbarrier ring
+//   warp 1   MMA issuer : one elected lane issues tcgen05.mma kind::f16, UMMA 128x256x16 (cta_group::1) or
+//            256x256x16 over a CTA pair (cta_group::2); fp32 accumulators in TMEM, 2 accumulator stages
+//            (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused math -> 16-byte global stores
+// Tiles are visited in groups of GROUP_M row-blocks so concurrently running CTAs share B (weights) in L2.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, ACC = 2, THREADS = 256, GROUP_M = 8;
+constexpr int A_BYTES = BM * BK * 2;
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SILU = 3, ACT_SWIGLU = 4, ACT_QUICKGELU = 5 };
+
+struct GemmArgs {
+  int M, N, K;
+  void* C; int ldc;
+  const __nv_bfloat16* bias; const __nv_bfloat16* colscale; const __nv_bfloat16* residual; int ldr;
+  int act; int out_f32;
+  int tiles_m, tiles_n;  // tiles_m counts 128*CG-row blocks
+};
+
+template <int CG> struct Cfg {
+  static constexpr int B_ROWS = BN / CG;               // B rows held by one CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = CG == 1 ? 4 : 6;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias, scale*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int per_group = GROUP_M * tiles_n;
+  const int group = t / per_group;
+  const int first = group * GROUP_M;
+  const int gsz = min(GROUP_M, tiles_m - first);
+  const int in = t - group * per_group;
+  tm = first + in % gsz;
+  tn = in / gsz;
+}
+
+template <int CG>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmArgs g) {
+  using C_ = Cfg<CG>;
+  constexpr int STAGES = C_::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * C_::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8 * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8 * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8 * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8 * (2 * STAGES + ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8 * (2 * STAGES + 2 * ACC);
+  uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + STAGES * C_::STAGE_BYTES + 8 * (2 * STAGES + 2 * ACC));
+  float* s_bias = reinterpret_cast<float*>(smem_gen + STAGES * C_::STAGE_BYTES + 256);
+  float* s_scale = s_bias + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? tc::cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x / CG, n_clusters = gridDim.x / CG;
+  const int n_tiles = g.tiles_m * g.tiles_n;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmap_a);
+    tc::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < ACC; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 4 * CG); }
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc<CG>(tmem_slot, ACC * BN);
+  tc::tc_fence_before();
+  if constexpr (CG == 2) tc::cluster_sync(); else __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (tc::elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = cluster_id; t < n_tiles; t += n_clusters) {
+        int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+        const int row_a = (tm * CG + (int)rank) * BM;
+        const int row_b = tn * BN + (int)rank * C_::B_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * C_::STAGE_BYTES, sb = sa + A_BYTES;
+          if constexpr (CG == 1) {
+            tc::mbar_arrive_expect_tx(full_bar(stage), C_::STAGE_BYTES);
+            tc::tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, row_a);
+            tc::tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, row_b);
+          } else {
+            if (leader) tc::mbar_arrive_expect_tx(full_bar(stage), 2 * C_::STAGE_BYTES);
+            tc::tma_load_2d_cg2(sa, &tmap_a, full_bar(stage), kb * BK, row_a);
+            tc::tma_load_2d_cg2(sb, &tmap_b, full_bar(stage), kb * BK, row_b);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (leader) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(BM * CG, BN);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int t = cluster_id; t < n_tiles; t += n_clusters) {
+        tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(full_bar(stage), phase);
+          tc::tc_fence_after();
+          if (tc::elect_one()) {
+            const uint32_t sa = smem_base + stage * C_::STAGE_BYTES, sb = sa + A_BYTES;
+            const uint64_t adesc = tc::umma_desc_kmajor_sw128(sa), bdesc = tc::umma_desc_kmajor_sw128(sb);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc::umma_f16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            tc::umma_commit<CG>(empty_bar(stage));
+            if (kb == num_kb - 1) tc::umma_commit<CG>(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;
+    const int et = threadIdx.x - 128;  // 0..127
+    int acc = 0; uint32_t acc_phase = 0;
+    const bool swiglu = g.act == ACT_SWIGLU;
+    for (int t = cluster_id; t < n_tiles; t += n_clusters) {
+      int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+      const int n0 = tn * BN;
+      const int row = (tm * CG + (int)rank) * BM + quarter * 32 + lane;
+      // stage bias / column scale for this tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = et; c < BN; c += 128) {
+        const int col = n0 + c;
+        s_bias[c] = (g.bias && col < g.N) ? __bfloat162float(g.bias[col]) : 0.f;
+        s_scale[c] = (g.colscale && col < g.N) ? __bfloat162float(g.colscale[col]) : 1.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      tc::mbar_wait(tfull_bar(acc), acc_phase);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      const bool row_ok = row < g.M;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int col0 = n0 + c;
+        if (col0 >= g.N) break;  // uniform
+        uint32_t r[32];
+        tc::tmem_ld_32x32(taddr + c, r);
+        tc::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c + j];
+        if (g.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (g.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (g.act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+        } else if (g.act == ACT_QUICKGELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-1.702f * v[j]));
+        }
+        if (swiglu) {
+          // columns (2j, 2j+1) = (gate, up) -> 16 outputs at column col0/2
+          if (row_ok) {
+            const int oc0 = col0 >> 1;
+            const int n_out = g.N >> 1;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = silu(v[2 * j]) * v[2 * j + 1];
+            if (g.residual) {
+              const __nv_bfloat16* rp = g.residual + (size_t)row * g.ldr + oc0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (oc0 + j < n_out) o[j] += __bfloat162float(rp[j]);
+            }
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (size_t)row * g.ldc + oc0;
+            if (oc0 + 16 <= n_out) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                uint4 pk;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(o[8 * q + 0], o[8 * q + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(o[8 * q + 2], o[8 * q + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(o[8 * q + 4], o[8 * q + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(o[8 * q + 6], o[8 * q + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(cp + 8 * q) = pk;
+              }
+            } else {
+              for (int j = 0; j < 16; ++j) if (oc0 + j < n_out) cp[j] = __float2bfloat16(o[j]);
+            }
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= s_scale[c + j];
+        if (row_ok) {
+          const bool full = col0 + 32 <= g.N;
+          if (g.residual) {
+            const __nv_bfloat16* rp = g.residual + (size_t)row * g.ldr + col0;
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rp + 8 * q);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(r2[j]);
+                  v[8 * q + 2 * j] += f.x; v[8 * q + 2 * j + 1] += f.y;
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (g.out_f32) {
+            float* cp = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col0;
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(cp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) cp[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (size_t)row * g.ldc + col0;
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 pk;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(cp + 8 * q) = pk;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.N) cp[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA issuer
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) tc::mbar_arrive(tempty_bar(acc));
+        else tc::mbar_arrive_cluster(tempty_bar(acc), 0);
+      }
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ===================== teardown =====================
+  tc::tc_fence_before();
+  if constexpr (CG == 2) tc::cluster_sync(); else __syncthreads();
+  if (warp == 2) tc::tmem_dealloc<CG>(tmem_base, ACC * BN);
+}
+
+int g_gemm_variant = 1;  // 1: cta_group::1, 2: cta_group::2 (CTA pairs)
+
+template <int CG>
+int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cudaStream_t st) {
+  using C_ = Cfg<CG>;
+  CUtensorMap ta, tb;
+  int rc = vllm_make_tmap_bf16(&ta, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)lda, BM);
+  if (rc) return rc;
+  rc = vllm_make_tmap_bf16(&tb, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, C_::B_ROWS);
+  if (rc) return rc;
+  g.tiles_m = (g.M + BM * CG - 1) / (BM * CG);
+  g.tiles_n = (g.N + BN - 1) / BN;
+  const int n_tiles = g.tiles_m * g.tiles_n;
+  int sms = vllm_num_sms();
+  int clusters = sms / CG;
+  if (clusters > n_tiles) clusters = n_tiles;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[CG]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C_::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[CG] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = C_::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<CG>, ta, tb, g);
+  if (e != cudaSuccess) return (int)e;
+  return VLLM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vllm_gemm_set_variant(int v) { g_gemm_variant = (v == 2) ? 2 : 1; return VLLM_OK; }
+
+int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                   const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
+                   void* stream) {
+  if (M < 0 || N <= 0 || K <= 0 || lda < K || ldb < K) return VLLM_EINVAL;
+  if (M == 0) return VLLM_OK;
+  if (!A || !B || !C) return VLLM_EINVAL;
+  if (act < 0 || act > ACT_QUICKGELU) return VLLM_EINVAL;
+  const int n_out = act == ACT_SWIGLU ? N / 2 : N;
+  if (act == ACT_SWIGLU && (N % 2 || out_f32 || colscale)) return VLLM_EUNSUPPORTED;
+  if (ldc < n_out || (residual && ldr < n_out)) return VLLM_EINVAL;
+  // TMA: 16-byte aligned bases and row pitches; vector epilogue: 16-byte aligned rows
+  if (!vllm_aligned(A, 16) || !vllm_aligned(B, 16) || (lda % 8) || (ldb % 8)) return VLLM_EALIGN;
+  const int celt = out_f32 ? 4 : 2;
+  if (!vllm_aligned(C, 16) || ((size_t)ldc * celt) % 16 || (residual && (!vllm_aligned(residual, 16) || ldr % 8)))
+    return VLLM_EALIGN;
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc;
+  g.bias = (const __nv_bfloat16*)bias; g.colscale = (const __nv_bfloat16*)colscale;
+  g.residual = (const __nv_bfloat16*)residual; g.ldr = ldr; g.act = act; g.out_f32 = out_f32;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_gemm_variant == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);
+  return launch_gemm<1>(A, lda, B, ldb, g, st);
+}
+
+}  // extern "C"

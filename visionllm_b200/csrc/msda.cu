@@ -175,18 +175,23 @@ __device__ __forceinline__ float ld_stream_f1(const float* p) {
 }
 
 // TH x TW query tile per CTA, NW warps; each warp owns TH*TW/NW queries.
-template <int TH, int TW, int NW, typename OutT>
+// KC > 0: compile-time K = L*P (and PC = P) for the common GDINO shape; KC == 0: runtime.
+// s_meta layout: [warp][corner][sample] of {byte offset, weight bits}, corner rows padded
+// by 16 B so the four corner groups of a warp hit different banks on LDS.128.
+constexpr int MSDA_META_ROW = 32 + 2;  // int2 per corner row (32 samples + pad)
+
+template <int TH, int TW, int NW, int KC, int PC, typename OutT>
 __global__ void __launch_bounds__(NW * 32)
 msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ attw, OutT* __restrict__ out,
-                     int S, int M, int L, int Lq, int P, const __grid_constant__ MsdaTiling tl) {
+                     int S, int M, int L, int Lq, int P_rt, const __grid_constant__ MsdaTiling tl) {
   constexpr int D = 32;
   constexpr int TQ = TH * TW;
   constexpr int QPW = TQ / NW;  // queries per warp
   static_assert(TQ % NW == 0, "tile must split evenly over warps");
   __shared__ int s_h[MSDA_MAX_LEVELS], s_w[MSDA_MAX_LEVELS], s_start[MSDA_MAX_LEVELS];
-  __shared__ int2 s_meta[NW][32][4];
+  __shared__ __align__(16) int2 s_meta[NW][4][MSDA_META_ROW];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < L) {
@@ -199,7 +204,8 @@ msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict_
   const int m = blockIdx.x % M;
   const int tile = blockIdx.x / M;
   const int b = blockIdx.y;
-  const int K = L * P;
+  const int P = KC > 0 ? PC : P_rt;
+  const int K = KC > 0 ? KC : L * P_rt;
   const int G = (32 / K) < QPW ? (32 / K) : QPW;  // (query, head) pairs per phase-1 pass
   const int MD = M * D;
 
@@ -217,55 +223,75 @@ msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict_
     return tl.q_start[lvl] + py * tl.W[lvl] + px;
   };
 
-  const float* vb = value + (size_t)b * S * MD + m * D;
   const int corner = lane >> 3, cq = lane & 7;
+  // per-lane base: batch, head and this lane's channel quad folded in; meta offsets are bytes
+  const char* vbl = reinterpret_cast<const char*>(value + (size_t)b * S * MD + m * D + cq * 4);
+  const int g1 = lane / K, s1 = lane - g1 * K;  // phase-1 role of this lane
+  const int l1 = s1 / P;
 
   for (int t0 = 0; t0 < QPW; t0 += G) {
     // ---- phase 1: one lane per sample ---------------------------------
+    int q = -1;
+    if (g1 < G && t0 + g1 < QPW) q = query_of(warp * QPW + t0 + g1);
+    bool clean = true;   // all four corners of this lane's sample are in bounds
     {
-      const int g = lane / K, s = lane - g * K;
-      int q = -1;
-      if (g < G && t0 + g < QPW) q = query_of(warp * QPW + t0 + g);
       int2 meta[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) meta[c] = make_int2(-1, 0);
       if (q >= 0) {
         const size_t pair = ((size_t)b * Lq + q) * M + m;
-        const size_t si = pair * K + s;
+        const size_t si = pair * K + s1;
         const float2 xy = ld_stream_f2(loc + 2 * si);
         const float aw = ld_stream_f1(attw + si);
-        const int l = s / P;
-        const int H = s_h[l], W = s_w[l];
+        const int H = s_h[l1], W = s_w[l1];
         const MsdaGeom<float> ge = msda_geom<float>(xy.x, xy.y, H, W);
+        clean = (ge.mask == 31);
         if (ge.mask & 1) {
           const float hh = 1.f - ge.lh, hw = 1.f - ge.lw;
-          const int base = (s_start[l] + ge.h_low * W + ge.w_low) * MD;
+          const int base = (s_start[l1] + ge.h_low * W + ge.w_low) * MD * 4;
           const float w1 = hh * hw, w2 = hh * ge.lw, w3 = ge.lh * hw, w4 = ge.lh * ge.lw;
           if (ge.mask & 2) meta[0] = make_int2(base, __float_as_int(w1 * aw));
-          if (ge.mask & 4) meta[1] = make_int2(base + MD, __float_as_int(w2 * aw));
-          if (ge.mask & 8) meta[2] = make_int2(base + W * MD, __float_as_int(w3 * aw));
-          if (ge.mask & 16) meta[3] = make_int2(base + W * MD + MD, __float_as_int(w4 * aw));
+          if (ge.mask & 4) meta[1] = make_int2(base + MD * 4, __float_as_int(w2 * aw));
+          if (ge.mask & 8) meta[2] = make_int2(base + W * MD * 4, __float_as_int(w3 * aw));
+          if (ge.mask & 16) meta[3] = make_int2(base + (W * MD + MD) * 4, __float_as_int(w4 * aw));
         }
       }
-      int4* dst = reinterpret_cast<int4*>(&s_meta[warp][lane][0]);
-      dst[0] = make_int4(meta[0].x, meta[0].y, meta[1].x, meta[1].y);
-      dst[1] = make_int4(meta[2].x, meta[2].y, meta[3].x, meta[3].y);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s_meta[warp][c][lane] = meta[c];
     }
+    const unsigned dirty = __ballot_sync(0xffffffffu, !clean);
     __syncwarp();
     // ---- phase 2: lane = (corner, channel quad) -------------------------
     for (int g = 0; g < G && t0 + g < QPW; ++g) {
-      const int q = query_of(warp * QPW + t0 + g);
-      if (q < 0) continue;  // warp-uniform
+      const int qg = __shfl_sync(0xffffffffu, q, g * K);
+      if (qg < 0) continue;  // warp-uniform
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int2* mp = &s_meta[warp][g * K][corner];
-#pragma unroll 4
-      for (int s = 0; s < K; ++s) {
-        const int2 me = mp[s * 4];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (me.x >= 0) v = __ldg(reinterpret_cast<const float4*>(vb + me.x) + cq);
-        const float w = __int_as_float(me.y);
-        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      const int2* mp = &s_meta[warp][corner][g * K];
+      const unsigned gmask = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)) << (g * K);
+      if (((dirty & gmask) == 0) && (K % 2 == 0)) {
+        // fast path: every corner of every sample of this pair is in bounds
+        const int4* mp4 = reinterpret_cast<const int4*>(mp);
+#pragma unroll (KC > 0 ? KC / 2 : 4)
+        for (int s = 0; s < K / 2; ++s) {
+          const int4 me = mp4[s];
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(vbl + (unsigned)me.x));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(vbl + (unsigned)me.z));
+          const float w0 = __int_as_float(me.y), w1 = __int_as_float(me.w);
+          acc.x = fmaf(w0, v0.x, acc.x); acc.y = fmaf(w0, v0.y, acc.y);
+          acc.z = fmaf(w0, v0.z, acc.z); acc.w = fmaf(w0, v0.w, acc.w);
+          acc.x = fmaf(w1, v1.x, acc.x); acc.y = fmaf(w1, v1.y, acc.y);
+          acc.z = fmaf(w1, v1.z, acc.z); acc.w = fmaf(w1, v1.w, acc.w);
+        }
+      } else {
+#pragma unroll 2
+        for (int s = 0; s < K; ++s) {
+          const int2 me = mp[s];
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (me.x >= 0) v = __ldg(reinterpret_cast<const float4*>(vbl + (unsigned)me.x));
+          const float w = __int_as_float(me.y);
+          acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+          acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+        }
       }
 #pragma unroll
       for (int o = 8; o <= 16; o <<= 1) {
@@ -275,7 +301,7 @@ msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict_
         acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
       }
       if (corner == 0) {
-        OutT* op = out + (((size_t)b * Lq + q) * M + m) * D + cq * 4;
+        OutT* op = out + (((size_t)b * Lq + qg) * M + m) * D + cq * 4;
         if constexpr (sizeof(OutT) == 4) {
           __stcs(reinterpret_cast<float4*>(op), acc);
         } else {
@@ -322,8 +348,12 @@ static int launch_warp(const float* value, const int64_t* shapes, const int64_t*
   build_tiling(tl, host_shapes, L, Lq, S, TH, TW);
   dim3 grid((unsigned)(tl.n_tiles * M), (unsigned)N);
   if (N > 65535) return VLLM_EUNSUPPORTED;
-  msda_fwd_warp_kernel<TH, TW, NW, OutT><<<grid, NW * 32, 0, st>>>(value, shapes, lsi, loc, attw, out, S, M, L,
-                                                                   Lq, P, tl);
+  if (L == 4 && P == 4)
+    msda_fwd_warp_kernel<TH, TW, NW, 16, 4, OutT><<<grid, NW * 32, 0, st>>>(value, shapes, lsi, loc, attw, out, S,
+                                                                            M, L, Lq, P, tl);
+  else
+    msda_fwd_warp_kernel<TH, TW, NW, 0, 0, OutT><<<grid, NW * 32, 0, st>>>(value, shapes, lsi, loc, attw, out, S,
+                                                                           M, L, Lq, P, tl);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
 }
@@ -348,7 +378,7 @@ static int check_common(const void* value, const void* shapes, const void* lsi, 
   if (L > MSDA_MAX_LEVELS) return VLLM_EUNSUPPORTED;
   if ((long long)N * Lq == 0) return VLLM_OK + 1000;  // empty: nothing to do
   if (!value || !shapes || !lsi || !loc || !attw || !out) return VLLM_EINVAL;
-  if ((long long)S * M * D > INT_MAX) return VLLM_EUNSUPPORTED;  // per-image offsets are int32
+  if ((long long)S * M * D * 4 > INT_MAX) return VLLM_EUNSUPPORTED;  // per-image byte offsets are int32
   return VLLM_OK;
 }
 

@@ -1,0 +1,121 @@
+"""Torch-tensor front end of the C-ABI compute kernels (no math happens in Python).
+
+Every function validates shapes/dtypes/contiguity, allocates the output with
+torch (device memory is torch's job), and enqueues ONE kernel on the current
+CUDA stream through ``_lib``.  No fallbacks: a failing launch raises.
+"""
+import torch
+
+from . import _lib
+
+ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "silu": 3, "swiglu": 4, "quick_gelu": 5}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf16_2d(t, name):
+    if t.dtype != torch.bfloat16 or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA bfloat16 tensor")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"{name} must be 2-D with unit inner stride")
+    return t
+
+
+def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dtype=torch.bfloat16, out=None):
+    """y = epi(x @ weight.T): x [..., K] bf16, weight [N, K] bf16 (nn.Linear layout).
+
+    epi = (+bias) -> act -> (*colscale) -> (+residual); act='swiglu' expects gate/up rows
+    interleaved in `weight` and returns N/2 columns.  One tcgen05 kernel launch.
+    """
+    lead = x.shape[:-1]
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K) if x.dim() != 2 else x
+    _bf16_2d(x2, "x"); _bf16_2d(weight, "weight")
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise RuntimeError(f"linear: x has K={K} but weight is {tuple(weight.shape)}")
+    a = ACT[act]
+    n_out = N // 2 if a == 4 else N
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty((M, n_out), dtype=out_dtype, device=x.device)
+    else:
+        if out.shape != (M, n_out) or out.stride(1) != 1:
+            raise RuntimeError("linear: bad `out`")
+        out_dtype = out.dtype
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("linear: out dtype must be bf16 or fp32")
+    res2 = None
+    if residual is not None:
+        res2 = residual.reshape(-1, n_out) if residual.dim() != 2 else residual
+        _bf16_2d(res2, "residual")
+        if res2.shape != (M, n_out):
+            raise RuntimeError("linear: residual shape mismatch")
+    for v, nm in ((bias, "bias"), (colscale, "colscale")):
+        if v is not None and (v.dtype != torch.bfloat16 or v.numel() != N or not v.is_contiguous()):
+            raise RuntimeError(f"linear: {nm} must be contiguous bf16 [N]")
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().vllm_gemm_bf16(
+            x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(), out.stride(0),
+            M, N, K, bias.data_ptr() if bias is not None else None,
+            colscale.data_ptr() if colscale is not None else None,
+            res2.data_ptr() if res2 is not None else None, res2.stride(0) if res2 is not None else 0,
+            a, 1 if out_dtype == torch.float32 else 0, _stream())
+    _lib.check(rc, "vllm_gemm_bf16")
+    return out.reshape(*lead, n_out)
+
+
+def _rows(x, name):
+    if x.dtype != torch.bfloat16 or not x.is_cuda or x.stride(-1) != 1:
+        raise RuntimeError(f"{name} must be CUDA bf16 with unit inner stride")
+    if x.dim() == 2:
+        return x, x.shape[0], x.stride(0)
+    xc = x if x.is_contiguous() else None
+    if xc is None:
+        raise RuntimeError(f"{name}: >2-D inputs must be contiguous")
+    return xc, xc.numel() // xc.shape[-1], xc.shape[-1]
+
+
+def rmsnorm(x, weight, eps, out=None):
+    """apex FusedRMSNorm / InternRMSNorm / LlamaRMSNorm forward; x may be a strided 2-D view."""
+    xv, rows, ldx = _rows(x, "x")
+    cols = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    ov, _, ldy = _rows(out, "out")
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().vllm_rmsnorm_bf16(xv.data_ptr(), ldx, weight.data_ptr(), ov.data_ptr(), ldy, rows, cols,
+                                          float(eps), _stream())
+    _lib.check(rc, "vllm_rmsnorm_bf16")
+    return out
+
+
+def layernorm(x, weight, bias, eps, out=None):
+    xv, rows, ldx = _rows(x, "x")
+    cols = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    ov, _, ldy = _rows(out, "out")
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().vllm_layernorm_bf16(xv.data_ptr(), ldx, weight.data_ptr(), bias.data_ptr(), ov.data_ptr(),
+                                            ldy, rows, cols, float(eps), _stream())
+    _lib.check(rc, "vllm_layernorm_bf16")
+    return out
+
+
+def rope_(x, cos, sin, heads, head_dim):
+    """In-place rotate-half RoPE on x [tokens, >= heads*head_dim] (2-D, possibly a strided slice)."""
+    if x.dim() != 2 or x.dtype != torch.bfloat16 or x.stride(1) != 1:
+        raise RuntimeError("rope_: x must be 2-D bf16 with unit inner stride")
+    tokens = x.shape[0]
+    if tuple(cos.shape) != (tokens, head_dim) or tuple(sin.shape) != (tokens, head_dim):
+        raise RuntimeError("rope_: cos/sin must be [tokens, head_dim]")
+    if cos.dtype != torch.bfloat16 or not cos.is_contiguous() or not sin.is_contiguous():
+        raise RuntimeError("rope_: cos/sin must be contiguous bf16")
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().vllm_rope_bf16(x.data_ptr(), x.stride(0), cos.data_ptr(), sin.data_ptr(), tokens, heads,
+                                       head_dim, _stream())
+    _lib.check(rc, "vllm_rope_bf16")
+    return x
