@@ -108,6 +108,21 @@ int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const 
 int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long long tokens, int heads,
                    int head_dim, void* stream);
 
+/* ---- fused attention (flash dataflow; scores never reach HBM) ---------------------
+ * Replaces flash_attn_varlen_qkvpacked_func (internvit/flash_attention.py:51-54), the
+ * FA2 / eager paths of HF Llama and internlm2/modeling_internlm2.py:362-546, and
+ * internvit/modeling_intern_vit.py:145-160.  q/k/v: [batch, tokens, heads, head_dim]
+ * bf16 views with explicit batch/token pitches in elements (heads contiguous, so a
+ * packed qkv GEMM output is read in place); o: [batch, Tq, heads*head_dim] bf16.
+ * kv_heads < heads = grouped-query attention.  seqlens (int32[batch], may be NULL):
+ * keys >= seqlens[b] are masked, query rows >= seqlens[b] are written as zeros.
+ * causal != 0: query i sees keys <= i + (Tk - Tq).  head_dim in {32, 64, 128}. */
+int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
+                        int heads, int kv_heads, int head_dim, long long q_batch_pitch,
+                        long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
+                        long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
+                        long long o_token_pitch, const int* seqlens, int causal, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,77 @@
+"""GPU parity of the fused attention kernel against a plain PyTorch fp32 reference
+(softmax in fp32 like the reference's eager paths, internlm2/modeling_internlm2.py:394).
+Tolerance: bf16 P and bf16 output rounding -> |out - ref| <= 2^-7*|ref| + 2e-3*max|ref|."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_attn(q, k, v, causal, seqlens=None):
+    B, Tq, H, D = q.shape
+    Tk, Hkv = k.shape[1], k.shape[2]
+    qf = q.float().permute(0, 2, 1, 3)
+    kf = k.float().permute(0, 2, 1, 3).repeat_interleave(H // Hkv, 1)
+    vf = v.float().permute(0, 2, 1, 3).repeat_interleave(H // Hkv, 1)
+    s = qf @ kf.transpose(-1, -2) * D ** -0.5
+    if causal:
+        i = torch.arange(Tq, device=q.device)[:, None] + (Tk - Tq)
+        j = torch.arange(Tk, device=q.device)[None, :]
+        s = s.masked_fill(j > i, float("-inf"))
+    if seqlens is not None:
+        j = torch.arange(Tk, device=q.device)[None, None, None, :]
+        s = s.masked_fill(j >= seqlens[:, None, None, None], float("-inf"))
+    o = torch.softmax(s, -1) @ vf
+    o = o.permute(0, 2, 1, 3).reshape(B, Tq, H * D)
+    if seqlens is not None:
+        i = torch.arange(Tq, device=q.device)[None, :, None]
+        o = o.masked_fill(i >= seqlens[:, None, None], 0.0)
+    return o
+
+
+def check(out, ref):
+    tol = ref.abs() * 2.0 ** -7 + 2e-3 * ref.abs().max()
+    bad = (out.float() - ref).abs() > tol
+    assert not bad.any(), f"{int(bad.sum())}/{bad.numel()} off, max {(out.float() - ref).abs().max().item()}"
+
+
+@pytest.mark.parametrize("B,T,H,D,causal", [
+    (2, 1025, 5, 128, False),     # InternViT tile: 1025 = 16*64 + 1 (ragged last tile)
+    (1, 577, 4, 64, False),       # CLIP-L tile
+    (2, 300, 8, 32, False),       # GDINO-size heads
+    (2, 1536, 4, 128, True),      # LLM causal
+    (1, 64, 2, 128, True),
+    (1, 1, 2, 128, True),
+    (3, 130, 3, 128, True),
+])
+def test_attention_packed_qkv(B, T, H, D, causal):
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(T)
+    qkv = torch.randn(B, T, 3, H, D, device="cuda", generator=g).bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]       # strided views, no copies
+    out = ops.attention(q, k, v, causal=causal)
+    check(out, ref_attn(q, k, v, causal))
+
+
+def test_attention_gqa_and_seqlens_and_cross():
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B, Tq, Tk, H, Hkv, D = 3, 200, 333, 8, 2, 128
+    q = torch.randn(B, Tq, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Tk, Hkv, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Tk, Hkv, D, device="cuda", generator=g).bfloat16()
+    check(ops.attention(q, k, v), ref_attn(q, k, v, False))
+    check(ops.attention(q, k, v, causal=True), ref_attn(q, k, v, True))
+    sl = torch.tensor([333, 17, 150], dtype=torch.int32, device="cuda")
+    check(ops.attention(q, k, v, seqlens=sl), ref_attn(q, k, v, False, sl))
+
+
+def test_attention_large_magnitude_is_stable():
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    q = (torch.randn(1, 256, 2, 128, device="cuda", generator=g) * 8).bfloat16()
+    k = (torch.randn(1, 256, 2, 128, device="cuda", generator=g) * 8).bfloat16()
+    v = torch.randn(1, 256, 2, 128, device="cuda", generator=g).bfloat16()
+    out = ops.attention(q, k, v)
+    assert torch.isfinite(out.float()).all()
+    check(out, ref_attn(q, k, v, False))

@@ -1,0 +1,295 @@
+// Fused softmax(Q K^T * scale [+ causal / length mask]) V for the ViT and LLM blocks.
+//
+// Replaces the reference's flash-attn 2.3.3 library calls
+//   internvit/flash_attention.py:51-54 (flash_attn_varlen_qkvpacked_func, non-causal, d=128, 25 heads)
+//   HF Llama FA2 / internlm2/modeling_internlm2.py:494-546 (causal, d=128, 32 heads, GQA for InternLM2)
+// and the naive paths (internvit/modeling_intern_vit.py:145-160; modeling_internlm2.py:362-411).
+//
+// Round-1 implementation: FlashAttention-2 dataflow on the legacy warp-level tensor path
+// (ldmatrix + mma.sync.m16n8k16 bf16, fp32 accumulate) with online softmax in registers,
+// cp.async double-buffered K/V tiles in XOR-swizzled shared memory.  CTA = 64 query rows x one head
+// (4 warps x 16 rows), K/V tiles of 64 keys.  Scores never touch HBM: traffic = Q, K, V read once
+// per CTA wave + O written once.  The tcgen05/TMEM version (S and O accumulators in TMEM) is the
+// planned replacement; attention is ~5-6 % of the forward FLOPs.
+//
+// Layout: q/k/v are [batch, tokens, heads, D] views with arbitrary token/batch pitches (elements), so the
+// packed qkv GEMM output is consumed in place; o is [batch, tokens, heads*D].  seqlens (optional, int32
+// [batch]) masks keys >= len (right padding) and skips query rows >= len (their output rows are zeroed).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, NW = 4;
+
+struct AttnArgs {
+  const __nv_bfloat16 *q, *k, *v;
+  __nv_bfloat16* o;
+  long long q_bs, k_bs, v_bs, o_bs;  // batch pitches
+  long long q_ts, k_ts, v_ts, o_ts;  // token pitches
+  const int* seqlens;
+  int Tq, Tk, heads, kv_heads, causal;
+  float scale_log2;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// smem tile [rows][D] bf16, 16-byte chunks XOR-swizzled with (row & 7)
+template <int D>
+__device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
+  constexpr int CH = D / 8;                       // 16-byte chunks per row
+  const int x = CH >= 8 ? (row & 7) : ((row >> 1) & (CH - 1));   // D=32: two rows share a 128-byte line
+  return (uint32_t)(row * D * 2 + ((chunk ^ x) << 4));
+}
+
+template <int D, int ROWS>
+__device__ __forceinline__ void load_tile(uint32_t smem, const __nv_bfloat16* base, long long ts, int row0, int nrows_valid) {
+  // ROWS x D tile, 128 threads, 16 B per cp.async
+  constexpr int CH = D / 8;
+  for (int i = threadIdx.x; i < ROWS * CH; i += NW * 32) {
+    const int r = i / CH, c = i % CH;
+    const bool ok = (row0 + r) < nrows_valid;
+    const __nv_bfloat16* src = base + (long long)(ok ? row0 + r : 0) * ts + c * 8;
+    cp_async16(smem + sw_off<D>(r, c), src, ok);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(NW * 32)
+flash_fwd_kernel(const AttnArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int QB = BM * D * 2, KB = BN * D * 2;
+  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t sK0 = sQ + QB, sV0 = sK0 + 2 * KB;
+
+  const int mblk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int kvh = head / (a.heads / a.kv_heads);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = a.seqlens ? a.seqlens[b] : a.Tk;
+  const int q_len = a.seqlens ? min(len, a.Tq) : a.Tq;
+  const int m0 = mblk * BM;
+
+  const __nv_bfloat16* qb = a.q + b * a.q_bs + (long long)head * D;
+  const __nv_bfloat16* kb = a.k + b * a.k_bs + (long long)kvh * D;
+  const __nv_bfloat16* vb = a.v + b * a.v_bs + (long long)kvh * D;
+  __nv_bfloat16* ob = a.o + b * a.o_bs + (long long)head * D;
+
+  // causal offset: query i attends keys <= i + (Tk - Tq)  (bottom-right aligned, like flash-attn)
+  const int coff = a.Tk - a.Tq;
+  int k_end = len;
+  if (a.causal) k_end = min(k_end, m0 + BM + coff);
+  const int n_tiles = (k_end + BN - 1) / BN;
+
+  load_tile<D, BM>(sQ, qb, a.q_ts, m0, a.Tq);
+  cp_async_commit();
+  if (n_tiles > 0) {
+    load_tile<D, BN>(sK0, kb, a.k_ts, 0, len);
+    load_tile<D, BN>(sV0, vb, a.v_ts, 0, len);
+  }
+  cp_async_commit();
+
+  // Q fragments -> registers
+  cp_async_wait<1>();
+  __syncthreads();
+  uint32_t qf[D / 16][4];
+  {
+    const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      const int chunk = kk * 2 + (lane >> 4);
+      ldsm_x4(sQ + sw_off<D>(r, chunk), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+    }
+  }
+
+  float o[D / 8][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const int g = lane >> 2, tq = lane & 3;
+  const int qrow0 = m0 + warp * 16 + g;  // and +8
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int buf = t & 1;
+    const uint32_t sK = sK0 + buf * KB, sV = sV0 + buf * KB;
+    if (t + 1 < n_tiles) {
+      load_tile<D, BN>(sK0 + (buf ^ 1) * KB, kb, a.k_ts, (t + 1) * BN, len);
+      load_tile<D, BN>(sV0 + (buf ^ 1) * KB, vb, a.v_ts, (t + 1) * BN, len);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    // ---- S = Q K^T (16 x 64 per warp) ----
+    float s[BN / 8][4];
+#pragma unroll
+    for (int j = 0; j < BN / 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+      for (int j = 0; j < BN / 8; j += 2) {
+        const int key = j * 8 + (lane & 7) + 8 * (lane >> 4);
+        const int chunk = kk * 2 + ((lane >> 3) & 1);
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(sK + sw_off<D>(key, chunk), b0, b1, b2, b3);
+        mma_bf16(s[j], qf[kk], b0, b1);
+        mma_bf16(s[j + 1], qf[kk], b2, b3);
+      }
+    }
+    // ---- mask + online softmax (scores scaled into log2 domain) ----
+    const int n0 = t * BN;
+    const bool need_mask = (n0 + BN > len) || (a.causal && (n0 + BN - 1 > m0 + coff));
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < BN / 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = s[j][e] * a.scale_log2;
+        if (need_mask) {
+          const int key = n0 + j * 8 + tq * 2 + (e & 1);
+          const int qr = qrow0 + (e >> 1) * 8;
+          if (key >= len || (a.causal && key > qr + coff)) v = -INFINITY;
+        }
+        s[j][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float mnew = fmaxf(mrow[r], mx[r]);
+      const float msafe = (mnew == -INFINITY) ? 0.f : mnew;
+      corr[r] = exp2f(mrow[r] - msafe);   // mrow = -inf -> 0
+      mrow[r] = mnew;
+      mx[r] = msafe;
+      lrow[r] *= corr[r];
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < BN / 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = exp2f(s[j][e] - mx[e >> 1]);
+        s[j][e] = p;
+        rs[e >> 1] += p;
+      }
+    }
+    lrow[0] += rs[0]; lrow[1] += rs[1];
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) {
+      o[j][0] *= corr[0]; o[j][1] *= corr[0]; o[j][2] *= corr[1]; o[j][3] *= corr[1];
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < BN / 16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int j = 0; j < D / 8; j += 2) {
+        const int key = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int chunk = j + (lane >> 4);
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(sV + sw_off<D>(key, chunk), b0, b1, b2, b3);
+        mma_bf16(o[j], pa, b0, b1);
+        mma_bf16(o[j + 1], pa, b2, b3);
+      }
+    }
+    __syncthreads();  // tile buffers are overwritten by the next iteration's prefetch
+  }
+
+  // ---- finalize: O / l, write bf16 ----
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+  const float inv0 = lrow[0] > 0.f ? 1.f / lrow[0] : 0.f, inv1 = lrow[1] > 0.f ? 1.f / lrow[1] : 0.f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = qrow0 + r * 8;
+    if (row >= a.Tq) continue;
+    const bool live = row < q_len;
+    __nv_bfloat16* op = ob + (long long)row * a.o_ts;
+    const float inv = r ? inv1 : inv0;
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) {
+      const float x = live ? o[j][2 * r] * inv : 0.f, y = live ? o[j][2 * r + 1] * inv : 0.f;
+      *reinterpret_cast<__nv_bfloat162*>(op + j * 8 + tq * 2) = __floats2bfloat162_rn(x, y);
+    }
+  }
+}
+
+template <int D>
+int launch(const AttnArgs& a, int batch, cudaStream_t st) {
+  constexpr int SMEM = BM * D * 2 + 4 * BN * D * 2;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return (int)e;
+    set = true;
+  }
+  dim3 grid((a.Tq + BM - 1) / BM, a.heads, batch);
+  flash_fwd_kernel<D><<<grid, NW * 32, SMEM, st>>>(a);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+}  // namespace
+
+extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
+                                   int heads, int kv_heads, int head_dim, long long q_batch_pitch,
+                                   long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
+                                   long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
+                                   long long o_token_pitch, const int* seqlens, int causal, float scale,
+                                   void* stream) {
+  if (batch < 0 || Tq < 0 || Tk < 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads) return VLLM_EINVAL;
+  if (batch == 0 || Tq == 0) return VLLM_OK;
+  if (!q || !k || !v || !o) return VLLM_EINVAL;
+  if (batch > 65535 || heads > 65535) return VLLM_EUNSUPPORTED;
+  const long long p[] = {q_batch_pitch, q_token_pitch, k_batch_pitch, k_token_pitch,
+                         v_batch_pitch, v_token_pitch, o_batch_pitch, o_token_pitch};
+  for (long long x : p) if (x % 8) return VLLM_EALIGN;
+  if (!vllm_aligned(q, 16) || !vllm_aligned(k, 16) || !vllm_aligned(v, 16) || !vllm_aligned(o, 16)) return VLLM_EALIGN;
+  AttnArgs a;
+  a.q = (const __nv_bfloat16*)q; a.k = (const __nv_bfloat16*)k; a.v = (const __nv_bfloat16*)v;
+  a.o = (__nv_bfloat16*)o;
+  a.q_bs = q_batch_pitch; a.k_bs = k_batch_pitch; a.v_bs = v_batch_pitch; a.o_bs = o_batch_pitch;
+  a.q_ts = q_token_pitch; a.k_ts = k_token_pitch; a.v_ts = v_token_pitch; a.o_ts = o_token_pitch;
+  a.seqlens = seqlens; a.Tq = Tq; a.Tk = Tk; a.heads = heads; a.kv_heads = kv_heads; a.causal = causal;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (head_dim) {
+    case 128: return launch<128>(a, batch, st);
+    case 64: return launch<64>(a, batch, st);
+    case 32: return launch<32>(a, batch, st);
+    default: return VLLM_EUNSUPPORTED;
+  }
+}

@@ -295,7 +295,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 2) tc::tmem_dealloc<CG>(tmem_base, ACC * BN);
 }
 
-int g_gemm_variant = 1;  // 1: cta_group::1, 2: cta_group::2 (CTA pairs)
+int g_gemm_variant = 2;  // 1: cta_group::1 (128x256 tiles), 2: cta_group::2 CTA pairs (256x256), the default
 
 template <int CG>
 int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cudaStream_t st) {
@@ -336,7 +336,7 @@ int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cuda
 
 extern "C" {
 
-int vllm_gemm_set_variant(int v) { g_gemm_variant = (v == 2) ? 2 : 1; return VLLM_OK; }
+int vllm_gemm_set_variant(int v) { g_gemm_variant = (v == 1) ? 1 : 2; return VLLM_OK; }
 
 int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                    const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,

@@ -119,3 +119,33 @@ def rope_(x, cos, sin, heads, head_dim):
                                        head_dim, _stream())
     _lib.check(rc, "vllm_rope_bf16")
     return x
+
+
+def attention(q, k, v, causal=False, scale=None, seqlens=None, out=None):
+    """softmax(q k^T * scale) v.  q [B, Tq, H, D], k/v [B, Tk, Hkv, D] bf16 views whose last two dims are
+    contiguous (any batch/token pitch, e.g. slices of a packed qkv tensor).  Returns [B, Tq, H*D]."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
+            raise RuntimeError(f"attention: {nm} must be a 4-D CUDA bf16 tensor")
+        if t.stride(3) != 1 or t.stride(2) != t.shape[3]:
+            raise RuntimeError(f"attention: {nm} must have contiguous (heads, head_dim)")
+    B, Tq, H, D = q.shape
+    Tk, Hkv = k.shape[1], k.shape[2]
+    if k.shape != v.shape or k.shape[0] != B or k.shape[3] != D or H % Hkv:
+        raise RuntimeError("attention: inconsistent q/k/v shapes")
+    if out is None:
+        out = torch.empty((B, Tq, H * D), dtype=torch.bfloat16, device=q.device)
+    if scale is None:
+        scale = D ** -0.5
+    sl = None
+    if seqlens is not None:
+        if seqlens.dtype != torch.int32 or seqlens.numel() != B or not seqlens.is_cuda:
+            raise RuntimeError("attention: seqlens must be CUDA int32 [B]")
+        sl = seqlens.data_ptr()
+    with torch.cuda.device(q.device):
+        rc = _lib.lib().vllm_attention_bf16(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Tq, Tk, H, Hkv, D,
+            q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+            out.stride(0), out.stride(1), sl, 1 if causal else 0, float(scale), _stream())
+    _lib.check(rc, "vllm_attention_bf16")
+    return out
