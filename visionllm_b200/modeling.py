@@ -1,0 +1,212 @@
+"""Composite forward: B200 drop-in for ``VisionLLMv2Model.forward`` on the perception / chat eval path.
+
+Restates visionllmv2/model/modeling_visionllmv2.py (paths relative to /root/reference/VisionLLMv2/):
+  :119-198  constructor-injected sub-models (vis_encoder, llm, gdino) and the vl_bridge variants
+  :381-392  pixel_shuffle (space-to-depth x2)
+  :419-527  [EMB] super-link injection after tool tokens (overwrite form used by train/eval batches)
+  :559-605  ViT -> hidden_states[vis_output_layer][:, 1:] -> pixel shuffle -> vl_bridge -> scatter into
+            the <im_patch> positions
+  :724-738  llm(inputs_embeds, output_hidden_states=True) -> hidden_states[-1], fp32 logits
+  :769-791  [EMB] hidden states -> text_query / text_query_masks -> gdino(...)
+Integer index work (token positions, scatter/gather indices) is vectorised but produces the same
+indices as the reference's python loops; it is checked index-for-index in tests/test_modeling_cpu.py.
+"""
+import re
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class BridgeLinear(nn.Linear):
+    """nn.Linear whose forward is the tcgen05 GEMM (optionally with a fused activation)."""
+
+    def forward(self, x, act=None):
+        return ops.linear(x, self.weight, bias=self.bias, act=act)
+
+
+class BridgeLayerNorm(nn.LayerNorm):
+    def forward(self, x):
+        return ops.layernorm(x, self.weight, self.bias, self.eps)
+
+
+class VLBridge(nn.Sequential):
+    """Same module indices / state-dict keys as the reference nn.Sequential (mv2.py:162-184); GELU modules
+    are kept as placeholders (so indices match) and fused into the preceding GEMM's epilogue."""
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, BridgeLinear):
+                fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU)
+                x = m(x, act="gelu" if fuse else None)
+                i += 2 if fuse else 1
+            else:
+                x = m(x)
+                i += 1
+        return x
+
+
+def build_vl_bridge(vl_bridge_type, v_hidden, l_hidden):
+    if vl_bridge_type == "linear":
+        return VLBridge(BridgeLinear(v_hidden, l_hidden))
+    if vl_bridge_type in ("internvl_mlp", "internvl"):
+        return VLBridge(BridgeLayerNorm(v_hidden), BridgeLinear(v_hidden, l_hidden), nn.GELU(),
+                        BridgeLinear(l_hidden, l_hidden))
+    m = re.match(r"^mlp(\d+)x_gelu*", vl_bridge_type)
+    if not m:
+        raise NotImplementedError(f"{vl_bridge_type} not supported yet.")
+    mods = [BridgeLinear(v_hidden, l_hidden)]
+    for _ in range(1, int(m.group(1))):
+        mods += [nn.GELU(), BridgeLinear(l_hidden, l_hidden)]
+    return VLBridge(*mods)
+
+
+def pixel_shuffle(x, scale_factor=0.5):
+    """mv2.py:381-392, verbatim semantics: [n, w, h, c] -> [n, w/2, h/2, 4c]."""
+    n, w, h, c = x.size()
+    x = x.view(n, w, int(h * scale_factor), int(c / scale_factor))
+    x = x.permute(0, 2, 1, 3).contiguous()
+    x = x.view(n, int(h * scale_factor), int(w * scale_factor), int(c / (scale_factor * scale_factor)))
+    return x.permute(0, 2, 1, 3).contiguous()
+
+
+def emb_overwrite_indices(input_ids, tool_ids, num_embs):
+    """Flat positions (b, p+1+j) that follow a tool token in `tool_ids` -- the slots the reference overwrites
+    with the [EMB] ids / embeddings (mv2.py:447-468 with gap_len == num_embs).  Returns (batch_idx, pos_idx, j)."""
+    is_tool = torch.zeros_like(input_ids, dtype=torch.bool)
+    for t in tool_ids:
+        is_tool |= input_ids == t
+    b, p = torch.nonzero(is_tool, as_tuple=True)
+    j = torch.arange(num_embs, device=input_ids.device)
+    pos = p[:, None] + 1 + j[None, :]
+    return b[:, None].expand_as(pos).reshape(-1), pos.reshape(-1), j[None, :].expand_as(pos).reshape(-1)
+
+
+class B200VisionLLMv2Model(nn.Module):
+    def __init__(self, config, vis_encoder, llm, gdino=None):
+        super().__init__()
+        self.config = config
+        self.vis_encoder = vis_encoder
+        self.llm = llm
+        self.use_pixelshuffle = bool(getattr(config, "use_pixelshuffle", False))
+        self.v_hidden_size = vis_encoder.config.hidden_size
+        self.l_hidden_size = llm.config.hidden_size
+        vh = self.v_hidden_size * 4 if self.use_pixelshuffle else self.v_hidden_size
+        self.vl_bridge = build_vl_bridge(getattr(config, "vl_bridge_type", "linear"), vh, self.l_hidden_size)
+        self.use_gdino = gdino is not None
+        if gdino is not None:
+            self.gdino = gdino
+        self.num_embs = int(getattr(config, "num_embs", 4))
+        self.emb_embeddings_det = nn.Embedding(self.num_embs, self.l_hidden_size)
+        self.emb_embeddings_pose = nn.Embedding(self.num_embs, self.l_hidden_size)
+        # special-token ids are assigned by init_special_token_ids (mv2.py:281-353)
+        for k in ("imp_token_id", "emb_token_id", "det_tool_id", "seg_tool_id", "grd_tool_id", "pose_tool_id"):
+            setattr(self, k, getattr(config, k, -1))
+
+    # ---- pieces ------------------------------------------------------------------------------
+    def inject_emb(self, input_ids, inputs_embeds):
+        """[EMB] ids/embeddings after det/seg/grd (and pose) tool tokens -- overwrite form."""
+        ids, emb = input_ids.clone(), inputs_embeds
+        L = ids.shape[1]
+        for tools, table in (((self.det_tool_id, self.seg_tool_id, self.grd_tool_id), self.emb_embeddings_det),
+                             ((self.pose_tool_id,), self.emb_embeddings_pose)):
+            tools = [t for t in tools if t is not None and t >= 0]
+            if not tools:
+                continue
+            b, p, j = emb_overwrite_indices(ids, tools, self.num_embs)
+            if b.numel() == 0:
+                continue
+            if int(p.max()) >= L:
+                raise NotImplementedError("tool token without its [EMB] slots: generation-time insertion "
+                                          "(mv2.py:428-429, gap_len == 0) is outside the forward hot path")
+            ids[b, p] = self.emb_token_id + j
+            emb = emb.clone() if emb is inputs_embeds else emb
+            emb[b, p] = table.weight.to(emb.dtype)[j]
+        return ids, emb
+
+    def encode_images(self, images):
+        if isinstance(images, (list, tuple)):                      # 'anyres': bs x [1 + n_split, 3, h, w]
+            images = [x.unsqueeze(0) if x.ndim == 3 else x for x in images]
+            split_sizes = [im.shape[0] for im in images]
+            concat = torch.cat(list(images), dim=0)
+        else:
+            split_sizes, concat = None, images
+        outs = self.vis_encoder(concat, output_hidden_states=True)
+        feats = outs.hidden_states[getattr(self.config, "vis_output_layer", -2)][:, 1:].to(self.llm.dtype)
+        if self.use_pixelshuffle:
+            h = w = int(feats.shape[1] ** 0.5)
+            feats = pixel_shuffle(feats.reshape(feats.shape[0], h, w, -1), 0.5)
+            feats = feats.reshape(feats.shape[0], -1, feats.shape[-1])
+        return self.vl_bridge(feats), split_sizes, outs
+
+    def scatter_image_tokens(self, input_ids, inputs_embeds, image_features, split_sizes):
+        B, L, C = inputs_embeds.shape
+        selected = input_ids == self.imp_token_id
+        has_image = selected.sum(-1) != 0
+        if split_sizes is not None:
+            has_image = torch.repeat_interleave(has_image, torch.tensor(split_sizes, device=has_image.device))
+        vit_embeds = image_features[has_image].reshape(-1, C)
+        flat = inputs_embeds.reshape(B * L, C).clone()
+        sel = selected.reshape(-1)
+        n_sel = int(sel.sum())
+        if n_sel != vit_embeds.shape[0]:
+            raise RuntimeError(f"image token count mismatch: {n_sel} <im_patch> slots vs {vit_embeds.shape[0]} "
+                               "ViT tokens (the reference tiles/trims and zeroes the loss here, mv2.py:591-604; "
+                               "this drop-in refuses instead of guessing)")
+        flat[sel] = vit_embeds.to(flat.dtype)
+        return flat.reshape(B, L, C)
+
+    def gather_text_query(self, input_ids, hidden_states):
+        """mv2.py:776-787: [EMB] hidden states -> text_query [bs, max_cls, num_embs, C], masks [bs, max_cls]."""
+        B, L, C = hidden_states.shape
+        emb_select = (input_ids >= self.emb_token_id) & (input_ids <= self.emb_token_id + self.num_embs - 1)
+        counts = emb_select.sum(-1)
+        if int(counts.sum()) == 0:
+            return None, None
+        num_patches = counts // self.num_embs
+        mx = int(num_patches.max())
+        tq = torch.zeros((B, mx, self.num_embs, C), dtype=hidden_states.dtype, device=hidden_states.device)
+        tm = torch.zeros((B, mx), dtype=torch.bool, device=hidden_states.device)
+        b, p = torch.nonzero(emb_select, as_tuple=True)
+        rank = torch.cumsum(emb_select.int(), -1)[b, p] - 1          # order of the [EMB] token within its row
+        keep = rank < (num_patches * self.num_embs)[b]
+        b, p, rank = b[keep], p[keep], rank[keep]
+        tq.view(B, mx * self.num_embs, C)[b, rank] = hidden_states[b, p]
+        tm[b, rank // self.num_embs] = True
+        return tq, tm
+
+    # ---- forward -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, images=None, images_aug=None,
+                img_metas=None, targets=None, labels=None, past_key_values=None, use_cache=False,
+                output_attentions=False, output_hidden_states=False, return_dict=True, **unused):
+        if past_key_values is not None or use_cache:
+            raise NotImplementedError("generation with KV cache is outside the forward hot path")
+        if labels is not None or targets is not None:
+            raise NotImplementedError("training losses are outside the forward hot path (SURVEY 8f)")
+        if inputs_embeds is None:
+            inputs_embeds = self.llm.get_input_embeddings()(input_ids)
+        input_ids, inputs_embeds = self.inject_emb(input_ids, inputs_embeds)
+        vit_out = None
+        if images is not None:
+            feats, split_sizes, vit_out = self.encode_images(images)
+            inputs_embeds = self.scatter_image_tokens(input_ids, inputs_embeds, feats.to(inputs_embeds.dtype),
+                                                      split_sizes)
+        out = self.llm(attention_mask=attention_mask, inputs_embeds=inputs_embeds, output_hidden_states=True)
+        hidden = out.hidden_states[-1]
+        gdino_outputs = None
+        if self.use_gdino and images_aug is not None:
+            tq, tm = self.gather_text_query(input_ids, hidden)
+            if tq is not None:
+                pixel_values = images_aug if torch.is_tensor(images_aug) else torch.stack(list(images_aug))
+                pixel_mask = pixel_values[:, 0, :, :] != 0                                  # mv2.py:773
+                gdino_outputs = self.gdino(pixel_values, pixel_mask=pixel_mask, text_query=tq,
+                                           text_query_masks=tm, img_metas=img_metas, labels=None)
+        return SimpleNamespace(loss=None, logits=out.logits, hidden_states=out.hidden_states,
+                               last_hidden_state=hidden, vit_outputs=vit_out, gdino_outputs=gdino_outputs,
+                               input_ids=input_ids)
