@@ -110,8 +110,133 @@ class MsdaEncoderWorkload:
         return {}
 
 
-WORKLOADS = {"msda_encoder": MsdaEncoderWorkload}
-DEFAULT_WORKLOAD = "msda_encoder"
+def anyres_tiles_1024(torch, n_pairs, device, seed, tile=448, dtype=None):
+    """What the reference's data pipeline hands to forward() for a 1024x1024 image under 'anyres'
+    (mm_utils.py:39-75: image_size 448, max 6 tiles -> (2,2) grid + thumbnail = 5 tiles): a list of
+    [5, 3, 448, 448] tensors, floats already cast to bf16 by dict_to_cuda (util/misc.py:499-515)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    return [torch.randn(5, 3, tile, tile, device=device, generator=g).to(dtype or torch.bfloat16)
+            for _ in range(n_pairs)]
+
+
+class PairForwardWorkload:
+    """BASELINE cfg 3: VisionLLMv2 (InternViT-6B + Vicuna-7B), random init, bf16 forward of B (image, prompt)
+    pairs per GPU: 5 anyres tiles of a 1024^2 image -> 48-layer ViT -> pixel shuffle -> internvl_mlp bridge ->
+    1280 image tokens + 256 text tokens -> 32-layer LLM -> fp32 logits for every position."""
+    metric = "img_text_pairs_per_sec_fwd_1024px_256tok"
+    unit = "pairs/s"
+    dtype = "bf16"
+    PAIRS = 8
+    IMP, VOCAB = 32002, 32026
+    vit = dict(hidden_size=3200, num_attention_heads=25, num_hidden_layers=48, intermediate_size=12800,
+               image_size=448, patch_size=14)
+    llm = dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
+               num_key_value_heads=32, vocab_size=VOCAB, rms_norm_eps=1e-5, max_position_embeddings=4096)
+
+    def __init__(self, rank, world, device):
+        self.rank, self.world, self.device = rank, world, device
+
+    def build(self):
+        import torch
+        from types import SimpleNamespace
+        from transformers import LlamaConfig
+        from visionllm_b200.internvit import B200InternVisionModel, InternVisionConfig
+        from visionllm_b200.llama import B200LlamaForCausalLM
+        from visionllm_b200.modeling import B200VisionLLMv2Model
+        cfg = SimpleNamespace(use_pixelshuffle=True, vl_bridge_type="internvl_mlp", vis_output_layer=-1, num_embs=4,
+                              imp_token_id=self.IMP, emb_token_id=32010, det_tool_id=32003, seg_tool_id=32005,
+                              grd_tool_id=32004, pose_tool_id=32006)
+        with torch.device("meta"):
+            model = B200VisionLLMv2Model(cfg, B200InternVisionModel(InternVisionConfig(**self.vit)),
+                                         B200LlamaForCausalLM(LlamaConfig(**self.llm)))
+        model = model.to_empty(device=self.device).to(torch.bfloat16)
+        g = torch.Generator(device=self.device).manual_seed(0)      # same weights on every rank
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                last = name.split(".")[-1]
+                if "norm" in name and last == "weight":
+                    p.fill_(1.0)
+                elif last in ("ls1", "ls2"):
+                    p.fill_(0.1)
+                elif p.dim() <= 1:
+                    p.zero_()
+                else:
+                    p.copy_(torch.randn(p.shape, device=self.device, generator=g, dtype=torch.float32) * 0.02)
+        return model.eval()
+
+    def setup(self):
+        import torch
+        self.torch = torch
+        self.model = self.build()
+        n_img = 5 * 256
+        T = n_img + 256
+        g = torch.Generator(device=self.device).manual_seed(1234 + self.rank)
+        ids = torch.randint(0, 32000, (self.PAIRS, T), device=self.device, generator=g)
+        ids[:, :n_img] = self.IMP
+        self.ids = ids
+        self.mask = torch.ones_like(ids)
+        self.images = anyres_tiles_1024(torch, self.PAIRS, self.device, 99 + self.rank)
+        self.h_images = [t.cpu().pin_memory() for t in self.images]
+        self.h_ids = ids.cpu().pin_memory()
+        self.d_images = [torch.empty_like(t) for t in self.images]
+        self.d_ids = torch.empty_like(ids)
+        self.h_out = torch.empty((self.PAIRS, self.VOCAB), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(t.numel() * 2 for t in self.h_images) + ids.numel() * 8
+        self.d2h_bytes = self.h_out.numel() * 4
+        self.T = T
+
+    def step_device(self):
+        self.out = self.model(input_ids=self.ids, attention_mask=None, images=self.images)
+
+    def step_e2e(self):
+        for d, h in zip(self.d_images, self.h_images):
+            d.copy_(h, non_blocking=True)
+        self.d_ids.copy_(self.h_ids, non_blocking=True)
+        out = self.model(input_ids=self.d_ids, attention_mask=None, images=self.d_images)
+        self.h_out.copy_(out.logits[:, -1, :], non_blocking=True)    # next-token distribution per pair
+
+    def units_per_step(self):
+        return self.PAIRS
+
+    def dominant_kernel_ms(self, steps):
+        """One extra instrumented step: CUDA events around every C-ABI launch, on the launch stream."""
+        from visionllm_b200 import ops
+        torch = self.torch
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        self.step_device()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for name, fl, by, e0, e1 in prof:
+            a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl; a[3] += by
+        self.breakdown = {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / v[1] / 1e9 if v[1] else 0.0,
+                              "gbps": v[3] / v[1] / 1e6 if v[1] else 0.0} for k, v in agg.items()}
+        self.gemm_flops = agg["gemm"][2]
+        return agg["gemm"][1]
+
+    def roofline(self, kern_ms, peaks):
+        ach = self.gemm_flops / (kern_ms * 1e-3) / 1e12
+        pk = peaks["bf16_tflops_sustained"]
+        return {"kernel": "gemm_bf16_tcgen05_kernel<2> (all GEMM launches of one step, flop-weighted)",
+                "bound": "tensor", "achieved": ach, "peak": pk, "peak_source": peaks["source"] + " (sustained)",
+                "unit": "TFLOP/s", "frac": ach / pk, "traffic": None, "kernel_ms_per_step": kern_ms,
+                "algorithmic_flops_per_step": self.gemm_flops}
+
+    def config(self):
+        return {"workload": "BASELINE cfg 3: InternViT-6B(448, 5 anyres tiles of a 1024^2 image) + pixel-shuffle + "
+                            "internvl_mlp + Vicuna-7B, T=1536 (1280 image + 256 text), fp32 logits all positions",
+                "pairs_per_gpu_per_step": self.PAIRS, "seq_len": self.T, "tiles_per_image": 5,
+                "l2_policy": "inputs_exceed_l2 (weights 25 GB, activations > 126 MB L2)",
+                "parallelism": f"dp{self.world} (batch shard, no forward collective)"}
+
+    def extra(self):
+        return {"kernel_breakdown": self.breakdown}
+
+
+WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "pair_forward": PairForwardWorkload}
+DEFAULT_WORKLOAD = "pair_forward"
 
 
 # --------------------------------------------------------------------------------------
@@ -135,7 +260,53 @@ def _cpu_msda_encoder(steps, warmup):
             "ms_per_step": dt * 1e3}
 
 
-_CPU = {"msda_encoder": _cpu_msda_encoder}
+def _cpu_pair_forward(steps, warmup):
+    """Reference CPU path of one pair, bounded sample: ONE InternViT-6B layer on one 448^2 tile (1025 tokens) and
+    ONE Vicuna-7B layer on the 1536-token sequence, fp32 torch on all host cores (oracle/vit_llm_oracle.py);
+    pair time extrapolated as 5 tiles x 48 layers x t_vit + 32 layers x t_llm (embeddings, bridge, lm_head
+    left out, so the CPU figure is slightly optimistic)."""
+    import torch
+    from oracle import vit_llm_oracle as VO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    C, I, H, F_ = 3200, 12800, 4096, 11008
+    r = lambda *s: torch.randn(*s, generator=g) * 0.02  # noqa: E731
+    vsd = {"l.norm1.weight": torch.ones(C), "l.norm2.weight": torch.ones(C), "l.attn.qkv.weight": r(3 * C, C),
+           "l.attn.q_norm.weight": torch.ones(C), "l.attn.k_norm.weight": torch.ones(C), "l.attn.proj.weight": r(C, C),
+           "l.attn.proj.bias": torch.zeros(C), "l.ls1": torch.full((C,), 0.1), "l.ls2": torch.full((C,), 0.1),
+           "l.mlp.fc1.weight": r(I, C), "l.mlp.fc1.bias": torch.zeros(I), "l.mlp.fc2.weight": r(C, I),
+           "l.mlp.fc2.bias": torch.zeros(C)}
+    lsd = {"l.input_layernorm.weight": torch.ones(H), "l.post_attention_layernorm.weight": torch.ones(H),
+           "l.self_attn.q_proj.weight": r(H, H), "l.self_attn.k_proj.weight": r(H, H),
+           "l.self_attn.v_proj.weight": r(H, H), "l.self_attn.o_proj.weight": r(H, H),
+           "l.mlp.gate_proj.weight": r(F_, H), "l.mlp.up_proj.weight": r(F_, H), "l.mlp.down_proj.weight": r(H, F_)}
+    xv, xl = torch.randn(1, 1025, C, generator=g), torch.randn(1, 1536, H, generator=g)
+
+    def once():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            VO.internvit_layer(xv, vsd, "l.", 25, 1e-6)
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            VO.llama_layer(xl, lsd, "l.", 32, 1e-5)
+        return t1 - t0, time.perf_counter() - t1
+
+    for _ in range(warmup):
+        once()
+    tv = tl = 0.0
+    for _ in range(steps):
+        a, b = once()
+        tv += a; tl += b
+    tv /= steps; tl /= steps
+    pair_s = 5 * 48 * tv + 32 * tl
+    return {"value": 1.0 / pair_s, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"1 InternViT-6B layer x 1 tile ({tv * 1e3:.0f} ms) + 1 Vicuna-7B layer x 1536 tokens "
+                      f"({tl * 1e3:.0f} ms), fp32 torch CPU; pair = 240 x vit + 32 x llm (extrapolated)",
+            "ms_per_step": pair_s * 1e3}
+
+
+_CPU = {"msda_encoder": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward}
 
 
 def cpu_baseline(name):

@@ -10,6 +10,30 @@ from . import _lib
 
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "silu": 3, "swiglu": 4, "quick_gelu": 5}
 
+# Optional per-launch CUDA-event profile (bench.py's live roofline numbers): set PROFILE = [] to collect
+# (kernel, algorithmic flops, algorithmic bytes, start_event, end_event) tuples; None = off (default).
+PROFILE = None
+
+
+class _Prof:
+    __slots__ = ("name", "flops", "bytes", "e0")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.bytes = name, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+        return False
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -56,7 +80,8 @@ def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dty
     for v, nm in ((bias, "bias"), (colscale, "colscale")):
         if v is not None and (v.dtype != torch.bfloat16 or v.numel() != N or not v.is_contiguous()):
             raise RuntimeError(f"linear: {nm} must be contiguous bf16 [N]")
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Prof("gemm", 2.0 * M * N * K,
+                                            2.0 * (M * K + N * K) + out.element_size() * M * n_out):
         rc = _lib.lib().vllm_gemm_bf16(
             x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(), out.stride(0),
             M, N, K, bias.data_ptr() if bias is not None else None,
@@ -85,7 +110,7 @@ def rmsnorm(x, weight, eps, out=None):
     if out is None:
         out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
     ov, _, ldy = _rows(out, "out")
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Prof("rmsnorm", 0.0, 4.0 * rows * cols):
         rc = _lib.lib().vllm_rmsnorm_bf16(xv.data_ptr(), ldx, weight.data_ptr(), ov.data_ptr(), ldy, rows, cols,
                                           float(eps), _stream())
     _lib.check(rc, "vllm_rmsnorm_bf16")
@@ -98,7 +123,7 @@ def layernorm(x, weight, bias, eps, out=None):
     if out is None:
         out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
     ov, _, ldy = _rows(out, "out")
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Prof("layernorm", 0.0, 4.0 * rows * cols):
         rc = _lib.lib().vllm_layernorm_bf16(xv.data_ptr(), ldx, weight.data_ptr(), bias.data_ptr(), ov.data_ptr(),
                                             ldy, rows, cols, float(eps), _stream())
     _lib.check(rc, "vllm_layernorm_bf16")
@@ -114,7 +139,7 @@ def rope_(x, cos, sin, heads, head_dim):
         raise RuntimeError("rope_: cos/sin must be [tokens, head_dim]")
     if cos.dtype != torch.bfloat16 or not cos.is_contiguous() or not sin.is_contiguous():
         raise RuntimeError("rope_: cos/sin must be contiguous bf16")
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Prof("rope", 0.0, 4.0 * tokens * heads * head_dim):
         rc = _lib.lib().vllm_rope_bf16(x.data_ptr(), x.stride(0), cos.data_ptr(), sin.data_ptr(), tokens, heads,
                                        head_dim, _stream())
     _lib.check(rc, "vllm_rope_bf16")
@@ -142,7 +167,8 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, out=None):
         if seqlens.dtype != torch.int32 or seqlens.numel() != B or not seqlens.is_cuda:
             raise RuntimeError("attention: seqlens must be CUDA int32 [B]")
         sl = seqlens.data_ptr()
-    with torch.cuda.device(q.device):
+    fl = 4.0 * B * H * Tq * Tk * D * (0.5 if causal and Tq == Tk else 1.0)
+    with torch.cuda.device(q.device), _Prof("attention", fl, 2.0 * B * D * (2 * Tq * H + 2 * Tk * Hkv)):
         rc = _lib.lib().vllm_attention_bf16(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Tq, Tk, H, Hkv, D,
             q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
