@@ -115,7 +115,7 @@ int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long
  * bf16 views with explicit batch/token pitches in elements (heads contiguous, so a
  * packed qkv GEMM output is read in place); o: [batch, Tq, heads*head_dim] bf16.
  * kv_heads < heads = grouped-query attention.  seqlens (int32[batch], may be NULL):
- * keys >= seqlens[b] are masked, query rows >= seqlens[b] are written as zeros.
+ * keys >= seqlens[b] are masked (right padding / key_padding_mask); all query rows are computed.
  * causal != 0: query i sees keys <= i + (Tk - Tq).  head_dim in {32, 64, 128}. */
 int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
                         int heads, int kv_heads, int head_dim, long long q_batch_pitch,

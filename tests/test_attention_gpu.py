@@ -23,9 +23,6 @@ def ref_attn(q, k, v, causal, seqlens=None):
         s = s.masked_fill(j >= seqlens[:, None, None, None], float("-inf"))
     o = torch.softmax(s, -1) @ vf
     o = o.permute(0, 2, 1, 3).reshape(B, Tq, H * D)
-    if seqlens is not None:
-        i = torch.arange(Tq, device=q.device)[None, :, None]
-        o = o.masked_fill(i >= seqlens[:, None, None], 0.0)
     return o
 
 

@@ -14,7 +14,8 @@
 //
 // Layout: q/k/v are [batch, tokens, heads, D] views with arbitrary token/batch pitches (elements), so the
 // packed qkv GEMM output is consumed in place; o is [batch, tokens, heads*D].  seqlens (optional, int32
-// [batch]) masks keys >= len (right padding) and skips query rows >= len (their output rows are zeroed).
+// [batch]) masks keys >= len (right padding / key_padding_mask); every query row is computed (rows of
+// padded queries hold finite don't-care values, as in the reference).
 #include "common.cuh"
 
 namespace {
@@ -90,7 +91,6 @@ flash_fwd_kernel(const AttnArgs a) {
   const int kvh = head / (a.heads / a.kv_heads);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int len = a.seqlens ? a.seqlens[b] : a.Tk;
-  const int q_len = a.seqlens ? min(len, a.Tq) : a.Tq;
   const int m0 = mblk * BM;
 
   const __nv_bfloat16* qb = a.q + b * a.q_bs + (long long)head * D;
@@ -236,7 +236,7 @@ flash_fwd_kernel(const AttnArgs a) {
   for (int r = 0; r < 2; ++r) {
     const int row = qrow0 + r * 8;
     if (row >= a.Tq) continue;
-    const bool live = row < q_len;
+    const bool live = true;
     __nv_bfloat16* op = ob + (long long)row * a.o_ts;
     const float inv = r ? inv1 : inv0;
 #pragma unroll

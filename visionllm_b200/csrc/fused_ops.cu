@@ -13,99 +13,136 @@
 // One CTA per row; 16-byte loads; the row stays in registers between the reduction and the scaling pass
 // (1 read + 1 write of the activation -- the roofline for these ops).
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
-constexpr int NT = 256;          // threads per row CTA
-constexpr int MAX_VEC = 8;       // up to 8 x (8 bf16) per thread = 16384 columns
+constexpr int NT = 256;          // threads per CTA
 
-__device__ __forceinline__ float block_sum(float v, float* sh) {
+// A row is owned by TPR threads (a warp, 4 warps or the whole CTA); a CTA carries NT/TPR rows.  Each thread keeps
+// VPT 16-byte vectors of the row in registers (packed bf16) between the statistics pass and the scaling pass.
+template <int TPR>
+__device__ __forceinline__ float group_sum(float v, float* sh) {
   v = warp_sum(v);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) sh[w] = v;
-  __syncthreads();
-  float t = (l < NT / 32) ? sh[l] : 0.f;
-  t = warp_sum(t);
-  __syncthreads();
-  return t;
+  if constexpr (TPR > 32) {
+    constexpr int WPR = TPR / 32;                      // warps per row
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int grp = w / WPR;
+    __syncthreads();                                   // previous use of sh is over
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) t += sh[grp * WPR + i];
+    v = t;
+  }
+  return v;
 }
 
-struct Row8 { float v[8]; };
-__device__ __forceinline__ Row8 ld8(const __nv_bfloat16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-  Row8 r;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
-  return r;
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 u; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
 }
 
 // mode 0: RMSNorm (weight only); mode 1: LayerNorm (weight + bias)
-template <int MODE>
+template <int MODE, int VPT, int TPR>
 __global__ void __launch_bounds__(NT)
-norm_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
-                 const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, long long ldy, int cols,
-                 float eps) {
+norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                 const __nv_bfloat16* __restrict__ b, __nv_bfloat16* y, long long ldy, long long rows,
+                 int cols, float eps) {
   __shared__ float sh[NT / 32];
-  const long long row = blockIdx.x;
-  const __nv_bfloat16* xr = x + row * ldx;
-  __nv_bfloat16* yr = y + row * ldy;
+  constexpr int RPC = NT / TPR;
+  const int tr = threadIdx.x % TPR;
+  const long long row = (long long)blockIdx.x * RPC + threadIdx.x / TPR;
+  const bool row_ok = row < rows;
+  const __nv_bfloat16* xr = x + (row_ok ? row : 0) * ldx;
+  __nv_bfloat16* yr = y + (row_ok ? row : 0) * ldy;
   const int nvec = cols / 8;
-  Row8 reg[MAX_VEC];
+  uint4 reg[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = tr + i * TPR;
+    reg[i] = (v < nvec && row_ok) ? *(reinterpret_cast<const uint4*>(xr) + v) : make_uint4(0, 0, 0, 0);  // may alias y
+  }
   float s = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
-    const int v = threadIdx.x + i * NT;
-    if (v < nvec) {
-      reg[i] = ld8(xr + v * 8);
+  for (int i = 0; i < VPT; ++i) {
+    float f[8]; unpack8(reg[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s += reg[i].v[j]; s2 += reg[i].v[j] * reg[i].v[j]; }
-    }
+    for (int j = 0; j < 8; ++j) { s += f[j]; s2 += f[j] * f[j]; }
   }
   float mean = 0.f, inv;
   if (MODE == 1) {
-    mean = block_sum(s, sh) / cols;
-    // two-pass variance on the register-resident row
-    float d2 = 0.f;
+    mean = group_sum<TPR>(s, sh) / cols;
+    float d2 = 0.f;                                    // two-pass variance on the register-resident row
 #pragma unroll
-    for (int i = 0; i < MAX_VEC; ++i) {
-      const int v = threadIdx.x + i * NT;
-      if (v < nvec) {
+    for (int i = 0; i < VPT; ++i) {
+      if (tr + i * TPR < nvec) {
+        float f[8]; unpack8(reg[i], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = reg[i].v[j] - mean; d2 += d * d; }
+        for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; d2 += d * d; }
       }
     }
-    inv = rsqrtf(block_sum(d2, sh) / cols + eps);
+    inv = rsqrtf(group_sum<TPR>(d2, sh) / cols + eps);
   } else {
-    inv = rsqrtf(block_sum(s2, sh) / cols + eps);
+    inv = rsqrtf(group_sum<TPR>(s2, sh) / cols + eps);
   }
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
-    const int v = threadIdx.x + i * NT;
-    if (v < nvec) {
-      const Row8 wv = ld8(w + v * 8);
-      float o[8];
+  for (int i = 0; i < VPT; ++i) {
+    const int v = tr + i * TPR;
+    if (v < nvec && row_ok) {
+      float f[8], wv[8], o[8];
+      unpack8(reg[i], f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + v), wv);
       if (MODE == 1) {
-        const Row8 bv = ld8(b + v * 8);
+        float bv[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(b) + v), bv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (reg[i].v[j] - mean) * inv * wv.v[j] + bv.v[j];
+        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * inv * wv[j] + bv[j];
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           // reference: (x * rsqrt).to(input_dtype) first, then weight * that (both bf16 roundings kept)
-          const float n = __bfloat162float(__float2bfloat16(reg[i].v[j] * inv));
-          o[j] = wv.v[j] * n;
+          const float n = __bfloat162float(__float2bfloat16(f[j] * inv));
+          o[j] = wv[j] * n;
         }
       }
-      st8(yr + v * 8, o);
+      *(reinterpret_cast<uint4*>(yr) + v) = pack8(o);
     }
   }
+}
+
+template <int MODE>
+int launch_norm(const void* x, long long ldx, const void* w, const void* b, void* y, long long ldy, long long rows,
+                int cols, float eps, cudaStream_t st) {
+  const int nvec = cols / 8;
+  auto go = [&](auto vpt, auto tpr) -> int {
+    constexpr int VPT = decltype(vpt)::value, TPR = decltype(tpr)::value;
+    const long long blocks = (rows + NT / TPR - 1) / (NT / TPR);
+    if (blocks > 2147483647LL) return VLLM_EUNSUPPORTED;
+    norm_rows_kernel<MODE, VPT, TPR><<<(unsigned)blocks, NT, 0, st>>>(
+        (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, rows,
+        cols, eps);
+    VLLM_CHECK_LAUNCH();
+    return VLLM_OK;
+  };
+  using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+  using I4 = std::integral_constant<int, 4>; using I8 = std::integral_constant<int, 8>;
+  using T32 = std::integral_constant<int, 32>; using T128 = std::integral_constant<int, 128>;
+  using T256 = std::integral_constant<int, 256>;
+  if (nvec <= 32) return go(I1{}, T32{});
+  if (nvec <= 64) return go(I2{}, T32{});
+  if (nvec <= 128) return go(I4{}, T32{});
+  if (nvec <= 256) return go(I2{}, T128{});
+  if (nvec <= 512) return go(I4{}, T128{});
+  if (nvec <= 1024) return go(I8{}, T128{});
+  return go(I8{}, T256{});
 }
 
 // qk [T, heads, 128]-style rows inside a packed tensor: element (t, h, d) at base + t*ld + h*hd + d.
@@ -144,7 +181,7 @@ int check_rows(const void* x, long long ldx, const void* y, long long ldy, long 
   if (rows < 0 || cols <= 0) return VLLM_EINVAL;
   if (rows == 0) return 1000;
   if (!x || !y) return VLLM_EINVAL;
-  if (cols % 8 || cols > 8 * NT * MAX_VEC) return VLLM_EUNSUPPORTED;
+  if (cols % 8 || cols > 8 * 256 * 8) return VLLM_EUNSUPPORTED;
   if (ldx % 8 || ldy % 8 || !vllm_aligned(x, 16) || !vllm_aligned(y, 16)) return VLLM_EALIGN;
   if (rows > 2147483647LL) return VLLM_EUNSUPPORTED;
   return VLLM_OK;
@@ -160,10 +197,7 @@ int vllm_rmsnorm_bf16(const void* x, long long ldx, const void* weight, void* y,
   if (rc == 1000) return VLLM_OK;
   if (rc) return rc;
   if (!weight || !vllm_aligned(weight, 16)) return VLLM_EINVAL;
-  norm_rows_kernel<0><<<(unsigned)rows, NT, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)weight, nullptr, (__nv_bfloat16*)y, ldy, cols, eps);
-  VLLM_CHECK_LAUNCH();
-  return VLLM_OK;
+  return launch_norm<0>(x, ldx, weight, nullptr, y, ldy, rows, cols, eps, (cudaStream_t)stream);
 }
 
 int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const void* bias, void* y, long long ldy,
@@ -172,11 +206,7 @@ int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const 
   if (rc == 1000) return VLLM_OK;
   if (rc) return rc;
   if (!weight || !bias || !vllm_aligned(weight, 16) || !vllm_aligned(bias, 16)) return VLLM_EINVAL;
-  norm_rows_kernel<1><<<(unsigned)rows, NT, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)weight, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, ldy,
-      cols, eps);
-  VLLM_CHECK_LAUNCH();
-  return VLLM_OK;
+  return launch_norm<1>(x, ldx, weight, bias, y, ldy, rows, cols, eps, (cudaStream_t)stream);
 }
 
 int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long long tokens, int heads,
