@@ -122,6 +122,8 @@ int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, in
                         long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
                         long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
                         long long o_token_pitch, const int* seqlens, int causal, float scale, void* stream);
+/* Tuning knob (process-global): 0 = tcgen05/TMEM kernel for head_dim 128 (default), 1 = warp-MMA kernel always. */
+int vllm_attention_set_variant(int variant);
 
 #ifdef __cplusplus
 }

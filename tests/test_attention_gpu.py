@@ -26,6 +26,15 @@ def ref_attn(q, k, v, causal, seqlens=None):
     return o
 
 
+@pytest.fixture(params=[0, 1], ids=["tcgen05", "warp_mma"])
+def variant(request):
+    """Run every case on the tcgen05/TMEM kernel (head_dim 128) and on the warp-MMA kernel."""
+    from visionllm_b200 import _lib
+    _lib.lib().vllm_attention_set_variant(request.param)
+    yield request.param
+    _lib.lib().vllm_attention_set_variant(0)
+
+
 def check(out, ref):
     tol = ref.abs() * 2.0 ** -7 + 2e-3 * ref.abs().max()
     bad = (out.float() - ref).abs() > tol
@@ -40,8 +49,10 @@ def check(out, ref):
     (1, 64, 2, 128, True),
     (1, 1, 2, 128, True),
     (3, 130, 3, 128, True),
+    (2, 257, 2, 128, False),      # one key past two KV tiles, one row past the first CTA
+    (1, 3136, 2, 128, True),      # released-7B sequence length
 ])
-def test_attention_packed_qkv(B, T, H, D, causal):
+def test_attention_packed_qkv(B, T, H, D, causal, variant):
     from visionllm_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(T)
     qkv = torch.randn(B, T, 3, H, D, device="cuda", generator=g).bfloat16()
@@ -50,7 +61,7 @@ def test_attention_packed_qkv(B, T, H, D, causal):
     check(out, ref_attn(q, k, v, causal))
 
 
-def test_attention_gqa_and_seqlens_and_cross():
+def test_attention_gqa_and_seqlens_and_cross(variant):
     from visionllm_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(1)
     B, Tq, Tk, H, Hkv, D = 3, 200, 333, 8, 2, 128
@@ -63,7 +74,7 @@ def test_attention_gqa_and_seqlens_and_cross():
     check(ops.attention(q, k, v, seqlens=sl), ref_attn(q, k, v, False, sl))
 
 
-def test_attention_large_magnitude_is_stable():
+def test_attention_large_magnitude_is_stable(variant):
     from visionllm_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(2)
     q = (torch.randn(1, 256, 2, 128, device="cuda", generator=g) * 8).bfloat16()

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "vllm_rope_bf16": (ci, [vp, cll, vp, vp, cll, ci, ci, vp]),
     "vllm_attention_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cll, cll, cll, cll, cll, cll, cll, cll,
                                  vp, ci, cf, vp]),
+    "vllm_attention_set_variant": (ci, [ci]),
 }
 
 
