@@ -75,6 +75,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuprof", action="store_true",
+                    help="wrap ONE extra device step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else max(args.warmup, 1)
 
@@ -129,6 +131,12 @@ def main():
     if rank == 0:
         sampler.start()
     ms_dev, launches = timed(wl.step_device, args.steps, args.warmup)
+    if args.cuprof:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        wl.step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     kern = wl.dominant_kernel_ms(args.steps)            # live CUDA-event time of the dominant kernel
     ms_e2e, _ = timed(wl.step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
