@@ -122,10 +122,7 @@ def main():
         e1.record()
         launches = _lib.launch_count() - l0
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), launches
+        return benchlib.max_over_ranks(e0.elapsed_time(e1), dist if world > 1 else None, "cuda"), launches
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

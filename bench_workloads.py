@@ -22,6 +22,23 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def shard_range(total, rank, world):
+    """Contiguous batch shard of SURVEY 8e: rank r owns units [r*total/world, (r+1)*total/world)."""
+    if total % world:
+        raise ValueError(f"global batch {total} must divide over {world} ranks")
+    per = total // world
+    return rank * per, (rank + 1) * per
+
+
+def max_over_ranks(value, dist=None, device="cpu"):
+    """Multi-GPU timing rule: the step time of the job is the MAX over ranks (all_reduce MAX)."""
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 GDINO_LEVELS_1024 = [(128, 128), (64, 64), (32, 32), (16, 16)]   # strides 8..64 of a 1024x1024 image
 
 
