@@ -12,8 +12,10 @@
 //                                       O_i = P_i V_j     (TS form: A = P_i read from TMEM, B = V_j MN-major smem)
 //   warp 2      TMEM allocator (512 columns: S0 | S1 | O0 | O1; P_i aliases the first 64 columns of S_i)
 //   warps 4-7   softmax warpgroup of Q tile 0, warps 8-11 of Q tile 1: ONE THREAD PER QUERY ROW (TMEM lane = row),
-//               so row max / row sum need no shuffles: tcgen05.ld S -> max -> exp2 -> bf16 P -> tcgen05.st,
-//               then O_i tile -> registers, acc = acc * corr + O_i (online-softmax rescale in registers).
+//               so row max / row sum need no shuffles: tcgen05.ld S (once, 128 registers) -> max -> exp2 -> bf16 P
+//               -> tcgen05.st.  O_i accumulates IN TMEM across KV tiles (PV MMA with accumulate); the online-softmax
+//               rescale of O is lazy: a row keeps a stale reference max until the true max has grown by more
+//               than 2^8, and only then (warp-uniform vote) O_i is loaded, scaled and stored back.
 //   Scores and probabilities never leave the SM; HBM traffic = Q, K, V read + O written.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -116,7 +118,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc::mbar_init(k_full(s), 1); tc::mbar_init(v_full(s), 1); tc::mbar_init(k_empty(s), 1); tc::mbar_init(v_empty(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(s_full(i), 1); tc::mbar_init(p_ready(i), 128); tc::mbar_init(o_full(i), 1); tc::mbar_init(o_free(i), 128);
+      tc::mbar_init(s_full(i), 1); tc::mbar_init(p_ready(i), 128); tc::mbar_init(o_full(i), 1); tc::mbar_init(o_free(i), 128);  /* unused since O accumulates in TMEM */
     }
     tc::mbar_fence_init();
   }
@@ -164,13 +166,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         tc::umma_commit<1>(s_full(i));
       };
-      auto issue_pv = [&](int i, int j) {  // O_i = P_i V_j (fresh accumulator every tile)
+      auto issue_pv = [&](int i, int j) {  // O_i (+)= P_i V_j, accumulator lives in TMEM across tiles
         const int s = j % KV_STAGES;
         const uint32_t va = sV + s * TILE_BYTES;
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk)
           umma_ts_f16(tmem + 256 + i * 128, tmem + i * 128 + kk * 8,
-                      umma_desc_sw128(va + kk * 2048, HALF_BYTES, 1024), idesc_pv, kk != 0);
+                      umma_desc_sw128(va + kk * 2048, HALF_BYTES, 1024), idesc_pv, (j | kk) != 0);
         tc::umma_commit<1>(o_full(i));
       };
       if (n_tiles > 0) {
@@ -185,7 +187,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const bool more = j + 1 < n_tiles;
           tc::mbar_wait(v_full(s), kv_ph);
           tc::mbar_wait(p_ready(0), jp);
-          tc::mbar_wait(o_free(0), jp ^ 1);
           tc::tc_fence_after();
           if (tc::elect_one()) issue_pv(0, j);
           __syncwarp();
@@ -196,7 +197,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             __syncwarp();
           }
           tc::mbar_wait(p_ready(1), jp);
-          tc::mbar_wait(o_free(1), jp ^ 1);
           tc::tc_fence_after();
           if (tc::elect_one()) {
             issue_pv(1, j);
@@ -209,72 +209,72 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else {
     // ===================== softmax warpgroups: one thread per query row =====================
-    reg_inc<224>();
+    reg_inc<200>();
     const int i = (warp - 4) >> 2;                    // Q tile of this warpgroup
     const int quarter = warp & 3;
     const int row = q0 + i * BQ + quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t tS = tmem + lane_addr + i * 128, tO = tmem + lane_addr + 256 + i * 128;
-    float acc[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] = 0.f;
-    float m = -INFINITY, l = 0.f, corr = 1.f;
+    constexpr float RESCALE_THRESHOLD = 8.f;          // log2 domain: tolerate a 2^8 stale reference max
+    float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t jp = j & 1;
-      if (j > 0) {
-        // fold the previous tile's O into the running accumulator (its scale factor is `corr`)
-        tc::mbar_wait(o_full(i), jp ^ 1);
+      tc::mbar_wait(s_full(i), jp);
+      tc::tc_fence_after();
+      uint32_t r[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) tc::tmem_ld_32x32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&r[c]));
+      tc::tmem_ld_wait();
+      const int n0 = j * BKV;
+      const bool need_mask = (n0 + BKV > len) || (a.causal && (n0 + BKV - 1 > q0 + i * BQ + coff));
+      const int lim = (a.causal ? min(len, row + coff + 1) : len) - n0;   // tile-local keys < lim are visible
+      if (need_mask) {
+#pragma unroll
+        for (int k = 0; k < BKV; ++k) if (k >= lim) r[k] = 0xff800000u;   // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < BKV; k += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[k]), __uint_as_float(r[k + 1])));
+      const float m_tile = mx * a.scale_log2;
+      // lazy online-softmax rescale (first tile: just adopt the max, O is overwritten by the first PV MMA)
+      const bool grow = m_tile > m + RESCALE_THRESHOLD;            // also true while m == -inf and the tile has a key
+      if (j == 0) {
+        m = m_tile;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? m_tile : m;
+        const float corr = (m == -INFINITY) ? 0.f : ex2(m - m_new);   // rows that do not grow: corr == 1
+        l *= corr;
+        m = m_new;
+        tc::mbar_wait(o_full(i), jp ^ 1);                              // PV of tile j-1 has landed in O_i
         tc::tc_fence_after();
 #pragma unroll
         for (int c = 0; c < D; c += 32) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(tO + c, r);
+          uint32_t o[32];
+          tc::tmem_ld_32x32(tO + c, o);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) acc[c + k] = fmaf(acc[c + k], corr, __uint_as_float(r[k]));
-        }
-        tc::tc_fence_before();
-        tc::mbar_arrive(o_free(i));
-      }
-      tc::mbar_wait(s_full(i), jp);
-      tc::tc_fence_after();
-      const int n0 = j * BKV;
-      const bool need_mask = (n0 + BKV > len) || (a.causal && (n0 + BKV - 1 > q0 + i * BQ + coff));
-      const int lim = a.causal ? min(len, row + coff + 1) : len;     // keys < lim are visible to this row
-      // pass 1: row max of the raw scores
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tS + c, r);
-        tc::tmem_ld_wait();
-        if (need_mask) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) if (n0 + c + k < lim) mx = fmaxf(mx, __uint_as_float(r[k]));
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]));
+          for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * corr);
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+              "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+              "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(tO + c),
+              "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]),
+              "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]), "r"(o[16]),
+              "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]), "r"(o[21]), "r"(o[22]), "r"(o[23]), "r"(o[24]),
+              "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]), "r"(o[31])
+              : "memory");
         }
       }
-      const float m_new = fmaxf(m, mx * a.scale_log2);
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      corr = ex2(m - m_safe);
-      // pass 2: p = exp2(s*scale - m), bf16 P written over the first 64 columns of S
+      const float m_use = (m == -INFINITY) ? 0.f : m;
+      // p = exp2(s*scale - m): bf16 P written over the first 64 columns of S
       float rs = 0.f;
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tS + c, r);
-        tc::tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(r[k]), a.scale_log2, -m_safe));
-          float p1 = ex2(fmaf(__uint_as_float(r[k + 1]), a.scale_log2, -m_safe));
-          if (need_mask) {
-            if (n0 + c + k >= lim) p0 = 0.f;
-            if (n0 + c + k + 1 >= lim) p1 = 0.f;
-          }
+          const float p0 = ex2(fmaf(__uint_as_float(r[c + k]), a.scale_log2, -m_use));
+          const float p1 = ex2(fmaf(__uint_as_float(r[c + k + 1]), a.scale_log2, -m_use));
           rs += p0 + p1;
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           pk[k >> 1] = *reinterpret_cast<uint32_t*>(&h);
@@ -284,20 +284,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(p_ready(i));
-      l = l * corr + rs;
-      m = m_new;
+      l += rs;
     }
+    float acc[D];
     if (n_tiles > 0) {
       tc::mbar_wait(o_full(i), (n_tiles - 1) & 1);
       tc::tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < D; c += 32) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tO + c, r);
-        tc::tmem_ld_wait();
+      for (int c = 0; c < D; c += 32) tc::tmem_ld_32x32(tO + c, *reinterpret_cast<uint32_t(*)[32]>(&acc[c]));
+      tc::tmem_ld_wait();
+    } else {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) acc[c + k] = fmaf(acc[c + k], corr, __uint_as_float(r[k]));
-      }
+      for (int d = 0; d < D; ++d) acc[d] = 0.f;
     }
     if (row < a.Tq) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
