@@ -90,6 +90,8 @@ int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int 
                    void* stream);
 /* Tuning knob (process-global): 1 = cta_group::1 tiles 128x256, 2 = CTA-pair tiles 256x256. */
 int vllm_gemm_set_variant(int variant);
+/* Tuning knob: force the tile-rasterisation group size (row-blocks per group); 0 = heuristic. */
+int vllm_gemm_set_group_m(int group_m);
 
 /* ---- row-wise norms and RoPE (bf16 in/out, fp32 statistics) ----------------------
  * vllm_rmsnorm_bf16 replaces apex.normalization.FusedRMSNorm forward

@@ -74,6 +74,18 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, max rel. error 1.0e-4 -- below bf16's 3.9e-3
+// resolution of P).  The MUFU unit issues one warp-wide ex2 per 8 cycles per sub-partition and is co-critical
+// with the tensor pipe for this kernel, so half of the exponentials are computed here instead.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float xr = x + 12582912.f;                 // 1.5 * 2^23: low mantissa bits now hold round(x)
+  const float f = x - (xr - 12582912.f);           // f in [-0.5, 0.5]
+  float p = fmaf(0.055008938f, f, 0.24221096f);
+  p = fmaf(p, f, 0.69328293f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -267,24 +279,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       const float m_use = (m == -INFINITY) ? 0.f : m;
       // p = exp2(s*scale - m): bf16 P written over the first 64 columns of S
-      float rs = 0.f;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;       // independent chains for the row sum
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) {
         uint32_t pk[16];
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[c + k]), a.scale_log2, -m_use));
-          const float p1 = ex2(fmaf(__uint_as_float(r[c + k + 1]), a.scale_log2, -m_use));
-          rs += p0 + p1;
-          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          pk[k >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        for (int k = 0; k < 32; k += 4) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[c + k]), a.scale_log2, -m_use));           // MUFU
+          const float p1 = ex2_poly(fmaf(__uint_as_float(r[c + k + 1]), a.scale_log2, -m_use));  // FMA pipe
+          const float p2 = ex2(fmaf(__uint_as_float(r[c + k + 2]), a.scale_log2, -m_use));
+          const float p3 = ex2_poly(fmaf(__uint_as_float(r[c + k + 3]), a.scale_log2, -m_use));
+          rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
+          pk[k >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[(k >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
         }
         tmem_st_32x16(tS + (c >> 1), pk);
       }
       tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(p_ready(i));
-      l += rs;
+      l += (rs0 + rs1) + (rs2 + rs3);
     }
     float acc[D];
     if (n_tiles > 0) {

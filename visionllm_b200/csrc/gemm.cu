@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, ACC = 2, THREADS = 256, GROUP_M = 8;
+constexpr int BM = 128, BN = 256, BK = 64, ACC = 2, THREADS = 256;
 constexpr int A_BYTES = BM * BK * 2;
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SILU = 3, ACT_SWIGLU = 4, ACT_QUICKGELU = 5 };
@@ -35,6 +35,7 @@ struct GemmArgs {
   const __nv_bfloat16* bias; const __nv_bfloat16* colscale; const __nv_bfloat16* residual; int ldr;
   int act; int out_f32;
   int tiles_m, tiles_n;  // tiles_m counts 128*CG-row blocks
+  int group_m;           // row-blocks per rasterisation group (see pick_group_m)
 };
 
 template <int CG> struct Cfg {
@@ -48,11 +49,11 @@ template <int CG> struct Cfg {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
-  const int per_group = GROUP_M * tiles_n;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
+  const int per_group = group_m * tiles_n;
   const int group = t / per_group;
-  const int first = group * GROUP_M;
-  const int gsz = min(GROUP_M, tiles_m - first);
+  const int first = group * group_m;
+  const int gsz = min(group_m, tiles_m - first);
   const int in = t - group * per_group;
   tm = first + in % gsz;
   tn = in / gsz;
@@ -104,7 +105,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (tc::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = cluster_id; t < n_tiles; t += n_clusters) {
-        int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+        int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
         const int row_a = (tm * CG + (int)rank) * BM;
         const int row_b = tn * BN + (int)rank * C_::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -158,7 +159,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int acc = 0; uint32_t acc_phase = 0;
     const bool swiglu = g.act == ACT_SWIGLU;
     for (int t = cluster_id; t < n_tiles; t += n_clusters) {
-      int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+      int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
       const int n0 = tn * BN;
       const int row = (tm * CG + (int)rank) * BM + quarter * 32 + lane;
       // stage bias / column scale for this tile
@@ -295,6 +296,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 2) tc::tmem_dealloc<CG>(tmem_base, ACC * BN);
 }
 
+// Rasterisation: a group of `group_m` row-blocks sweeps all column-blocks before the next group starts.
+// When the whole weight matrix B fits comfortably in L2 (126 MB) the best schedule streams A exactly once:
+// one wave of CTAs = (clusters / tiles_n) row-blocks x ALL column-blocks, so every A k-slab is fetched by
+// its sharers at the same time and B stays L2-resident across waves.  Larger B falls back to ~square waves.
+int g_group_m_override = 0;
+int pick_group_m(int n_clusters, int tiles_n, long long b_bytes) {
+  if (g_group_m_override > 0) return g_group_m_override;
+  if (b_bytes <= 100ll * 1000 * 1000) {
+    const int gm = n_clusters / tiles_n;
+    return gm < 1 ? 1 : gm;
+  }
+  return 8;
+}
+
 int g_gemm_variant = 2;  // 1: cta_group::1 (128x256 tiles), 2: cta_group::2 CTA pairs (256x256), the default
 
 template <int CG>
@@ -311,6 +326,7 @@ int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cuda
   int sms = vllm_num_sms();
   int clusters = sms / CG;
   if (clusters > n_tiles) clusters = n_tiles;
+  g.group_m = pick_group_m(sms / CG, g.tiles_n, (long long)g.N * g.K * 2);
   static bool attr_set[3] = {false, false, false};
   if (!attr_set[CG]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -337,6 +353,7 @@ int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cuda
 extern "C" {
 
 int vllm_gemm_set_variant(int v) { g_gemm_variant = (v == 1) ? 1 : 2; return VLLM_OK; }
+int vllm_gemm_set_group_m(int gm) { g_group_m_override = gm; return VLLM_OK; }
 
 int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                    const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
