@@ -74,9 +74,10 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, max rel. error 1.0e-4 -- below bf16's 3.9e-3
-// resolution of P).  The MUFU unit issues one warp-wide ex2 per 8 cycles per sub-partition and is co-critical
-// with the tensor pipe for this kernel, so half of the exponentials are computed here instead.
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, max rel. error 1.0e-4).  Tried for half of the
+// exponentials to relieve the MUFU unit (FA4's trick): measured SLOWER here (598 vs 678 TFLOP/s at the ViT shape,
+// profiles/r1_attn_bench.json history) -- the softmax warps are issue/latency-bound, not MUFU-bound, at two warps
+// per scheduler -- so it is kept for reference but not used.
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -126.f);
   const float xr = x + 12582912.f;                 // 1.5 * 2^23: low mantissa bits now hold round(x)
@@ -285,10 +286,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         uint32_t pk[16];
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[c + k]), a.scale_log2, -m_use));           // MUFU
-          const float p1 = ex2_poly(fmaf(__uint_as_float(r[c + k + 1]), a.scale_log2, -m_use));  // FMA pipe
+          const float p0 = ex2(fmaf(__uint_as_float(r[c + k]), a.scale_log2, -m_use));
+          const float p1 = ex2(fmaf(__uint_as_float(r[c + k + 1]), a.scale_log2, -m_use));
           const float p2 = ex2(fmaf(__uint_as_float(r[c + k + 2]), a.scale_log2, -m_use));
-          const float p3 = ex2_poly(fmaf(__uint_as_float(r[c + k + 3]), a.scale_log2, -m_use));
+          const float p3 = ex2(fmaf(__uint_as_float(r[c + k + 3]), a.scale_log2, -m_use));
           rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
           __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
           pk[k >> 1] = *reinterpret_cast<uint32_t*>(&h0);

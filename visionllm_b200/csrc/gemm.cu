@@ -296,19 +296,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 2) tc::tmem_dealloc<CG>(tmem_base, ACC * BN);
 }
 
-// Rasterisation: a group of `group_m` row-blocks sweeps all column-blocks before the next group starts.
-// When the whole weight matrix B fits comfortably in L2 (126 MB) the best schedule streams A exactly once:
-// one wave of CTAs = (clusters / tiles_n) row-blocks x ALL column-blocks, so every A k-slab is fetched by
-// its sharers at the same time and B stays L2-resident across waves.  Larger B falls back to ~square waves.
+// Rasterisation: a group of `group_m` row-blocks sweeps all column-blocks before the next group starts, so a wave
+// of 74 CTA pairs covers ~8 x 9 tiles (near-square = minimal A+B bytes per wave).  Measured (profiles/
+// r1_gemm_raster_experiment.md): DRAM traffic and ncu durations move by < 3 % between group sizes 1..8 at the
+// ViT shapes and get worse below 8 for the wide LLM gate|up GEMM, so 8 stays; the knob remains for sweeps.
 int g_group_m_override = 0;
-int pick_group_m(int n_clusters, int tiles_n, long long b_bytes) {
-  if (g_group_m_override > 0) return g_group_m_override;
-  if (b_bytes <= 100ll * 1000 * 1000) {
-    const int gm = n_clusters / tiles_n;
-    return gm < 1 ? 1 : gm;
-  }
-  return 8;
-}
+int pick_group_m(int, int, long long) { return g_group_m_override > 0 ? g_group_m_override : 8; }
 
 int g_gemm_variant = 2;  // 1: cta_group::1 (128x256 tiles), 2: cta_group::2 CTA pairs (256x256), the default
 
