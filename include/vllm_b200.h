@@ -67,6 +67,21 @@ int vllm_msda_sample_indices_f32(const int64_t* spatial_shapes, const float* sam
 /* Tuning knob for bench sweeps (process-global, not part of the drop-in API). */
 int vllm_msda_set_variant(int variant);
 
+/* ---- DCNv3 forward (InternImage core op) ------------------------------------------
+ * Replaces `dcnv3_forward` of the reference extension module `DCNv3`
+ * (visionllmv2/model/ops_dcnv3/src/dcnv3.h:20-38, vision.cpp:14-17; kernel
+ * src/cuda/dcnv3_im2col_cuda.cuh:32-80,216-277; caller functions/dcnv3_func.py:39-58).
+ * input [N,H_in,W_in,group*group_channels] (NHWC), offset [N,H_out,W_out,group*K*2] (x,y per
+ * tap, taps kernel_w-major), mask [N,H_out,W_out,group*K], out [N,H_out,W_out,group*
+ * group_channels]; K = kernel_h*kernel_w; offsets are in pixels and scaled by offset_scale.
+ * flags bit0: strict kernel (reference thread mapping, no FMA contraction; bit-exact vs
+ * oracle/dcnv3_oracle.c).  fp32 only (the reference module always upcasts,
+ * ops_dcnv3/modules/dcnv3.py:331-340). */
+int vllm_dcnv3_forward_f32(const float* input, const float* offset, const float* mask, float* out, int N,
+                           int H_in, int W_in, int H_out, int W_out, int group, int group_channels,
+                           int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                           int dilation_h, int dilation_w, float offset_scale, int flags, void* stream);
+
 /* ---- bf16 tensor-core GEMM with fused epilogue (tcgen05 / TMEM / TMA) ----------
  * C[M, n_out] = epi(A[M,K] . B[N,K]^T): every nn.Linear on the hot path
  * (internvit/modeling_intern_vit.py:112,124,172-173; modeling_visionllmv2.py:162-184;

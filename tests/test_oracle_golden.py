@@ -95,3 +95,16 @@ def test_pixel_centre_non_power_of_two():
     expect = np.floor((prod - np.float32(0.5)).astype(np.float32)).astype(np.int32)
     assert (idx[0, :, 0, 0, 0, 1] == expect).all()
     assert (idx[0, :, 0, 0, 0, 0] == expect).all()
+
+
+@pytest.mark.parametrize("name", ["dcnv3_ref_testpy.npz", "dcnv3_ref_c32_s2.npz", "dcnv3_ref_c32_k5.npz"])
+def test_dcnv3_oracle_vs_reference(golden_dir, name):
+    """oracle/dcnv3_oracle.c vs outputs of the reference's own dcnv3_core_pytorch (fp64); the reference's own
+    fp32 check is allclose(rtol=1e-2, atol=1e-3) (ops_dcnv3/test.py:79)."""
+    from oracle import dcnv3_oracle as DO
+    g = np.load(os.path.join(golden_dir, name))
+    p = [int(x) for x in g["params"]]
+    out = DO.forward(g["input"], g["offset"], g["mask"], *p[:8], p[8], p[9], float(g["offset_scale"]))
+    ref = g["out_f64"]
+    assert np.allclose(out, ref, rtol=1e-2, atol=1e-3)
+    assert np.abs(out - ref).max() < 1e-7
