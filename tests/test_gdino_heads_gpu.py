@@ -51,8 +51,12 @@ def test_proposals_class_bbox_and_topk(g):
     shapes = t(g, "shapes").long()
     pad = t(g, "pad").bool()
     oq, prop = prop_mod(t(g, "enc", torch.bfloat16), pad, shapes)
-    # proposals are fp32 index/geometry arithmetic: exact, including where the +inf sentinels sit
-    assert torch.equal(prop, t(g, "prop"))
+    # proposals: the +inf sentinels (padded / out-of-range pixels) must sit identically; the finite values are
+    # fp32 log/div whose last ulp differs between CPU and GPU libm
+    ref_prop = t(g, "prop")
+    assert torch.equal(torch.isinf(prop), torch.isinf(ref_prop))
+    fin = torch.isfinite(ref_prop)
+    assert torch.allclose(prop[fin], ref_prop[fin], rtol=1e-5, atol=1e-6)
     close(oq, t(g, "oq"))
     cls = contr(oq, t(g, "text", torch.bfloat16), t(g, "tmask").bool())
     assert cls.dtype == torch.float32 and cls.shape == (2, oq.shape[1], 16)
@@ -62,7 +66,7 @@ def test_proposals_class_bbox_and_topk(g):
     # integer contract: same logits in -> identical proposal indices and gathered reference points
     idx, ref_pts, _, _, _ = H.select_topk_proposals(t(g, "cls"), t(g, "coord"), t(g, "oq"), 20)
     assert torch.equal(idx.cpu(), torch.from_numpy(g["topk"]))
-    assert torch.equal(ref_pts, t(g, "ref_pts"))
+    assert torch.allclose(ref_pts, t(g, "ref_pts"), rtol=1e-6, atol=1e-7)          # sigmoid: libm ulp
 
 
 def test_mask_head_einsum_as_gemm(g):
