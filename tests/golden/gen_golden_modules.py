@@ -128,6 +128,53 @@ def gdino():
          keys=np.array(json.dumps(key_shapes(dec))))
 
 
+def gdino_encoder_layer():
+    """Full GroundingDinoEncoderLayer (fusion bi-attention + text enhancer + deformable layer), gd.py:1216-1289."""
+    cfgm, mod = ref_shim.load_gdino()
+    cfg = cfgm.GroundingDinoConfig(d_model=256, encoder_attention_heads=8, decoder_attention_heads=8,
+                                   encoder_ffn_dim=512, decoder_ffn_dim=512, num_feature_levels=4, encoder_n_points=4,
+                                   decoder_n_points=4, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0,
+                                   fusion_dropout=0.0, fusion_droppath=0.0, text_enhancer_dropout=0.0,
+                                   disable_custom_kernels=True)
+    shapes_l = [(12, 16), (6, 8), (3, 4), (2, 2)]
+    shapes = torch.tensor(shapes_l, dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    B, T = 2, 9
+    g = torch.Generator().manual_seed(17)
+    src = bf16r(torch.randn(B, S, 256, generator=g))
+    pos = bf16r(torch.randn(B, S, 256, generator=g) * 0.5)
+    text = bf16r(torch.randn(B, T, 256, generator=g))
+    refs = []
+    for (H, W) in shapes_l:
+        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+        refs.append(torch.stack(((xs + 0.5) / W, (ys + 0.5) / H), -1).reshape(-1, 2))
+    ref2 = torch.cat(refs, 0)[None, :, None, :].repeat(B, 1, 4, 1)
+    kpm = torch.zeros(B, S, dtype=torch.bool)                    # key_padding_mask: True = padded pixel
+    kpm[1, 150:192] = True; kpm[1, -3:] = True
+    tq_mask = torch.ones(B, T, dtype=torch.bool); tq_mask[1, 5:] = False     # text_query_masks: valid = 1
+    tsa, pids = mod.generate_masks_with_text_query_masks(tq_mask)
+    lay = mod.GroundingDinoEncoderLayer(cfg)
+    sd = seeded_state_dict(lay, 505)
+    for k in sd:                                                  # LayerScale params big enough to matter
+        if k.endswith("vision_param") or k.endswith("text_param"):
+            sd[k] = sd[k] * 0 + 0.5
+    lay.load_state_dict(sd)
+
+    def fn(mm, dt):
+        (v, t), _ = mm(vision_features=src.to(dt), vision_position_embedding=pos.to(dt), spatial_shapes=shapes,
+                       level_start_index=lsi, key_padding_mask=kpm, reference_points=ref2, text_features=text.to(dt),
+                       text_attention_mask=~tq_mask, text_position_embedding=None, text_self_attention_masks=tsa,
+                       text_position_ids=pids)
+        return torch.cat([v.float().flatten(1), t.float().flatten(1)], 1)
+
+    o32, o16 = run_both(lay, fn, mod)
+    save("mod_gdino_encoder_layer.npz", src=src, pos=pos, text=text, ref=ref2, kpm=kpm.numpy(), tq_mask=tq_mask.numpy(),
+         tsa=tsa.numpy(), pids=pids.numpy(), shapes=shapes.numpy(), lsi=lsi.numpy(), out_f32=o32, out_refbf16=o16,
+         keys=np.array(json.dumps(key_shapes(lay))))
+
+
 if __name__ == "__main__":
-    internvit()
-    gdino()
+    which = sys.argv[1:] or ["internvit", "gdino", "gdino_encoder_layer"]
+    for w in which:
+        globals()[w]()

@@ -83,3 +83,27 @@ def test_attention_large_magnitude_is_stable(variant):
     out = ops.attention(q, k, v)
     assert torch.isfinite(out.float()).all()
     check(out, ref_attn(q, k, v, False))
+
+
+def test_attention_head_dim_256_and_key_mask():
+    """GDINO bi-attention shapes: head_dim 256, arbitrary key_padding_mask (padded pixels are not a suffix)."""
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, Tq, Tk, H, D = 2, 70, 333, 4, 256
+    q = torch.randn(B, Tq, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Tk, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Tk, H, D, device="cuda", generator=g).bfloat16()
+    km = torch.rand(B, Tk, device="cuda", generator=g) > 0.3
+    km[:, 0] = True
+    out = ops.attention(q, k, v, key_mask=km)
+    s = (q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 3, 1)) * D ** -0.5
+    s = s.masked_fill(~km[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
+    check(out, ref)
+    # head_dim 128 with a key mask takes the warp-MMA kernel (the TMEM kernel has no mask operand)
+    q2, k2, v2 = q[..., :128].contiguous(), k[..., :128].contiguous(), v[..., :128].contiguous()
+    out2 = ops.attention(q2, k2, v2, key_mask=km)
+    s2 = (q2.float().permute(0, 2, 1, 3) @ k2.float().permute(0, 2, 3, 1)) * 128 ** -0.5
+    s2 = s2.masked_fill(~km[:, None, None, :], float("-inf"))
+    ref2 = (torch.softmax(s2, -1) @ v2.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Tq, H * 128)
+    check(out2, ref2)

@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, NW = 4;
+constexpr int BM = 64, NW = 4;
 
 struct AttnArgs {
   const __nv_bfloat16 *q, *k, *v;
@@ -28,6 +28,7 @@ struct AttnArgs {
   long long q_bs, k_bs, v_bs, o_bs;  // batch pitches
   long long q_ts, k_ts, v_ts, o_ts;  // token pitches
   const int* seqlens;
+  const unsigned char* key_mask;   // optional [batch, Tk], 1 = attend (arbitrary key_padding_mask)
   int Tq, Tk, heads, kv_heads, causal;
   float scale_log2;
 };
@@ -79,7 +80,7 @@ __device__ __forceinline__ void load_tile(uint32_t smem, const __nv_bfloat16* ba
   }
 }
 
-template <int D>
+template <int D, int BN>
 __global__ void __launch_bounds__(NW * 32)
 flash_fwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -161,7 +162,8 @@ flash_fwd_kernel(const AttnArgs a) {
     }
     // ---- mask + online softmax (scores scaled into log2 domain) ----
     const int n0 = t * BN;
-    const bool need_mask = (n0 + BN > len) || (a.causal && (n0 + BN - 1 > m0 + coff));
+    const unsigned char* km = a.key_mask ? a.key_mask + (long long)b * a.Tk : nullptr;
+    const bool need_mask = km || (n0 + BN > len) || (a.causal && (n0 + BN - 1 > m0 + coff));
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < BN / 8; ++j) {
@@ -171,7 +173,7 @@ flash_fwd_kernel(const AttnArgs a) {
         if (need_mask) {
           const int key = n0 + j * 8 + tq * 2 + (e & 1);
           const int qr = qrow0 + (e >> 1) * 8;
-          if (key >= len || (a.causal && key > qr + coff)) v = -INFINITY;
+          if (key >= len || (a.causal && key > qr + coff) || (km && !km[key])) v = -INFINITY;
         }
         s[j][e] = v;
         mx[e >> 1] = fmaxf(mx[e >> 1], v);
@@ -247,17 +249,17 @@ flash_fwd_kernel(const AttnArgs a) {
   }
 }
 
-template <int D>
+template <int D, int BN = 64>
 int launch(const AttnArgs& a, int batch, cudaStream_t st) {
   constexpr int SMEM = BM * D * 2 + 4 * BN * D * 2;
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return (int)e;
     set = true;
   }
   dim3 grid((a.Tq + BM - 1) / BM, a.heads, batch);
-  flash_fwd_kernel<D><<<grid, NW * 32, SMEM, st>>>(a);
+  flash_fwd_kernel<D, BN><<<grid, NW * 32, SMEM, st>>>(a);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
 }
@@ -275,8 +277,8 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
                                    int heads, int kv_heads, int head_dim, long long q_batch_pitch,
                                    long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
                                    long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
-                                   long long o_token_pitch, const int* seqlens, int causal, float scale,
-                                   void* stream) {
+                                   long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
+                                   int causal, float scale, void* stream) {
   if (batch < 0 || Tq < 0 || Tk < 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads) return VLLM_EINVAL;
   if (batch == 0 || Tq == 0) return VLLM_OK;
   if (!q || !k || !v || !o) return VLLM_EINVAL;
@@ -290,10 +292,10 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
   a.o = (__nv_bfloat16*)o;
   a.q_bs = q_batch_pitch; a.k_bs = k_batch_pitch; a.v_bs = v_batch_pitch; a.o_bs = o_batch_pitch;
   a.q_ts = q_token_pitch; a.k_ts = k_token_pitch; a.v_ts = v_token_pitch; a.o_ts = o_token_pitch;
-  a.seqlens = seqlens; a.Tq = Tq; a.Tk = Tk; a.heads = heads; a.kv_heads = kv_heads; a.causal = causal;
+  a.seqlens = seqlens; a.key_mask = key_mask; a.Tq = Tq; a.Tk = Tk; a.heads = heads; a.kv_heads = kv_heads; a.causal = causal;
   a.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream;
-  if (head_dim == 128 && g_attn_variant == 0) {
+  if (head_dim == 128 && g_attn_variant == 0 && !key_mask) {
     const int rc = vllm_attention_tc_d128(q, k, v, o, batch, Tq, Tk, heads, kv_heads, q_batch_pitch, q_token_pitch,
                                           k_batch_pitch, k_token_pitch, v_batch_pitch, v_token_pitch, o_batch_pitch,
                                           o_token_pitch, seqlens, causal, scale, st);
@@ -303,6 +305,7 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
     case 128: return launch<128>(a, batch, st);
     case 64: return launch<64>(a, batch, st);
     case 32: return launch<32>(a, batch, st);
+    case 256: return launch<256, 32>(a, batch, st);
     default: return VLLM_EUNSUPPORTED;
   }
 }

@@ -6,6 +6,10 @@ visionllmv2/model/grounding_dino/modeling_ov_grounding_dino_mask_dn.py:
                                                            output_proj -> MSDA gather)
   GroundingDinoDeformableLayer                :1104-1182 (encoder: MSDA + LN + FFN + LN)
   GroundingDinoDecoderLayer                   :1292-1407 (self-MHA, text cross-MHA, MSDA cross-attn, FFN)
+  GroundingDinoTextEnhancerLayer              :793-857   (text self-MHA 4x64 + FFN)
+  GroundingDinoBiMultiHeadAttention           :860-1006  (vision<->text bi-attention, 4 heads x 256)
+  GroundingDinoFusionLayer                    :1039-1102 (LN, bi-attention, LayerScale residuals)
+  GroundingDinoEncoderLayer                   :1216-1289 (fusion -> text enhancer -> deformable layer)
 so reference state dicts load unchanged and the modules can be assigned over the reference classes
 (INTEGRATION.md).  Projections run on the tcgen05 GEMM (offset and weight projections share one launch),
 LayerNorm/residuals on the row kernels, attention on the fused attention kernel, the gather on
@@ -144,7 +148,7 @@ class GroundingDinoDeformableLayer(nn.Module):
 class _MHA(nn.MultiheadAttention):
     """nn.MultiheadAttention parameters (in_proj_weight/in_proj_bias/out_proj) with a kernel forward."""
 
-    def run(self, query, key, value, key_lengths=None, residual=None):
+    def run(self, query, key, value, key_lengths=None, key_mask=None, residual=None):
         E, H = self.embed_dim, self.num_heads
         B, Tq, _ = query.shape
         Tk = key.shape[1]
@@ -157,7 +161,7 @@ class _MHA(nn.MultiheadAttention):
             k = ops.linear(key, w[E:2 * E], bias=b[E:2 * E])
         v = ops.linear(value, w[2 * E:], bias=b[2 * E:])
         ctx = ops.attention(q.unflatten(-1, (H, E // H)), k.unflatten(-1, (H, E // H)),
-                            v.unflatten(-1, (H, E // H)), causal=False, seqlens=key_lengths)
+                            v.unflatten(-1, (H, E // H)), causal=False, seqlens=key_lengths, key_mask=key_mask)
         return ops.linear(ctx, self.out_proj.weight, bias=self.out_proj.bias, residual=residual)
 
 
@@ -216,3 +220,160 @@ class GroundingDinoDecoderLayer(nn.Module):
         h = ops.linear(x, self.fc1.weight, bias=self.fc1.bias, act=self.act)
         x = self.final_layer_norm(ops.linear(h, self.fc2.weight, bias=self.fc2.bias, residual=x))
         return (x,)
+
+
+def get_sine_pos_embed(pos_tensor, num_pos_feats=128, temperature=10000, exchange_xy=True):
+    """gd.py:1185-1213: sin/cos features of each coordinate; fp32 like the reference."""
+    scale = 2 * math.pi
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=pos_tensor.device)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+
+    def sine(x):
+        sx = x * scale / dim_t
+        return torch.stack((sx[..., 0::2].sin(), sx[..., 1::2].cos()), dim=3).flatten(2)
+
+    res = [sine(x) for x in pos_tensor.split([1] * pos_tensor.shape[-1], dim=-1)]
+    if exchange_xy:
+        res[0], res[1] = res[1], res[0]
+    return torch.cat(res, dim=-1)
+
+
+class GroundingDinoTextEnhancerLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.self_attn = _MHA(config.d_model, config.encoder_attention_heads // 2,
+                              dropout=getattr(config, "text_enhancer_dropout", 0.0), batch_first=True)
+        self.fc1 = nn.Linear(config.d_model, config.encoder_ffn_dim // 2)
+        self.fc2 = nn.Linear(config.encoder_ffn_dim // 2, config.d_model)
+        self.layer_norm_before = _LN(config.d_model)
+        self.layer_norm_after = _LN(config.d_model)
+        self.act = _act(config)
+        self.num_heads = config.encoder_attention_heads // 2
+
+    @torch.no_grad()
+    def forward(self, hidden_states, attention_masks=None, position_embeddings=None):
+        """attention_masks: [bs, T, T] bool, True = masked.  The reference builds it with
+        generate_masks_with_text_query_masks (gd.py:2025-2042): the valid tokens form one leading block and padded
+        tokens see only themselves, so every valid row shares row 0's key set; rows of padded tokens are
+        don't-care (they are masked as keys everywhere downstream)."""
+        key_mask = None
+        if attention_masks is not None:
+            am = attention_masks if attention_masks.dim() == 3 else attention_masks[None]
+            key_mask = ~am[:, 0, :]
+        qk = hidden_states if position_embeddings is None else hidden_states + position_embeddings
+        x = self.layer_norm_before(self.self_attn.run(qk, qk, hidden_states, key_mask=key_mask, residual=hidden_states))
+        h = ops.linear(x, self.fc1.weight, bias=self.fc1.bias, act=self.act)
+        x = self.layer_norm_after(ops.linear(h, self.fc2.weight, bias=self.fc2.bias, residual=x))
+        return x, None
+
+
+class GroundingDinoBiMultiHeadAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        vision_dim = text_dim = config.d_model
+        self.embed_dim = config.encoder_ffn_dim // 2
+        self.num_heads = config.encoder_attention_heads // 2
+        self.head_dim = self.embed_dim // self.num_heads
+        if self.head_dim * self.num_heads != self.embed_dim:
+            raise ValueError("`embed_dim` must be divisible by `num_heads`")
+        self.scale = self.head_dim ** (-0.5)
+        self.vision_proj = nn.Linear(vision_dim, self.embed_dim)
+        self.text_proj = nn.Linear(text_dim, self.embed_dim)
+        self.values_vision_proj = nn.Linear(vision_dim, self.embed_dim)
+        self.values_text_proj = nn.Linear(text_dim, self.embed_dim)
+        self.out_vision_proj = nn.Linear(self.embed_dim, vision_dim)
+        self.out_text_proj = nn.Linear(self.embed_dim, text_dim)
+        self._packed = None
+
+    def _packed_proj(self):
+        ms = (self.vision_proj, self.values_vision_proj, self.text_proj, self.values_text_proj)
+        key = tuple((m.weight.data_ptr(), m.weight._version, m.bias._version) for m in ms)
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key,
+                            torch.cat([ms[0].weight.detach(), ms[1].weight.detach()], 0).contiguous(),
+                            torch.cat([ms[0].bias.detach(), ms[1].bias.detach()], 0).contiguous(),
+                            torch.cat([ms[2].weight.detach(), ms[3].weight.detach()], 0).contiguous(),
+                            torch.cat([ms[2].bias.detach(), ms[3].bias.detach()], 0).contiguous())
+        return self._packed[1:]
+
+    @torch.no_grad()
+    def forward(self, vision_features, text_features, vision_attention_mask=None, text_attention_mask=None,
+                vision_epilogue=None, text_epilogue=None):
+        """Both directions share S = (vision_proj(v) * scale) text_proj(t)^T; softmax over text keys gives the
+        vision update, softmax over vision keys of S^T the text update (gd.py:927-1004).  The reference's global
+        `S - S.max()` and the +-50000 clamp do not change either softmax; masks are True = padded."""
+        E, H, D = self.embed_dim, self.num_heads, self.head_dim
+        wv, bv, wt, bt = self._packed_proj()
+        pv = ops.linear(vision_features, wv, bias=bv)              # [B, S, 2E]: query-side | values
+        pt = ops.linear(text_features, wt, bias=bt)                # [B, T, 2E]: key-side | values
+        vq, vval = pv[..., :E].unflatten(-1, (H, D)), pv[..., E:].unflatten(-1, (H, D))
+        tk, tval = pt[..., :E].unflatten(-1, (H, D)), pt[..., E:].unflatten(-1, (H, D))
+        tkm = None if text_attention_mask is None else ~text_attention_mask
+        vkm = None if vision_attention_mask is None else ~vision_attention_mask
+        v_ctx = ops.attention(vq, tk, tval, scale=self.scale, key_mask=tkm)     # vision queries over text keys
+        t_ctx = ops.attention(tk, vq, vval, scale=self.scale, key_mask=vkm)     # text queries over vision keys
+        ve = vision_epilogue or {}
+        te = text_epilogue or {}
+        dv = ops.linear(v_ctx, self.out_vision_proj.weight, bias=self.out_vision_proj.bias, **ve)
+        dt = ops.linear(t_ctx, self.out_text_proj.weight, bias=self.out_text_proj.bias, **te)
+        return (dv, None), (dt, None)
+
+
+class GroundingDinoFusionLayer(nn.Module):
+    def __init__(self, config, init_values=1e-4):
+        super().__init__()
+        if getattr(config, "fusion_droppath", 0.0) and False:
+            pass
+        self.layer_norm_vision = _LN(config.d_model)
+        self.layer_norm_text = _LN(config.d_model)
+        self.attn = GroundingDinoBiMultiHeadAttention(config)
+        self.vision_param = nn.Parameter(init_values * torch.ones((config.d_model)), requires_grad=True)
+        self.text_param = nn.Parameter(init_values * torch.ones((config.d_model)), requires_grad=True)
+
+    @torch.no_grad()
+    def forward(self, vision_features, text_features, attention_mask_vision=None, attention_mask_text=None):
+        v = self.layer_norm_vision(vision_features)
+        t = self.layer_norm_text(text_features)
+        # residual = the NORMALISED features (gd.py:1092-1099); LayerScale + residual ride in the GEMM epilogue
+        (v_new, va), (t_new, ta) = self.attn(v, t, vision_attention_mask=attention_mask_vision,
+                                             text_attention_mask=attention_mask_text,
+                                             vision_epilogue=dict(colscale=self.vision_param, residual=v),
+                                             text_epilogue=dict(colscale=self.text_param, residual=t))
+        return (v_new, va), (t_new, ta)
+
+
+class GroundingDinoEncoderLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.d_model = config.d_model
+        self.text_enhancer_layer = GroundingDinoTextEnhancerLayer(config)
+        self.fusion_layer = GroundingDinoFusionLayer(config)
+        self.deformable_layer = GroundingDinoDeformableLayer(config)
+
+    def get_text_position_embeddings(self, text_features, text_position_embedding, text_position_ids):
+        B, T, _ = text_features.shape
+        if text_position_embedding is None and text_position_ids is None:
+            pos = torch.arange(T, device=text_features.device).float()[None, :, None].repeat(B, 1, 1)
+            text_position_embedding = get_sine_pos_embed(pos, num_pos_feats=self.d_model, exchange_xy=False)
+        if text_position_ids is not None:
+            text_position_embedding = get_sine_pos_embed(text_position_ids[..., None], num_pos_feats=self.d_model,
+                                                         exchange_xy=False)
+        return text_position_embedding
+
+    @torch.no_grad()
+    def forward(self, vision_features, vision_position_embedding, spatial_shapes, level_start_index, key_padding_mask,
+                reference_points, text_features=None, text_attention_mask=None, text_position_embedding=None,
+                text_self_attention_masks=None, text_position_ids=None):
+        tpos = self.get_text_position_embeddings(text_features, text_position_embedding, text_position_ids).to(
+            vision_features.dtype)
+        (vision_features, va), (text_features, ta) = self.fusion_layer(
+            vision_features=vision_features, text_features=text_features, attention_mask_vision=key_padding_mask,
+            attention_mask_text=text_attention_mask)
+        text_features, te = self.text_enhancer_layer(hidden_states=text_features,
+                                                     attention_masks=~text_self_attention_masks,
+                                                     position_embeddings=tpos)
+        vision_features, vd = self.deformable_layer(
+            hidden_states=vision_features, attention_mask=~key_padding_mask,
+            position_embeddings=vision_position_embedding, reference_points=reference_points,
+            spatial_shapes=spatial_shapes, level_start_index=level_start_index)
+        return (vision_features, text_features), (va, ta, te, vd)
