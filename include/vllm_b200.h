@@ -135,13 +135,15 @@ int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long
  * keys >= seqlens[b] are masked (right padding / key_padding_mask); all query rows are computed.
  * key_mask (uint8 [batch, Tk], may be NULL): 1 = attend, 0 = masked -- an arbitrary key_padding_mask
  * (nn.MultiheadAttention / GroundingDinoBiMultiHeadAttention semantics, inverted).
+ * attn_mask (uint8 [batch*heads, Tq, Tk], may be NULL): 1 = attend; exactly the [N*H, L, S] tensor
+ * nn.MultiheadAttention receives as `attn_mask` (inverted), indexed by batch*heads + head.
  * causal != 0: query i sees keys <= i + (Tk - Tq).  head_dim in {32, 64, 128, 256}. */
 int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
                         int heads, int kv_heads, int head_dim, long long q_batch_pitch,
                         long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
                         long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
-                        long long o_token_pitch, const int* seqlens, const unsigned char* key_mask, int causal,
-                        float scale, void* stream);
+                        long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
+                        const unsigned char* attn_mask, int causal, float scale, void* stream);
 /* Tuning knob (process-global): 0 = tcgen05/TMEM kernel for head_dim 128 (default), 1 = warp-MMA kernel always. */
 int vllm_attention_set_variant(int variant);
 

@@ -107,3 +107,20 @@ def test_attention_head_dim_256_and_key_mask():
     s2 = s2.masked_fill(~km[:, None, None, :], float("-inf"))
     ref2 = (torch.softmax(s2, -1) @ v2.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Tq, H * 128)
     check(out2, ref2)
+
+
+def test_attention_full_attn_mask():
+    """nn.MultiheadAttention-style [B*H, Tq, Tk] boolean mask (True = attend here), head_dim 64."""
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(10)
+    B, T, H, D = 2, 37, 4, 64
+    q = torch.randn(B, T, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, T, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, T, H, D, device="cuda", generator=g).bfloat16()
+    am = torch.rand(B * H, T, T, device="cuda", generator=g) > 0.4
+    am |= torch.eye(T, device="cuda", dtype=torch.bool)[None]
+    out = ops.attention(q, k, v, attn_mask=am)
+    s = (q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 3, 1)) * D ** -0.5
+    s = s.masked_fill(~am.view(B, H, T, T), float("-inf"))
+    ref = (torch.softmax(s, -1) @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, T, H * D)
+    check(out, ref)

@@ -148,7 +148,7 @@ class GroundingDinoDeformableLayer(nn.Module):
 class _MHA(nn.MultiheadAttention):
     """nn.MultiheadAttention parameters (in_proj_weight/in_proj_bias/out_proj) with a kernel forward."""
 
-    def run(self, query, key, value, key_lengths=None, key_mask=None, residual=None):
+    def run(self, query, key, value, key_lengths=None, key_mask=None, attn_mask=None, residual=None):
         E, H = self.embed_dim, self.num_heads
         B, Tq, _ = query.shape
         Tk = key.shape[1]
@@ -161,7 +161,8 @@ class _MHA(nn.MultiheadAttention):
             k = ops.linear(key, w[E:2 * E], bias=b[E:2 * E])
         v = ops.linear(value, w[2 * E:], bias=b[2 * E:])
         ctx = ops.attention(q.unflatten(-1, (H, E // H)), k.unflatten(-1, (H, E // H)),
-                            v.unflatten(-1, (H, E // H)), causal=False, seqlens=key_lengths, key_mask=key_mask)
+                            v.unflatten(-1, (H, E // H)), causal=False, seqlens=key_lengths, key_mask=key_mask,
+                            attn_mask=attn_mask)
         return ops.linear(ctx, self.out_proj.weight, bias=self.out_proj.bias, residual=residual)
 
 
@@ -252,16 +253,20 @@ class GroundingDinoTextEnhancerLayer(nn.Module):
 
     @torch.no_grad()
     def forward(self, hidden_states, attention_masks=None, position_embeddings=None):
-        """attention_masks: [bs, T, T] bool, True = masked.  The reference builds it with
-        generate_masks_with_text_query_masks (gd.py:2025-2042): the valid tokens form one leading block and padded
-        tokens see only themselves, so every valid row shares row 0's key set; rows of padded tokens are
-        don't-care (they are masked as keys everywhere downstream)."""
-        key_mask = None
+        """attention_masks: [bs, T, T] bool, True = masked.  Bug-compatible with the reference (gd.py:841-842): it
+        expands the mask with ``attention_masks.repeat(num_heads, 1, 1)`` -- batch-minor order -- while
+        nn.MultiheadAttention indexes attn_mask as batch*heads + head, so (batch b, head h) uses the mask of batch
+        (b*H + h) % bs.  Identical for bs == 1 (the reference's eval setting); reproduced exactly for bs > 1."""
+        full = None
         if attention_masks is not None:
-            am = attention_masks if attention_masks.dim() == 3 else attention_masks[None]
-            key_mask = ~am[:, 0, :]
+            am = attention_masks
+            if am.dim() == 3 and am.shape[0] == hidden_states.shape[0]:
+                am = am.repeat(self.num_heads, 1, 1)                  # the [bs*H, T, T] tensor MHA receives
+            elif am.dim() == 2:
+                am = am[None].expand(hidden_states.shape[0] * self.num_heads, -1, -1)
+            full = ~am
         qk = hidden_states if position_embeddings is None else hidden_states + position_embeddings
-        x = self.layer_norm_before(self.self_attn.run(qk, qk, hidden_states, key_mask=key_mask, residual=hidden_states))
+        x = self.layer_norm_before(self.self_attn.run(qk, qk, hidden_states, attn_mask=full, residual=hidden_states))
         h = ops.linear(x, self.fc1.weight, bias=self.fc1.bias, act=self.act)
         x = self.layer_norm_after(ops.linear(h, self.fc2.weight, bias=self.fc2.bias, residual=x))
         return x, None

@@ -146,10 +146,11 @@ def rope_(x, cos, sin, heads, head_dim):
     return x
 
 
-def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, out=None):
+def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, attn_mask=None, out=None):
     """softmax(q k^T * scale) v.  q [B, Tq, H, D], k/v [B, Tk, Hkv, D] bf16 views whose last two dims are
     contiguous (any batch/token pitch, e.g. slices of a packed qkv tensor).  Returns [B, Tq, H*D].
-    seqlens: int32 [B] key lengths; key_mask: bool/uint8 [B, Tk], True = attend (arbitrary key padding)."""
+    seqlens: int32 [B] key lengths; key_mask: bool/uint8 [B, Tk], True = attend (arbitrary key padding);
+    attn_mask: bool/uint8 [B*H, Tq, Tk], True = attend (nn.MultiheadAttention's attn_mask, inverted)."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
             raise RuntimeError(f"attention: {nm} must be a 4-D CUDA bf16 tensor")
@@ -174,11 +175,17 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, ou
             raise RuntimeError("attention: key_mask must be CUDA [B, Tk]")
         key_mask = key_mask.to(torch.uint8).contiguous()
         km = key_mask.data_ptr()
+    amp = None
+    if attn_mask is not None:
+        if attn_mask.shape != (B * H, Tq, Tk) or not attn_mask.is_cuda:
+            raise RuntimeError("attention: attn_mask must be CUDA [B*H, Tq, Tk]")
+        attn_mask = attn_mask.to(torch.uint8).contiguous()
+        amp = attn_mask.data_ptr()
     fl = 4.0 * B * H * Tq * Tk * D * (0.5 if causal and Tq == Tk else 1.0)
     with torch.cuda.device(q.device), _Prof("attention", fl, 2.0 * B * D * (2 * Tq * H + 2 * Tk * Hkv)):
         rc = _lib.lib().vllm_attention_bf16(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Tq, Tk, H, Hkv, D,
             q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
-            out.stride(0), out.stride(1), sl, km, 1 if causal else 0, float(scale), _stream())
+            out.stride(0), out.stride(1), sl, km, amp, 1 if causal else 0, float(scale), _stream())
     _lib.check(rc, "vllm_attention_bf16")
     return out
