@@ -252,7 +252,142 @@ class PairForwardWorkload:
         return {"kernel_breakdown": self.breakdown}
 
 
-WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "pair_forward": PairForwardWorkload}
+class GdinoHeadWorkload:
+    """BASELINE cfg 4's region-decoder stage in isolation: Grounding-DINO-tiny enc/dec layers on the 4-level pyramid
+    of a 1024^2 image (S = 21760), 80 class queries as text, 100 object queries: 6 x encoder layer (bi-attention
+    fusion + text enhancer + MSDA deformable layer) + 6 x decoder layer (self-MHA, text cross-MHA, MSDA cross-attn,
+    FFN).  Backbone / input projections are stubbed by synthetic features (they are cuDNN convs in the reference)."""
+    metric = "gdino_encdec_images_per_sec_1024px"
+    unit = "images/s"
+    dtype = "bf16 (MSDA gather fp32)"
+    N, Q, T = 8, 100, 80
+
+    def __init__(self, rank, world, device):
+        self.rank, self.world, self.device = rank, world, device
+
+    def setup(self):
+        import torch
+        from types import SimpleNamespace
+        from visionllm_b200.gdino import GroundingDinoDecoderLayer, GroundingDinoEncoderLayer
+        self.torch = torch
+        cfg = SimpleNamespace(d_model=256, encoder_attention_heads=8, decoder_attention_heads=8, encoder_ffn_dim=2048,
+                              decoder_ffn_dim=2048, num_feature_levels=4, encoder_n_points=4, decoder_n_points=4,
+                              dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, activation_function="relu")
+        torch.manual_seed(0)
+        dev = self.device
+        self.enc = torch.nn.ModuleList([GroundingDinoEncoderLayer(cfg) for _ in range(6)]).to(dev, torch.bfloat16).eval()
+        self.dec = torch.nn.ModuleList([GroundingDinoDecoderLayer(cfg) for _ in range(6)]).to(dev, torch.bfloat16).eval()
+        g = torch.Generator(device=dev).manual_seed(7 + self.rank)
+        shapes_l = GDINO_LEVELS_1024
+        self.shapes = torch.tensor(shapes_l, dtype=torch.int64, device=dev)
+        self.lsi = torch.cat((self.shapes.new_zeros(1), self.shapes.prod(1).cumsum(0)[:-1]))
+        S = sum(h * w for h, w in shapes_l)
+        N, Q, T = self.N, self.Q, self.T
+        self.src = torch.randn(N, S, 256, device=dev, generator=g).bfloat16()
+        self.pos = (torch.randn(N, S, 256, device=dev, generator=g) * 0.5).bfloat16()
+        self.text = torch.randn(N, T, 256, device=dev, generator=g).bfloat16()
+        refs = []
+        for (H, W) in shapes_l:
+            ys, xs = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float32),
+                                    torch.arange(W, device=dev, dtype=torch.float32), indexing="ij")
+            refs.append(torch.stack(((xs + 0.5) / W, (ys + 0.5) / H), -1).reshape(-1, 2))
+        self.ref2 = torch.cat(refs, 0)[None, :, None, :].repeat(N, 1, 4, 1).contiguous()
+        self.kpm = torch.zeros(N, S, dtype=torch.bool, device=dev)
+        self.tmask = torch.zeros(N, T, dtype=torch.bool, device=dev)                 # no padded text
+        self.tsa = torch.ones(N, T, T, dtype=torch.bool, device=dev)
+        self.pids = torch.arange(T, device=dev)[None].repeat(N, 1)
+        self.hs = torch.randn(N, Q, 256, device=dev, generator=g).bfloat16()
+        self.qpos = (torch.randn(N, Q, 256, device=dev, generator=g) * 0.5).bfloat16()
+        boxes = torch.rand(N, Q, 4, device=dev, generator=g) * 0.4 + 0.2
+        self.ref4 = boxes[:, :, None, :].repeat(1, 1, 4, 1).contiguous()
+        self.h_in = [t.cpu().pin_memory() for t in (self.src, self.pos, self.text)]
+        self.d_in = [torch.empty_like(t) for t in (self.src, self.pos, self.text)]
+        self.h_out = torch.empty((N, Q, 256), dtype=torch.bfloat16).pin_memory()
+        self.h2d_bytes = sum(t.numel() * 2 for t in self.h_in)
+        self.d2h_bytes = self.h_out.numel() * 2
+
+    def _run(self, src, pos, text):
+        v, t = src, text
+        for layer in self.enc:
+            (v, t), _ = layer(vision_features=v, vision_position_embedding=pos, spatial_shapes=self.shapes,
+                              level_start_index=self.lsi, key_padding_mask=self.kpm, reference_points=self.ref2,
+                              text_features=t, text_attention_mask=self.tmask, text_position_embedding=None,
+                              text_self_attention_masks=self.tsa, text_position_ids=self.pids)
+        h = self.hs
+        for layer in self.dec:
+            (h,) = layer(h, position_embeddings=self.qpos, reference_points=self.ref4, spatial_shapes=self.shapes,
+                         level_start_index=self.lsi, vision_encoder_hidden_states=v,
+                         vision_encoder_attention_mask=~self.kpm, text_encoder_hidden_states=t,
+                         text_encoder_attention_mask=self.tmask)
+        return h
+
+    def step_device(self):
+        self.out = self._run(self.src, self.pos, self.text)
+
+    def step_e2e(self):
+        for d, h in zip(self.d_in, self.h_in):
+            d.copy_(h, non_blocking=True)
+        self.h_out.copy_(self._run(*self.d_in), non_blocking=True)
+
+    def units_per_step(self):
+        return self.N
+
+    def dominant_kernel_ms(self, steps):
+        from visionllm_b200 import ops
+        import visionllm_b200.msda as msda_mod
+        torch = self.torch
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        orig = msda_mod.ms_deform_attn_forward
+        msda_ms = []
+
+        def timed_msda(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig(*a, **k); e1.record()
+            msda_ms.append((e0, e1, a[0].shape, a[3].shape))
+            return r
+
+        import visionllm_b200.gdino as gd_mod
+        gd_mod.msda_ext.ms_deform_attn_forward = timed_msda
+        try:
+            self.step_device()
+            torch.cuda.synchronize()
+        finally:
+            gd_mod.msda_ext.ms_deform_attn_forward = orig
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for name, fl, by, e0, e1 in prof:
+            a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl; a[3] += by
+        self.breakdown = {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / v[1] / 1e9 if v[1] else 0.0,
+                              "gbps": v[3] / v[1] / 1e6 if v[1] else 0.0} for k, v in agg.items()}
+        enc_ms = [a.elapsed_time(b) for a, b, vs, ls in msda_ms if ls[1] == vs[1]]
+        dec_ms = [a.elapsed_time(b) for a, b, vs, ls in msda_ms if ls[1] != vs[1]]
+        self.breakdown["msda_encoder"] = {"launches": len(enc_ms), "ms": sum(enc_ms)}
+        self.breakdown["msda_decoder"] = {"launches": len(dec_ms), "ms": sum(dec_ms)}
+        self.msda_enc_ms = sum(enc_ms) / max(1, len(enc_ms))
+        return self.msda_enc_ms
+
+    def roofline(self, kern_ms, peaks):
+        S = self.src.shape[1]
+        alg = (S * 256 + S * 8 * 16 * 2 + S * 8 * 16 + S * 256) * 4 * self.N
+        ach = alg / (kern_ms * 1e-3) / 1e9
+        return {"kernel": "msda_fwd_warp_kernel (encoder launches inside the GDINO step)", "bound": "hbm",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": alg}
+
+    def config(self):
+        return {"workload": "GDINO-tiny 6 enc + 6 dec layers, N=8 images, S=21760 (1024^2, 4 levels), 80 text "
+                            "tokens, 100 queries (BASELINE cfg 4 region decoder, backbone/input_proj stubbed)",
+                "l2_policy": "inputs_exceed_l2 (activations 8 x 21760 x 256 x ... > 126 MB)",
+                "parallelism": f"dp{self.world}"}
+
+    def extra(self):
+        return {"kernel_breakdown": self.breakdown}
+
+
+WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
 
@@ -323,7 +458,7 @@ def _cpu_pair_forward(steps, warmup):
             "ms_per_step": pair_s * 1e3}
 
 
-_CPU = {"msda_encoder": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward}
+_CPU = {"msda_encoder": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder}
 
 
 def cpu_baseline(name):
