@@ -57,6 +57,20 @@ int vllm_msda_forward_f64(const double* value, const int64_t* spatial_shapes, co
                           const double* sampling_loc, const double* attn_weight, double* out, int batch,
                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,
                           int num_point, void* stream);
+/* Backward of the same operator (`ms_deform_attn_backward`, unipose ops/src/ms_deform_attn.h:42-62; mmcv
+ * pybind.cpp:793-798; kernels ms_deform_attn_cuda_kernel.cuh:66-124,256-801).  grad_output [batch, num_query,
+ * num_heads*channels].  grad_value MUST be zero-initialised by the caller (corner contributions are accumulated
+ * with atomics, like the reference); grad_sampling_loc / grad_attn_weight are fully written. */
+int vllm_msda_backward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                           const float* sampling_loc, const float* attn_weight, const float* grad_output,
+                           float* grad_value, float* grad_sampling_loc, float* grad_attn_weight, int batch,
+                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                           int num_point, void* stream);
+int vllm_msda_backward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                           const double* sampling_loc, const double* attn_weight, const double* grad_output,
+                           double* grad_value, double* grad_sampling_loc, double* grad_attn_weight, int batch,
+                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                           int num_point, void* stream);
 /* Parity instrumentation: for each of n_samples = batch*num_query*num_heads*
  * num_levels*num_point samples writes (h_low, w_low, mask) int32 triples using
  * the SAME device function the forward kernels use.  mask bit0 = sample in

@@ -58,6 +58,21 @@ def forward_kernel_semantics(value, shapes, lsi, loc, attw):
     return out
 
 
+def backward_kernel_semantics(value, shapes, lsi, loc, attw, grad_out):
+    """numpy in / out: (grad_value, grad_loc, grad_attw); fp32 or fp64 (dtype of value)."""
+    value = np.ascontiguousarray(value)
+    dt = value.dtype
+    loc = np.ascontiguousarray(loc, dtype=dt); attw = np.ascontiguousarray(attw, dtype=dt)
+    grad_out = np.ascontiguousarray(grad_out, dtype=dt)
+    shapes = np.ascontiguousarray(shapes, dtype=np.int64); lsi = np.ascontiguousarray(lsi, dtype=np.int64)
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = loc.shape
+    gv, gl, gw = np.zeros_like(value), np.empty_like(loc), np.empty_like(attw)
+    fn = _lib().oracle_msda_backward_f32 if dt == np.float32 else _lib().oracle_msda_backward_f64
+    fn(_p(value), _p(shapes), _p(lsi), _p(loc), _p(attw), _p(grad_out), _p(gv), _p(gl), _p(gw), N, S, M, D, L, Lq, P)
+    return gv, gl, gw
+
+
 def sample_indices(shapes, loc):
     loc = np.ascontiguousarray(loc, dtype=np.float32)
     shapes = np.ascontiguousarray(shapes, dtype=np.int64)

@@ -81,6 +81,30 @@ def main():
                  loc=loc.numpy(), attw=attw.numpy(), out_f64=out.numpy())
         print(name, tuple(out.shape), float(out.abs().mean()))
 
+    # --- 3. backward: autograd through the reference's own pytorch function, fp64 (the channel counts of
+    #        mmcv/tests/test_ops/test_ms_deformable_attn.py:137-181 that are small enough to ship) ------------
+    def bwd_case(name, shapes_l, N, M, D, Lq, P, seed):
+        g = torch.Generator().manual_seed(seed)
+        shapes = torch.as_tensor(shapes_l, dtype=torch.long)
+        L = len(shapes_l)
+        S = int(shapes.prod(1).sum())
+        value = torch.randn(N, S, M, D, generator=g, dtype=torch.float64).requires_grad_()
+        loc = (torch.rand(N, Lq, M, L, P, 2, generator=g, dtype=torch.float64) * 1.2 - 0.1).requires_grad_()
+        attw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g, dtype=torch.float64), -1).view(
+            N, Lq, M, L, P).detach().requires_grad_()
+        gout = torch.randn(N, Lq, M * D, generator=g, dtype=torch.float64)
+        out = ref(value, shapes, loc, attw)
+        gv, gl, gw = torch.autograd.grad(out, (value, loc, attw), gout)
+        np.savez(os.path.join(OUT, name), value=value.detach().numpy(), shapes=shapes.numpy(),
+                 lsi=lsi_of(shapes).numpy(), loc=loc.detach().numpy(), attw=attw.detach().numpy(),
+                 grad_out=gout.numpy(), grad_value=gv.numpy(), grad_loc=gl.numpy(), grad_attw=gw.numpy())
+        print(name, float(gv.abs().mean()), float(gl.abs().mean()), float(gw.abs().mean()))
+
+    bwd_case("msda_bwd_d32.npz", [(9, 11), (5, 6), (3, 3), (2, 2)], 2, 4, 32, 23, 4, 31)
+    bwd_case("msda_bwd_d4.npz", [(6, 4), (3, 2)], 1, 2, 4, 7, 2, 32)
+    bwd_case("msda_bwd_d30.npz", [(7, 5)], 1, 3, 30, 5, 3, 33)
+    bwd_case("msda_bwd_d71.npz", [(6, 6), (3, 3)], 1, 2, 71, 4, 2, 34)
+
     case("msda_ref_d32_npot.npz", [(13, 17), (7, 9), (4, 5), (2, 3)], 2, 8, 32, 37, 4, 11, "uniform")
     case("msda_ref_d32_pixel.npz", [(12, 10), (6, 5), (3, 3)], 1, 4, 32, 159, 4, 12, "pixel")
     case("msda_ref_d16_l2p2.npz", [(9, 11), (5, 6)], 3, 3, 16, 21, 2, 13, "uniform")

@@ -108,3 +108,13 @@ def test_dcnv3_oracle_vs_reference(golden_dir, name):
     ref = g["out_f64"]
     assert np.allclose(out, ref, rtol=1e-2, atol=1e-3)
     assert np.abs(out - ref).max() < 1e-7
+
+
+@pytest.mark.parametrize("name", ["msda_bwd_d32.npz", "msda_bwd_d4.npz", "msda_bwd_d30.npz", "msda_bwd_d71.npz"])
+def test_backward_oracle_vs_reference_autograd(golden_dir, name):
+    """C backward restatement vs autograd through the reference's own pytorch function (fp64)."""
+    g = np.load(os.path.join(golden_dir, name))
+    gv, gl, gw = O.backward_kernel_semantics(g["value"], g["shapes"], g["lsi"], g["loc"], g["attw"], g["grad_out"])
+    assert np.abs(gv - g["grad_value"]).max() < 1e-10
+    assert np.abs(gl - g["grad_loc"]).max() < 1e-9 * max(1.0, np.abs(g["grad_loc"]).max())
+    assert np.abs(gw - g["grad_attw"]).max() < 1e-10

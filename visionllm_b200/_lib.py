@@ -26,6 +26,8 @@ _SIGNATURES = {
     "vllm_version": (ctypes.c_char_p, []),
     "vllm_msda_forward_f32": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
     "vllm_msda_forward_f64": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
+    "vllm_msda_backward_f32": (ci, [vp] * 9 + [ci] * 7 + [vp]),
+    "vllm_msda_backward_f64": (ci, [vp] * 9 + [ci] * 7 + [vp]),
     "vllm_msda_sample_indices_f32": (ci, [vp, vp, vp, cll, ci, ci, vp]),
     "vllm_msda_set_variant": (ci, [ci]),
     "vllm_dcnv3_forward_f32": (ci, [vp, vp, vp, vp] + [ci] * 15 + [cf, ci, vp]),

@@ -316,6 +316,94 @@ msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------
+// Backward: grad_value (atomics), grad_sampling_loc, grad_attn_weight.
+// Restates ms_deform_attn_col2im_bilinear + the col2im kernels (reference .cuh:66-124, 256-801): per output
+// channel c of a (b, q, m) pair and per sample: top_grad_value = grad_out * weight; each in-bounds corner
+// adds w_corner * top_grad_value to grad_value; grad_h/grad_w collect +-(other-axis weight) * v; the three
+// per-sample scalars are then summed over the D channels.  One warp owns a pair: lanes stride over channels,
+// three butterfly reductions per sample, lane 0 stores (each (b,q,m,l,p) has one owner, so no atomics there).
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum_t(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_bwd_warp_kernel(long long n_pairs, const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lsi, const T* __restrict__ loc, const T* __restrict__ attw,
+                     const T* __restrict__ grad_out, T* __restrict__ grad_value, T* __restrict__ grad_loc,
+                     T* __restrict__ grad_attw, int S, int M, int D, int L, int Lq, int P) {
+  __shared__ int s_h[MSDA_MAX_LEVELS], s_w[MSDA_MAX_LEVELS], s_start[MSDA_MAX_LEVELS];
+  if (threadIdx.x < L) {
+    s_h[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    s_w[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    s_start[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pair < n_pairs; pair += warps) {
+    const int m = (int)(pair % M);
+    const long long b = pair / M / Lq;
+    const int qs = M * D;
+    const long long vbase = b * (long long)S * qs + m * D;
+    const T* go = grad_out + pair * D;
+    long long wp = pair * L * P;
+    for (int l = 0; l < L; ++l) {
+      const int H = s_h[l], W = s_w[l];
+      const long long lbase = vbase + (long long)s_start[l] * qs;
+      for (int p = 0; p < P; ++p, ++wp) {
+        const T weight = attw[wp];
+        const MsdaGeom<T> g = msda_geom<T>(loc[2 * wp], loc[2 * wp + 1], H, W);
+        T g_attn = 0, g_w = 0, g_h = 0;
+        if (g.mask & 1) {
+          const T hh = (T)1 - g.lh, hw = (T)1 - g.lw;
+          const T w1 = hh * hw, w2 = hh * g.lw, w3 = g.lh * hw, w4 = g.lh * g.lw;
+          const long long o1 = lbase + ((long long)g.h_low * W + g.w_low) * qs;
+          const long long o2 = o1 + qs, o3 = o1 + (long long)W * qs, o4 = o3 + qs;
+          for (int c = lane; c < D; c += 32) {
+            const T tg = go[c];
+            const T tgv = tg * weight;
+            T v1 = 0, v2 = 0, v3 = 0, v4 = 0, gh = 0, gw = 0;
+            if (g.mask & 2) { v1 = value[o1 + c]; gh -= hw * v1; gw -= hh * v1; atomicAdd(grad_value + o1 + c, w1 * tgv); }
+            if (g.mask & 4) { v2 = value[o2 + c]; gh -= g.lw * v2; gw += hh * v2; atomicAdd(grad_value + o2 + c, w2 * tgv); }
+            if (g.mask & 8) { v3 = value[o3 + c]; gh += hw * v3; gw -= g.lh * v3; atomicAdd(grad_value + o3 + c, w3 * tgv); }
+            if (g.mask & 16) { v4 = value[o4 + c]; gh += g.lw * v4; gw += g.lh * v4; atomicAdd(grad_value + o4 + c, w4 * tgv); }
+            g_attn += tg * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+            g_w += (T)W * gw * tgv;
+            g_h += (T)H * gh * tgv;
+          }
+        }
+        g_attn = warp_sum_t(g_attn); g_w = warp_sum_t(g_w); g_h = warp_sum_t(g_h);
+        if (lane == 0) {
+          grad_attw[wp] = g_attn;
+          grad_loc[2 * wp] = g_w;
+          grad_loc[2 * wp + 1] = g_h;
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_bwd(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* attw,
+                      const T* grad_out, T* grad_value, T* grad_loc, T* grad_attw, int N, int S, int M, int D, int L,
+                      int Lq, int P, cudaStream_t st) {
+  const long long pairs = (long long)N * Lq * M;
+  if (pairs == 0) return VLLM_OK;
+  long long blocks = (pairs + 7) / 8;
+  const long long cap = (long long)vllm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  msda_bwd_warp_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(pairs, value, shapes, lsi, loc, attw, grad_out, grad_value,
+                                                             grad_loc, grad_attw, S, M, D, L, Lq, P);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
 static int g_msda_variant = 0;  // bench/tuning knob, see vllm_msda_set_variant
@@ -432,6 +520,36 @@ int vllm_msda_forward_f64(const double* value, const int64_t* spatial_shapes, co
   return launch_strict<double>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, batch,
                                spatial_size, num_heads, channels, num_levels, num_query, num_point,
                                (cudaStream_t)stream);
+}
+
+int vllm_msda_backward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                           const float* sampling_loc, const float* attn_weight, const float* grad_output,
+                           float* grad_value, float* grad_sampling_loc, float* grad_attn_weight, int batch,
+                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                           int num_point, void* stream) {
+  int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, batch,
+                        spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (rc == 1000) return VLLM_OK;
+  if (rc) return rc;
+  if (!grad_value || !grad_sampling_loc || !grad_attn_weight) return VLLM_EINVAL;
+  return launch_bwd<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                           grad_value, grad_sampling_loc, grad_attn_weight, batch, spatial_size, num_heads, channels,
+                           num_levels, num_query, num_point, (cudaStream_t)stream);
+}
+
+int vllm_msda_backward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                           const double* sampling_loc, const double* attn_weight, const double* grad_output,
+                           double* grad_value, double* grad_sampling_loc, double* grad_attn_weight, int batch,
+                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                           int num_point, void* stream) {
+  int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, batch,
+                        spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (rc == 1000) return VLLM_OK;
+  if (rc) return rc;
+  if (!grad_value || !grad_sampling_loc || !grad_attn_weight) return VLLM_EINVAL;
+  return launch_bwd<double>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            grad_value, grad_sampling_loc, grad_attn_weight, batch, spatial_size, num_heads, channels,
+                            num_levels, num_query, num_point, (cudaStream_t)stream);
 }
 
 int vllm_msda_sample_indices_f32(const int64_t* spatial_shapes, const float* sampling_loc, int32_t* out_hwm,

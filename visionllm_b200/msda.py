@@ -105,6 +105,63 @@ def ms_deform_attn_sample_indices(spatial_shapes, sampling_loc):
     return out
 
 
-def ms_deform_attn_backward(*args, **kwargs):
-    raise NotImplementedError(
-        "ms_deform_attn_backward is a SURVEY 8(f) 'next' row (forward-only hot path this round)")
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, *rest,
+                            im2col_step=64):
+    """Both reference flavours:
+      unipose / HF (vision.cpp:13-16):  backward(v, shapes, lsi, loc, w, grad_out, im2col_step) -> [gv, gloc, gw]
+      mmcv (pybind.cpp:793-798):        backward(v, shapes, lsi, loc, w, grad_out, gv, gloc, gw, im2col_step=) -> None
+                                        with the three grads pre-zeroed by the caller
+                                        (mmcv/ops/multi_scale_deform_attn.py:80-94)."""
+    if len(rest) == 1:
+        im2col_step, grads = rest[0], None
+    elif len(rest) == 3:
+        grads = rest
+    elif len(rest) == 0:
+        grads = None
+    else:
+        raise TypeError("ms_deform_attn_backward: unexpected arguments")
+    N, S, M, D, L, Lq, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                         im2col_step)
+    if not grad_output.is_contiguous() or grad_output.dtype != value.dtype or not grad_output.is_cuda:
+        raise RuntimeError("grad_output tensor has to be a contiguous CUDA tensor of the dtype of value")
+    if grad_output.numel() != N * Lq * M * D:
+        raise RuntimeError("grad_output shape mismatch")
+    if grads is None:
+        gv, gl, gw = torch.zeros_like(value), torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
+    else:
+        gv, gl, gw = grads
+        for t, ref in ((gv, value), (gl, sampling_loc), (gw, attn_weight)):
+            if t.shape != ref.shape or t.dtype != ref.dtype or not t.is_contiguous() or not t.is_cuda:
+                raise RuntimeError("gradient buffers must match their inputs (shape, dtype, contiguous, CUDA)")
+    if value.numel() and Lq:
+        L_ = _lib.lib()
+        fn = L_.vllm_msda_backward_f32 if value.dtype == torch.float32 else L_.vllm_msda_backward_f64
+        with torch.cuda.device(value.device):
+            rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                    attn_weight.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), gl.data_ptr(), gw.data_ptr(),
+                    N, S, M, D, L, Lq, P, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "ms_deform_attn_backward")
+    elif grads is None:
+        gl.zero_(); gw.zero_()
+    return None if grads is not None else [gv, gl, gw]
+
+
+class MultiScaleDeformableAttentionFunction(torch.autograd.Function):
+    """Same autograd wrapper the reference defines around the extension (gd.py:135-180)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step):
+        ctx.im2col_step = im2col_step
+        out = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                     attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        v, shapes, lsi, loc, w = ctx.saved_tensors
+        gv, gl, gw = ms_deform_attn_backward(v, shapes, lsi, loc, w, grad_output.contiguous(), ctx.im2col_step)
+        return gv, None, None, gl, gw, None
