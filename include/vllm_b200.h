@@ -158,7 +158,8 @@ int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, in
                         long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
                         long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
                         const unsigned char* attn_mask, int causal, float scale, void* stream);
-/* Tuning knob (process-global): 0 = tcgen05/TMEM kernel for head_dim 128 (default), 1 = warp-MMA kernel always. */
+/* Tuning knob (process-global), head_dim 128 without masks: 0 = tcgen05/TMEM kernel, schedule "tc2" (default),
+ * 2 = tcgen05/TMEM ping-pong schedule, 1 = warp-MMA kernel always. */
 int vllm_attention_set_variant(int variant);
 
 #ifdef __cplusplus

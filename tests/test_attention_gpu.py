@@ -26,7 +26,7 @@ def ref_attn(q, k, v, causal, seqlens=None):
     return o
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["tcgen05", "warp_mma", "tcgen05_tc2"])
+@pytest.fixture(params=[0, 1, 2], ids=["tcgen05_tc2", "warp_mma", "tcgen05_pingpong"])
 def variant(request):
     """Run every case on the tcgen05/TMEM kernel (head_dim 128) and on the warp-MMA kernel."""
     from visionllm_b200 import _lib

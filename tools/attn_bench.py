@@ -26,7 +26,7 @@ for name, (B, T, H, causal) in SHAPES.items():
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
     fl = 4.0 * B * H * T * T * 128 * (0.5 if causal else 1.0)
     r = {}
-    for var, nm in ((0, "tcgen05"), (2, "tcgen05_tc2"), (1, "warp_mma")):
+    for var, nm in ((0, "tcgen05_tc2"), (2, "tcgen05_pingpong"), (1, "warp_mma")):
         _lib.lib().vllm_attention_set_variant(var)
         try:
             ms = timeit(lambda: ops.attention(q, k, v, causal=causal))

@@ -278,7 +278,8 @@ int vllm_attention_tc2_d128(const void* q, const void* k, const void* v, void* o
                             int kv_heads, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
                             long long v_ts, long long o_bs, long long o_ts, const int* seqlens, int causal, float scale,
                             cudaStream_t st);
-// 0: tcgen05 ping-pong kernel (head_dim 128), warp-MMA otherwise; 1: always warp-MMA; 2: tcgen05 "tc2" schedule
+// head_dim 128 without masks: 0 = tcgen05 "tc2" schedule (default: 1 Q tile/CTA, 2 CTAs/SM, double-buffered S),
+// 2 = tcgen05 ping-pong schedule (attention_tc.cu); 1 = always the warp-MMA kernel.
 static int g_attn_variant = 0;
 extern "C" int vllm_attention_set_variant(int v) { g_attn_variant = v; return VLLM_OK; }
 
@@ -304,13 +305,13 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
   a.seqlens = seqlens; a.key_mask = key_mask; a.attn_mask = attn_mask; a.Tq = Tq; a.Tk = Tk; a.heads = heads; a.kv_heads = kv_heads; a.causal = causal;
   a.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream;
-  if (head_dim == 128 && g_attn_variant == 2 && !key_mask && !attn_mask) {
+  if (head_dim == 128 && g_attn_variant == 0 && !key_mask && !attn_mask) {
     const int rc = vllm_attention_tc2_d128(q, k, v, o, batch, Tq, Tk, heads, kv_heads, q_batch_pitch, q_token_pitch,
                                            k_batch_pitch, k_token_pitch, v_batch_pitch, v_token_pitch, o_batch_pitch,
                                            o_token_pitch, seqlens, causal, scale, st);
     if (rc != VLLM_EUNSUPPORTED) return rc;
   }
-  if (head_dim == 128 && g_attn_variant == 0 && !key_mask && !attn_mask) {
+  if (head_dim == 128 && g_attn_variant == 2 && !key_mask && !attn_mask) {
     const int rc = vllm_attention_tc_d128(q, k, v, o, batch, Tq, Tk, heads, kv_heads, q_batch_pitch, q_token_pitch,
                                           k_batch_pitch, k_token_pitch, v_batch_pitch, v_token_pitch, o_batch_pitch,
                                           o_token_pitch, seqlens, causal, scale, st);
