@@ -17,14 +17,15 @@
 //            256x256x16 over a CTA pair (cta_group::2); fp32 accumulators in TMEM, 2 accumulator stages
 //            (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused math -> 16-byte global stores
+//   warps 4-11 epilogue (two warpgroups, one per 128-column half of the tile): tcgen05.ld 32 lanes x 32 columns ->
+//            registers -> fused math -> 16-byte global stores
 // Tiles are visited in groups of GROUP_M row-blocks so concurrently running CTAs share B (weights) in L2.
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, ACC = 2, THREADS = 256;
+constexpr int BM = 128, BN = 256, BK = 64, ACC = 2, THREADS = 384, EPI_WARPS = 8;
 constexpr int A_BYTES = BM * BK * 2;
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SILU = 3, ACT_SWIGLU = 4, ACT_QUICKGELU = 5 };
@@ -91,7 +92,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < ACC; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 4 * CG); }
+    for (int a = 0; a < ACC; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), EPI_WARPS * CG); }
     tc::mbar_fence_init();
   }
   if (warp == 2) tc::tmem_alloc<CG>(tmem_slot, ACC * BN);
@@ -154,8 +155,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // 8 epilogue warps: warp w reads TMEM lanes 32*(w%4).. (hardware rule); warps 4-7 take columns 0-127 of the
+    // tile, warps 8-11 columns 128-255, so a tile drains twice as fast (matters when K is short: GDINO K = 256)
     const int quarter = warp & 3;
-    const int et = threadIdx.x - 128;  // 0..127
+    const int col_half = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128;  // 0..255
     int acc = 0; uint32_t acc_phase = 0;
     const bool swiglu = g.act == ACT_SWIGLU;
     for (int t = cluster_id; t < n_tiles; t += n_clusters) {
@@ -163,19 +167,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int n0 = tn * BN;
       const int row = (tm * CG + (int)rank) * BM + quarter * 32 + lane;
       // stage bias / column scale for this tile
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = et; c < BN; c += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = et; c < BN; c += 256) {
         const int col = n0 + c;
         s_bias[c] = (g.bias && col < g.N) ? __bfloat162float(g.bias[col]) : 0.f;
         s_scale[c] = (g.colscale && col < g.N) ? __bfloat162float(g.colscale[col]) : 1.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       const bool row_ok = row < g.M;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = col_half * (BN / 2); c < (col_half + 1) * (BN / 2); c += 32) {
         const int col0 = n0 + c;
         if (col0 >= g.N) break;  // uniform
         uint32_t r[32];
