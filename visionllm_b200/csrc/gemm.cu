@@ -27,6 +27,8 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, ACC = 2, THREADS = 384, EPI_WARPS = 8;
 constexpr int A_BYTES = BM * BK * 2;
+constexpr int EPI_PITCH = 128 + 16;                 // 64 bf16 columns + 16 B pad: conflict-free 16-byte accesses
+constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH;     // 32 rows per epilogue warp
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SILU = 3, ACT_SWIGLU = 4, ACT_QUICKGELU = 5 };
 
@@ -43,8 +45,9 @@ template <int CG> struct Cfg {
   static constexpr int B_ROWS = BN / CG;               // B rows held by one CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CG == 1 ? 4 : 6;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias, scale*/;
+  static constexpr int STAGES = CG == 1 ? 3 : 5;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias, scale*/ +
+                              EPI_WARPS * EPI_STAGE_BYTES /*per-warp store staging*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -78,6 +81,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + STAGES * C_::STAGE_BYTES + 8 * (2 * STAGES + 2 * ACC));
   float* s_bias = reinterpret_cast<float*>(smem_gen + STAGES * C_::STAGE_BYTES + 256);
   float* s_scale = s_bias + BN;
+  uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_scale + BN);   // EPI_WARPS x 32 rows x EPI_PITCH bytes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? tc::cluster_ctarank() : 0;
@@ -178,10 +182,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       const bool row_ok = row < g.M;
-#pragma unroll 1
-      for (int c = col_half * (BN / 2); c < (col_half + 1) * (BN / 2); c += 32) {
+      // the 32-column step of the general path: direct row-per-thread stores (fp32 output, SwiGLU, ragged N)
+      auto direct32 = [&](int c) {
         const int col0 = n0 + c;
-        if (col0 >= g.N) break;  // uniform
+        if (col0 >= g.N) return;  // uniform
         uint32_t r[32];
         tc::tmem_ld_32x32(taddr + c, r);
         tc::tmem_ld_wait();
@@ -231,7 +235,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               for (int j = 0; j < 16; ++j) if (oc0 + j < n_out) cp[j] = __float2bfloat16(o[j]);
             }
           }
-          continue;
+          return;
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= s_scale[c + j];
@@ -282,6 +286,75 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
           }
         }
+            };
+      uint8_t* my_stage = s_epi + (warp - 4) * EPI_STAGE_BYTES;
+#pragma unroll 1
+      for (int c = col_half * (BN / 2); c < (col_half + 1) * (BN / 2); c += 64) {
+        const int col0 = n0 + c;
+        if (col0 >= g.N) break;  // uniform
+        if (swiglu || g.out_f32 || col0 + 64 > g.N) { direct32(c); direct32(c + 32); continue; }
+        // ---- bf16 fast path: stage 32 rows x 64 columns per warp in smem, then store 128-byte row runs ----
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(taddr + c + 32 * h, r);
+          tc::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c + 32 * h + j];
+          if (g.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (g.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (g.act == ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+          } else if (g.act == ACT_QUICKGELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-1.702f * v[j]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= s_scale[c + 32 * h + j];
+          if (g.residual && row_ok) {
+            const __nv_bfloat16* rp = g.residual + (size_t)row * g.ldr + col0 + 32 * h;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(rp + 8 * q);
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(r2[j]);
+                v[8 * q + 2 * j] += f.x; v[8 * q + 2 * j + 1] += f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(my_stage + lane * EPI_PITCH + h * 64 + q * 16) = pk;
+          }
+        }
+        __syncwarp();
+        {
+          const int row_base = (tm * CG + (int)rank) * BM + quarter * 32;
+          __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(g.C) + col0;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {           // each instruction: 4 rows x 128 contiguous bytes
+            const int rr = it * 4 + (lane >> 3), piece = lane & 7;
+            const uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * EPI_PITCH + piece * 16);
+            if (row_base + rr < g.M)
+              *reinterpret_cast<uint4*>(cbase + (size_t)(row_base + rr) * g.ldc + piece * 8) = val;
+          }
+        }
+        __syncwarp();
       }
       // accumulator stage drained: hand it back to the MMA issuer
       tc::tc_fence_before();
