@@ -166,19 +166,6 @@ class _MHA(nn.MultiheadAttention):
         return ops.linear(ctx, self.out_proj.weight, bias=self.out_proj.bias, residual=residual)
 
 
-def _prefix_lengths(pad_mask):
-    """key_padding_mask (True = ignore) -> int32 lengths; only right padding is expressible."""
-    if pad_mask is None:
-        return None
-    keep = ~pad_mask
-    lens = keep.sum(-1).to(torch.int32)
-    T = pad_mask.shape[1]
-    if not bool((keep == (torch.arange(T, device=pad_mask.device)[None] < lens[:, None])).all()):
-        raise NotImplementedError("text_encoder_attention_mask must mask a suffix (it does on the reference path: "
-                                  "text_query_masks marks the first num_patches entries, mv2.py:779-786)")
-    return lens
-
-
 class GroundingDinoDecoderLayer(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -211,7 +198,8 @@ class GroundingDinoDecoderLayer(nn.Module):
         q = x if pos is None else x + pos
         x = self.encoder_attn_text_layer_norm(
             self.encoder_attn_text.run(q, text_encoder_hidden_states, text_encoder_hidden_states,
-                                       key_lengths=_prefix_lengths(text_encoder_attention_mask), residual=x))
+                                       key_mask=None if text_encoder_attention_mask is None
+                                       else ~text_encoder_attention_mask, residual=x))
         attn, _ = self.encoder_attn(hidden_states=x, attention_mask=vision_encoder_attention_mask,
                                     encoder_hidden_states=vision_encoder_hidden_states,
                                     encoder_attention_mask=vision_encoder_attention_mask, position_embeddings=pos,
