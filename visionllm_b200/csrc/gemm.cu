@@ -300,8 +300,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tc::tmem_ld_32x32(taddr + c + 32 * h, r);
           tc::tmem_ld_wait();
           float v[32];
+          if (g.bias) {                      // 16-byte broadcast reads: 8 LDS.128 instead of 32 LDS.32
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c + 32 * h + j];
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c + 32 * h + 4 * q]);
+              v[4 * q] = __uint_as_float(r[4 * q]) + b4.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+              v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
           if (g.act == ACT_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -315,8 +324,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + __expf(-1.702f * v[j]));
           }
+          if (g.colscale) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= s_scale[c + 32 * h + j];
+            for (int q = 0; q < 8; ++q) {
+              const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[c + 32 * h + 4 * q]);
+              v[4 * q] *= s4.x; v[4 * q + 1] *= s4.y; v[4 * q + 2] *= s4.z; v[4 * q + 3] *= s4.w;
+            }
+          }
           if (g.residual && row_ok) {
             const __nv_bfloat16* rp = g.residual + (size_t)row * g.ldr + col0 + 32 * h;
 #pragma unroll
