@@ -294,11 +294,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (col0 >= g.N) break;  // uniform
         if (swiglu || g.out_f32 || col0 + 64 > g.N) { direct32(c); direct32(c + 32); continue; }
         // ---- bf16 fast path: stage 32 rows x 64 columns per warp in smem, then store 128-byte row runs ----
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(taddr + c + 32 * h, r);
-          tc::tmem_ld_wait();
+        auto half = [&](const uint32_t (&r)[32], const int h) {
           float v[32];
           if (g.bias) {                      // 16-byte broadcast reads: 8 LDS.128 instead of 32 LDS.32
 #pragma unroll
@@ -355,6 +351,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
             *reinterpret_cast<uint4*>(my_stage + lane * EPI_PITCH + h * 64 + q * 16) = pk;
           }
+                };
+        {
+          uint32_t r0[32], r1[32];
+          tc::tmem_ld_32x32(taddr + c, r0);
+          tc::tmem_ld_wait();
+          tc::tmem_ld_32x32(taddr + c + 32, r1);     // in flight while the first half is processed
+          half(r0, 0);
+          tc::tmem_ld_wait();
+          half(r1, 1);
         }
         __syncwarp();
         {
