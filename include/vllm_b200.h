@@ -117,7 +117,7 @@ int vllm_dcnv3_forward_f32(const float* input, const float* offset, const float*
 int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                    const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
                    void* stream);
-/* Tuning knob (process-global): 1 = cta_group::1 tiles 128x256, 2 = CTA-pair tiles 256x256. */
+/* Tuning knob (process-global): 0 = auto (default), 1 = cta_group::1 tiles 128x256, 2 = CTA-pair tiles 256x256. */
 int vllm_gemm_set_variant(int variant);
 /* Tuning knob: force the tile-rasterisation group size (row-blocks per group); 0 = heuristic. */
 int vllm_gemm_set_group_m(int group_m);

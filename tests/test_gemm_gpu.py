@@ -50,7 +50,7 @@ def test_gemm_plain(M, N, K, variant):
         out = ops().linear(x, w)
         torch.cuda.synchronize()
     finally:
-        _lib.lib().vllm_gemm_set_variant(2)
+        _lib.lib().vllm_gemm_set_variant(0)
     ref = x.float() @ w.float().T
     close(out, ref)
 
@@ -70,7 +70,7 @@ def test_gemm_epilogues(act, variant):
         out = ops().linear(x, w, bias=bias, act=act, colscale=ls, residual=res)
         out32 = ops().linear(x, w, bias=bias, act=act, out_dtype=torch.float32)
     finally:
-        _lib.lib().vllm_gemm_set_variant(2)
+        _lib.lib().vllm_gemm_set_variant(0)
     y = x.float() @ w.float().T + bias.float()
     if act == "gelu":
         y = torch.nn.functional.gelu(y)
@@ -98,7 +98,7 @@ def test_gemm_swiglu_interleaved(variant):
     try:
         out = ops().linear(x, w, act="swiglu")
     finally:
-        _lib.lib().vllm_gemm_set_variant(2)
+        _lib.lib().vllm_gemm_set_variant(0)
     ref = torch.nn.functional.silu(x.float() @ wg.float().T) * (x.float() @ wu.float().T)
     assert out.shape == (M, I)
     close(out, ref)

@@ -35,7 +35,7 @@ for name, (M, N, K) in SHAPES.items():
             r[f"cg{v}_tflops"] = fl / ms / 1e9
         except Exception as e:
             r[f"cg{v}_error"] = str(e)
-    _lib.lib().vllm_gemm_set_variant(2)
+    _lib.lib().vllm_gemm_set_variant(0)
     ms = timeit(lambda: torch.matmul(x, w.T, out=out))
     r["cublas_tflops"] = fl / ms / 1e9
     res[name] = r

@@ -399,7 +399,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 int g_group_m_override = 0;
 int pick_group_m(int, int, long long) { return g_group_m_override > 0 ? g_group_m_override : 8; }
 
-int g_gemm_variant = 2;  // 1: cta_group::1 (128x256 tiles), 2: cta_group::2 CTA pairs (256x256), the default
+// 0: auto (cta_group::2 CTA pairs, 256x256 tiles; cta_group::1 when K <= 512, where the cross-CTA hand-offs of
+// a pair cost more than the halved B traffic saves: 617 vs 494 TFLOP/s at K = 256); 1 / 2: force
+int g_gemm_variant = 0;
 
 template <int CG>
 int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cudaStream_t st) {
@@ -441,7 +443,7 @@ int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cuda
 
 extern "C" {
 
-int vllm_gemm_set_variant(int v) { g_gemm_variant = (v == 1) ? 1 : 2; return VLLM_OK; }
+int vllm_gemm_set_variant(int v) { g_gemm_variant = (v == 1 || v == 2) ? v : 0; return VLLM_OK; }
 int vllm_gemm_set_group_m(int gm) { g_group_m_override = gm; return VLLM_OK; }
 
 int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
@@ -464,7 +466,8 @@ int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int 
   g.bias = (const __nv_bfloat16*)bias; g.colscale = (const __nv_bfloat16*)colscale;
   g.residual = (const __nv_bfloat16*)residual; g.ldr = ldr; g.act = act; g.out_f32 = out_f32;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_gemm_variant == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);
+  const int cg = g_gemm_variant ? g_gemm_variant : (K <= 512 ? 1 : 2);
+  if (cg == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);
   return launch_gemm<1>(A, lda, B, ldb, g, st);
 }
 
