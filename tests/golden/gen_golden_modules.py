@@ -174,7 +174,30 @@ def gdino_encoder_layer():
          keys=np.array(json.dumps(key_shapes(lay))))
 
 
+def internlm2():
+    """Vendored InternLM2ForCausalLM (GQA, fused wqkv), eager attention, fp32 + bf16 legs."""
+    cfgm, mod = ref_shim.load_internlm2()
+    cfg = cfgm.InternLM2Config(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                               num_attention_heads=4, num_key_value_heads=2, rms_norm_eps=1e-5,
+                               max_position_embeddings=256, attn_implementation="eager", bias=False)
+    cfg.rope_scaling = None          # transformers 5.x rewrites the field into a dict the 4.34-era code cannot read
+    m = mod.InternLM2ForCausalLM(cfg)
+    m.load_state_dict(seeded_state_dict(m, 606))
+    B, T = 2, 33
+    g = torch.Generator().manual_seed(9)
+    emb = bf16r(torch.randn(B, T, 512, generator=g) * 0.5)
+    am = torch.ones(B, T, dtype=torch.long); am[1, 20:] = 0
+
+    def fn(mm, dt):
+        o = mm(inputs_embeds=emb.to(dt), attention_mask=am, output_hidden_states=True, return_dict=True, use_cache=False)
+        return torch.cat([o.hidden_states[-1].float(), o.hidden_states[1].float(), o.logits.float()], -1)
+
+    o32, o16 = run_both(m, fn)
+    save("mod_internlm2_small.npz", emb=emb, am=am.numpy(), out_f32=o32, out_refbf16=o16,
+         keys=np.array(json.dumps(key_shapes(m))))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["internvit", "gdino", "gdino_encoder_layer"]
+    which = sys.argv[1:] or ["internvit", "gdino", "gdino_encoder_layer", "internlm2"]
     for w in which:
         globals()[w]()

@@ -121,3 +121,12 @@ def load_gdino():
     cfg = load_file(pkg, "configuration_grounding_dino", f"{REF}/grounding_dino/configuration_grounding_dino.py")
     mod = load_file(pkg, "modeling_ov_grounding_dino_mask_dn", f"{REF}/grounding_dino/modeling_ov_grounding_dino_mask_dn.py")
     return cfg, mod
+
+
+def load_internlm2():
+    install_stubs()
+    pkg = "refpkg_internlm2"
+    p = types.ModuleType(pkg); p.__path__ = [f"{REF}/internlm2"]; sys.modules[pkg] = p
+    cfg = load_file(pkg, "configuration_internlm2", f"{REF}/internlm2/configuration_internlm2.py")
+    mod = load_file(pkg, "modeling_internlm2", f"{REF}/internlm2/modeling_internlm2.py")
+    return cfg, mod

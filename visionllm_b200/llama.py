@@ -73,6 +73,46 @@ class LlamaMLP(nn.Module):
         return self._packed[1]
 
 
+def decoder_layer_forward(x, cos, sin, seqlens, norm1_w, norm2_w, eps, wqkv, bqkv, wo, bo, w_gate_up, w_down,
+                          nq, nkv, D):
+    """One pre-norm decoder layer on packed operands (shared by the Llama and InternLM2 drop-ins): RMSNorm, packed
+    QKV GEMM, in-place RoPE on the q and k heads, fused causal attention (GQA aware), O GEMM (+residual), RMSNorm,
+    gate|up GEMM with SwiGLU epilogue, down GEMM (+residual)."""
+    B, T, H = x.shape
+    qkv = ops.linear(ops.rmsnorm(x, norm1_w, eps), wqkv, bias=bqkv)          # [B, T, (nq + 2 nkv) D]
+    ops.rope_(qkv.view(B * T, (nq + 2 * nkv) * D), cos, sin, nq + nkv, D)
+    q = qkv[..., :nq * D].unflatten(-1, (nq, D))
+    k = qkv[..., nq * D:(nq + nkv) * D].unflatten(-1, (nkv, D))
+    v = qkv[..., (nq + nkv) * D:].unflatten(-1, (nkv, D))
+    ctx = ops.attention(q, k, v, causal=True, seqlens=seqlens)
+    x = ops.linear(ctx, wo, bias=bo, residual=x)
+    h = ops.linear(ops.rmsnorm(x, norm2_w, eps), w_gate_up, act="swiglu")
+    return ops.linear(h, w_down, residual=x)
+
+
+def rope_tables(position_ids, head_dim, theta, dtype):
+    """cos/sin [B*T, D] in the model dtype: fp32 angles then cast, like HF LlamaRotaryEmbedding and
+    InternLM2RotaryEmbedding (internlm2/modeling_internlm2.py:132-166)."""
+    dev = position_ids.device
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64, device=dev).float() / head_dim))
+    fr = position_ids.reshape(-1, 1).float() * inv[None, :]
+    emb = torch.cat((fr, fr), -1)
+    return emb.cos().to(dtype).contiguous(), emb.sin().to(dtype).contiguous()
+
+
+def right_padding_lengths(attention_mask):
+    """attention_mask [B, T] (1 = real) -> int32 key lengths, or None when nothing is padded.  Only right padding
+    is expressible as lengths (the reference tokenizer pads right, train.py:345)."""
+    if attention_mask is None or bool(attention_mask.all()):
+        return None
+    am = attention_mask.to(torch.int32)
+    lens = am.sum(-1).to(torch.int32)
+    T = am.shape[1]
+    if not bool((am == (torch.arange(T, device=am.device)[None] < lens[:, None]).int()).all()):
+        raise NotImplementedError("attention_mask must be right-padded")
+    return lens
+
+
 class LlamaDecoderLayer(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -82,20 +122,12 @@ class LlamaDecoderLayer(nn.Module):
         self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
     def forward(self, x, cos, sin, seqlens=None):
-        B, T, H = x.shape
         at = self.self_attn
-        nq, nkv, D = at.num_heads, at.num_kv_heads, at.head_dim
         wqkv, bqkv = at.packed_qkv()
-        qkv = ops.linear(self.input_layernorm(x), wqkv, bias=bqkv)           # [B, T, (nq + 2 nkv) D]
-        flat = qkv.view(B * T, (nq + 2 * nkv) * D)
-        ops.rope_(flat, cos, sin, nq + nkv, D)                               # q heads then k heads, in place
-        q = qkv[..., :nq * D].unflatten(-1, (nq, D))
-        k = qkv[..., nq * D:(nq + nkv) * D].unflatten(-1, (nkv, D))
-        v = qkv[..., (nq + nkv) * D:].unflatten(-1, (nkv, D))
-        ctx = ops.attention(q, k, v, causal=True, seqlens=seqlens)
-        x = ops.linear(ctx, at.o_proj.weight, bias=at.o_proj.bias, residual=x)
-        h = ops.linear(self.post_attention_layernorm(x), self.mlp.packed_gate_up(), act="swiglu")
-        return ops.linear(h, self.mlp.down_proj.weight, residual=x)
+        return decoder_layer_forward(x, cos, sin, seqlens, self.input_layernorm.weight,
+                                     self.post_attention_layernorm.weight, self.input_layernorm.variance_epsilon,
+                                     wqkv, bqkv, at.o_proj.weight, at.o_proj.bias, self.mlp.packed_gate_up(),
+                                     self.mlp.down_proj.weight, at.num_heads, at.num_kv_heads, at.head_dim)
 
 
 class LlamaModel(nn.Module):
@@ -108,30 +140,19 @@ class LlamaModel(nn.Module):
         self._rope = None
 
     def rope_tables(self, position_ids, dtype):
-        """cos/sin [B*T, D] in the model dtype: fp32 angles then cast, like HF LlamaRotaryEmbedding."""
         cfg = self.config
         D = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
         theta = getattr(cfg, "rope_theta", None)
         if theta is None:
             rp = getattr(cfg, "rope_parameters", None) or {}
             theta = rp.get("rope_theta", 10000.0) if isinstance(rp, dict) else 10000.0
-        dev = position_ids.device
-        inv = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.int64, device=dev).float() / D))
-        fr = position_ids.reshape(-1, 1).float() * inv[None, :]
-        emb = torch.cat((fr, fr), -1)
-        return emb.cos().to(dtype).contiguous(), emb.sin().to(dtype).contiguous()
+        return rope_tables(position_ids, D, theta, dtype)
 
     @torch.no_grad()
     def forward(self, inputs_embeds, attention_mask=None, position_ids=None, output_hidden_states=False):
         B, T, _ = inputs_embeds.shape
         dev = inputs_embeds.device
-        seqlens = None
-        if attention_mask is not None and not bool(attention_mask.all()):
-            am = attention_mask.to(torch.int32)
-            seqlens = am.sum(-1).to(torch.int32)
-            # only right padding is expressible as lengths (the reference tokenizer pads right, train.py:345)
-            if not bool((am == (torch.arange(T, device=dev)[None] < seqlens[:, None]).int()).all()):
-                raise NotImplementedError("attention_mask must be right-padded")
+        seqlens = right_padding_lengths(attention_mask)
         if position_ids is None:
             position_ids = torch.arange(T, device=dev)[None].expand(B, T)
         cos, sin = self.rope_tables(position_ids, inputs_embeds.dtype)
