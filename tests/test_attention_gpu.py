@@ -124,3 +124,23 @@ def test_attention_full_attn_mask():
     s = s.masked_fill(~am.view(B, H, T, T), float("-inf"))
     ref = (torch.softmax(s, -1) @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, T, H * D)
     check(out, ref)
+
+
+@pytest.mark.parametrize("D,H", [(256, 4), (64, 4), (32, 8)])
+def test_attention_split_kv_few_queries_many_keys(D, H):
+    """GDINO text->vision shape class: a handful of queries over thousands of keys -> the key axis is split across
+    CTAs and merged (vllm_attention_bf16 workspace path); with and without a key mask."""
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(D)
+    B, Tq, Tk = 2, 80, 5000
+    q = torch.randn(B, Tq, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Tk, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Tk, H, D, device="cuda", generator=g).bfloat16()
+    km = torch.rand(B, Tk, device="cuda", generator=g) > 0.2
+    for mask in (None, km):
+        out = ops.attention(q, k, v, key_mask=mask)
+        s_ = (q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 3, 1)) * D ** -0.5
+        if mask is not None:
+            s_ = s_.masked_fill(~mask[:, None, None, :], float("-inf"))
+        ref = (torch.softmax(s_, -1) @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
+        check(out, ref)

@@ -38,7 +38,7 @@ _SIGNATURES = {
     "vllm_layernorm_bf16": (ci, [vp, cll, vp, vp, vp, cll, cll, ci, cf, vp]),
     "vllm_rope_bf16": (ci, [vp, cll, vp, vp, cll, ci, ci, vp]),
     "vllm_attention_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cll, cll, cll, cll, cll, cll, cll, cll,
-                                 vp, vp, vp, ci, cf, vp]),
+                                 vp, vp, vp, ci, cf, vp, cll, vp]),
     "vllm_attention_set_variant": (ci, [ci]),
 }
 

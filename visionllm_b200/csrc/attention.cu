@@ -32,6 +32,8 @@ struct AttnArgs {
   const unsigned char* attn_mask;  // optional [batch*heads, Tq, Tk], 1 = attend (nn.MultiheadAttention attn_mask, inverted)
   int Tq, Tk, heads, kv_heads, causal;
   float scale_log2;
+  int n_splits;      // split-KV: CTAs along the key axis per query block (1 = off)
+  float* ws;         // workspace [batch*heads*n_splits*Tq][D + 2] fp32 partials (unnormalised O, m, l)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
@@ -89,7 +91,7 @@ flash_fwd_kernel(const AttnArgs a) {
   const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t sK0 = sQ + QB, sV0 = sK0 + 2 * KB;
 
-  const int mblk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int split = blockIdx.x % a.n_splits, mblk = blockIdx.x / a.n_splits, head = blockIdx.y, b = blockIdx.z;
   const int kvh = head / (a.heads / a.kv_heads);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int len = a.seqlens ? a.seqlens[b] : a.Tk;
@@ -104,13 +106,17 @@ flash_fwd_kernel(const AttnArgs a) {
   const int coff = a.Tk - a.Tq;
   int k_end = len;
   if (a.causal) k_end = min(k_end, m0 + BM + coff);
-  const int n_tiles = (k_end + BN - 1) / BN;
+  const int n_tiles_all = (k_end + BN - 1) / BN;
+  // split-KV: this CTA owns key tiles [t_begin, t_begin + n_tiles)
+  const int per_split = (n_tiles_all + a.n_splits - 1) / a.n_splits;
+  const int t_begin = split * per_split;
+  const int n_tiles = max(0, min(n_tiles_all, t_begin + per_split) - t_begin);
 
   load_tile<D, BM>(sQ, qb, a.q_ts, m0, a.Tq);
   cp_async_commit();
   if (n_tiles > 0) {
-    load_tile<D, BN>(sK0, kb, a.k_ts, 0, len);
-    load_tile<D, BN>(sV0, vb, a.v_ts, 0, len);
+    load_tile<D, BN>(sK0, kb, a.k_ts, t_begin * BN, len);
+    load_tile<D, BN>(sV0, vb, a.v_ts, t_begin * BN, len);
   }
   cp_async_commit();
 
@@ -138,8 +144,8 @@ flash_fwd_kernel(const AttnArgs a) {
     const int buf = t & 1;
     const uint32_t sK = sK0 + buf * KB, sV = sV0 + buf * KB;
     if (t + 1 < n_tiles) {
-      load_tile<D, BN>(sK0 + (buf ^ 1) * KB, kb, a.k_ts, (t + 1) * BN, len);
-      load_tile<D, BN>(sV0 + (buf ^ 1) * KB, vb, a.v_ts, (t + 1) * BN, len);
+      load_tile<D, BN>(sK0 + (buf ^ 1) * KB, kb, a.k_ts, (t_begin + t + 1) * BN, len);
+      load_tile<D, BN>(sV0 + (buf ^ 1) * KB, vb, a.v_ts, (t_begin + t + 1) * BN, len);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -162,7 +168,7 @@ flash_fwd_kernel(const AttnArgs a) {
       }
     }
     // ---- mask + online softmax (scores scaled into log2 domain) ----
-    const int n0 = t * BN;
+    const int n0 = (t_begin + t) * BN;
     const unsigned char* km = a.key_mask ? a.key_mask + (long long)b * a.Tk : nullptr;
     const unsigned char* am = a.attn_mask ? a.attn_mask + ((long long)b * a.heads + head) * a.Tq * a.Tk : nullptr;
     const bool need_mask = km || am || (n0 + BN > len) || (a.causal && (n0 + BN - 1 > m0 + coff));
@@ -237,6 +243,20 @@ flash_fwd_kernel(const AttnArgs a) {
     lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
     lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
   }
+  if (a.n_splits > 1) {
+    // partial result of this key range: unnormalised O, running max (log2 domain) and sum
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = qrow0 + r * 8;
+      if (row >= a.Tq) continue;
+      float* wp = a.ws + ((((size_t)b * a.heads + head) * a.n_splits + split) * a.Tq + row) * (D + 2);
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j)
+        *reinterpret_cast<float2*>(wp + j * 8 + tq * 2) = make_float2(o[j][2 * r], o[j][2 * r + 1]);
+      if (tq == 0) { wp[D] = mrow[r]; wp[D + 1] = lrow[r]; }
+    }
+    return;
+  }
   const float inv0 = lrow[0] > 0.f ? 1.f / lrow[0] : 0.f, inv1 = lrow[1] > 0.f ? 1.f / lrow[1] : 0.f;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -253,8 +273,40 @@ flash_fwd_kernel(const AttnArgs a) {
   }
 }
 
+// merge the split-KV partials of one query row: one warp per (batch, head, row), lanes over head_dim
+template <int D>
+__global__ void __launch_bounds__(128)
+splitkv_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ o, long long o_bs, long long o_ts,
+                       int Tq, int heads, int n_splits, long long n_rows) {
+  const long long wid = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wid >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int row = (int)(wid % Tq);
+  const long long bh = wid / Tq;
+  const int head = (int)(bh % heads);
+  const long long b = bh / heads;
+  float m = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) m = fmaxf(m, ws[((bh * n_splits + s) * Tq + row) * (D + 2) + D]);
+  const float msafe = (m == -INFINITY) ? 0.f : m;
+  float l = 0.f;
+  float acc[D / 32];
+#pragma unroll
+  for (int i = 0; i < D / 32; ++i) acc[i] = 0.f;
+  for (int s = 0; s < n_splits; ++s) {
+    const float* wp = ws + ((bh * n_splits + s) * Tq + row) * (D + 2);
+    const float sc = exp2f(wp[D] - msafe);      // -inf -> 0 for empty ranges
+    l += wp[D + 1] * sc;
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) acc[i] += wp[lane + 32 * i] * sc;
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  __nv_bfloat16* op = o + b * o_bs + (long long)row * o_ts + (long long)head * D;
+#pragma unroll
+  for (int i = 0; i < D / 32; ++i) op[lane + 32 * i] = __float2bfloat16(acc[i] * inv);
+}
+
 template <int D, int BN = 64>
-int launch(const AttnArgs& a, int batch, cudaStream_t st) {
+int launch(AttnArgs a, int batch, cudaStream_t st, void* workspace, long long workspace_bytes) {
   constexpr int SMEM = BM * D * 2 + 4 * BN * D * 2;
   static bool set = false;
   if (!set) {
@@ -262,9 +314,27 @@ int launch(const AttnArgs& a, int batch, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     set = true;
   }
-  dim3 grid((a.Tq + BM - 1) / BM, a.heads, batch);
+  const int m_blocks = (a.Tq + BM - 1) / BM;
+  // split-KV when the query side alone cannot fill the machine (e.g. 80 text queries over 21760 pixels)
+  a.n_splits = 1; a.ws = nullptr;
+  const long long ctas = (long long)m_blocks * a.heads * batch;
+  const int n_tiles = (a.Tk + BN - 1) / BN;
+  if (workspace && !a.causal && ctas < 2LL * vllm_num_sms() && n_tiles >= 16) {
+    long long want = (4LL * vllm_num_sms() + ctas - 1) / ctas;
+    if (want > n_tiles / 8) want = n_tiles / 8;
+    if (want > 64) want = 64;
+    const long long need = (long long)batch * a.heads * want * a.Tq * (D + 2) * 4;
+    if (want >= 2 && need <= workspace_bytes) { a.n_splits = (int)want; a.ws = (float*)workspace; }
+  }
+  dim3 grid((unsigned)(m_blocks * a.n_splits), a.heads, batch);
   flash_fwd_kernel<D, BN><<<grid, NW * 32, SMEM, st>>>(a);
   VLLM_CHECK_LAUNCH();
+  if (a.n_splits > 1) {
+    const long long n_rows = (long long)batch * a.heads * a.Tq;
+    splitkv_combine_kernel<D><<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>(a.ws, a.o, a.o_bs, a.o_ts, a.Tq, a.heads,
+                                                                           a.n_splits, n_rows);
+    VLLM_CHECK_LAUNCH();
+  }
   return VLLM_OK;
 }
 
@@ -288,7 +358,8 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
                                    long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
                                    long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
                                    long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
-                                   const unsigned char* attn_mask, int causal, float scale, void* stream) {
+                                   const unsigned char* attn_mask, int causal, float scale, void* workspace,
+                                   long long workspace_bytes, void* stream) {
   if (batch < 0 || Tq < 0 || Tk < 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads) return VLLM_EINVAL;
   if (batch == 0 || Tq == 0) return VLLM_OK;
   if (!q || !k || !v || !o) return VLLM_EINVAL;
@@ -318,10 +389,10 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
     if (rc != VLLM_EUNSUPPORTED) return rc;   // views a TMA descriptor cannot express use the warp-MMA kernel
   }
   switch (head_dim) {
-    case 128: return launch<128>(a, batch, st);
-    case 64: return launch<64>(a, batch, st);
-    case 32: return launch<32>(a, batch, st);
-    case 256: return launch<256, 32>(a, batch, st);
+    case 128: return launch<128>(a, batch, st, workspace, workspace_bytes);
+    case 64: return launch<64>(a, batch, st, workspace, workspace_bytes);
+    case 32: return launch<32>(a, batch, st, workspace, workspace_bytes);
+    case 256: return launch<256, 32>(a, batch, st, workspace, workspace_bytes);
     default: return VLLM_EUNSUPPORTED;
   }
 }

@@ -146,6 +146,17 @@ def rope_(x, cos, sin, heads, head_dim):
     return x
 
 
+_ATTN_WS = {}          # per-device split-KV scratch (grow-only), see vllm_attention_bf16
+
+
+def _attn_workspace(device, nbytes):
+    ws = _ATTN_WS.get(device.index)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ATTN_WS[device.index] = ws
+    return ws
+
+
 def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, attn_mask=None, out=None):
     """softmax(q k^T * scale) v.  q [B, Tq, H, D], k/v [B, Tk, Hkv, D] bf16 views whose last two dims are
     contiguous (any batch/token pitch, e.g. slices of a packed qkv tensor).  Returns [B, Tq, H*D].
@@ -181,11 +192,15 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
             raise RuntimeError("attention: attn_mask must be CUDA [B*H, Tq, Tk]")
         attn_mask = attn_mask.to(torch.uint8).contiguous()
         amp = attn_mask.data_ptr()
+    ws_ptr, ws_bytes = None, 0
+    if not causal and Tq <= 1024 and Tk >= 16 * 32:          # few queries, many keys: let the kernel split the keys
+        ws_bytes = min(B * H * 64 * Tq * (D + 2) * 4, 256 << 20)
+        ws_ptr = _attn_workspace(q.device, ws_bytes).data_ptr()
     fl = 4.0 * B * H * Tq * Tk * D * (0.5 if causal and Tq == Tk else 1.0)
     with torch.cuda.device(q.device), _Prof("attention", fl, 2.0 * B * D * (2 * Tq * H + 2 * Tk * Hkv)):
         rc = _lib.lib().vllm_attention_bf16(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Tq, Tk, H, Hkv, D,
             q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
-            out.stride(0), out.stride(1), sl, km, amp, 1 if causal else 0, float(scale), _stream())
+            out.stride(0), out.stride(1), sl, km, amp, 1 if causal else 0, float(scale), ws_ptr, ws_bytes, _stream())
     _lib.check(rc, "vllm_attention_bf16")
     return out
