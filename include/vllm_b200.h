@@ -133,6 +133,16 @@ int vllm_rmsnorm_bf16(const void* x, long long ldx, const void* weight, void* y,
                       int cols, float eps, void* stream);
 int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const void* bias, void* y, long long ldy,
                         long long rows, int cols, float eps, void* stream);
+/* GroupNorm over channels-last rows x[batch, hw, channels] (bf16, fp32 statistics, optional fused ReLU): the
+ * nn.GroupNorm(32, d_model) after each Grounding-DINO input projection
+ * (grounding_dino/modeling_ov_grounding_dino_mask_dn.py:2085-2110, :2393-2405) and the detectron2
+ * Conv2d(norm=GN, activation=relu) blocks of the mask-feature FPN (:2126-2151, :2470-2478).
+ * channels/groups % 8 == 0, channels <= 2048.  workspace: vllm_groupnorm_workspace_bytes(batch, groups) bytes of
+ * device memory (per-chunk partial sums; combined in a fixed order, so results are run-to-run identical). */
+long long vllm_groupnorm_workspace_bytes(int batch, int groups);
+int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, int batch, long long hw,
+                             int channels, int groups, float eps, int relu, void* workspace, long long workspace_bytes,
+                             void* stream);
 /* In-place rotate-half RoPE on x[tokens, heads, head_dim] rows with pitch ld; cos/sin
  * [tokens, head_dim] bf16 gathered per position (HF Llama apply_rotary_pos_emb;
  * internlm2/modeling_internlm2.py:218-232). */

@@ -1,0 +1,107 @@
+"""CPU, build container only (needs /root/reference): the whole Grounding-DINO stage -- backbone, neck, encoder,
+mask FPN, two-stage selection, decoder, heads -- of `visionllm_b200.gdino_model.B200GroundingDinoForObjectDetection`
+against the REFERENCE'S OWN `OVGroundingDinoForObjectDetection.forward_test` on CPU in fp32, same state dict.
+Kernels are replaced by fp32 torch stand-ins in this test only (no GPU here); this pins the host logic: layouts,
+masks, valid ratios, reference points, top-k selection, box refinement, head wiring, parameter names."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.skipif(not os.path.exists("/root/reference/VisionLLMv2"), reason="reference tree not mounted")
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from test_gdino_logic_cpu import torch_kernels  # noqa: E402,F401  (fixture)
+
+
+def build_pair(seed=11, **over):
+    import ref_shim
+    from transformers import SwinConfig
+    from weights_util import seeded_state_dict
+    from visionllm_b200.gdino_model import B200GroundingDinoForObjectDetection
+    cfgm, gd = ref_shim.load_gdino()
+    bc = SwinConfig(image_size=64, embed_dim=24, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8], window_size=4,
+                    out_features=["stage1", "stage2", "stage3", "stage4"])
+    kw = dict(backbone_config=bc, d_model=256, encoder_layers=2, decoder_layers=2, encoder_ffn_dim=256, decoder_ffn_dim=256,
+              num_queries=20, num_feature_levels=4, dropout=0., attention_dropout=0., activation_dropout=0.,
+              fusion_dropout=0., fusion_droppath=0., text_enhancer_dropout=0., disable_custom_kernels=True, mask_dim=256,
+              norm="GN", l_hidden_size=64)
+    kw.update(over)
+    cfg = cfgm.GroundingDinoConfig(**kw)
+    ref = gd.OVGroundingDinoForObjectDetection(cfg).eval()
+    sd = seeded_state_dict(ref, seed)
+    for k in sd:                                                  # LayerScale-style gates: make the fusion path count
+        if k.endswith("vision_param") or k.endswith("text_param"):
+            sd[k] = sd[k] * 0 + 0.5
+    ref.load_state_dict(sd)
+    cfg.activation_function = "relu"
+    ours = B200GroundingDinoForObjectDetection(cfg).eval()
+    missing, unexpected = ours.load_state_dict(sd, strict=False)
+    # identical parameter names; the only keys we do not hold are Swin's non-persistent-in-ours buffers (none expected)
+    assert not unexpected, unexpected
+    assert not missing, missing
+    return cfg, ref, ours
+
+
+@pytest.fixture()
+def gn_kernel(monkeypatch, torch_kernels):  # noqa: F811
+    import visionllm_b200.ops as ops
+
+    def groupnorm_nhwc(x, w, b, groups, eps, relu=False):
+        y = F.group_norm(x.float().transpose(1, 2), groups, w.float(), b.float(), eps).transpose(1, 2)
+        return torch.relu(y) if relu else y
+
+    monkeypatch.setattr(ops, "groupnorm_nhwc", groupnorm_nhwc)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_whole_stage_matches_reference_forward_test(gn_kernel, ragged):
+    cfg, ref, ours = build_pair()
+    g = torch.Generator().manual_seed(5)
+    B, Hh, W = 2, 128, 160
+    x = torch.randn(B, 3, Hh, W, generator=g)
+    pm = torch.ones(B, Hh, W, dtype=torch.long)
+    if ragged:
+        pm[1, 96:, :] = 0
+        pm[1, :, 120:] = 0
+    tq = torch.randn(B, 5, 4, cfg.l_hidden_size, generator=g)
+    tm = torch.ones(B, 5, dtype=torch.bool)
+    tm[1, 3:] = False
+    with torch.no_grad():
+        a = ref.forward_test(pixel_values=x, pixel_mask=pm, text_query=tq, text_query_masks=tm, return_dict=True)
+        b = ours.forward_test(x, pixel_mask=pm, text_query=tq, text_query_masks=tm)
+    assert a.logits.shape == b.logits.shape and a.pred_masks.shape == b.pred_masks.shape
+    finite = torch.isfinite(a.logits)
+    assert torch.equal(finite, torch.isfinite(b.logits))                      # -inf padding pattern identical
+    assert (a.logits[finite] - b.logits[finite]).abs().max() < 2e-3
+    assert (a.pred_boxes - b.pred_boxes).abs().max() < 1e-4
+    assert (a.pred_masks - b.pred_masks).abs().max() < 2e-2 * a.pred_masks.abs().max().clamp(min=1)
+
+
+def test_neck_integer_outputs_match_reference(gn_kernel):
+    """spatial_shapes / level_start_index (int64) exactly; valid_ratios, masks exactly (same torch ops)."""
+    cfg, ref, ours = build_pair(seed=12)
+    x = torch.randn(1, 3, 100, 136)
+    pm = torch.ones(1, 100, 136, dtype=torch.long)
+    pm[0, 80:] = 0
+    tq, tm = torch.randn(1, 3, 4, cfg.l_hidden_size), torch.ones(1, 3, dtype=torch.bool)
+    with torch.no_grad():
+        feats = ours.model.backbone_features(x)
+        src, mflat, pos, shapes, lsi, vr = ours.model.neck(feats, pm)
+        # reference: hook the encoder call to capture what the neck hands over
+        cap = {}
+        orig = ref.model.encoder.forward
+
+        def spy(**kw):
+            cap.update(kw)
+            return orig(**kw)
+
+        ref.model.encoder.forward = spy
+        ref.forward_test(pixel_values=x, pixel_mask=pm, text_query=tq, text_query_masks=tm, return_dict=True)
+    assert torch.equal(shapes, cap["spatial_shapes"]) and shapes.dtype == torch.int64
+    assert torch.equal(lsi, cap["level_start_index"])
+    assert torch.equal(~mflat, cap["vision_attention_mask"])
+    assert torch.equal(vr, cap["valid_ratios"])
+    assert (src - cap["vision_features"]).abs().max() < 1e-4
+    assert (pos - cap["vision_position_embedding"]).abs().max() < 1e-5

@@ -1,0 +1,155 @@
+// GroupNorm over channels-last activations x[n, hw, c] (bf16 in/out, fp32 statistics), optional fused ReLU.
+//
+// Replaces nn.GroupNorm(32, d_model) after the 1x1 / 3x3 input projections of the Grounding-DINO neck
+// (grounding_dino/modeling_ov_grounding_dino_mask_dn.py:2085-2110, applied at :2393-2405) and the
+// detectron2 Conv2d(norm=GN[, activation=relu]) blocks of the mask-feature FPN (:2126-2151, :2470-2478).
+// The reference runs them NCHW through cuDNN/ATen; our projections are GEMMs over NHWC rows, so the norm
+// reads and writes the same [pixels, channels] matrix the GEMM produced -- no layout change in between.
+//
+// HBM-bound: 1 read for the statistics + 1 read + 1 write for the apply pass (2 B each) = 6 B / element.
+// Statistics are deterministic: per-chunk (sum, sum^2) partials in fp32, combined in double in a fixed order.
+#include "common.cuh"
+#include "vllm_b200.h"
+
+namespace {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_CHUNKS = 128;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// grid (chunks, n).  Thread t owns the channel octet (t % c8) of pixels t / c8, t / c8 + ppi, ...  Octets of one
+// group are reduced through shared memory; partial[n][chunk][g] = (sum, sumsq).
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial,
+                                                              long long hw, int c, int groups, int chunks) {
+  extern __shared__ float2 sh[];  // [pixels-per-iteration][c8]
+  const int c8 = c >> 3, cpg8 = (c / groups) >> 3;
+  const int ppi = GN_THREADS / c8;  // pixels per iteration
+  const int oct = threadIdx.x % c8, prow = threadIdx.x / c8;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const long long per = (hw + chunks - 1) / chunks;
+  const long long p0 = chunk * per, p1 = min(hw, p0 + per);
+  float s = 0.f, ss = 0.f;
+  if (prow < ppi) {
+    const uint4* base = reinterpret_cast<const uint4*>(x + (long long)n * hw * c) + oct;
+    for (long long p = p0 + prow; p < p1; p += ppi) {
+      float f[8];
+      unpack8(__ldg(base + p * c8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s += f[i];
+        ss = fmaf(f[i], f[i], ss);
+      }
+    }
+    sh[prow * c8 + oct] = make_float2(s, ss);
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    double ds = 0.0, dss = 0.0;
+    for (int r = 0; r < ppi; ++r)
+      for (int o = 0; o < cpg8; ++o) {
+        const float2 v = sh[r * c8 + threadIdx.x * cpg8 + o];
+        ds += v.x;
+        dss += v.y;
+      }
+    partial[((long long)n * chunks + chunk) * groups + threadIdx.x] = make_float2((float)ds, (float)dss);
+  }
+}
+
+// grid (blocks, n).  Every CTA first folds the chunk partials of its image into (mean, rstd) per group.
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                              const __nv_bfloat16* __restrict__ gamma,
+                                                              const __nv_bfloat16* __restrict__ beta,
+                                                              const float2* __restrict__ partial, long long hw, int c, int groups,
+                                                              int chunks, float eps, int relu) {
+  __shared__ float2 stat[256];
+  const int n = blockIdx.y;
+  const int c8 = c >> 3, cpg = c / groups;
+  for (int g = threadIdx.x; g < groups; g += GN_THREADS) {
+    double ds = 0.0, dss = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+      const float2 v = partial[((long long)n * chunks + k) * groups + g];
+      ds += v.x;
+      dss += v.y;
+    }
+    const double cnt = (double)hw * cpg, mean = ds / cnt;
+    double var = dss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+  __syncthreads();
+  const int oct = threadIdx.x % c8, prow = threadIdx.x / c8, ppi = GN_THREADS / c8;
+  if (prow >= ppi) return;
+  float ga[8], be[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + oct), ga);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + oct), be);
+  const float2 st = stat[(oct * 8) / cpg];
+  const uint4* xin = reinterpret_cast<const uint4*>(x + (long long)n * hw * c) + oct;
+  uint4* yout = reinterpret_cast<uint4*>(y + (long long)n * hw * c) + oct;
+  for (long long p = (long long)blockIdx.x * ppi + prow; p < hw; p += (long long)gridDim.x * ppi) {
+    float f[8];
+    unpack8(__ldg(xin + p * c8), f);
+    uint4 o;
+    __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // ATen's GroupNorm: y = (x - mean) * rstd * gamma + beta evaluated in fp32, rounded once.
+      float a = (f[2 * i] - st.x) * st.y * ga[2 * i] + be[2 * i];
+      float b = (f[2 * i + 1] - st.x) * st.y * ga[2 * i + 1] + be[2 * i + 1];
+      if (relu) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      op[i] = __floats2bfloat162_rn(a, b);
+    }
+    yout[p * c8] = o;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+long long vllm_groupnorm_workspace_bytes(int batch, int groups) {
+  return (long long)batch * GN_MAX_CHUNKS * groups * (long long)sizeof(float2);
+}
+
+int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, int batch, long long hw,
+                             int channels, int groups, float eps, int relu, void* workspace, long long workspace_bytes,
+                             void* stream) {
+  if (batch < 0 || hw < 0 || channels <= 0 || groups <= 0) return VLLM_EINVAL;
+  if (batch == 0 || hw == 0) return VLLM_OK;
+  if (!x || !y || !gamma || !beta || !workspace) return VLLM_EINVAL;
+  if (channels % groups) return VLLM_EINVAL;
+  const int cpg = channels / groups;
+  // one thread per 8-channel vector; a vector must not straddle two groups; a pixel row must fit one CTA pass
+  if (cpg % 8 || channels > 8 * GN_THREADS || groups > 256) return VLLM_EUNSUPPORTED;
+  if (!vllm_aligned(x, 16) || !vllm_aligned(y, 16) || !vllm_aligned(gamma, 16) || !vllm_aligned(beta, 16)) return VLLM_EALIGN;
+  const int c8 = channels / 8, ppi = GN_THREADS / c8;
+  long long want = (hw + (long long)ppi * 8 - 1) / ((long long)ppi * 8);  // >= 8 iterations per chunk
+  int chunks = (int)(want < 1 ? 1 : (want > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : want));
+  if (workspace_bytes < (long long)batch * chunks * groups * (long long)sizeof(float2)) return VLLM_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  gn_stats_kernel<<<dim3(chunks, batch), GN_THREADS, (size_t)ppi * c8 * sizeof(float2), st>>>(
+      (const __nv_bfloat16*)x, (float2*)workspace, hw, channels, groups, chunks);
+  VLLM_CHECK_LAUNCH();
+  long long blocks = (hw + (long long)ppi * 4 - 1) / ((long long)ppi * 4);
+  const long long cap = (long long)vllm_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  gn_apply_kernel<<<dim3((unsigned)blocks, batch), GN_THREADS, 0, st>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+      (const float2*)workspace, hw, channels, groups, chunks, eps, relu);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+}  // extern "C"

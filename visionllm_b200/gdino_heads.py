@@ -60,6 +60,36 @@ class GroundingDinoContrastiveEmbedding(nn.Module):
         return out
 
 
+@torch.no_grad()
+def gen_encoder_output_proposals(enc_output_linear, enc_output_norm, enc_output, padding_mask, spatial_shapes):
+    """OVGroundingDinoModel.gen_encoder_output_proposals (gd.py:2228-2276): one (cx, cy, w, h) proposal per pixel,
+    validity window (0.01, 0.99), inverse sigmoid with +inf for padded / invalid pixels, zeroed features through
+    enc_output + enc_output_norm."""
+    B = enc_output.shape[0]
+    dev = enc_output.device
+    proposals, pos = [], 0
+    for level, (H, W) in enumerate([(int(h), int(w)) for h, w in spatial_shapes.tolist()]):
+        m = padding_mask[:, pos:pos + H * W].view(B, H, W)
+        valid_h = (~m[:, :, 0]).sum(1)
+        valid_w = (~m[:, 0, :]).sum(1)
+        gy, gx = torch.meshgrid(torch.linspace(0, H - 1, H, dtype=torch.float32, device=dev),
+                                torch.linspace(0, W - 1, W, dtype=torch.float32, device=dev), indexing="ij")
+        grid = torch.stack((gx, gy), -1)[None].expand(B, -1, -1, -1)
+        scale = torch.stack((valid_w, valid_h), 1).view(B, 1, 1, 2)
+        grid = (grid + 0.5) / scale
+        wh = torch.ones_like(grid) * 0.05 * (2.0 ** level)
+        proposals.append(torch.cat((grid, wh), -1).view(B, -1, 4))
+        pos += H * W
+    prop = torch.cat(proposals, 1)
+    valid = ((prop > 0.01) & (prop < 0.99)).all(-1, keepdim=True)
+    prop = torch.log(prop / (1 - prop))
+    prop = prop.masked_fill(padding_mask.unsqueeze(-1), float("inf")).masked_fill(~valid, float("inf"))
+    q = enc_output.masked_fill(padding_mask.unsqueeze(-1), 0.0).masked_fill(~valid, 0.0)
+    q = ops.linear(q, enc_output_linear.weight, bias=enc_output_linear.bias)
+    q = ops.layernorm(q, enc_output_norm.weight, enc_output_norm.bias, enc_output_norm.eps)
+    return q, prop
+
+
 class EncoderOutputProposals(nn.Module):
     """gen_encoder_output_proposals + enc_output / enc_output_norm (same parameter names as OVGroundingDinoModel)."""
 
@@ -68,31 +98,8 @@ class EncoderOutputProposals(nn.Module):
         self.enc_output = nn.Linear(d_model, d_model)
         self.enc_output_norm = nn.LayerNorm(d_model)
 
-    @torch.no_grad()
     def forward(self, enc_output, padding_mask, spatial_shapes):
-        B = enc_output.shape[0]
-        dev = enc_output.device
-        proposals, pos = [], 0
-        for level, (H, W) in enumerate([(int(h), int(w)) for h, w in spatial_shapes.tolist()]):
-            m = padding_mask[:, pos:pos + H * W].view(B, H, W)
-            valid_h = (~m[:, :, 0]).sum(1)
-            valid_w = (~m[:, 0, :]).sum(1)
-            gy, gx = torch.meshgrid(torch.linspace(0, H - 1, H, dtype=torch.float32, device=dev),
-                                    torch.linspace(0, W - 1, W, dtype=torch.float32, device=dev), indexing="ij")
-            grid = torch.stack((gx, gy), -1)[None].expand(B, -1, -1, -1)
-            scale = torch.stack((valid_w, valid_h), 1).view(B, 1, 1, 2)
-            grid = (grid + 0.5) / scale
-            wh = torch.ones_like(grid) * 0.05 * (2.0 ** level)
-            proposals.append(torch.cat((grid, wh), -1).view(B, -1, 4))
-            pos += H * W
-        prop = torch.cat(proposals, 1)
-        valid = ((prop > 0.01) & (prop < 0.99)).all(-1, keepdim=True)
-        prop = torch.log(prop / (1 - prop))
-        prop = prop.masked_fill(padding_mask.unsqueeze(-1), float("inf")).masked_fill(~valid, float("inf"))
-        q = enc_output.masked_fill(padding_mask.unsqueeze(-1), 0.0).masked_fill(~valid, 0.0)
-        q = ops.linear(q, self.enc_output.weight, bias=self.enc_output.bias)
-        q = ops.layernorm(q, self.enc_output_norm.weight, self.enc_output_norm.bias, self.enc_output_norm.eps)
-        return q, prop
+        return gen_encoder_output_proposals(self.enc_output, self.enc_output_norm, enc_output, padding_mask, spatial_shapes)
 
 
 @torch.no_grad()
@@ -111,10 +118,14 @@ def select_topk_proposals(enc_outputs_class, enc_outputs_coord_logits, object_qu
 def forward_seg_heads(mask_embed_head, output, mask_features):
     """einsum('bqc,bchw->bqhw', mask_embed(output), mask_features) as one [Q,C] x [HW,C]^T GEMM per image."""
     e = mask_embed_head(output)
-    B, C, H, W = mask_features.shape
-    f = mask_features.permute(0, 2, 3, 1).reshape(B, H * W, C)          # free for channels_last features
-    if not f.is_contiguous():
-        f = f.contiguous()
+    if isinstance(mask_features, tuple):                                  # (rows [B, H*W, C], H, W): the neck's own layout
+        f, H, W = mask_features
+        B = f.shape[0]
+    else:
+        B, C, H, W = mask_features.shape
+        f = mask_features.permute(0, 2, 3, 1).reshape(B, H * W, C)      # free for channels_last features
+        if not f.is_contiguous():
+            f = f.contiguous()
     out = torch.empty((B, e.shape[1], H * W), dtype=e.dtype, device=e.device)
     for b in range(B):
         ops.linear(e[b].contiguous(), f[b], out=out[b])

@@ -130,6 +130,29 @@ def layernorm(x, weight, bias, eps, out=None):
     return out
 
 
+_GN_WS = {}
+
+
+def groupnorm_nhwc(x, weight, bias, groups, eps, relu=False):
+    """GroupNorm of channels-last rows x [batch, pixels, channels] (bf16), optional fused ReLU -- nn.GroupNorm(32, 256)
+    of the Grounding-DINO neck (modeling_ov_grounding_dino_mask_dn.py:2085-2110) without leaving the GEMM's layout."""
+    if x.dim() != 3 or x.dtype != torch.bfloat16 or not x.is_contiguous() or not x.is_cuda:
+        raise RuntimeError("groupnorm_nhwc: x must be a contiguous CUDA bf16 [batch, pixels, channels] tensor")
+    n, hw, c = x.shape
+    if weight.dtype != torch.bfloat16 or bias.dtype != torch.bfloat16 or weight.numel() != c or bias.numel() != c:
+        raise RuntimeError("groupnorm_nhwc: weight/bias must be bf16 [channels]")
+    need = _lib.lib().vllm_groupnorm_workspace_bytes(n, groups)
+    ws = _GN_WS.get(x.device)
+    if ws is None or ws.numel() < need:
+        ws = _GN_WS[x.device] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=x.device)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device), _Prof("groupnorm", 0.0, 6.0 * n * hw * c):
+        rc = _lib.lib().vllm_groupnorm_nhwc_bf16(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(), n, hw, c,
+                                                 groups, float(eps), int(bool(relu)), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "vllm_groupnorm_nhwc_bf16")
+    return out
+
+
 def rope_(x, cos, sin, heads, head_dim):
     """In-place rotate-half RoPE on x [tokens, >= heads*head_dim] (2-D, possibly a strided slice)."""
     if x.dim() != 2 or x.dtype != torch.bfloat16 or x.stride(1) != 1:
