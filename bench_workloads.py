@@ -387,77 +387,69 @@ class GdinoHeadWorkload:
         return {"kernel_breakdown": self.breakdown}
 
 
-class _GdinoStage:
-    """The region-decoder stage as the composite model calls it (`gdino(pixel_values, pixel_mask=, text_query=,
-    text_query_masks=)`): patch2query MLP over the [EMB] hidden states, 6 encoder + 6 decoder layers, bbox / class /
-    mask heads of the last layer, two-stage top-k.  Backbone + input projections are synthetic features (cuDNN convs
-    in the reference, outside this build)."""
+def build_gdino_stage(torch, device, hidden, backbone="b200"):
+    """Grounding-DINO-tiny (Swin-T: embed 96, depths 2/2/6/2, window 7; 6 enc + 6 dec layers, d_model 256, FFN 2048,
+    100 queries, mask head) as `visionllm_b200.gdino_model.B200GroundingDinoForObjectDetection`, random init."""
+    from types import SimpleNamespace
+    from transformers import SwinConfig
+    from visionllm_b200.gdino_model import B200GroundingDinoForObjectDetection
+    from visionllm_b200.swin import B200SwinBackbone
+    bc = SwinConfig(image_size=224, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
+                    out_features=["stage1", "stage2", "stage3", "stage4"])
+    cfg = SimpleNamespace(backbone_config=bc, d_model=256, encoder_layers=6, decoder_layers=6, encoder_ffn_dim=2048,
+                          decoder_ffn_dim=2048, encoder_attention_heads=8, decoder_attention_heads=8, num_queries=100,
+                          num_feature_levels=4, encoder_n_points=4, decoder_n_points=4, dropout=0., attention_dropout=0.,
+                          activation_dropout=0., activation_function="relu", mask_dim=256, norm="GN", l_hidden_size=hidden,
+                          max_text_len=256, query_dim=4, two_stage=True, embedding_init_target=True,
+                          two_stage_bbox_embed_share=False, decoder_bbox_embed_share=True, position_embedding_type="sine",
+                          positional_embedding_temperature=20)
+    torch.manual_seed(0)
+    m = B200GroundingDinoForObjectDetection(cfg, backbone_model=B200SwinBackbone(bc) if backbone == "b200" else None)
+    torch.nn.init.normal_(m.model.level_embed)
+    return m.to(device, torch.bfloat16).eval()
 
-    def __init__(self, torch, device, n_images, hidden):
-        from types import SimpleNamespace
+
+class GdinoStageWorkload(GdinoHeadWorkload):
+    """BASELINE cfg 4's WHOLE region-decoder stage on real inputs: 8 images [3,1024,1024] + text_query [8,80,4,4096]
+    -> Swin-T backbone -> neck (GEMM + GroupNorm kernel) -> 6 encoder layers -> mask FPN -> two-stage top-k ->
+    6 decoder layers -> class / box / mask heads -> detection post-processing (top-100 over Q x K)."""
+    metric = "gdino_stage_images_per_sec_1024px"
+    N_CLS = 80
+
+    def setup(self):
+        import torch
+        self.torch = torch
+        dev = self.device
+        self.model = build_gdino_stage(torch, dev, 4096, backbone=os.environ.get("VLLM_BENCH_GDINO_BACKBONE", "b200"))
+        g = torch.Generator(device=dev).manual_seed(7 + self.rank)
+        N = self.N
+        self.images = torch.randn(N, 3, 1024, 1024, device=dev, generator=g).bfloat16()
+        self.tq = torch.randn(N, self.N_CLS, 4, 4096, device=dev, generator=g).bfloat16()
+        self.tm = torch.ones(N, self.N_CLS, dtype=torch.bool, device=dev)
+        self.h_in = [t.cpu().pin_memory() for t in (self.images, self.tq)]
+        self.d_in = [torch.empty_like(t) for t in (self.images, self.tq)]
+        self.h_out = torch.empty((N, 100, 6), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(t.numel() * 2 for t in self.h_in)
+        self.d2h_bytes = self.h_out.numel() * 4
+        self.src = torch.empty(N, sum(h * w for h, w in GDINO_LEVELS_1024), 1, device="meta")     # shape only (roofline)
+
+    def _run(self, images, tq):
         from visionllm_b200 import gdino_heads as H
-        from visionllm_b200.gdino import GroundingDinoDecoderLayer, GroundingDinoEncoderLayer
-        self.torch, self.H = torch, H
-        cfg = SimpleNamespace(d_model=256, encoder_attention_heads=8, decoder_attention_heads=8, encoder_ffn_dim=2048,
-                              decoder_ffn_dim=2048, num_feature_levels=4, encoder_n_points=4, decoder_n_points=4,
-                              dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, activation_function="relu",
-                              max_text_len=256)
-        mk = lambda m: m.to(device, torch.bfloat16).eval()  # noqa: E731
-        self.enc = mk(torch.nn.ModuleList([GroundingDinoEncoderLayer(cfg) for _ in range(6)]))
-        self.dec = mk(torch.nn.ModuleList([GroundingDinoDecoderLayer(cfg) for _ in range(6)]))
-        self.patch2query = mk(H.GroundingDinoMLPPredictionHead(hidden, 256, 256, 3))
-        self.proposals = mk(H.EncoderOutputProposals(256))
-        self.enc_bbox = mk(H.GroundingDinoMLPPredictionHead(256, 256, 4, 3))
-        self.bbox = mk(H.GroundingDinoMLPPredictionHead(256, 256, 4, 3))
-        self.mask_embed = mk(H.GroundingDinoMLPPredictionHead(256, 256, 256, 3))
-        self.contrast = H.GroundingDinoContrastiveEmbedding(cfg)
-        g = torch.Generator(device=device).manual_seed(3)
-        self.shapes = torch.tensor(GDINO_LEVELS_1024, dtype=torch.int64, device=device)
-        self.lsi = torch.cat((self.shapes.new_zeros(1), self.shapes.prod(1).cumsum(0)[:-1]))
-        S = sum(h * w for h, w in GDINO_LEVELS_1024)
-        N = n_images
-        self.src = torch.randn(N, S, 256, device=device, generator=g).bfloat16()
-        self.pos = (torch.randn(N, S, 256, device=device, generator=g) * 0.5).bfloat16()
-        self.mask_features = torch.randn(N, 256, 256, 256, device=device, generator=g).bfloat16().contiguous(
-            memory_format=torch.channels_last)
-        refs = []
-        for (Hh, W) in GDINO_LEVELS_1024:
-            ys, xs = torch.meshgrid(torch.arange(Hh, device=device, dtype=torch.float32),
-                                    torch.arange(W, device=device, dtype=torch.float32), indexing="ij")
-            refs.append(torch.stack(((xs + 0.5) / W, (ys + 0.5) / Hh), -1).reshape(-1, 2))
-        self.ref2 = torch.cat(refs, 0)[None, :, None, :].repeat(N, 1, 4, 1).contiguous()
-        self.kpm = torch.zeros(N, S, dtype=torch.bool, device=device)
-        self.qpos = (torch.randn(N, 100, 256, device=device, generator=g) * 0.5).bfloat16()
+        o = self.model(images, pixel_mask=None, text_query=tq, text_query_masks=self.tm)
+        res, _, _ = H.post_process_det_gdino(o.logits, o.pred_boxes, [(1024, 1024)] * self.N, self.N_CLS, topk=100)
+        self.masks = o.pred_masks
+        return self.torch.stack([self.torch.cat([r["boxes"], r["scores"][:, None], r["labels"][:, None].float()], 1)
+                                 for r in res])
 
-    def __call__(self, pixel_values, pixel_mask=None, text_query=None, text_query_masks=None, **kw):
-        torch, H = self.torch, self.H
-        text = H.patch2query_mean(self.patch2query, text_query)                  # [N, n_cls, 256]
-        N, T, _ = text.shape
-        tpad = ~text_query_masks
-        tsa = (text_query_masks[:, :, None] & text_query_masks[:, None, :]) | torch.eye(T, dtype=torch.bool, device=text.device)
-        pids = torch.arange(T, device=text.device)[None].repeat(N, 1)
-        v, t = self.src, text
-        for layer in self.enc:
-            (v, t), _ = layer(vision_features=v, vision_position_embedding=self.pos, spatial_shapes=self.shapes,
-                              level_start_index=self.lsi, key_padding_mask=self.kpm, reference_points=self.ref2,
-                              text_features=t, text_attention_mask=tpad, text_position_embedding=None,
-                              text_self_attention_masks=tsa, text_position_ids=pids)
-        oq, prop = self.proposals(v, self.kpm, self.shapes)
-        cls = self.contrast(oq, t, text_query_masks)
-        coord = self.enc_bbox(oq).float() + prop
-        idx, ref_pts, _, _, target = H.select_topk_proposals(cls, coord, oq, 100)
-        h = target
-        ref4 = ref_pts[:, :, None, :].repeat(1, 1, 4, 1).contiguous()
-        for layer in self.dec:
-            (h,) = layer(h, position_embeddings=self.qpos, reference_points=ref4, spatial_shapes=self.shapes,
-                         level_start_index=self.lsi, vision_encoder_hidden_states=v,
-                         vision_encoder_attention_mask=~self.kpm, text_encoder_hidden_states=t,
-                         text_encoder_attention_mask=tpad)
-        from types import SimpleNamespace
-        logits = self.contrast(h, t, text_query_masks)
-        boxes = (self.bbox(h).float() + torch.logit(ref_pts.clamp(1e-3, 1 - 1e-3))).sigmoid()
-        masks = H.forward_seg_heads(self.mask_embed, h, self.mask_features)
-        return SimpleNamespace(logits=logits, pred_boxes=boxes, pred_masks=masks)
+    def step_device(self):
+        self.out = self._run(self.images, self.tq)
+
+    def config(self):
+        return {"workload": "Grounding-DINO-tiny whole stage (BASELINE cfg 4 region decoder): N=8 images 1024^2, Swin-T "
+                            "backbone on our kernels, neck, 6 enc + 6 dec layers (S=21760), 80 classes x 4 [EMB] text "
+                            "queries, 100 object queries, box/class/mask heads, det post-processing",
+                "l2_policy": "inputs_exceed_l2 (activations 8 x 65536 x 96 x ... > 126 MB)",
+                "parallelism": f"dp{self.world}"}
 
 
 class PairForwardGdinoWorkload(PairForwardWorkload):
@@ -478,10 +470,12 @@ class PairForwardGdinoWorkload(PairForwardWorkload):
         self.T = self.ids.shape[1]
         self.h_ids = self.ids.cpu().pin_memory()
         self.d_ids = torch.empty_like(self.ids)
-        self.model.gdino = _GdinoStage(torch, self.device, self.PAIRS, 4096)
+        self.model.gdino = build_gdino_stage(torch, self.device, 4096)
         self.model.use_gdino = True
-        self.aug = torch.randn(self.PAIRS, 3, 64, 64, device=self.device).bfloat16()   # stand-in; backbone is stubbed
-        self.h2d_bytes = sum(t.numel() * 2 for t in self.h_images) + self.ids.numel() * 8
+        self.aug = torch.randn(self.PAIRS, 3, 1024, 1024, device=self.device).bfloat16()   # mmdet-normalised images_aug
+        self.h_aug = self.aug.cpu().pin_memory()
+        self.d_aug = torch.empty_like(self.aug)
+        self.h2d_bytes = sum(t.numel() * 2 for t in self.h_images) + self.ids.numel() * 8 + self.aug.numel() * 2
         self.h_out = torch.empty((self.PAIRS, 100, 6), dtype=torch.float32).pin_memory()
         self.d2h_bytes = self.h_out.numel() * 4
 
@@ -500,19 +494,20 @@ class PairForwardGdinoWorkload(PairForwardWorkload):
         for d, h in zip(self.d_images, self.h_images):
             d.copy_(h, non_blocking=True)
         self.d_ids.copy_(self.h_ids, non_blocking=True)
-        out = self._post(self.model(input_ids=self.d_ids, attention_mask=None, images=self.d_images, images_aug=self.aug))
+        self.d_aug.copy_(self.h_aug, non_blocking=True)
+        out = self._post(self.model(input_ids=self.d_ids, attention_mask=None, images=self.d_images, images_aug=self.d_aug))
         self.h_out.copy_(out, non_blocking=True)                     # boxes, scores, labels of the top-100 detections
 
     def config(self):
         c = super().config()
         c["workload"] = ("BASELINE cfg 4: cfg 3 + GDINO region decoder (80 classes x ([DET] + 4 [EMB]), 100 queries, "
-                         "4-level 1024^2 pyramid, backbone/input_proj stubbed), heads + det post-processing in the step")
+                         "Swin-T backbone + neck + 6 enc + 6 dec layers on the 1024^2 images_aug), heads + det post-processing in the step")
         c["seq_len"] = self.T
         return c
 
 
 WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
-             "pair_forward_gdino": PairForwardGdinoWorkload}
+             "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
 
@@ -584,6 +579,7 @@ def _cpu_pair_forward(steps, warmup):
 
 
 _CPU = {"msda_encoder": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
+        "gdino_stage": _cpu_msda_encoder,
         "pair_forward_gdino": _cpu_pair_forward}
 
 

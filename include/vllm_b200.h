@@ -163,6 +163,10 @@ int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long
  * nn.MultiheadAttention receives as `attn_mask` (inverted), indexed by batch*heads + head.
  * causal != 0: query i sees keys <= i + (Tk - Tq).  head_dim in {32, 64, 128, 256}.
  * workspace (may be NULL): caller-owned scratch of workspace_bytes; when the query side alone cannot fill the
+ * attn_bias (fp32 [bias_batches, heads, Tq, Tk], may be NULL): added to the scaled scores before the softmax;
+ * batch b reads slab b % bias_batches -- Swin's relative-position bias (+ shifted-window mask, one slab per window
+ * of an image; HF modeling_swin.py SwinSelfAttention.forward, used by the reference through AutoBackbone,
+ * modeling_ov_grounding_dino_mask_dn.py:471-504).
  * GPU (few queries, many keys: GDINO text->vision attention, 80 x 21760) the key axis is split across CTAs and
  * the partials (unnormalised O, running max, sum) are merged by a second kernel -- never needed for results. */
 int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
@@ -170,8 +174,8 @@ int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, in
                         long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
                         long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
                         long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
-                        const unsigned char* attn_mask, int causal, float scale, void* workspace,
-                        long long workspace_bytes, void* stream);
+                        const unsigned char* attn_mask, const float* attn_bias, int bias_batches, int causal,
+                        float scale, void* workspace, long long workspace_bytes, void* stream);
 /* Tuning knob (process-global), head_dim 128 without masks: 0 = tcgen05/TMEM kernel, schedule "tc2" (default),
  * 2 = tcgen05/TMEM ping-pong schedule, 1 = warp-MMA kernel always. */
 int vllm_attention_set_variant(int variant);

@@ -26,7 +26,7 @@ def bf16r(t):
 
 def config(cfgm):
     from transformers import SwinConfig
-    bc = SwinConfig(image_size=64, embed_dim=24, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=4,
+    bc = SwinConfig(image_size=64, embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8], window_size=4,
                     out_features=["stage1", "stage2", "stage3", "stage4"])
     return cfgm.GroundingDinoConfig(
         backbone_config=bc, d_model=256, encoder_layers=2, decoder_layers=2, encoder_ffn_dim=512, decoder_ffn_dim=512,

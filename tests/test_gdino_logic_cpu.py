@@ -34,10 +34,12 @@ def torch_kernels(monkeypatch):
             return out
         return y
 
-    def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, attn_mask=None, out=None):
+    def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, attn_mask=None, attn_bias=None, out=None):
         B, Tq, H, D = q.shape
         Tk = k.shape[1]
         s = (q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 3, 1)) * (scale or D ** -0.5)
+        if attn_bias is not None:
+            s = s + attn_bias[torch.arange(B) % attn_bias.shape[0]]
         if attn_mask is not None:
             s = s.masked_fill(~attn_mask.bool().view(B, H, Tq, Tk), float("-inf"))
         if key_mask is not None:

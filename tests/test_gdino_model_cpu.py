@@ -15,13 +15,13 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
 from test_gdino_logic_cpu import torch_kernels  # noqa: E402,F401  (fixture)
 
 
-def build_pair(seed=11, **over):
+def build_pair(seed=11, b200_backbone=False, **over):
     import ref_shim
     from transformers import SwinConfig
     from weights_util import seeded_state_dict
     from visionllm_b200.gdino_model import B200GroundingDinoForObjectDetection
     cfgm, gd = ref_shim.load_gdino()
-    bc = SwinConfig(image_size=64, embed_dim=24, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8], window_size=4,
+    bc = SwinConfig(image_size=64, embed_dim=32 if b200_backbone else 24, depths=[1, 2, 1, 1], num_heads=[1, 2, 4, 8], window_size=4,
                     out_features=["stage1", "stage2", "stage3", "stage4"])
     kw = dict(backbone_config=bc, d_model=256, encoder_layers=2, decoder_layers=2, encoder_ffn_dim=256, decoder_ffn_dim=256,
               num_queries=20, num_feature_levels=4, dropout=0., attention_dropout=0., activation_dropout=0.,
@@ -36,7 +36,8 @@ def build_pair(seed=11, **over):
             sd[k] = sd[k] * 0 + 0.5
     ref.load_state_dict(sd)
     cfg.activation_function = "relu"
-    ours = B200GroundingDinoForObjectDetection(cfg).eval()
+    from visionllm_b200.swin import B200SwinBackbone
+    ours = B200GroundingDinoForObjectDetection(cfg, backbone_model=B200SwinBackbone(bc) if b200_backbone else None).eval()
     missing, unexpected = ours.load_state_dict(sd, strict=False)
     # identical parameter names; the only keys we do not hold are Swin's non-persistent-in-ours buffers (none expected)
     assert not unexpected, unexpected
@@ -55,9 +56,9 @@ def gn_kernel(monkeypatch, torch_kernels):  # noqa: F811
     monkeypatch.setattr(ops, "groupnorm_nhwc", groupnorm_nhwc)
 
 
-@pytest.mark.parametrize("ragged", [False, True])
-def test_whole_stage_matches_reference_forward_test(gn_kernel, ragged):
-    cfg, ref, ours = build_pair()
+@pytest.mark.parametrize("ragged,b200_backbone", [(False, False), (True, False), (True, True)])
+def test_whole_stage_matches_reference_forward_test(gn_kernel, ragged, b200_backbone):
+    cfg, ref, ours = build_pair(b200_backbone=b200_backbone)
     g = torch.Generator().manual_seed(5)
     B, Hh, W = 2, 128, 160
     x = torch.randn(B, 3, Hh, W, generator=g)

@@ -28,7 +28,7 @@ def rel(a, b):
 def stage_config():
     from transformers import SwinConfig
     from types import SimpleNamespace
-    bc = SwinConfig(image_size=64, embed_dim=24, depths=[1, 1, 2, 1], num_heads=[1, 2, 4, 8], window_size=4,
+    bc = SwinConfig(image_size=64, embed_dim=32, depths=[2, 2, 2, 2], num_heads=[1, 2, 4, 8], window_size=4,
                     out_features=["stage1", "stage2", "stage3", "stage4"])
     return SimpleNamespace(backbone_config=bc, d_model=256, encoder_layers=2, decoder_layers=2, encoder_ffn_dim=512,
                            decoder_ffn_dim=512, encoder_attention_heads=8, decoder_attention_heads=8, num_queries=20,
@@ -39,12 +39,16 @@ def stage_config():
                            positional_embedding_temperature=20)
 
 
-@pytest.fixture(scope="module")
-def stage(golden_dir):
+@pytest.fixture(scope="module", params=["hf_swin", "b200_swin"])
+def stage(golden_dir, request):
+    """Backbone either HF's SwinBackbone run by torch (how the reference builds it) or ours on the B200 kernels."""
     from weights_util import key_shapes, seeded_state_dict
     from visionllm_b200.gdino_model import B200GroundingDinoForObjectDetection
+    from visionllm_b200.swin import B200SwinBackbone
     g = np.load(os.path.join(golden_dir, "mod_gdino_model.npz"))
-    m = B200GroundingDinoForObjectDetection(stage_config()).eval()
+    cfg = stage_config()
+    m = B200GroundingDinoForObjectDetection(
+        cfg, backbone_model=B200SwinBackbone(cfg.backbone_config) if request.param == "b200_swin" else None).eval()
     assert json.loads(str(g["keys"])) == [list(k) for k in key_shapes(m)]          # the reference's state-dict keys
     sd = seeded_state_dict(m, int(g["seed"]))
     for k in sd:

@@ -37,7 +37,7 @@ def mk(M, N, K, seed=0):
 
 SHAPES = [(128, 256, 64), (128, 256, 128), (256, 512, 256), (1025, 3200, 3200), (300, 9600, 3200), (77, 384, 256),
           (2000, 2048, 256), (1536, 4096, 4096), (513, 1376, 4096), (640, 4096, 1376), (100, 256, 2048),
-          (130, 264, 72), (4100, 3200, 640)]
+          (130, 264, 72), (4100, 3200, 640), (300, 96, 48), (200, 96, 32), (4096, 288, 96), (777, 96, 384)]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

@@ -40,7 +40,7 @@ _SIGNATURES = {
     "vllm_groupnorm_workspace_bytes": (cll, [ci, ci]),
     "vllm_groupnorm_nhwc_bf16": (ci, [vp, vp, vp, vp, ci, cll, ci, ci, cf, ci, vp, cll, vp]),
     "vllm_attention_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cll, cll, cll, cll, cll, cll, cll, cll,
-                                 vp, vp, vp, ci, cf, vp, cll, vp]),
+                                 vp, vp, vp, vp, ci, ci, cf, vp, cll, vp]),
     "vllm_attention_set_variant": (ci, [ci]),
 }
 

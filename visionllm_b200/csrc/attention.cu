@@ -30,6 +30,8 @@ struct AttnArgs {
   const int* seqlens;
   const unsigned char* key_mask;   // optional [batch, Tk], 1 = attend (arbitrary key_padding_mask)
   const unsigned char* attn_mask;  // optional [batch*heads, Tq, Tk], 1 = attend (nn.MultiheadAttention attn_mask, inverted)
+  const float* attn_bias;          // optional additive bias [bias_batches, heads, Tq, Tk] fp32; batch b reads slab b % bias_batches
+  int bias_batches;
   int Tq, Tk, heads, kv_heads, causal;
   float scale_log2;
   int n_splits;      // split-KV: CTAs along the key axis per query block (1 = off)
@@ -171,7 +173,9 @@ flash_fwd_kernel(const AttnArgs a) {
     const int n0 = (t_begin + t) * BN;
     const unsigned char* km = a.key_mask ? a.key_mask + (long long)b * a.Tk : nullptr;
     const unsigned char* am = a.attn_mask ? a.attn_mask + ((long long)b * a.heads + head) * a.Tq * a.Tk : nullptr;
-    const bool need_mask = km || am || (n0 + BN > len) || (a.causal && (n0 + BN - 1 > m0 + coff));
+    const float* ab = a.attn_bias
+                          ? a.attn_bias + ((long long)(b % a.bias_batches) * a.heads + head) * a.Tq * a.Tk : nullptr;
+    const bool need_mask = km || am || ab || (n0 + BN > len) || (a.causal && (n0 + BN - 1 > m0 + coff));
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < BN / 8; ++j) {
@@ -184,6 +188,8 @@ flash_fwd_kernel(const AttnArgs a) {
           if (key >= len || (a.causal && key > qr + coff) || (km && !km[key]) ||
               (am && qr < a.Tq && !am[(long long)qr * a.Tk + key]))
             v = -INFINITY;
+          else if (ab && qr < a.Tq)
+            v = fmaf(ab[(long long)qr * a.Tk + key], 1.4426950408889634f, v);
         }
         s[j][e] = v;
         mx[e >> 1] = fmaxf(mx[e >> 1], v);
@@ -358,11 +364,12 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
                                    long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
                                    long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
                                    long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
-                                   const unsigned char* attn_mask, int causal, float scale, void* workspace,
-                                   long long workspace_bytes, void* stream) {
+                                   const unsigned char* attn_mask, const float* attn_bias, int bias_batches,
+                                   int causal, float scale, void* workspace, long long workspace_bytes, void* stream) {
   if (batch < 0 || Tq < 0 || Tk < 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads) return VLLM_EINVAL;
   if (batch == 0 || Tq == 0) return VLLM_OK;
   if (!q || !k || !v || !o) return VLLM_EINVAL;
+  if (attn_bias && bias_batches <= 0) return VLLM_EINVAL;
   if (batch > 65535 || heads > 65535) return VLLM_EUNSUPPORTED;
   const long long p[] = {q_batch_pitch, q_token_pitch, k_batch_pitch, k_token_pitch,
                          v_batch_pitch, v_token_pitch, o_batch_pitch, o_token_pitch};
@@ -373,16 +380,16 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
   a.o = (__nv_bfloat16*)o;
   a.q_bs = q_batch_pitch; a.k_bs = k_batch_pitch; a.v_bs = v_batch_pitch; a.o_bs = o_batch_pitch;
   a.q_ts = q_token_pitch; a.k_ts = k_token_pitch; a.v_ts = v_token_pitch; a.o_ts = o_token_pitch;
-  a.seqlens = seqlens; a.key_mask = key_mask; a.attn_mask = attn_mask; a.Tq = Tq; a.Tk = Tk; a.heads = heads; a.kv_heads = kv_heads; a.causal = causal;
+  a.seqlens = seqlens; a.key_mask = key_mask; a.attn_mask = attn_mask; a.attn_bias = attn_bias; a.bias_batches = bias_batches; a.Tq = Tq; a.Tk = Tk; a.heads = heads; a.kv_heads = kv_heads; a.causal = causal;
   a.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream;
-  if (head_dim == 128 && g_attn_variant == 0 && !key_mask && !attn_mask) {
+  if (head_dim == 128 && g_attn_variant == 0 && !key_mask && !attn_mask && !attn_bias) {
     const int rc = vllm_attention_tc2_d128(q, k, v, o, batch, Tq, Tk, heads, kv_heads, q_batch_pitch, q_token_pitch,
                                            k_batch_pitch, k_token_pitch, v_batch_pitch, v_token_pitch, o_batch_pitch,
                                            o_token_pitch, seqlens, causal, scale, st);
     if (rc != VLLM_EUNSUPPORTED) return rc;
   }
-  if (head_dim == 128 && g_attn_variant == 2 && !key_mask && !attn_mask) {
+  if (head_dim == 128 && g_attn_variant == 2 && !key_mask && !attn_mask && !attn_bias) {
     const int rc = vllm_attention_tc_d128(q, k, v, o, batch, Tq, Tk, heads, kv_heads, q_batch_pitch, q_token_pitch,
                                           k_batch_pitch, k_token_pitch, v_batch_pitch, v_token_pitch, o_batch_pitch,
                                           o_token_pitch, seqlens, causal, scale, st);

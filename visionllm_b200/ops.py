@@ -180,11 +180,12 @@ def _attn_workspace(device, nbytes):
     return ws
 
 
-def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, attn_mask=None, out=None):
+def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, attn_mask=None, attn_bias=None, out=None):
     """softmax(q k^T * scale) v.  q [B, Tq, H, D], k/v [B, Tk, Hkv, D] bf16 views whose last two dims are
     contiguous (any batch/token pitch, e.g. slices of a packed qkv tensor).  Returns [B, Tq, H*D].
     seqlens: int32 [B] key lengths; key_mask: bool/uint8 [B, Tk], True = attend (arbitrary key padding);
-    attn_mask: bool/uint8 [B*H, Tq, Tk], True = attend (nn.MultiheadAttention's attn_mask, inverted)."""
+    attn_mask: bool/uint8 [B*H, Tq, Tk], True = attend (nn.MultiheadAttention's attn_mask, inverted);
+    attn_bias: fp32 [nB, H, Tq, Tk] added to the scaled scores, batch b uses slab b % nB (Swin windows)."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
             raise RuntimeError(f"attention: {nm} must be a 4-D CUDA bf16 tensor")
@@ -215,6 +216,12 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
             raise RuntimeError("attention: attn_mask must be CUDA [B*H, Tq, Tk]")
         attn_mask = attn_mask.to(torch.uint8).contiguous()
         amp = attn_mask.data_ptr()
+    abp, nb = None, 0
+    if attn_bias is not None:
+        if (attn_bias.dim() != 4 or tuple(attn_bias.shape[1:]) != (H, Tq, Tk) or attn_bias.dtype != torch.float32
+                or not attn_bias.is_cuda or not attn_bias.is_contiguous()):
+            raise RuntimeError("attention: attn_bias must be a contiguous CUDA fp32 [nB, H, Tq, Tk] tensor")
+        abp, nb = attn_bias.data_ptr(), attn_bias.shape[0]
     ws_ptr, ws_bytes = None, 0
     if not causal and Tq <= 1024 and Tk >= 16 * 32:          # few queries, many keys: let the kernel split the keys
         ws_bytes = min(B * H * 64 * Tq * (D + 2) * 4, 256 << 20)
@@ -224,6 +231,6 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
         rc = _lib.lib().vllm_attention_bf16(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Tq, Tk, H, Hkv, D,
             q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
-            out.stride(0), out.stride(1), sl, km, amp, 1 if causal else 0, float(scale), ws_ptr, ws_bytes, _stream())
+            out.stride(0), out.stride(1), sl, km, amp, abp, nb, 1 if causal else 0, float(scale), ws_ptr, ws_bytes, _stream())
     _lib.check(rc, "vllm_attention_bf16")
     return out
