@@ -96,6 +96,16 @@ int vllm_dcnv3_forward_f32(const float* input, const float* offset, const float*
                            int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
                            int dilation_h, int dilation_w, float offset_scale, int flags, void* stream);
 
+/* DCNv3 backward: `dcnv3_backward` of the same extension module (dcnv3.h:40-59; col2im kernels
+ * dcnv3_im2col_cuda.cuh:82-147,278-370; caller functions/dcnv3_func.py:60-77).  grad_input [N,H_in,W_in,G*C] MUST
+ * be zero-filled by the caller (accumulated with atomicAdd like the reference, dcnv3_cuda.cu:131 at::zeros_like);
+ * grad_offset / grad_mask are written in full. */
+int vllm_dcnv3_backward_f32(const float* input, const float* offset, const float* mask, const float* grad_output,
+                            float* grad_input, float* grad_offset, float* grad_mask, int N, int H_in, int W_in,
+                            int H_out, int W_out, int group, int group_channels, int kernel_h, int kernel_w,
+                            int stride_h, int stride_w, int pad_h, int pad_w, int dilation_h, int dilation_w,
+                            float offset_scale, void* stream);
+
 /* ---- bf16 tensor-core GEMM with fused epilogue (tcgen05 / TMEM / TMA) ----------
  * C[M, n_out] = epi(A[M,K] . B[N,K]^T): every nn.Linear on the hot path
  * (internvit/modeling_intern_vit.py:112,124,172-173; modeling_visionllmv2.py:162-184;

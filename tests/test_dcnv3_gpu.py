@@ -65,3 +65,54 @@ def test_errors_and_interior_partition_of_unity():
         ext.dcnv3_forward(t[0].transpose(1, 2), t[1], t[2], *p[:8], p[8], p[9], 1.0, 2)
     with pytest.raises(RuntimeError):
         ext.dcnv3_forward(t[0].cpu(), t[1], t[2], *p[:8], p[8], p[9], 1.0, 2)
+
+
+# ---- backward: dcnv3_backward vs the C oracle and the reference-autograd golden ----
+def run_bwd(inp, off, m, gout, p, scale):
+    import visionllm_b200.dcnv3 as ext
+    t = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda() for a in (inp, off, m)]
+    go = torch.from_numpy(np.ascontiguousarray(gout, dtype=np.float32)).cuda()
+    return [x.cpu().numpy() for x in ext.dcnv3_backward(*t, *p[:8], p[8], p[9], scale, go, 2 if t[0].shape[0] % 2 == 0 else 1)]
+
+
+@pytest.mark.parametrize("name", ["dcnv3_bwd_testpy.npz", "dcnv3_bwd_c32_s2.npz"])
+def test_backward_golden_reference_autograd(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    p = [int(x) for x in g["params"]]
+    gi, go, gm = run_bwd(g["input"], g["offset"], g["mask"], g["grad_out"], p, float(g["offset_scale"]))
+    for ours, key in ((gi, "grad_input"), (go, "grad_offset"), (gm, "grad_mask")):
+        ref = g[key]
+        assert np.abs(ours - ref).max() <= 2e-5 * np.abs(ref).max(), key       # fp32 op vs fp64 autograd
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_backward_vs_oracle(case):
+    inp, off, m, p = make(*case[:9], seed=12, amp=case[9])
+    rng = np.random.default_rng(5)
+    H_out, W_out = off.shape[1], off.shape[2]
+    gout = rng.standard_normal((inp.shape[0], H_out, W_out, p[8] * p[9]), dtype=np.float32)
+    ref = DO.backward(inp, off, m, gout, *p[:8], p[8], p[9], 1.5)
+    ours = run_bwd(inp, off, m, gout, p, 1.5)
+    for a, b, k in zip(ours, ref, ("grad_input", "grad_offset", "grad_mask")):
+        assert np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(b).max()), k      # atomics / shuffle order only
+
+
+def test_backward_autograd_function_and_adjoint_identity():
+    """<grad_out, J_input . d> == <J_input^T . grad_out, d>: forward is linear in `input`, so the backward's
+    grad_input must be its exact adjoint (size-independent property, run at an InternImage-like shape)."""
+    import visionllm_b200.dcnv3 as ext
+    inp, off, m, p = make(2, 40, 56, 10, 32, 3, 1, 1, 1, seed=21, amp=3.0)
+    ti, to, tm = (torch.from_numpy(a).cuda() for a in (inp, off, m))
+    ti.requires_grad_(True); to.requires_grad_(True); tm.requires_grad_(True)
+    out = ext.DCNv3Function.apply(ti, to, tm, *p[:8], p[8], p[9], 1.0, 2)
+    gout = torch.randn_like(out)
+    gi, go, gm = torch.autograd.grad(out, (ti, to, tm), gout)
+    d = torch.randn_like(ti)
+    lhs = (ext.dcnv3_forward(d.contiguous(), to.detach(), tm.detach(), *p[:8], p[8], p[9], 1.0, 2).double() * gout.double()).sum()
+    rhs = (gi.double() * d.double()).sum()
+    assert abs(lhs.item() - rhs.item()) <= 1e-4 * abs(lhs.item())
+    # forward is linear in mask too: <grad_mask, mask> == <grad_out, out>
+    assert abs((gm.double() * tm.detach().double()).sum().item() - (gout.double() * out.detach().double()).sum().item()) \
+        <= 1e-4 * abs((gout.double() * out.detach().double()).sum().item())
+    with pytest.raises(RuntimeError):
+        ext.dcnv3_backward(ti.detach(), to.detach(), tm.detach(), *p[:8], p[8], p[9], 1.0, gout[:, :, :-1].contiguous(), 2)

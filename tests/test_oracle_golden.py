@@ -118,3 +118,16 @@ def test_backward_oracle_vs_reference_autograd(golden_dir, name):
     assert np.abs(gv - g["grad_value"]).max() < 1e-10
     assert np.abs(gl - g["grad_loc"]).max() < 1e-9 * max(1.0, np.abs(g["grad_loc"]).max())
     assert np.abs(gw - g["grad_attw"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["dcnv3_bwd_testpy.npz", "dcnv3_bwd_c32_s2.npz"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_dcnv3_backward_oracle_vs_reference_autograd(golden_dir, name, dtype):
+    """oracle_dcnv3_backward_* vs fp64 autograd through the reference's own dcnv3_core_pytorch.  The reference builds
+    its sampling grid with float32 linspace (dcnv3_func.py:85-101), so even its fp64 run carries ~1e-7 noise."""
+    from oracle import dcnv3_oracle as DO
+    g = np.load(os.path.join(golden_dir, name))
+    p = [int(x) for x in g["params"]]
+    got = DO.backward(g["input"], g["offset"], g["mask"], g["grad_out"], *p, float(g["offset_scale"]), dtype=dtype)
+    for a, key in zip(got, ("grad_input", "grad_offset", "grad_mask")):
+        assert np.abs(a - g[key]).max() <= 5e-6 * np.abs(g[key]).max(), key

@@ -180,6 +180,53 @@ dcnv3_fwd_warp_kernel(const float* __restrict__ in, const float* __restrict__ of
   }
 }
 
+// Backward (dcnv3_col2im_bilinear + col2im kernels, dcnv3_im2col_cuda.cuh:82-147, 278-370): one warp per
+// (output pixel, group); the location arithmetic of a tap is done once per warp (the reference repeats it in every
+// channel thread), lanes own channels c, c+32, ...; grad_input through fp32 atomicAdd exactly like the reference,
+// grad_offset / grad_mask reduced over the channels with warp shuffles (the reference serialises that sum through
+// shared memory in thread 0).
+__global__ void __launch_bounds__(256)
+dcnv3_bwd_warp_kernel(long long n_pg, const float* __restrict__ in, const float* __restrict__ off,
+                      const float* __restrict__ msk, const float* __restrict__ gout, float* __restrict__ gin,
+                      float* __restrict__ goff, float* __restrict__ gmsk, const DcnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int qs = p.group * p.gc;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long pg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pg < n_pg; pg += warps) {
+    long long t = pg;
+    const int g = (int)(t % p.group); t /= p.group;
+    const int ow = (int)(t % p.W_out); t /= p.W_out;
+    const int oh = (int)(t % p.H_out); t /= p.H_out;
+    const long long ib = t * (long long)p.H_in * p.W_in * qs + g * p.gc;
+    const float* go = gout + pg * p.gc;
+    long long wp = pg * p.kernel_h * p.kernel_w;
+    for (int i = 0; i < p.kernel_w; ++i)
+      for (int j = 0; j < p.kernel_h; ++j, ++wp) {
+        const DcnGeom ge = dcn_geom(p, ow, oh, i, j, off[2 * wp], off[2 * wp + 1]);
+        float ga = 0.f, gw = 0.f, gh = 0.f;
+        if (ge.mask & 1) {
+          const float weight = msk[wp];
+          const float hh = 1.f - ge.lh, hw = 1.f - ge.lw;
+          const float w1 = hh * hw, w2 = hh * ge.lw, w3 = ge.lh * hw, w4 = ge.lh * ge.lw;
+          const long long ws = qs, hs = (long long)p.W_in * qs, o1 = ib + ge.h_low * hs + ge.w_low * ws;
+          for (int c = lane; c < p.gc; c += 32) {
+            const float tg = go[c], tgi = tg * weight;
+            float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, dh = 0.f, dw = 0.f;
+            if (ge.mask & 2) { v1 = in[o1 + c]; dh -= hw * v1; dw -= hh * v1; atomicAdd(gin + o1 + c, w1 * tgi); }
+            if (ge.mask & 4) { v2 = in[o1 + ws + c]; dh -= ge.lw * v2; dw += hh * v2; atomicAdd(gin + o1 + ws + c, w2 * tgi); }
+            if (ge.mask & 8) { v3 = in[o1 + hs + c]; dh += hw * v3; dw -= ge.lh * v3; atomicAdd(gin + o1 + hs + c, w3 * tgi); }
+            if (ge.mask & 16) { v4 = in[o1 + hs + ws + c]; dh += ge.lw * v4; dw += ge.lh * v4; atomicAdd(gin + o1 + hs + ws + c, w4 * tgi); }
+            ga += tg * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+            gw += p.offset_scale * dw * tgi;
+            gh += p.offset_scale * dh * tgi;
+          }
+        }
+        ga = warp_sum(ga); gw = warp_sum(gw); gh = warp_sum(gh);
+        if (lane == 0) { gmsk[wp] = ga; goff[2 * wp] = gw; goff[2 * wp + 1] = gh; }
+      }
+  }
+}
+
 }  // namespace
 
 extern "C" int vllm_dcnv3_forward_f32(const float* input, const float* offset, const float* mask, float* out, int N,
@@ -208,6 +255,29 @@ extern "C" int vllm_dcnv3_forward_f32(const float* input, const float* offset, c
   const long long cap = (long long)vllm_num_sms() * 32;
   if (blocks > cap) blocks = cap;
   dcnv3_fwd_strict_kernel<<<(unsigned)blocks, 256, 0, st>>>(n, input, offset, mask, out, p);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+extern "C" int vllm_dcnv3_backward_f32(const float* input, const float* offset, const float* mask,
+                                       const float* grad_output, float* grad_input, float* grad_offset,
+                                       float* grad_mask, int N, int H_in, int W_in, int H_out, int W_out, int group,
+                                       int group_channels, int kernel_h, int kernel_w, int stride_h, int stride_w,
+                                       int pad_h, int pad_w, int dilation_h, int dilation_w, float offset_scale,
+                                       void* stream) {
+  if (N < 0 || H_in <= 0 || W_in <= 0 || H_out < 0 || W_out < 0 || group <= 0 || group_channels <= 0 ||
+      kernel_h <= 0 || kernel_w <= 0 || stride_h <= 0 || stride_w <= 0 || dilation_h <= 0 || dilation_w <= 0)
+    return VLLM_EINVAL;
+  const long long n_pg = (long long)N * H_out * W_out * group;
+  if (n_pg == 0) return VLLM_OK;
+  if (!input || !offset || !mask || !grad_output || !grad_input || !grad_offset || !grad_mask) return VLLM_EINVAL;
+  DcnParams p{kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+              group, group_channels, H_in, W_in, H_out, W_out, offset_scale};
+  long long blocks = (n_pg + 7) / 8;
+  const long long cap = (long long)vllm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dcnv3_bwd_warp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n_pg, input, offset, mask, grad_output,
+                                                                            grad_input, grad_offset, grad_mask, p);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
 }
