@@ -1,0 +1,105 @@
+"""GPU: achieved bandwidth / throughput of the secondary kernels (DCNv3 fwd/bwd, MSDA bwd, GroupNorm, the GDINO and
+Swin attention shapes) against the measured peaks in MEASURED_PEAKS.json.  CUDA events, 3 warm-ups, L2 flushed between
+iterations by rotating over input sets larger than L2 where the tensors are small.  -> gpurun_out/op_bench.json"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from visionllm_b200 import dcnv3 as dcn, msda, ops  # noqa: E402
+
+PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+res = {}
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+
+def timeit(fn, iters=5):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def rec(name, ms, bytes_=None, flops=None, note=""):
+    r = {"ms": ms, "note": note}
+    if bytes_:
+        r["gbps"] = bytes_ / ms / 1e6
+        r["hbm_frac"] = r["gbps"] / PEAKS["hbm_gbs"]
+    if flops:
+        r["tflops"] = flops / ms / 1e9
+        r["tensor_frac"] = r["tflops"] / PEAKS["bf16_tflops"]
+    res[name] = r
+    print(name, {k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}, flush=True)
+
+
+g = torch.Generator(device="cuda").manual_seed(0)
+# ---- DCNv3, InternImage-H stage shapes (group_channels 32): stage1 320ch @ 1/4, stage3 1280ch @ 1/16 of 1024^2 ----
+for name, (N, Hh, W, G) in {"dcnv3_s1_8x256x256x320": (8, 256, 256, 10), "dcnv3_s3_8x64x64x1280": (8, 64, 64, 40)}.items():
+    C, K = 32, 9
+    x = torch.randn(N, Hh, W, G * C, device="cuda", generator=g)
+    off = (torch.rand(N, Hh, W, G * K * 2, device="cuda", generator=g) - 0.5) * 4
+    m = torch.softmax(torch.randn(N, Hh, W, G, K, device="cuda", generator=g), -1).reshape(N, Hh, W, G * K).contiguous()
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, C, 1.0)
+    alg = (x.numel() * 2 + off.numel() + m.numel()) * 4
+    rec(name + "_fwd", timeit(lambda: dcn.dcnv3_forward(x, off, m, *args, 256)), alg, note="in + offset + mask read, out written (fp32)")
+    rec(name + "_fwd_strict", timeit(lambda: dcn.dcnv3_forward(x, off, m, *args, 256, flags=1)), alg, note="reference thread mapping")
+    go = torch.randn_like(x)
+    algb = (x.numel() * 3 + off.numel() * 2 + m.numel() * 2) * 4
+    rec(name + "_bwd", timeit(lambda: dcn.dcnv3_backward(x, off, m, *args, go, 256)), algb,
+        note="in, grad_out, offset, mask read; grad_in, grad_offset, grad_mask written (incl. zero fill)")
+
+# ---- MSDA backward at the GDINO encoder shape (2 images) ----
+shapes_l = [(128, 128), (64, 64), (32, 32), (16, 16)]
+shapes = torch.tensor(shapes_l, dtype=torch.int64, device="cuda")
+lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+S = int(shapes.prod(1).sum())
+N, M, D, L, P = 2, 8, 32, 4, 4
+val = torch.randn(N, S, M, D, device="cuda", generator=g)
+loc = torch.rand(N, S, M, L, P, 2, device="cuda", generator=g)
+aw = torch.softmax(torch.randn(N, S, M, L * P, device="cuda", generator=g), -1).view(N, S, M, L, P).contiguous()
+gout = torch.randn(N, S, M * D, device="cuda", generator=g)
+algb = (val.numel() * 2 + gout.numel() + loc.numel() * 2 + aw.numel() * 2) * 4
+rec("msda_bwd_enc_2img", timeit(lambda: msda.ms_deform_attn_backward(val, shapes, lsi, loc, aw, gout, 64)), algb,
+    note="value, grad_out, loc, weights read; grad_value (atomics), grad_loc, grad_weights written")
+rec("msda_fwd_enc_2img", timeit(lambda: msda.ms_deform_attn_forward(val, shapes, lsi, loc, aw, 64)),
+    (val.numel() + loc.numel() + aw.numel() + gout.numel()) * 4)
+
+# ---- GroupNorm(32) over channels-last rows ----
+for name, (N, HW) in {"groupnorm_8x65536x256": (8, 65536), "groupnorm_8x16384x256": (8, 16384)}.items():
+    x = torch.randn(N, HW, 256, device="cuda", generator=g).bfloat16()
+    w = torch.ones(256, device="cuda").bfloat16(); b = torch.zeros(256, device="cuda").bfloat16()
+    rec(name, timeit(lambda: ops.groupnorm_nhwc(x, w, b, 32, 1e-5)), x.numel() * 6.0, note="read (stats) + read + write, bf16")
+
+# ---- attention shapes of the GDINO stage and Swin-T @1024^2 ----
+def attn(name, B, Tq, Tk, H, D, bias_nb=0, key_mask=False):
+    q = torch.randn(B, Tq, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Tk, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Tk, H, D, device="cuda", generator=g).bfloat16()
+    kw = {}
+    if bias_nb:
+        kw["attn_bias"] = torch.randn(bias_nb, H, Tq, Tk, device="cuda", generator=g)
+    if key_mask:
+        kw["key_mask"] = torch.ones(B, Tk, dtype=torch.bool, device="cuda")
+    fl = 4.0 * B * H * Tq * Tk * D
+    by = 2.0 * B * H * D * (2 * Tq + 2 * Tk)
+    rec(name, timeit(lambda: ops.attention(q, k, v, **kw)), by, fl)
+
+
+attn("attn_gdino_vision_to_text_8x21760x80_h4d256", 8, 21760, 80, 4, 256, key_mask=True)
+attn("attn_gdino_text_to_vision_8x80x21760_h4d256", 8, 80, 21760, 4, 256, key_mask=True)
+attn("attn_gdino_dec_self_8x100x100_h8d32", 8, 100, 100, 8, 32)
+attn("attn_swin_s1_10952win_49_h3d32", 8 * 1369, 49, 49, 3, 32, bias_nb=1369)
+attn("attn_swin_s2_2888win_49_h6d32", 8 * 361, 49, 49, 6, 32, bias_nb=361)
+attn("attn_swin_s3_800win_49_h12d32", 8 * 100, 49, 49, 12, 32, bias_nb=100)
+
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump({"peaks": {k: PEAKS[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained")}, "results": res},
+          open("gpurun_out/op_bench.json", "w"), indent=1)
