@@ -145,3 +145,20 @@ def test_groupnorm_rejects_bad_arguments():
         ops.groupnorm_nhwc(x, w, w, 12, 1e-5)            # 4 channels per group: not a multiple of 8
     with pytest.raises(RuntimeError):
         ops.groupnorm_nhwc(x.float(), w, w, 2, 1e-5)
+
+
+def test_cuda_graph_replay_matches_eager(stage):
+    """visionllm_b200.graphs.GraphedForward: the whole stage captured into one CUDA graph (no host sync inside the
+    forward) replays to exactly the eager result, also after the inputs change."""
+    from visionllm_b200.graphs import GraphedForward
+    m, g = stage
+    x, pm, tq, tm = _inputs(g)
+    gf = GraphedForward(lambda a, b, c, d: m.forward_test(a, pixel_mask=b, text_query=c, text_query_masks=d))
+    for trial in range(3):
+        xi = x if trial == 0 else (x * (1.0 + 0.25 * trial)).contiguous()
+        eager = m.forward_test(xi, pixel_mask=pm, text_query=tq, text_query_masks=tm)
+        e = [t.clone() for t in (eager.logits, eager.pred_boxes, eager.pred_masks)]
+        o = gf(xi, pm, tq, tm)
+        for a, b in zip(e, (o.logits, o.pred_boxes, o.pred_masks)):
+            assert torch.equal(a, b)
+    assert gf.launches_per_replay > 50 and len(gf._cache) == 1

@@ -89,3 +89,9 @@ def check(rc, what):
 
 def launch_count():
     return _launches
+
+
+def add_launches(n):
+    """Account for launches replayed from a captured CUDA graph (visionllm_b200.graphs)."""
+    global _launches
+    _launches += int(n)

@@ -80,7 +80,7 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
             hidden_states = hidden_states + position_embeddings
         B, Lq, _ = hidden_states.shape
         _, S, _ = encoder_hidden_states.shape
-        if (spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum() != S:
+        if sum(h * w for h, w in msda_ext.host_shape_list(spatial_shapes)) != S:      # host copy if attached: no sync
             raise ValueError("Make sure to align the spatial shapes with the sequence length of the encoder "
                              "hidden states")
         M, L, P, D = self.n_heads, self.n_levels, self.n_points, self.d_model // self.n_heads

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import msda, ops
 
 
 class GroundingDinoMLPPredictionHead(nn.Module):
@@ -68,7 +68,7 @@ def gen_encoder_output_proposals(enc_output_linear, enc_output_norm, enc_output,
     B = enc_output.shape[0]
     dev = enc_output.device
     proposals, pos = [], 0
-    for level, (H, W) in enumerate([(int(h), int(w)) for h, w in spatial_shapes.tolist()]):
+    for level, (H, W) in enumerate(msda.host_shape_list(spatial_shapes)):
         m = padding_mask[:, pos:pos + H * W].view(B, H, W)
         valid_h = (~m[:, :, 0]).sum(1)
         valid_w = (~m[:, 0, :]).sum(1)

@@ -27,7 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import gdino_heads as H
-from . import ops
+from . import msda, ops
 from .gdino import GroundingDinoDecoderLayer, GroundingDinoEncoderLayer
 
 
@@ -138,7 +138,7 @@ class _Encoder(nn.Module):
     def get_reference_points(spatial_shapes, valid_ratios, device):
         """gd.py:1577-1605."""
         refs = []
-        for level, (height, width) in enumerate(spatial_shapes.tolist()):
+        for level, (height, width) in enumerate(msda.host_shape_list(spatial_shapes)):
             ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, height - 0.5, height, dtype=torch.float32, device=device),
                                           torch.linspace(0.5, width - 0.5, width, dtype=torch.float32, device=device),
                                           indexing="ij")
@@ -221,6 +221,7 @@ class B200GroundingDinoModel(nn.Module):
             raise NotImplementedError("two_stage_bbox_embed_share")
         self.encoder_output_bbox_embed = H.GroundingDinoMLPPredictionHead(d, d, 4, 3)
         self.encoder_output_class_embed = H.GroundingDinoContrastiveEmbedding(config)
+        self._shape_cache = {}
 
     @staticmethod
     def get_valid_ratio(mask):
@@ -236,6 +237,16 @@ class B200GroundingDinoModel(nn.Module):
         out = self.backbone.conv_encoder.model(pixel_values)
         maps = out.feature_maps if hasattr(out, "feature_maps") else out
         return [m if getattr(m, "_b200_nhwc", False) else m.permute(0, 2, 3, 1).contiguous() for m in maps]
+
+    def _shape_tensors(self, shapes, device):
+        """int64 `spatial_shapes` [L, 2] and `level_start_index` [L] (exclusive cumsum, gd.py:2434-2437); built once
+        per pyramid (a host->device copy) with the host list attached, so a forward has no sync."""
+        key = (shapes, str(device))
+        if key not in self._shape_cache:
+            ss = msda.attach_host_shapes(torch.as_tensor(shapes, dtype=torch.long, device=device), shapes)
+            lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+            self._shape_cache[key] = (ss, lsi)
+        return self._shape_cache[key]
 
     @torch.no_grad()
     def neck(self, feats, pixel_mask):
@@ -264,8 +275,7 @@ class B200GroundingDinoModel(nn.Module):
         source_flatten = torch.cat(sources, 1)
         mask_flatten = torch.cat([m.flatten(1) for m in masks], 1)
         lvl_pos_embed_flatten = torch.cat(poss, 1)
-        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=source_flatten.device)
-        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        spatial_shapes, level_start_index = self._shape_tensors(tuple(shapes), source_flatten.device)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1).float()
         return source_flatten, mask_flatten, lvl_pos_embed_flatten, spatial_shapes, level_start_index, valid_ratios
 
@@ -273,7 +283,7 @@ class B200GroundingDinoModel(nn.Module):
     def build_mask_features(self, feats, enc_vision, spatial_shapes):
         """gd.py:2470-2497 for num_fpn_levels == 1: returns (rows [B, H*W, mask_dim], H, W)."""
         B = enc_vision.shape[0]
-        H0, W0 = (int(v) for v in spatial_shapes[0].tolist())
+        H0, W0 = msda.host_shape_list(spatial_shapes)[0]
         top = enc_vision[:, :H0 * W0].reshape(B, H0, W0, -1)                              # level-0 slab, channels-last
         for idx in range(self.num_fpn_levels):
             cur, Hc, Wc = self.lateral_convs[idx].rows(feats[idx])

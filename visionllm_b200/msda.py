@@ -29,8 +29,25 @@ STRICT = 1
 _shape_cache = {}
 
 
+def attach_host_shapes(spatial_shapes, shapes_list):
+    """Remember the python-side (H, W) list a device `spatial_shapes` tensor was built from, so that later consumers
+    (tiling hint here, reference points / proposals in the GDINO stage) never read it back from the device -- a
+    device->host copy is a sync and is illegal during CUDA-graph capture."""
+    spatial_shapes._b200_host = torch.tensor([[int(h), int(w)] for h, w in shapes_list], dtype=torch.int64)
+    return spatial_shapes
+
+
+def host_shape_list(spatial_shapes):
+    """[(H, W), ...] of a spatial_shapes tensor: the attached host copy if there is one, else a device read."""
+    hs = getattr(spatial_shapes, "_b200_host", None)
+    return [(int(h), int(w)) for h, w in (hs if hs is not None else spatial_shapes).tolist()]
+
+
 def _host_shapes(spatial_shapes):
     """Cached host copy of the (tiny) spatial_shapes tensor: work-ordering hint only."""
+    hs = getattr(spatial_shapes, "_b200_host", None)
+    if hs is not None:
+        return hs
     key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.device.index)
     hit = _shape_cache.get(key)
     if hit is None:
