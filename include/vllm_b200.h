@@ -128,6 +128,17 @@ int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int 
                    const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
                    void* stream);
 /* Tuning knob (process-global): 0 = auto (default), 1 = cta_group::1 tiles 128x256, 2 = CTA-pair tiles 256x256. */
+/* Stride-1 KxK convolution over a zero-padded channels-last map as ONE implicit GEMM (no im2col buffer): the 3x3
+ * `output_convs` of the Grounding-DINO mask-feature FPN (modeling_ov_grounding_dino_mask_dn.py:2136-2146, :2476).
+ * xpad: [pad_pixels, channels] bf16 = the padded images flattened (image rows of `padded_width` pixels, images back
+ * to back); weight [out_channels, kernel_h*kernel_w*channels] in (dy, dx, c) order, pitch ldw.  Row i of `out`
+ * ([pad_pixels, out_channels], pitch ldo) is the window whose TOP-LEFT tap is padded pixel i; the caller keeps the rows
+ * whose window lies inside one image.  The A tensor map has row pitch `channels` and row length kernel_w*channels
+ * (rows overlap), and the K loop walks kernel_h row segments shifted by `padded_width` rows.
+ * Needs kernel_w*channels % 64 == 0.  act: 0 none, 1 gelu, 2 relu, 3 silu, 5 quick-gelu. */
+int vllm_conv_rows_bf16(const void* xpad, long long pad_pixels, int channels, int padded_width, int kernel_h,
+                        int kernel_w, const void* weight, int ldw, void* out, int ldo, int out_channels,
+                        const void* bias, int act, void* stream);
 int vllm_gemm_set_variant(int variant);
 /* Tuning knob: force the tile-rasterisation group size (row-blocks per group); 0 = heuristic. */
 int vllm_gemm_set_group_m(int group_m);

@@ -53,7 +53,14 @@ def gn_kernel(monkeypatch, torch_kernels):  # noqa: F811
         y = F.group_norm(x.float().transpose(1, 2), groups, w.float(), b.float(), eps).transpose(1, 2)
         return torch.relu(y) if relu else y
 
+    def conv2d_s1_rows(x, w_rows, bias, kernel, padding, act=None):
+        Cout, C = w_rows.shape[0], x.shape[-1]
+        w = w_rows.float().view(Cout, kernel, kernel, C).permute(0, 3, 1, 2)
+        y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None if bias is None else bias.float(), padding=padding)
+        return y.permute(0, 2, 3, 1)
+
     monkeypatch.setattr(ops, "groupnorm_nhwc", groupnorm_nhwc)
+    monkeypatch.setattr(ops, "conv2d_s1_rows", conv2d_s1_rows)
 
 
 @pytest.mark.parametrize("ragged,b200_backbone", [(False, False), (True, False), (True, True)])

@@ -162,3 +162,19 @@ def test_cuda_graph_replay_matches_eager(stage):
         for a, b in zip(e, (o.logits, o.pred_boxes, o.pred_masks)):
             assert torch.equal(a, b)
     assert gf.launches_per_replay > 50 and len(gf._cache) == 1
+
+
+@pytest.mark.parametrize("B,Hh,W,C,Cout,k,p", [(2, 24, 32, 256, 256, 3, 1), (1, 7, 5, 64, 72, 3, 1), (3, 16, 16, 128, 256, 3, 0),
+                                               (1, 256, 256, 256, 256, 3, 1), (2, 9, 11, 64, 32, 5, 2)])
+def test_implicit_gemm_conv_vs_torch(B, Hh, W, C, Cout, k, p):
+    """vllm_conv_rows_bf16 (overlapping-row TMA map over the zero-padded map, K walked in kernel_h shifted segments)
+    vs F.conv2d in fp32 on the same bf16 values: one bf16 output rounding."""
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + Hh)
+    x = torch.randn(B, Hh, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, C, k, k, device="cuda", generator=g) / (C * k * k) ** 0.5).bfloat16()
+    b = torch.randn(Cout, device="cuda", generator=g).bfloat16()
+    y = ops.conv2d_s1_rows(x, w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), b, k, p, act="relu")
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=p).relu().permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert ((y.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 2e-3).all(), (y.float() - ref).abs().max().item()

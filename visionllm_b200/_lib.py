@@ -33,6 +33,7 @@ _SIGNATURES = {
     "vllm_dcnv3_forward_f32": (ci, [vp, vp, vp, vp] + [ci] * 15 + [cf, ci, vp]),
     "vllm_dcnv3_backward_f32": (ci, [vp] * 7 + [ci] * 15 + [cf, vp]),
     "vllm_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp]),
+    "vllm_conv_rows_bf16": (ci, [vp, cll, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp, ci, vp]),
     "vllm_gemm_set_variant": (ci, [ci]),
     "vllm_gemm_set_group_m": (ci, [ci]),
     "vllm_rmsnorm_bf16": (ci, [vp, cll, vp, vp, cll, cll, ci, cf, vp]),

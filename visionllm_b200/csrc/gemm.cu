@@ -39,6 +39,10 @@ struct GemmArgs {
   int act; int out_f32;
   int tiles_m, tiles_n;  // tiles_m counts 128*CG-row blocks
   int group_m;           // row-blocks per rasterisation group (see pick_group_m)
+  // Implicit convolution over a zero-padded channels-last image (vllm_conv_rows_bf16): the K axis is a_segs segments
+  // of a_seg_kb k-blocks; segment s reads A rows shifted by s * a_seg_rows (one image row of the padded map), and a
+  // row of the A tensor map spans kw consecutive pixels (row pitch = C elements, row length = kw*C: rows overlap).
+  int a_seg_kb, a_seg_rows;
 };
 
 template <int CG> struct Cfg {
@@ -116,13 +120,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C_::STAGE_BYTES, sb = sa + A_BYTES;
+          int ka = kb * BK, ra = row_a;
+          if (g.a_seg_kb) {
+            const int seg = kb / g.a_seg_kb;
+            ka = (kb - seg * g.a_seg_kb) * BK;
+            ra = row_a + seg * g.a_seg_rows;
+          }
           if constexpr (CG == 1) {
             tc::mbar_arrive_expect_tx(full_bar(stage), C_::STAGE_BYTES);
-            tc::tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, row_a);
+            tc::tma_load_2d(sa, &tmap_a, full_bar(stage), ka, ra);
             tc::tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, row_b);
           } else {
             if (leader) tc::mbar_arrive_expect_tx(full_bar(stage), 2 * C_::STAGE_BYTES);
-            tc::tma_load_2d_cg2(sa, &tmap_a, full_bar(stage), kb * BK, row_a);
+            tc::tma_load_2d_cg2(sa, &tmap_a, full_bar(stage), ka, ra);
             tc::tma_load_2d_cg2(sb, &tmap_b, full_bar(stage), kb * BK, row_b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -404,10 +414,12 @@ int pick_group_m(int, int, long long) { return g_group_m_override > 0 ? g_group_
 int g_gemm_variant = 0;
 
 template <int CG>
-int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cudaStream_t st) {
+int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cudaStream_t st, long long a_rows = -1,
+                int a_cols = -1) {
   using C_ = Cfg<CG>;
   CUtensorMap ta, tb;
-  int rc = vllm_make_tmap_bf16(&ta, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)lda, BM);
+  int rc = vllm_make_tmap_bf16(&ta, A, (uint64_t)(a_rows < 0 ? g.M : a_rows), (uint64_t)(a_cols < 0 ? g.K : a_cols),
+                               (uint64_t)lda, BM);
   if (rc) return rc;
   rc = vllm_make_tmap_bf16(&tb, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, C_::B_ROWS);
   if (rc) return rc;
@@ -469,6 +481,33 @@ int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int 
   const int cg = g_gemm_variant ? g_gemm_variant : (K <= 512 ? 1 : 2);
   if (cg == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);
   return launch_gemm<1>(A, lda, B, ldb, g, st);
+}
+
+int vllm_conv_rows_bf16(const void* xpad, long long pad_pixels, int channels, int padded_width, int kernel_h,
+                        int kernel_w, const void* weight, int ldw, void* out, int ldo, int out_channels,
+                        const void* bias, int act, void* stream) {
+  // out[i, :] = epi(sum_{dy,dx} xpad[i + dy*padded_width + dx, :] . weight[:, (dy*kw + dx)*C : +C]^T) for every flat
+  // pixel i of the padded map; rows whose window crosses an image edge are don't-care and sliced away by the caller.
+  if (pad_pixels < 0 || channels <= 0 || padded_width <= 0 || kernel_h <= 0 || kernel_w <= 0 || out_channels <= 0)
+    return VLLM_EINVAL;
+  if (pad_pixels == 0) return VLLM_OK;
+  if (!xpad || !weight || !out) return VLLM_EINVAL;
+  if (act < 0 || act > ACT_QUICKGELU || act == ACT_SWIGLU) return VLLM_EINVAL;
+  const long long seg_k = (long long)kernel_w * channels;
+  // a segment must be whole k-blocks so that A's and B's K coordinates stay aligned; 16-byte row pitches
+  if (seg_k % BK || channels % 8 || ldw % 8 || ldo % 8 || ldw < seg_k * kernel_h || ldo < out_channels) return VLLM_EUNSUPPORTED;
+  if (pad_pixels > 2147483647LL - 4096 || seg_k * kernel_h > 2147483647LL) return VLLM_EUNSUPPORTED;
+  if (!vllm_aligned(xpad, 16) || !vllm_aligned(weight, 16) || !vllm_aligned(out, 16)) return VLLM_EALIGN;
+  const long long a_rows = pad_pixels - (kernel_w - 1);      // last rows whose kw-pixel span stays inside the buffer
+  if (a_rows <= 0) return VLLM_EINVAL;
+  GemmArgs g{};
+  g.M = (int)pad_pixels; g.N = out_channels; g.K = (int)(seg_k * kernel_h); g.C = out; g.ldc = ldo;
+  g.bias = (const __nv_bfloat16*)bias; g.act = act;
+  g.a_seg_kb = (int)(seg_k / BK); g.a_seg_rows = padded_width;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cg = g_gemm_variant ? g_gemm_variant : (g.K <= 512 ? 1 : 2);
+  if (cg == 2) return launch_gemm<2>(xpad, channels, weight, ldw, g, st, a_rows, (int)seg_k);
+  return launch_gemm<1>(xpad, channels, weight, ldw, g, st, a_rows, (int)seg_k);
 }
 
 }  // extern "C"

@@ -85,6 +85,11 @@ def conv_rows(x, conv):
     s, p = conv.stride[0], conv.padding[0]
     if (kh, kw, s, p) == (1, 1, 1, 0):
         rows, Ho, Wo = x.reshape(B, Hh * W, C), Hh, W
+    elif s == 1 and kh == kw and (kw * C) % 64 == 0 and conv.padding[0] == conv.padding[1]:
+        # implicit GEMM over the zero-padded map: no [B*Ho*Wo, kh*kw*C] im2col buffer
+        w = conv.weight.permute(0, 2, 3, 1).reshape(conv.out_channels, -1).contiguous()
+        y = ops.conv2d_s1_rows(x, w, conv.bias, kh, p)
+        return y.reshape(B, y.shape[1] * y.shape[2], conv.out_channels), y.shape[1], y.shape[2]
     else:
         Ho, Wo = (Hh + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
         xp = F.pad(x, (0, 0, p, p, p, p))

@@ -92,6 +92,33 @@ def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dty
     return out.reshape(*lead, n_out)
 
 
+def conv2d_s1_rows(x, weight_rows, bias, kernel, padding, act=None):
+    """Stride-1 KxK convolution of a channels-last map x [B, H, W, C] (bf16) with `weight_rows` [Cout, K*K*C] in
+    (dy, dx, c) order -> [B, Ho, Wo, Cout] (a strided view of the kernel's padded-grid output).  One zero-pad copy of x,
+    then ONE implicit-GEMM launch (vllm_conv_rows_bf16) -- no im2col buffer (9x the activation for a 3x3)."""
+    if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_cuda:
+        raise RuntimeError("conv2d_s1_rows: x must be a CUDA bf16 [B, H, W, C] tensor")
+    B, Hh, W, C = x.shape
+    k, p = int(kernel), int(padding)
+    _bf16_2d(weight_rows, "weight_rows")
+    if weight_rows.shape[1] != k * k * C:
+        raise RuntimeError("conv2d_s1_rows: weight_rows must be [Cout, K*K*C]")
+    Cout = weight_rows.shape[0]
+    if bias is not None and (bias.dtype != torch.bfloat16 or bias.numel() != Cout or not bias.is_contiguous()):
+        raise RuntimeError("conv2d_s1_rows: bias must be contiguous bf16 [Cout]")
+    Hp, Wp = Hh + 2 * p, W + 2 * p
+    Ho, Wo = Hp - k + 1, Wp - k + 1
+    xp = torch.nn.functional.pad(x, (0, 0, p, p, p, p)) if p else x.contiguous()
+    out = torch.empty((B, Hp, Wp, Cout), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device), _Prof("gemm", 2.0 * B * Hp * Wp * Cout * k * k * C,
+                                            2.0 * (B * Hp * Wp * (C + Cout) + Cout * k * k * C)):
+        rc = _lib.lib().vllm_conv_rows_bf16(xp.data_ptr(), B * Hp * Wp, C, Wp, k, k, weight_rows.data_ptr(),
+                                            weight_rows.stride(0), out.data_ptr(), Cout, Cout,
+                                            bias.data_ptr() if bias is not None else None, ACT[act], _stream())
+    _lib.check(rc, "vllm_conv_rows_bf16")
+    return out[:, :Ho, :Wo]
+
+
 def _rows(x, name):
     if x.dtype != torch.bfloat16 or not x.is_cuda or x.stride(-1) != 1:
         raise RuntimeError(f"{name} must be CUDA bf16 with unit inner stride")
