@@ -127,6 +127,41 @@ class MsdaEncoderWorkload:
         return {}
 
 
+class MsdaEncoderBf16Workload(MsdaEncoderWorkload):
+    """cfg 2b "fast mode": value in bf16 (what the module's value_proj GEMM produces), sampling_loc / attn_weight fp32,
+    fp32 accumulation, bf16 output -- `ms_deform_attn_forward_bf16`."""
+    metric = "msda_encoder_layer_images_per_sec_bf16_value"
+    dtype = "bf16 value/out, f32 locations, weights and accumulation"
+
+    def setup(self):
+        super().setup()
+        torch = self.torch
+        self.value = self.value.bfloat16()
+        self.h_in = [t.cpu().pin_memory() for t in (self.value, self.loc, self.attw)]
+        self.d_in = [torch.empty_like(t) for t in (self.value, self.loc, self.attw)]
+        S = self.value.shape[1]
+        self.h_out = torch.empty((self.N, S, 256), dtype=torch.bfloat16).pin_memory()
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.h_in)
+        self.d2h_bytes = self.h_out.numel() * 2
+        self.alg_bytes_per_image = (self.value[0].numel() * 2 + self.loc[0].numel() * 4 + self.attw[0].numel() * 4
+                                    + S * 256 * 2)
+
+    def step_device(self):
+        self.out = self.ext.ms_deform_attn_forward_bf16(self.value, self.shapes, self.lsi, self.loc, self.attw)
+
+    def step_e2e(self):
+        for d, h in zip(self.d_in, self.h_in):
+            d.copy_(h, non_blocking=True)
+        out = self.ext.ms_deform_attn_forward_bf16(self.d_in[0], self.shapes, self.lsi, self.d_in[1], self.d_in[2])
+        self.h_out.copy_(out, non_blocking=True)
+
+    def config(self):
+        c = super().config()
+        c["workload"] = "msda_fwd encoder shape (BASELINE cfg 2b, fast mode): N=8 S=Lq=21760 M=8 D=32 L=4 P=4, bf16 value/out"
+        c["l2_policy"] = "inputs_exceed_l2 (446 MB per step > 126 MB L2)"
+        return c
+
+
 def anyres_tiles_1024(torch, n_pairs, device, seed, tile=448, dtype=None):
     """What the reference's data pipeline hands to forward() for a 1024x1024 image under 'anyres'
     (mm_utils.py:39-75: image_size 448, max 6 tiles -> (2,2) grid + thumbnail = 5 tiles): a list of
@@ -338,8 +373,9 @@ class GdinoHeadWorkload:
         torch = self.torch
         torch.cuda.synchronize()
         ops.PROFILE = []
-        orig = msda_mod.ms_deform_attn_forward
+        orig, orig16 = msda_mod.ms_deform_attn_forward, msda_mod.ms_deform_attn_forward_bf16
         msda_ms = []
+        self.msda_value_bytes = 4
 
         def timed_msda(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -347,13 +383,22 @@ class GdinoHeadWorkload:
             msda_ms.append((e0, e1, a[0].shape, a[3].shape))
             return r
 
+        def timed_msda16(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig16(*a, **k); e1.record()
+            msda_ms.append((e0, e1, a[0].shape, a[3].shape))
+            self.msda_value_bytes = 2
+            return r
+
         import visionllm_b200.gdino as gd_mod
         gd_mod.msda_ext.ms_deform_attn_forward = timed_msda
+        gd_mod.msda_ext.ms_deform_attn_forward_bf16 = timed_msda16
         try:
             self.step_device()
             torch.cuda.synchronize()
         finally:
             gd_mod.msda_ext.ms_deform_attn_forward = orig
+            gd_mod.msda_ext.ms_deform_attn_forward_bf16 = orig16
         prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
         for name, fl, by, e0, e1 in prof:
@@ -370,7 +415,8 @@ class GdinoHeadWorkload:
 
     def roofline(self, kern_ms, peaks):
         S = self.src.shape[1]
-        alg = (S * 256 + S * 8 * 16 * 2 + S * 8 * 16 + S * 256) * 4 * self.N
+        vb = getattr(self, "msda_value_bytes", 4)            # bf16 value + bf16 out when the module takes the fast mode
+        alg = (S * 256 * vb + (S * 8 * 16 * 2 + S * 8 * 16) * 4 + S * 256 * vb) * self.N
         ach = alg / (kern_ms * 1e-3) / 1e9
         return {"kernel": "msda_fwd_warp_kernel (encoder launches inside the GDINO step)", "bound": "hbm",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
@@ -521,7 +567,7 @@ class PairForwardGdinoWorkload(PairForwardWorkload):
         return c
 
 
-WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
+WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "msda_encoder_bf16": MsdaEncoderBf16Workload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
              "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
@@ -593,7 +639,7 @@ def _cpu_pair_forward(steps, warmup):
             "ms_per_step": pair_s * 1e3}
 
 
-_CPU = {"msda_encoder": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
+_CPU = {"msda_encoder": _cpu_msda_encoder, "msda_encoder_bf16": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
         "gdino_stage": _cpu_msda_encoder,
         "pair_forward_gdino": _cpu_pair_forward}
 

@@ -53,6 +53,15 @@ int vllm_msda_forward_f32(const float* value, const int64_t* spatial_shapes, con
                           int num_point, const int64_t* host_shapes_hint, int flags, void* stream);
 /* fp64 instance of the same operator (AT_DISPATCH_FLOATING_TYPES,
  * ms_deform_attn_cuda.cu:258); always the strict kernel. */
+/* "Fast mode" of the same operator (SURVEY 8d cfg 2b): value is bf16 [N,S,M,32] -- the bf16 value_proj output the
+ * reference upcasts with .float() before calling its fp32-only kernel (modeling_ov_grounding_dino_mask_dn.py:764-766)
+ * -- sampling_loc / attn_weight stay fp32, accumulation is fp32, out is fp32 or bf16 (out_bf16) [N,Lq,M*32].  Results
+ * equal vllm_msda_forward_f32 on the upcast value (bf16 -> fp32 is exact).  channels == 32, levels*points <= 32,
+ * else VLLM_EUNSUPPORTED. */
+int vllm_msda_forward_bf16v(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                            const float* sampling_loc, const float* attn_weight, void* out, int out_bf16, int batch,
+                            int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                            int num_point, const int64_t* host_shapes_hint, void* stream);
 int vllm_msda_forward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                           const double* sampling_loc, const double* attn_weight, double* out, int batch,
                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,

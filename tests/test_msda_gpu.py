@@ -237,3 +237,48 @@ def test_full_size_linearity_in_value():
     b = ext.ms_deform_attn_forward(v2, shapes, lsi, loc, attw, 64)
     c = ext.ms_deform_attn_forward(value * 2 + v2, shapes, lsi, loc, attw, 64)
     assert (c - (2 * a + b)).abs().max().item() < 1e-4
+
+
+# ---- "fast mode" (SURVEY 8d cfg 2b): bf16 value read in place ----
+@pytest.mark.parametrize("case", ["enc", "dec", "oob", "odd_points"])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_bf16_value_matches_fp32_op_on_upcast_value(case, out_dtype):
+    """ms_deform_attn_forward_bf16(value_bf16) == ms_deform_attn_forward(value_bf16.float()) (exact upcast inside the
+    kernel, same fp32 FMAs up to summation order) and vs the C oracle on the upcast value."""
+    import visionllm_b200.msda as ext
+    from oracle import msda_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(7)
+    shapes_l = [(20, 27), (10, 14), (5, 7), (3, 4)]
+    L, P = (4, 4) if case != "odd_points" else (4, 3)
+    shapes = torch.tensor(shapes_l, dtype=torch.int64, device="cuda")
+    lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N, M, D = 3, 8, 32
+    Lq = S if case != "dec" else 37
+    value = torch.randn(N, S, M, D, device="cuda", generator=g).bfloat16()
+    spread = 1.6 if case == "oob" else 1.0
+    loc = (torch.rand(N, Lq, M, L, P, 2, device="cuda", generator=g) - 0.5) * spread + 0.5
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, device="cuda", generator=g), -1).view(N, Lq, M, L, P).contiguous()
+    fast = ext.ms_deform_attn_forward_bf16(value, shapes, lsi, loc, aw, out_dtype)
+    ref = ext.ms_deform_attn_forward(value.float(), shapes, lsi, loc, aw, 64)
+    orc = torch.from_numpy(O.forward_kernel_semantics(value.float().cpu().numpy(), shapes.cpu().numpy(), lsi.cpu().numpy(),
+                                                      loc.cpu().numpy(), aw.cpu().numpy())).cuda()
+    assert fast.dtype == out_dtype and fast.shape == ref.shape
+    scale = orc.abs().max().item()
+    if out_dtype == torch.float32:
+        assert (fast - ref).abs().max().item() <= 1e-5 * scale
+        assert (fast - orc).abs().max().item() <= 1e-5 * scale
+    else:
+        assert torch.equal(fast, ref.bfloat16()) or ((fast.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-5 * scale).all()
+
+
+def test_bf16_value_rejects_unsupported():
+    import visionllm_b200.msda as ext
+    shapes = torch.tensor([[4, 4]], dtype=torch.int64, device="cuda")
+    lsi = torch.zeros(1, dtype=torch.int64, device="cuda")
+    v = torch.zeros(1, 16, 2, 16, device="cuda", dtype=torch.bfloat16)          # D = 16: not the fast-mode shape
+    loc = torch.zeros(1, 3, 2, 1, 4, 2, device="cuda"); aw = torch.zeros(1, 3, 2, 1, 4, device="cuda")
+    with pytest.raises(RuntimeError):
+        ext.ms_deform_attn_forward_bf16(v, shapes, lsi, loc, aw)
+    with pytest.raises(RuntimeError):
+        ext.ms_deform_attn_forward_bf16(v.float(), shapes, lsi, loc, aw)

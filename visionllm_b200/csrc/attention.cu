@@ -326,11 +326,24 @@ int launch(AttnArgs a, int batch, cudaStream_t st, void* workspace, long long wo
   const long long ctas = (long long)m_blocks * a.heads * batch;
   const int n_tiles = (a.Tk + BN - 1) / BN;
   if (workspace && !a.causal && ctas < 2LL * vllm_num_sms() && n_tiles >= 16) {
-    long long want = (4LL * vllm_num_sms() + ctas - 1) / ctas;
-    if (want > n_tiles / 8) want = n_tiles / 8;
-    if (want > 64) want = 64;
-    const long long need = (long long)batch * a.heads * want * a.Tq * (D + 2) * 4;
-    if (want >= 2 && need <= workspace_bytes) { a.n_splits = (int)want; a.ws = (float*)workspace; }
+    // pick the split count that minimises (waves of resident CTAs) x (key tiles per split): a count that spills a
+    // few CTAs into one more wave costs a whole extra pass (ncu: 640 CTAs on 296 slots = 2.16 waves ran as 3)
+    static int per_sm = 0;
+    if (!per_sm) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flash_fwd_kernel<D, BN>, NW * 32, SMEM) != cudaSuccess ||
+          per_sm < 1)
+        per_sm = 1;
+    }
+    const long long slots = (long long)vllm_num_sms() * per_sm;
+    long long best = 1, best_cost = (ctas + slots - 1) / slots * (n_tiles + 2);
+    const long long max_s = n_tiles / 8 < 64 ? n_tiles / 8 : 64;
+    for (long long sp = 2; sp <= max_s; ++sp) {
+      if ((long long)batch * a.heads * sp * a.Tq * (D + 2) * 4 > workspace_bytes) break;
+      const long long waves = (ctas * sp + slots - 1) / slots;
+      const long long cost = waves * ((n_tiles + sp - 1) / sp + 2);       // +2 tiles: prologue / partial write-out
+      if (cost < best_cost) { best_cost = cost; best = sp; }
+    }
+    if (best >= 2) { a.n_splits = (int)best; a.ws = (float*)workspace; }
   }
   dim3 grid((unsigned)(m_blocks * a.n_splits), a.heads, batch);
   flash_fwd_kernel<D, BN><<<grid, NW * 32, SMEM, st>>>(a);

@@ -180,9 +180,14 @@ __device__ __forceinline__ float ld_stream_f1(const float* p) {
 // by 16 B so the four corner groups of a warp hit different banks on LDS.128.
 constexpr int MSDA_META_ROW = 32 + 2;  // int2 per corner row (32 samples + pad)
 
-template <int TH, int TW, int NW, int KC, int PC, typename OutT>
+// ValT = __nv_bfloat16 ("fast mode", SURVEY 8d cfg 2b): the module's value projection is a bf16 GEMM output; reading it
+// in place halves the bytes every sample pulls through L1 (the kernel's real bound) and drops the fp32 upcast copy
+// the reference makes (modeling_ov_grounding_dino_mask_dn.py:764).  A corner row is then 64 B = 4 x 16 B, so 16 lanes
+// cover a sample and the two half-warps take the even / odd samples: half the gather instructions per (query, head).
+// Arithmetic is unchanged (bf16 -> fp32 is exact, fp32 FMAs), so results equal the fp32 kernel on the upcast value.
+template <int TH, int TW, int NW, int KC, int PC, typename OutT, typename ValT = float>
 __global__ void __launch_bounds__(NW * 32)
-msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+msda_fwd_warp_kernel(const ValT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ attw, OutT* __restrict__ out,
                      int S, int M, int L, int Lq, int P_rt, const __grid_constant__ MsdaTiling tl) {
@@ -223,9 +228,13 @@ msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict_
     return tl.q_start[lvl] + py * tl.W[lvl] + px;
   };
 
-  const int corner = lane >> 3, cq = lane & 7;
-  // per-lane base: batch, head and this lane's channel quad folded in; meta offsets are bytes
-  const char* vbl = reinterpret_cast<const char*>(value + (size_t)b * S * MD + m * D + cq * 4);
+  constexpr bool HALF = sizeof(ValT) == 2;
+  constexpr int VB = (int)sizeof(ValT);
+  // fp32: lane = (corner[4], channel quad[8]); bf16: lane = (sample parity[2], corner[4], channel octet[4])
+  const int corner = HALF ? ((lane >> 2) & 3) : (lane >> 3), cq = HALF ? (lane & 3) : (lane & 7);
+  const int sp = lane >> 4;
+  // per-lane base: batch, head and this lane's channel group folded in; meta offsets are bytes
+  const char* vbl = reinterpret_cast<const char*>(value + (size_t)b * S * MD + m * D + cq * (HALF ? 8 : 4));
   const int g1 = lane / K, s1 = lane - g1 * K;  // phase-1 role of this lane
   const int l1 = s1 / P;
 
@@ -248,12 +257,12 @@ msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict_
         clean = (ge.mask == 31);
         if (ge.mask & 1) {
           const float hh = 1.f - ge.lh, hw = 1.f - ge.lw;
-          const int base = (s_start[l1] + ge.h_low * W + ge.w_low) * MD * 4;
+          const int base = (s_start[l1] + ge.h_low * W + ge.w_low) * MD * VB;
           const float w1 = hh * hw, w2 = hh * ge.lw, w3 = ge.lh * hw, w4 = ge.lh * ge.lw;
           if (ge.mask & 2) meta[0] = make_int2(base, __float_as_int(w1 * aw));
-          if (ge.mask & 4) meta[1] = make_int2(base + MD * 4, __float_as_int(w2 * aw));
-          if (ge.mask & 8) meta[2] = make_int2(base + W * MD * 4, __float_as_int(w3 * aw));
-          if (ge.mask & 16) meta[3] = make_int2(base + (W * MD + MD) * 4, __float_as_int(w4 * aw));
+          if (ge.mask & 4) meta[1] = make_int2(base + MD * VB, __float_as_int(w2 * aw));
+          if (ge.mask & 8) meta[2] = make_int2(base + W * MD * VB, __float_as_int(w3 * aw));
+          if (ge.mask & 16) meta[3] = make_int2(base + (W * MD + MD) * VB, __float_as_int(w4 * aw));
         }
       }
 #pragma unroll
@@ -265,9 +274,57 @@ msda_fwd_warp_kernel(const float* __restrict__ value, const int64_t* __restrict_
     for (int g = 0; g < G && t0 + g < QPW; ++g) {
       const int qg = __shfl_sync(0xffffffffu, q, g * K);
       if (qg < 0) continue;  // warp-uniform
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       const int2* mp = &s_meta[warp][corner][g * K];
       const unsigned gmask = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)) << (g * K);
+      if constexpr (HALF) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        auto fma8 = [&](const uint4& raw, float w) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+            acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+          }
+        };
+        if (((dirty & gmask) == 0) && (K % 2 == 0)) {
+          const int4* mp4 = reinterpret_cast<const int4*>(mp);
+#pragma unroll (KC > 0 ? KC / 2 : 4)
+          for (int s = 0; s < K / 2; ++s) {
+            const int4 me = mp4[s];                       // samples 2s (x, y) and 2s + 1 (z, w) of this corner
+            const int off = sp ? me.z : me.x;
+            const float w = __int_as_float(sp ? me.w : me.y);
+            fma8(__ldg(reinterpret_cast<const uint4*>(vbl + (unsigned)off)), w);
+          }
+        } else {
+          for (int s = sp; s < K; s += 2) {
+            const int2 me = mp[s];
+            if (me.x >= 0) fma8(__ldg(reinterpret_cast<const uint4*>(vbl + (unsigned)me.x)), __int_as_float(me.y));
+          }
+        }
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        }
+        if (lane < 4) {
+          OutT* op = out + (((size_t)b * Lq + qg) * M + m) * D + cq * 8;
+          if constexpr (sizeof(OutT) == 4) {
+            __stcs(reinterpret_cast<float4*>(op), make_float4(acc[0], acc[1], acc[2], acc[3]));
+            __stcs(reinterpret_cast<float4*>(op) + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+          } else {
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+            *reinterpret_cast<uint4*>(op) = pk;
+          }
+        }
+        continue;
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (((dirty & gmask) == 0) && (K % 2 == 0)) {
         // fast path: every corner of every sample of this pair is in bounds
         const int4* mp4 = reinterpret_cast<const int4*>(mp);
@@ -428,8 +485,8 @@ static bool build_tiling(MsdaTiling& tl, const int64_t* host_shapes, int L, int 
   return true;
 }
 
-template <int TH, int TW, int NW, typename OutT>
-static int launch_warp(const float* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
+template <int TH, int TW, int NW, typename OutT, typename ValT = float>
+static int launch_warp(const ValT* value, const int64_t* shapes, const int64_t* lsi, const float* loc,
                        const float* attw, OutT* out, int N, int S, int M, int L, int Lq, int P,
                        const int64_t* host_shapes, cudaStream_t st) {
   MsdaTiling tl; memset(&tl, 0, sizeof(tl));
@@ -437,11 +494,11 @@ static int launch_warp(const float* value, const int64_t* shapes, const int64_t*
   dim3 grid((unsigned)(tl.n_tiles * M), (unsigned)N);
   if (N > 65535) return VLLM_EUNSUPPORTED;
   if (L == 4 && P == 4)
-    msda_fwd_warp_kernel<TH, TW, NW, 16, 4, OutT><<<grid, NW * 32, 0, st>>>(value, shapes, lsi, loc, attw, out, S,
-                                                                            M, L, Lq, P, tl);
+    msda_fwd_warp_kernel<TH, TW, NW, 16, 4, OutT, ValT><<<grid, NW * 32, 0, st>>>(value, shapes, lsi, loc, attw, out,
+                                                                                  S, M, L, Lq, P, tl);
   else
-    msda_fwd_warp_kernel<TH, TW, NW, 0, 0, OutT><<<grid, NW * 32, 0, st>>>(value, shapes, lsi, loc, attw, out, S,
-                                                                           M, L, Lq, P, tl);
+    msda_fwd_warp_kernel<TH, TW, NW, 0, 0, OutT, ValT><<<grid, NW * 32, 0, st>>>(value, shapes, lsi, loc, attw, out, S,
+                                                                                 M, L, Lq, P, tl);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
 }
@@ -507,6 +564,28 @@ int vllm_msda_forward_f32(const float* value, const int64_t* spatial_shapes, con
   }
   return launch_strict<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, batch,
                               spatial_size, num_heads, channels, num_levels, num_query, num_point, st);
+}
+
+int vllm_msda_forward_bf16v(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                            const float* sampling_loc, const float* attn_weight, void* out, int out_bf16, int batch,
+                            int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                            int num_point, const int64_t* host_shapes_hint, void* stream) {
+  int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, batch,
+                        spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (rc == 1000) return VLLM_OK;
+  if (rc) return rc;
+  if (channels != 32 || num_levels * num_point > 32) return VLLM_EUNSUPPORTED;   // caller upcasts and uses _f32
+  if (!vllm_aligned(value, 16) || !vllm_aligned(out, 16) || !vllm_aligned(sampling_loc, 8)) return VLLM_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* v = (const __nv_bfloat16*)value;
+  if (out_bf16)
+    return launch_warp<8, 16, 16, __nv_bfloat16, __nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc,
+                                                                attn_weight, (__nv_bfloat16*)out, batch, spatial_size,
+                                                                num_heads, num_levels, num_query, num_point,
+                                                                host_shapes_hint, st);
+  return launch_warp<8, 16, 16, float, __nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                                      (float*)out, batch, spatial_size, num_heads, num_levels,
+                                                      num_query, num_point, host_shapes_hint, st);
 }
 
 int vllm_msda_forward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start_index,

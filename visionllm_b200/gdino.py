@@ -100,11 +100,18 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
                    + sampling_offsets / self.n_points * reference_points[:, :, None, :, None, 2:] * 0.5)
         else:
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but got {reference_points.shape[-1]}")
-        # the reference upcasts value / weights to fp32 for the kernel (:764-766); locations follow type promotion
-        out = msda_ext.ms_deform_attn_forward(value.view(B, S, M, D).float().contiguous(), spatial_shapes,
-                                              level_start_index, loc.float().contiguous(),
-                                              attention_weights.float().contiguous(), self.im2col_step)
-        out = ops.linear(out.to(self.output_proj.weight.dtype), self.output_proj.weight, bias=self.output_proj.bias)
+        # the reference upcasts value / weights to fp32 for its fp32-only kernel (:764-766); locations follow type
+        # promotion.  With a bf16 value we read it in place (exact upcast inside the kernel) and write bf16 directly.
+        if value.dtype == torch.bfloat16 and msda_ext.supports_bf16_value(D, L, P):
+            out = msda_ext.ms_deform_attn_forward_bf16(value.view(B, S, M, D), spatial_shapes, level_start_index,
+                                                       loc.float().contiguous(), attention_weights.float().contiguous(),
+                                                       self.output_proj.weight.dtype)
+        else:
+            out = msda_ext.ms_deform_attn_forward(value.view(B, S, M, D).float().contiguous(), spatial_shapes,
+                                                  level_start_index, loc.float().contiguous(),
+                                                  attention_weights.float().contiguous(), self.im2col_step)
+            out = out.to(self.output_proj.weight.dtype)
+        out = ops.linear(out, self.output_proj.weight, bias=self.output_proj.bias)
         return out, attention_weights
 
 

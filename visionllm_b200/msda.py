@@ -122,6 +122,47 @@ def ms_deform_attn_sample_indices(spatial_shapes, sampling_loc):
     return out
 
 
+def ms_deform_attn_forward_bf16(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out_dtype=None):
+    """"Fast mode" (SURVEY 8d cfg 2b), an extension next to the reference API: value bf16 [N,S,M,32] read in place
+    (the reference upcasts it with .float() first, gd.py:764), sampling_loc / attn_weight fp32, fp32 accumulation,
+    out bf16 (default) or fp32.  Equal to ms_deform_attn_forward(value.float(), ...) up to the output rounding."""
+    for n, t in (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                 ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)):
+        if not t.is_contiguous():
+            raise RuntimeError(f"{n} tensor has to be contiguous")
+        if not t.is_cuda:
+            raise RuntimeError(f"{n} must be a CUDA tensor")
+    if value.dtype != torch.bfloat16 or sampling_loc.dtype != torch.float32 or attn_weight.dtype != torch.float32:
+        raise RuntimeError("ms_deform_attn_forward_bf16: value must be bf16, sampling_loc / attn_weight fp32")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes / level_start_index must be int64")
+    if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5:
+        raise RuntimeError("expected value[N,S,M,D], sampling_loc[N,Lq,M,L,P,2], attn_weight[N,Lq,M,L,P]")
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    _, Lq, M2, L2, P, two = sampling_loc.shape
+    if (M2, L2, two) != (M, L, 2) or tuple(attn_weight.shape) != (N, Lq, M, L, P) or sampling_loc.shape[0] != N:
+        raise RuntimeError("inconsistent MSDA shapes")
+    out_dtype = out_dtype or torch.bfloat16
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("out_dtype must be bf16 or fp32")
+    out = torch.empty((N, Lq, M * D), dtype=out_dtype, device=value.device)
+    if out.numel() == 0:
+        return out
+    hs = _host_shapes(spatial_shapes)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().vllm_msda_forward_bf16v(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+            attn_weight.data_ptr(), out.data_ptr(), 1 if out_dtype == torch.bfloat16 else 0, N, S, M, D, L, Lq, P,
+            hs.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_forward_bf16")
+    return out
+
+
+def supports_bf16_value(D, L, P):
+    return D == 32 and L * P <= 32
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, *rest,
                             im2col_step=64):
     """Both reference flavours:
