@@ -567,8 +567,65 @@ class PairForwardGdinoWorkload(PairForwardWorkload):
         return c
 
 
+class LlmTpWorkload(PairForwardWorkload):
+    """BASELINE cfg 5 (forward): Vicuna-7B split over the GPUs of the box (visionllm_b200/tp.py: tensor-parallel
+    attention + sequence-parallel MLP, one reduce-scatter + one all-gather per layer fused into the o_proj GEMM
+    epilogue and the RMSNorm kernel, no NCCL on the data path), 8 sequences of 2048 mixed visual/text tokens per step
+    for the WHOLE job (strong scaling: the same 16384 tokens at any world size), fp32 logits for every position."""
+    metric = "llm_tp_fwd_tokens_per_sec_2048tok"
+    unit = "tokens/s"
+    dtype = "bf16"
+    SEQS, T = 8, 2048
+
+    def setup(self):
+        import torch
+        import torch.distributed as dist
+        from transformers import LlamaConfig
+        from visionllm_b200 import tp
+        self.torch = torch
+        cfg = LlamaConfig(**self.llm)
+        M = self.SEQS * self.T
+        if self.world > 1:
+            self.comm = tp.PeerComm.from_process_group(M, cfg.hidden_size, self.device)
+        else:
+            self.comm = tp.PeerComm.virtual(1, M, cfg.hidden_size, self.device)[0]
+        self.model = tp.TPLlamaForCausalLM.random_init(cfg, self.comm, self.device, seed=0)
+        g = torch.Generator(device=self.device).manual_seed(1234)           # the same batch on every rank (TP)
+        self.ids = torch.randint(0, 32000, (self.SEQS, self.T), device=self.device, generator=g)
+        self.emb = torch.nn.functional.embedding(self.ids, self.model.shards["embed"])
+        self.h_ids = self.ids.cpu().pin_memory()
+        self.d_ids = torch.empty_like(self.ids)
+        self.h_out = torch.empty((self.SEQS, cfg.hidden_size), dtype=torch.bfloat16).pin_memory()
+        self.h2d_bytes = self.ids.numel() * 8
+        self.d2h_bytes = self.h_out.numel() * 2
+        self.dist = dist if self.world > 1 else None
+
+    def step_device(self):
+        self.out = self.model(inputs_embeds=self.emb)
+
+    def step_e2e(self):
+        self.d_ids.copy_(self.h_ids, non_blocking=True)
+        out = self.model(input_ids=self.d_ids)
+        self.h_out.copy_(out.last_hidden_state[:, -1, :], non_blocking=True)
+
+    def units_per_step(self):
+        return self.SEQS * self.T / self.world        # bench.py multiplies by world: the job's tokens per step
+
+    def config(self):
+        return {"workload": "BASELINE cfg 5 forward: Vicuna-7B, 8 x 2048-token sequences per step for the whole job, "
+                            "tensor-parallel attention + sequence-parallel MLP over peer memory, fp32 logits all positions",
+                "global_batch": self.SEQS, "seq_len": self.T,
+                "l2_policy": "inputs_exceed_l2 (weights 13.5 GB / TP shard + replicated MLP, activations > 126 MB L2)",
+                "parallelism": f"tp{self.world} (heads) x sp{self.world} (token rows); 1 reduce-scatter + 1 all-gather "
+                               "per layer inside the GEMM epilogue / norm kernel"}
+
+    def extra(self):
+        return {"kernel_breakdown": self.breakdown, "scaling": "strong"}
+
+
 WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "msda_encoder_bf16": MsdaEncoderBf16Workload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
-             "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload}
+             "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload,
+             "llm_tp": LlmTpWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
 
@@ -639,9 +696,40 @@ def _cpu_pair_forward(steps, warmup):
             "ms_per_step": pair_s * 1e3}
 
 
+def _cpu_llm_tp(steps, warmup):
+    """Reference CPU path of the LLM forward, bounded sample: ONE Vicuna-7B layer on one 2048-token sequence (fp32
+    torch, all host cores, oracle/vit_llm_oracle.llama_layer); tokens/s extrapolated over 32 layers (embedding, final
+    norm and lm_head left out, so the CPU figure is slightly optimistic)."""
+    import torch
+    from oracle import vit_llm_oracle as VO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    H, F_, T = 4096, 11008, 2048
+    r = lambda *s: torch.randn(*s, generator=g) * 0.02  # noqa: E731
+    lsd = {"l.input_layernorm.weight": torch.ones(H), "l.post_attention_layernorm.weight": torch.ones(H),
+           "l.self_attn.q_proj.weight": r(H, H), "l.self_attn.k_proj.weight": r(H, H),
+           "l.self_attn.v_proj.weight": r(H, H), "l.self_attn.o_proj.weight": r(H, H),
+           "l.mlp.gate_proj.weight": r(F_, H), "l.mlp.up_proj.weight": r(F_, H), "l.mlp.down_proj.weight": r(H, F_)}
+    x = torch.randn(1, T, H, generator=g)
+    for _ in range(warmup):
+        with torch.no_grad():
+            VO.llama_layer(x, lsd, "l.", 32, 1e-5)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        with torch.no_grad():
+            VO.llama_layer(x, lsd, "l.", 32, 1e-5)
+    tl = (time.perf_counter() - t0) / steps
+    seq_s = 32 * tl
+    return {"value": T / seq_s, "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"1 Vicuna-7B layer x one 2048-token sequence ({tl * 1e3:.0f} ms), fp32 torch CPU; "
+                      "sequence = 32 x layer (extrapolated)",
+            "ms_per_step": 8 * seq_s * 1e3}
+
+
 _CPU = {"msda_encoder": _cpu_msda_encoder, "msda_encoder_bf16": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
         "gdino_stage": _cpu_msda_encoder,
-        "pair_forward_gdino": _cpu_pair_forward}
+        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp}
 
 
 def cpu_baseline(name):
@@ -653,6 +741,6 @@ def run_reference_arm(name, n_gpus, steps, warmup):
     cb = _CPU[name](steps=max(1, min(steps, 5)), warmup=max(1, min(warmup, 1)))
     return {"impl": "reference", "metric": wl.metric, "value": cb["value"], "unit": wl.unit, "n_gpus": n_gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": {"workload": cb["sample"]}, "cpu_baseline": cb,
+            "scaling": "strong" if name == "llm_tp" else "weak", "vs_baseline": None, "dtype": wl.dtype,
+            "data": "synthetic", "config": {"workload": cb["sample"]}, "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -17,6 +17,7 @@
 #ifndef VLLM_B200_H
 #define VLLM_B200_H
 #include <stdint.h>
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -209,6 +210,43 @@ int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, in
 /* Tuning knob (process-global), head_dim 128 without masks: 0 = tcgen05/TMEM kernel, schedule "tc2" (default),
  * 2 = tcgen05/TMEM ping-pong schedule, 1 = warp-MMA kernel always. */
 int vllm_attention_set_variant(int variant);
+
+/* ---- tensor-parallel LLM decoder over peer memory (BASELINE cfg 5) -------
+ * The reference runs HF LlamaDecoderLayer unsharded (modeling_visionllmv2.py:724-732); the north-star splits it
+ * over the NVSwitch box.  These entry points are the exchange steps of that split, fused with the math either side
+ * (visionllm_b200/tp.py is the host mirror; nothing here calls NCCL):
+ *   vllm_peer_*            one cudaMalloc'ed, zero-filled exchange buffer per rank, shared through CUDA IPC
+ *                          (export = 64-byte handle a rank hands its peers through torch.distributed; open maps a
+ *                          peer's buffer and enables P2P access).  These four are setup calls: they allocate and
+ *                          synchronise (the only ones in the library that do).
+ *   vllm_gemm_bf16_scatter row-parallel o_proj fused with the reduce-scatter PUSH: C = A.B^T, row block d (rows
+ *                          [d*rows_per_dst, (d+1)*rows_per_dst)) is stored by the GEMM epilogue directly to dst[d]
+ *                          (a peer's receive slot, pitch ldc) tile by tile; each epilogue warp then adds 1 to
+ *                          flags[d] with release semantics at system scope: (rows_per_dst/128)*ceil(N/256)*8
+ *                          arrivals per destination and call.  rows_per_dst % 128 == 0, N % 64 == 0.
+ *   vllm_tp_reduce_norm_bf16  owner side: wait until *wait_flag - wait_target >= 0 (NULL: no wait), x[r,:] +=
+ *                          sum_s slots[s][r,:] (fp32, one bf16 rounding, stored in place when n_slots > 0), then
+ *                          RMSNorm(x) * weight (the two bf16 roundings of vllm_rmsnorm_bf16) written to dst[0..n_dst)
+ *                          at row pitch ld_dst (local MLP input, or every peer's gather buffer = the all-gather),
+ *                          then each CTA (one per row) adds 1 to signal[0..n_signal).  cols % 8 == 0, <= 8192.
+ *   vllm_tp_wait / vllm_tp_signal  one-thread kernels: spin until a counter reaches target / add to peers' counters
+ *                          (the barrier in front of a forward and the wait in front of a GEMM that reads the gather
+ *                          buffer through TMA).
+ * dst / flags / signal are HOST arrays of device pointers (<= 8 entries). */
+int vllm_peer_alloc(void** ptr, size_t bytes);
+int vllm_peer_free(void* ptr);
+int vllm_peer_handle_bytes(void);
+int vllm_peer_export(void* ptr, void* host_handle_out);
+int vllm_peer_open(const void* host_handle, void** ptr_out);
+int vllm_peer_close(void* ptr);
+int vllm_gemm_bf16_scatter(const void* A, int lda, const void* B, int ldb, void* const* dst, void* const* flags,
+                           int n_dst, int rows_per_dst, int ldc, int N, int K, void* stream);
+int vllm_tp_reduce_norm_bf16(const void* slots, int n_slots, long long slot_stride, void* x, const void* weight,
+                             float eps, void* const* dst, int n_dst, long long ld_dst, const void* wait_flag,
+                             unsigned wait_target, void* const* signal, int n_signal, int rows, int cols,
+                             void* stream);
+int vllm_tp_wait(const void* flag, unsigned target, void* stream);
+int vllm_tp_signal(void* const* signal, int n_signal, unsigned add, void* stream);
 
 #ifdef __cplusplus
 }

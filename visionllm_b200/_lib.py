@@ -45,6 +45,16 @@ _SIGNATURES = {
     "vllm_attention_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cll, cll, cll, cll, cll, cll, cll, cll,
                                  vp, vp, vp, vp, ci, ci, cf, vp, cll, vp]),
     "vllm_attention_set_variant": (ci, [ci]),
+    "vllm_peer_alloc": (ci, [ctypes.POINTER(vp), ctypes.c_size_t]),
+    "vllm_peer_free": (ci, [vp]),
+    "vllm_peer_handle_bytes": (ci, []),
+    "vllm_peer_export": (ci, [vp, vp]),
+    "vllm_peer_open": (ci, [vp, ctypes.POINTER(vp)]),
+    "vllm_peer_close": (ci, [vp]),
+    "vllm_gemm_bf16_scatter": (ci, [vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "vllm_tp_reduce_norm_bf16": (ci, [vp, ci, cll, vp, vp, cf, vp, ci, cll, vp, ctypes.c_uint, vp, ci, ci, ci, vp]),
+    "vllm_tp_wait": (ci, [vp, ctypes.c_uint, vp]),
+    "vllm_tp_signal": (ci, [vp, ci, ctypes.c_uint, vp]),
 }
 
 

@@ -43,6 +43,12 @@ struct GemmArgs {
   // of a_seg_kb k-blocks; segment s reads A rows shifted by s * a_seg_rows (one image row of the padded map), and a
   // row of the A tensor map spans kw consecutive pixels (row pitch = C elements, row length = kw*C: rows overlap).
   int a_seg_kb, a_seg_rows;
+  // Fused reduce-scatter push (vllm_gemm_bf16_scatter, tensor-parallel o_proj): row block d = row / sc_rows of C goes
+  // to sc_dst[d] (a peer GPU's receive slot, row pitch ldc, local row = row - d * sc_rows); every epilogue warp bumps
+  // sc_flag[d] once per tile after its stores (release at system scope).  sc_rows == 0: plain GEMM.
+  int sc_rows;
+  void* sc_dst[8];
+  uint32_t* sc_flag[8];
 };
 
 template <int CG> struct Cfg {
@@ -375,15 +381,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         {
           const int row_base = (tm * CG + (int)rank) * BM + quarter * 32;
           __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(g.C) + col0;
+          int row_local = row_base;
+          if (g.sc_rows && row_base < g.M) {         // peer push: the 32 rows of a warp share one destination
+            const int d = row_base / g.sc_rows;
+            cbase = reinterpret_cast<__nv_bfloat16*>(g.sc_dst[d]) + col0;
+            row_local = row_base - d * g.sc_rows;
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {           // each instruction: 4 rows x 128 contiguous bytes
             const int rr = it * 4 + (lane >> 3), piece = lane & 7;
             const uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * EPI_PITCH + piece * 16);
             if (row_base + rr < g.M)
-              *reinterpret_cast<uint4*>(cbase + (size_t)(row_base + rr) * g.ldc + piece * 8) = val;
+              *reinterpret_cast<uint4*>(cbase + (size_t)(row_local + rr) * g.ldc + piece * 8) = val;
           }
         }
         __syncwarp();
+      }
+      if (g.sc_rows) {                               // tile pushed: publish it to the owner of these rows
+        const int row_base = (tm * CG + (int)rank) * BM + quarter * 32;
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0 && row_base < g.M)
+          asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(g.sc_flag[row_base / g.sc_rows]), "r"(1u) : "memory");
       }
       // accumulator stage drained: hand it back to the MMA issuer
       tc::tc_fence_before();
@@ -477,6 +496,29 @@ int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int 
   g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc;
   g.bias = (const __nv_bfloat16*)bias; g.colscale = (const __nv_bfloat16*)colscale;
   g.residual = (const __nv_bfloat16*)residual; g.ldr = ldr; g.act = act; g.out_f32 = out_f32;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cg = g_gemm_variant ? g_gemm_variant : (K <= 512 ? 1 : 2);
+  if (cg == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);
+  return launch_gemm<1>(A, lda, B, ldb, g, st);
+}
+
+int vllm_gemm_bf16_scatter(const void* A, int lda, const void* B, int ldb, void* const* dst, void* const* flags,
+                           int n_dst, int rows_per_dst, int ldc, int N, int K, void* stream) {
+  // C = A . B^T (plain bf16, no epilogue math), M = n_dst * rows_per_dst; row block d is stored to dst[d] and
+  // counted on flags[d] (8 arrivals per 128 x 256 tile: (rows_per_dst / 128) * ceil(N / 256) * 8 per source and pass).
+  if (n_dst <= 0 || n_dst > 8 || rows_per_dst <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N) return VLLM_EINVAL;
+  if (!A || !B || !dst || !flags) return VLLM_EINVAL;
+  if (rows_per_dst % BM || N % 64) return VLLM_EUNSUPPORTED;    // a warp's 32 rows share a destination; bf16 fast path
+  if ((long long)n_dst * rows_per_dst > 2147483647LL) return VLLM_EUNSUPPORTED;
+  if (!vllm_aligned(A, 16) || !vllm_aligned(B, 16) || (lda % 8) || (ldb % 8) || (ldc % 8)) return VLLM_EALIGN;
+  GemmArgs g{};
+  g.M = n_dst * rows_per_dst; g.N = N; g.K = K; g.ldc = ldc; g.sc_rows = rows_per_dst;
+  for (int d = 0; d < n_dst; ++d) {
+    if (!dst[d] || !flags[d]) return VLLM_EINVAL;
+    if (!vllm_aligned(dst[d], 16)) return VLLM_EALIGN;
+    g.sc_dst[d] = dst[d]; g.sc_flag[d] = (uint32_t*)flags[d];
+  }
+  g.C = dst[0];
   cudaStream_t st = (cudaStream_t)stream;
   const int cg = g_gemm_variant ? g_gemm_variant : (K <= 512 ? 1 : 2);
   if (cg == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);

@@ -1,0 +1,377 @@
+"""Tensor-parallel Llama decoder over NVLink peer memory (BASELINE cfg 5).
+
+The reference runs HF ``LlamaForCausalLM`` unsharded inside ``VisionLLMv2Model.forward``
+(visionllmv2/model/modeling_visionllmv2.py:724-738).  The north-star splits the LLM over the 8 GPUs of one NVSwitch
+box "with a single all-reduce per layer".  This module is that split for `B200LlamaForCausalLM` (same config, same
+HF state-dict names on the way in, same `inputs_embeds -> fp32 logits + last hidden state` contract):
+
+* attention is tensor-parallel: rank r owns heads [r*nq/W, (r+1)*nq/W) -- column-parallel packed QKV, row-parallel
+  o_proj;
+* the residual stream, both RMSNorms and the MLP are sequence-parallel: rank r owns token rows [r*R, (r+1)*R) of the
+  flattened [B*T, H] activation (R = B*T/W) and runs the whole gate|up / down projection on them (replicated MLP
+  weights; the FLOPs per rank equal a column/row-parallel MLP, the second all-reduce of a Megatron layer disappears);
+* the only exchange of a layer is therefore ONE reduce-scatter (o_proj partials -> row owners) + ONE all-gather
+  (normalised rows -> everybody) = the volume of a single all-reduce, and neither is an NCCL call: the o_proj GEMM
+  epilogue pushes its tiles into the owners' receive slots (`vllm_gemm_bf16_scatter`), and the fused
+  reduce + residual + RMSNorm kernel pushes the normalised rows into every peer's gather buffer
+  (`vllm_tp_reduce_norm_bf16`); arrival counters in peer memory order the kernels (csrc/peer.cu).
+
+`PeerComm` owns the exchange buffer of one rank (cudaMalloc + CUDA IPC through the C-ABI; torch.distributed only
+carries the 64-byte handles at setup).  `PeerComm.virtual(W, ...)` builds W ranks on ONE device whose pointer tables
+cross-reference each other, and `run_lockstep` advances their forwards phase by phase on one stream -- the multi-rank
+protocol (pointer tables, slots, counters, epochs) is then testable on a single GPU.
+
+Forward only.  No CPU path: the collectives ARE the CUDA kernels; tests that run on CPU substitute a gloo-backed
+double for the comm object (tests/test_tp_cpu.py).
+"""
+import ctypes
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .llama import right_padding_lengths, rope_tables
+
+_FLAG_BYTES = 4096
+_GATHER_FLAG, _RECV_FLAG, _BARRIER_FLAG = 0, 256, 512      # byte offsets of the three arrival counters
+
+
+class _DeviceBytes:
+    """`__cuda_array_interface__` view of a raw device allocation so torch can wrap it without owning it."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) for p in ptrs])
+
+
+def exchange_bytes(rows_total, hidden, world):
+    """Size of one rank's exchange buffer: counters | gather [M, H] bf16 | receive slots [W, M/W, H] bf16."""
+    return _FLAG_BYTES + 2 * rows_total * hidden * 2
+
+
+class PeerComm:
+    """The exchange endpoint of one rank: its own buffer plus mapped pointers to every peer's buffer."""
+
+    def __init__(self, rank, world, rows_total, hidden, device, own_ptr, peer_ptrs, owner=None):
+        if rows_total % world:
+            raise ValueError(f"token rows ({rows_total}) must divide over {world} ranks")
+        self.rank, self.world, self.M, self.H = rank, world, rows_total, hidden
+        self.R = rows_total // world
+        if self.R % 128:
+            raise ValueError("rows per rank must be a multiple of 128 (GEMM row tile)")
+        if hidden % 64:
+            raise ValueError("hidden size must be a multiple of 64")
+        self.device = torch.device(device)
+        self.base = [int(p) for p in peer_ptrs]            # base[j] = rank j's buffer as mapped in this process
+        assert self.base[rank] == int(own_ptr)
+        self._owner = owner                                 # keeps the allocation(s) alive
+        nbytes = exchange_bytes(rows_total, hidden, world)
+        raw = torch.as_tensor(_DeviceBytes(own_ptr, nbytes), device=self.device)
+        g0 = _FLAG_BYTES
+        r0 = g0 + rows_total * hidden * 2
+        self.gather = raw[g0:r0].view(torch.bfloat16).view(rows_total, hidden)
+        self.recv = raw[r0:].view(torch.bfloat16).view(world, self.R, hidden)
+        self._g0, self._r0 = g0, r0
+        self.e_gather = self.e_recv = self.e_barrier = 0    # epochs (every rank advances them identically)
+        self.tiles_per_pass = (self.R // 128) * ((hidden + 255) // 256) * 8   # arrivals per source and o_proj pass
+        # where my pushes land on each peer
+        self._gather_dst = _ptr_array([b + g0 + rank * self.R * hidden * 2 for b in self.base])
+        self._recv_dst = _ptr_array([b + r0 + rank * self.R * hidden * 2 for b in self.base])
+        self._gather_flags = _ptr_array([b + _GATHER_FLAG for b in self.base])
+        self._recv_flags = _ptr_array([b + _RECV_FLAG for b in self.base])
+        self._barrier_flags = _ptr_array([b + _BARRIER_FLAG for b in self.base])
+        self._own = int(own_ptr)
+
+    # ---- construction -------------------------------------------------------------------------------------
+    @staticmethod
+    def _alloc(nbytes):
+        p = ctypes.c_void_p()
+        _lib.check(_lib.lib().vllm_peer_alloc(ctypes.byref(p), nbytes), "vllm_peer_alloc")
+        return p.value
+
+    @classmethod
+    def virtual(cls, world, rows_total, hidden, device="cuda"):
+        """`world` ranks on ONE device (tests, single-GPU debugging): W allocations, cross-referenced tables."""
+        dev = torch.device(device)
+        with torch.cuda.device(dev):
+            ptrs = [cls._alloc(exchange_bytes(rows_total, hidden, world)) for _ in range(world)]
+        owner = _Allocations(ptrs, [], dev)
+        return [cls(r, world, rows_total, hidden, dev, ptrs[r], ptrs, owner) for r in range(world)]
+
+    @classmethod
+    def from_process_group(cls, rows_total, hidden, device, group=None):
+        """One rank per process: allocate, all-gather the IPC handles over torch.distributed, map the peers."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device(device)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            own = cls._alloc(exchange_bytes(rows_total, hidden, world))
+            hb = L.vllm_peer_handle_bytes()
+            buf = ctypes.create_string_buffer(hb)
+            _lib.check(L.vllm_peer_export(own, buf), "vllm_peer_export")
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(buf.raw), group=group)
+            ptrs, opened = [], []
+            for j in range(world):
+                if j == rank:
+                    ptrs.append(own)
+                    continue
+                p = ctypes.c_void_p()
+                _lib.check(L.vllm_peer_open(ctypes.create_string_buffer(handles[j], hb), ctypes.byref(p)),
+                           "vllm_peer_open")
+                ptrs.append(p.value)
+                opened.append(p.value)
+            dist.barrier(group=group)
+        return cls(rank, world, rows_total, hidden, dev, own, ptrs, _Allocations([own], opened, dev))
+
+    # ---- exchange steps (each enqueues one kernel on the current stream) ------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def barrier(self):
+        """Arrive: every rank has finished reading the buffers of the previous forward before anybody overwrites
+        them.  Arrive and wait are separate launches so a lock-step driver can interleave virtual ranks."""
+        self.e_barrier += 1
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vllm_tp_signal(self._barrier_flags, self.world, 1, self._stream()), "vllm_tp_signal")
+
+    def barrier_wait(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vllm_tp_wait(self._own + _BARRIER_FLAG, self.e_barrier * self.world, self._stream()),
+                       "vllm_tp_wait")
+
+    def norm_push(self, x_local, weight, eps):
+        """gather[j][rank rows] = RMSNorm(x_local) * weight on every rank j (the all-gather, fused into the norm)."""
+        self._check_rows(x_local)
+        self.e_gather += 1
+        with torch.cuda.device(self.device), ops._Prof("tp_norm_push", 0.0, 2.0 * x_local.numel() * (1 + self.world)):
+            rc = _lib.lib().vllm_tp_reduce_norm_bf16(None, 0, 0, x_local.data_ptr(), weight.data_ptr(), float(eps),
+                                                     self._gather_dst, self.world, self.H, None, 0,
+                                                     self._gather_flags, self.world, self.R, self.H, self._stream())
+        _lib.check(rc, "vllm_tp_reduce_norm_bf16")
+
+    def gathered(self):
+        """Wait for every rank's rows of the current gather epoch; returns the [M, H] buffer (a view, not a copy)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vllm_tp_wait(self._own + _GATHER_FLAG, self.e_gather * self.world * self.R,
+                                               self._stream()), "vllm_tp_wait")
+        return self.gather
+
+    def oproj_scatter(self, ctx, w_shard):
+        """partial = ctx @ w_shard.T pushed tile by tile into the row owners' receive slot `rank` (reduce-scatter)."""
+        if ctx.dim() != 2 or ctx.shape[0] != self.M or ctx.dtype != torch.bfloat16 or ctx.stride(1) != 1:
+            raise RuntimeError("oproj_scatter: ctx must be bf16 [M, K_local]")
+        if w_shard.shape != (self.H, ctx.shape[1]) or w_shard.dtype != torch.bfloat16 or w_shard.stride(1) != 1:
+            raise RuntimeError("oproj_scatter: w_shard must be bf16 [H, K_local]")
+        self.e_recv += 1
+        K = ctx.shape[1]
+        with torch.cuda.device(self.device), ops._Prof("gemm", 2.0 * self.M * self.H * K,
+                                                       2.0 * (self.M * K + self.H * K + self.M * self.H)):
+            rc = _lib.lib().vllm_gemm_bf16_scatter(ctx.data_ptr(), ctx.stride(0), w_shard.data_ptr(),
+                                                   w_shard.stride(0), self._recv_dst, self._recv_flags, self.world,
+                                                   self.R, self.H, self.H, K, self._stream())
+        _lib.check(rc, "vllm_gemm_bf16_scatter")
+
+    def reduce_norm(self, x_local, weight, eps):
+        """x_local += sum of the W partial slots (in place); returns RMSNorm(x_local) * weight for the local rows."""
+        self._check_rows(x_local)
+        h = torch.empty_like(x_local)
+        dst = _ptr_array([h.data_ptr()])
+        with torch.cuda.device(self.device), ops._Prof("tp_reduce_norm", 0.0, 2.0 * x_local.numel() * (self.world + 3)):
+            rc = _lib.lib().vllm_tp_reduce_norm_bf16(self.recv.data_ptr(), self.world, self.R * self.H,
+                                                     x_local.data_ptr(), weight.data_ptr(), float(eps), dst, 1, self.H,
+                                                     self._own + _RECV_FLAG,
+                                                     self.e_recv * self.world * self.tiles_per_pass, None, 0,
+                                                     self.R, self.H, self._stream())
+        _lib.check(rc, "vllm_tp_reduce_norm_bf16")
+        return h
+
+    def _check_rows(self, x):
+        if x.shape != (self.R, self.H) or x.dtype != torch.bfloat16 or not x.is_contiguous():
+            raise RuntimeError(f"expected contiguous bf16 [{self.R}, {self.H}] local rows")
+
+
+class _Allocations:
+    """Frees the cudaMalloc'ed exchange buffers / closes the IPC mappings when the last PeerComm goes away."""
+
+    def __init__(self, owned, opened, device):
+        self.owned, self.opened, self.device = list(owned), list(opened), device
+
+    def __del__(self):
+        try:
+            L = _lib.lib()
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                for p in self.opened:
+                    L.vllm_peer_close(p)
+                for p in self.owned:
+                    L.vllm_peer_free(p)
+        except Exception:
+            pass
+
+
+def shard_llama_state_dict(sd, config, rank, world):
+    """HF-named full state dict -> the tensors rank `rank` holds: packed QKV rows of its heads, o_proj columns of its
+    heads, everything else replicated (gate/up row-interleaved for the SwiGLU epilogue, like llama.LlamaMLP)."""
+    nq = config.num_attention_heads
+    nkv = getattr(config, "num_key_value_heads", None) or nq
+    D = getattr(config, "head_dim", None) or config.hidden_size // nq
+    if nq % world or nkv % world:
+        raise ValueError(f"heads ({nq} q / {nkv} kv) must divide over {world} ranks")
+    ql, kl = nq // world * D, nkv // world * D
+    out = {"embed": sd["model.embed_tokens.weight"], "final_norm": sd["model.norm.weight"],
+           "lm_head": sd["lm_head.weight"], "layers": []}
+    for i in range(config.num_hidden_layers):
+        p = f"model.layers.{i}."
+        g, u = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
+        out["layers"].append({
+            "wqkv": torch.cat([sd[p + "self_attn.q_proj.weight"][rank * ql:(rank + 1) * ql],
+                               sd[p + "self_attn.k_proj.weight"][rank * kl:(rank + 1) * kl],
+                               sd[p + "self_attn.v_proj.weight"][rank * kl:(rank + 1) * kl]], 0).contiguous(),
+            "wo": sd[p + "self_attn.o_proj.weight"][:, rank * ql:(rank + 1) * ql].contiguous(),
+            "w_gate_up": torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]).contiguous(),
+            "w_down": sd[p + "mlp.down_proj.weight"],
+            "ln1": sd[p + "input_layernorm.weight"], "ln2": sd[p + "post_attention_layernorm.weight"],
+        })
+    return out
+
+
+class TPLlamaForCausalLM(nn.Module):
+    """One rank of the tensor-parallel `B200LlamaForCausalLM`.  `comm` is a `PeerComm` (or, in CPU tests, a double
+    with the same five methods)."""
+
+    def __init__(self, config, comm, shards=None, device=None, dtype=torch.bfloat16):
+        super().__init__()
+        self.config, self.comm = config, comm
+        self.nq = config.num_attention_heads
+        self.nkv = getattr(config, "num_key_value_heads", None) or self.nq
+        self.D = getattr(config, "head_dim", None) or config.hidden_size // self.nq
+        W = comm.world
+        if self.nq % W or self.nkv % W:
+            raise ValueError(f"heads ({self.nq} q / {self.nkv} kv) must divide over {W} ranks")
+        if getattr(config, "attention_bias", False):
+            raise NotImplementedError("TP path: attention_bias")
+        self.eps = config.rms_norm_eps
+        theta = getattr(config, "rope_theta", None)
+        if theta is None:
+            rp = getattr(config, "rope_parameters", None) or {}
+            theta = rp.get("rope_theta", 10000.0) if isinstance(rp, dict) else 10000.0
+        self.theta = theta
+        self.shards = None
+        if shards is not None:
+            self.load_shards(shards, device, dtype)
+
+    def load_shards(self, shards, device=None, dtype=torch.bfloat16):
+        mv = (lambda t: t.detach().to(device=device, dtype=dtype).contiguous())
+        self.shards = {k: (mv(v) if k != "layers" else [{n: mv(t) for n, t in lyr.items()} for lyr in v])
+                       for k, v in shards.items()}
+        return self
+
+    @classmethod
+    def from_full_state_dict(cls, config, comm, sd, device=None, dtype=torch.bfloat16):
+        return cls(config, comm, shard_llama_state_dict(sd, config, comm.rank, comm.world), device, dtype)
+
+    @classmethod
+    def random_init(cls, config, comm, device, seed=0, std=0.02):
+        """Random shards without ever materialising the full model (bench: 7B at TP=8).  Replicated tensors use the
+        same seed on every rank; sharded ones a rank-specific seed (they only have to be random)."""
+        g = torch.Generator(device=device).manual_seed(seed)
+        gr = torch.Generator(device=device).manual_seed(seed * 1000 + 17 + comm.rank)
+        H, I, V = config.hidden_size, config.intermediate_size, config.vocab_size
+        W = comm.world
+        nq = config.num_attention_heads
+        nkv = getattr(config, "num_key_value_heads", None) or nq
+        D = getattr(config, "head_dim", None) or H // nq
+        rn = lambda shape, gen: (torch.randn(shape, generator=gen, device=device, dtype=torch.float32) * std).to(torch.bfloat16)  # noqa: E731
+        shards = {"embed": rn((V, H), g), "final_norm": torch.ones(H, device=device, dtype=torch.bfloat16),
+                  "lm_head": rn((V, H), g), "layers": []}
+        for _ in range(config.num_hidden_layers):
+            shards["layers"].append({
+                "wqkv": rn(((nq + 2 * nkv) // W * D, H), gr), "wo": rn((H, nq // W * D), gr),
+                "w_gate_up": rn((2 * I, H), g), "w_down": rn((H, I), g),
+                "ln1": torch.ones(H, device=device, dtype=torch.bfloat16),
+                "ln2": torch.ones(H, device=device, dtype=torch.bfloat16)})
+        m = cls(config, comm)
+        m.shards = shards
+        return m
+
+    # ---- forward --------------------------------------------------------------------------------------------
+    def phases(self, inputs_embeds, attention_mask=None, position_ids=None, compute_logits=True):
+        """Generator: yields after every step that publishes data to peers, so `run_lockstep` can interleave the
+        virtual ranks of one device.  The result is left in `self.result`."""
+        c, S = self.comm, self.shards
+        B, T, H = inputs_embeds.shape
+        M = B * T
+        if M != c.M or H != c.H:
+            raise RuntimeError(f"comm was set up for [{c.M}, {c.H}] rows, got [{M}, {H}]")
+        W, R, r = c.world, c.R, c.rank
+        nql, nkvl, D = self.nq // W, self.nkv // W, self.D
+        dev = inputs_embeds.device
+        seqlens = right_padding_lengths(attention_mask)
+        if position_ids is None:
+            position_ids = torch.arange(T, device=dev)[None].expand(B, T)
+        cos, sin = rope_tables(position_ids, D, self.theta, inputs_embeds.dtype)
+        x = inputs_embeds.reshape(M, H)[r * R:(r + 1) * R].contiguous().clone()     # my rows of the residual stream
+        c.barrier()
+        yield "barrier"
+        c.barrier_wait()
+        c.norm_push(x, S["layers"][0]["ln1"], self.eps)
+        yield "push"
+        n_layers = len(S["layers"])
+        for i, ly in enumerate(S["layers"]):
+            hN = c.gathered()                                                         # [M, H], all tokens
+            qkv = ops.linear(hN, ly["wqkv"])                                          # [M, (nql + 2 nkvl) D]
+            ops.rope_(qkv, cos, sin, nql + nkvl, D)
+            q = qkv[:, :nql * D].view(B, T, nql, D)
+            k = qkv[:, nql * D:(nql + nkvl) * D].view(B, T, nkvl, D)
+            v = qkv[:, (nql + nkvl) * D:].view(B, T, nkvl, D)
+            ctx = ops.attention(q, k, v, causal=True, seqlens=seqlens)
+            c.oproj_scatter(ctx.reshape(M, nql * D), ly["wo"])
+            yield "scatter"
+            h = c.reduce_norm(x, ly["ln2"], self.eps)                                 # x += sum partials; h = norm2(x)
+            mid = ops.linear(h, ly["w_gate_up"], act="swiglu")
+            x = ops.linear(mid, ly["w_down"], residual=x)
+            nxt = S["layers"][i + 1]["ln1"] if i + 1 < n_layers else S["final_norm"]
+            c.norm_push(x, nxt, self.eps)
+            yield "push"
+        last = c.gathered().clone().view(B, T, H)                                     # final-norm'ed states, all tokens
+        logits = None
+        if compute_logits:
+            V = self.config.vocab_size
+            Vp = (V + 3) // 4 * 4
+            buf = torch.empty((R, Vp), dtype=torch.float32, device=dev)
+            ops.linear(last.view(M, H)[r * R:(r + 1) * R], S["lm_head"], out=buf[:, :V])
+            logits = buf[:, :V]
+        self.result = SimpleNamespace(last_hidden_state=last, logits_local=logits, row_range=(r * R, (r + 1) * R))
+
+    @torch.no_grad()
+    def forward(self, inputs_embeds=None, input_ids=None, attention_mask=None, position_ids=None,
+                compute_logits=True):
+        if inputs_embeds is None:
+            inputs_embeds = torch.nn.functional.embedding(input_ids, self.shards["embed"])
+        for _ in self.phases(inputs_embeds, attention_mask, position_ids, compute_logits):
+            pass
+        return self.result
+
+
+@torch.no_grad()
+def run_lockstep(ranks, inputs_embeds, **kw):
+    """Advance the forwards of several (virtual) ranks phase by phase on the current stream: every rank publishes
+    before any rank consumes, so no wait kernel ever spins.  Returns the per-rank results."""
+    gens = [m.phases(inputs_embeds, **kw) for m in ranks]
+    live = True
+    while live:
+        live = False
+        for g in gens:
+            try:
+                next(g)
+                live = True
+            except StopIteration:
+                pass
+    return [m.result for m in ranks]
