@@ -228,7 +228,7 @@ int vllm_attention_set_variant(int variant);
  *                          sum_s slots[s][r,:] (fp32, one bf16 rounding, stored in place when n_slots > 0), then
  *                          RMSNorm(x) * weight (the two bf16 roundings of vllm_rmsnorm_bf16) written to dst[0..n_dst)
  *                          at row pitch ld_dst (local MLP input, or every peer's gather buffer = the all-gather),
- *                          then each CTA (one per row) adds 1 to signal[0..n_signal).  cols % 8 == 0, <= 8192.
+ *                          then each CTA adds 1 to signal[0..n_signal) (vllm_tp_norm_ctas(rows) CTAs).  cols % 8 == 0, <= 8192.
  *   vllm_tp_wait / vllm_tp_signal  one-thread kernels: spin until a counter reaches target / add to peers' counters
  *                          (the barrier in front of a forward and the wait in front of a GEMM that reads the gather
  *                          buffer through TMA).
@@ -245,6 +245,7 @@ int vllm_tp_reduce_norm_bf16(const void* slots, int n_slots, long long slot_stri
                              float eps, void* const* dst, int n_dst, long long ld_dst, const void* wait_flag,
                              unsigned wait_target, void* const* signal, int n_signal, int rows, int cols,
                              void* stream);
+int vllm_tp_norm_ctas(int rows); /* counter arrivals per destination of one vllm_tp_reduce_norm_bf16 launch */
 int vllm_tp_wait(const void* flag, unsigned target, void* stream);
 int vllm_tp_signal(void* const* signal, int n_signal, unsigned add, void* stream);
 

@@ -76,7 +76,7 @@ def test_reduce_norm_kernel_matches_fp32():
     torch.cuda.synchronize()
     for d in comms:
         assert torch.equal(d.gather[c.rank * c.R:(c.rank + 1) * c.R], h)
-        assert _flag(d, tp._GATHER_FLAG) == c.R
+        assert _flag(d, tp._GATHER_FLAG) == c.push_ctas
 
 
 def _tiny_cfg():

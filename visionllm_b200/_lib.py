@@ -53,6 +53,7 @@ _SIGNATURES = {
     "vllm_peer_close": (ci, [vp]),
     "vllm_gemm_bf16_scatter": (ci, [vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]),
     "vllm_tp_reduce_norm_bf16": (ci, [vp, ci, cll, vp, vp, cf, vp, ci, cll, vp, ctypes.c_uint, vp, ci, ci, ci, vp]),
+    "vllm_tp_norm_ctas": (ci, [ci]),
     "vllm_tp_wait": (ci, [vp, ctypes.c_uint, vp]),
     "vllm_tp_signal": (ci, [vp, ci, ctypes.c_uint, vp]),
 }

@@ -177,6 +177,38 @@ rope_kernel(__nv_bfloat16* __restrict__ x, long long ld, const __nv_bfloat16* __
   }
 }
 
+// 16-byte form of the same arithmetic (bit-identical results): a thread owns 8 consecutive d of the low half and the
+// 8 partners of the high half of one (token, head); hd/16 threads per head, so a 128-d head is 8 threads x 6 x LDG.128.
+__global__ void __launch_bounds__(256)
+rope_vec_kernel(__nv_bfloat16* __restrict__ x, long long ld, const __nv_bfloat16* __restrict__ cs,
+                const __nv_bfloat16* __restrict__ sn, int heads, int hd, long long tokens) {
+  const int tph = hd / 16;                                   // threads per head
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = tokens * heads * tph;
+  if (idx >= total) return;
+  const int v = (int)(idx % tph);
+  const long long th = idx / tph;
+  const long long t = th / heads;
+  const int h = (int)(th % heads);
+  const int half = hd / 2, d = v * 8;
+  __nv_bfloat16* p = x + t * ld + (long long)h * hd;
+  float a[8], b[8], c0[8], c1[8], s0[8], s1[8], lo[8], hi[8];
+  unpack8(*reinterpret_cast<const uint4*>(p + d), a);
+  unpack8(*reinterpret_cast<const uint4*>(p + d + half), b);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(cs + t * hd + d)), c0);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(cs + t * hd + d + half)), c1);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(sn + t * hd + d)), s0);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(sn + t * hd + d + half)), s1);
+  auto r = [](float q) { return __bfloat162float(__float2bfloat16(q)); };
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    lo[j] = r(a[j] * c0[j]) + r(-b[j] * s0[j]);
+    hi[j] = r(b[j] * c1[j]) + r(a[j] * s1[j]);
+  }
+  *reinterpret_cast<uint4*>(p + d) = pack8(lo);
+  *reinterpret_cast<uint4*>(p + d + half) = pack8(hi);
+}
+
 int check_rows(const void* x, long long ldx, const void* y, long long ldy, long long rows, int cols) {
   if (rows < 0 || cols <= 0) return VLLM_EINVAL;
   if (rows == 0) return 1000;
@@ -216,6 +248,15 @@ int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long
   if (!x || !cos || !sin) return VLLM_EINVAL;
   if (head_dim % 4 || ld % 2) return VLLM_EUNSUPPORTED;
   if (!vllm_aligned(x, 4) || !vllm_aligned(cos, 4) || !vllm_aligned(sin, 4)) return VLLM_EALIGN;
+  if (head_dim % 16 == 0 && ld % 8 == 0 && vllm_aligned(x, 16) && vllm_aligned(cos, 16) && vllm_aligned(sin, 16)) {
+    const long long threads = tokens * heads * (head_dim / 16);
+    const long long vblocks = (threads + 255) / 256;
+    if (vblocks > 2147483647LL) return VLLM_EUNSUPPORTED;
+    rope_vec_kernel<<<(unsigned)vblocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, ld, (const __nv_bfloat16*)cos,
+                                                                        (const __nv_bfloat16*)sin, heads, head_dim, tokens);
+    VLLM_CHECK_LAUNCH();
+    return VLLM_OK;
+  }
   const long long warps = tokens * heads;
   const long long blocks = (warps + 3) / 4;
   if (blocks > 2147483647LL) return VLLM_EUNSUPPORTED;

@@ -397,19 +397,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         __syncwarp();
       }
-      if (g.sc_rows) {                               // tile pushed: publish it to the owner of these rows
-        const int row_base = (tm * CG + (int)rank) * BM + quarter * 32;
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0 && row_base < g.M)
-          asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(g.sc_flag[row_base / g.sc_rows]), "r"(1u) : "memory");
-      }
       // accumulator stage drained: hand it back to the MMA issuer
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (CG == 1) tc::mbar_arrive(tempty_bar(acc));
         else tc::mbar_arrive_cluster(tempty_bar(acc), 0);
+      }
+      if (g.sc_rows) {                               // tile pushed: publish it to the owner of these rows (after the
+        const int row_base = (tm * CG + (int)rank) * BM + quarter * 32;   // TMEM hand-back: the fence waits for NVLink acks)
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0 && row_base < g.M)
+          asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(g.sc_flag[row_base / g.sc_rows]), "r"(1u) : "memory");
       }
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }

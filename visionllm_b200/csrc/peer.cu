@@ -81,63 +81,67 @@ struct TpNormArgs {
 
 constexpr int TPN_THREADS = 256;
 
-// One CTA per row; thread t owns 16-byte vectors t, t+256, ... (VPT of them, cols <= 8 * 256 * VPT).
+// A CTA walks rows blockIdx.x, blockIdx.x + gridDim.x, ...; thread t owns 16-byte vectors t, t+256, ... of a row
+// (VPT of them, cols <= 8 * 256 * VPT).  One wait at the start and ONE fence + counter bump per CTA at the end (a
+// system-scope fence per row costs more than the row itself), so a push arrives as gridDim.x counts per source.
 template <int VPT>
 __global__ void __launch_bounds__(TPN_THREADS)
 tp_reduce_norm_kernel(const TpNormArgs a) {
-  __shared__ float sh[TPN_THREADS / 32];
-  const int row = blockIdx.x;
+  __shared__ float sh[2][TPN_THREADS / 32];
   const int nvec = a.cols / 8;
   if (a.wait_flag) {
     if (threadIdx.x == 0) spin_until(a.wait_flag, a.wait_target);
     __syncthreads();
   }
-  float acc[VPT][8];
-  __nv_bfloat16* xr = a.x + (size_t)row * a.cols;
-  float s2 = 0.f;
+  int it = 0;
+  for (int row = blockIdx.x; row < a.rows; row += gridDim.x, it ^= 1) {
+    float acc[VPT][8];
+    __nv_bfloat16* xr = a.x + (size_t)row * a.cols;
+    float s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int v = threadIdx.x + i * TPN_THREADS;
+    for (int i = 0; i < VPT; ++i) {
+      const int v = threadIdx.x + i * TPN_THREADS;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    if (v < nvec) {
-      for (int s = 0; s < a.n_slots; ++s) {
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      if (v < nvec) {
+        for (int s = 0; s < a.n_slots; ++s) {
+          float f[8];
+          unpack8(ld_cg_u4(a.slots + (size_t)s * a.slot_stride + (size_t)row * a.cols + 8 * v), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] += f[j];
+        }
         float f[8];
-        unpack8(ld_cg_u4(a.slots + (size_t)s * a.slot_stride + (size_t)row * a.cols + 8 * v), f);
+        unpack8(*(reinterpret_cast<const uint4*>(xr) + v), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] += f[j];
-      }
-      float f[8];
-      unpack8(*(reinterpret_cast<const uint4*>(xr) + v), f);
+        if (a.n_slots > 0) {
+          const uint4 pk = pack8(acc[i]);               // the new residual, rounded once to bf16 like a GEMM epilogue
+          *(reinterpret_cast<uint4*>(xr) + v) = pk;
+          unpack8(pk, acc[i]);                          // RMSNorm sees the stored (rounded) residual
+        }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] += f[j];
-      if (a.n_slots > 0) {
-        const uint4 pk = pack8(acc[i]);                 // the new residual, rounded once to bf16 like a GEMM epilogue
-        *(reinterpret_cast<uint4*>(xr) + v) = pk;
-        unpack8(pk, acc[i]);                            // RMSNorm sees the stored (rounded) residual
+        for (int j = 0; j < 8; ++j) s2 += acc[i][j] * acc[i][j];
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s2 += acc[i][j] * acc[i][j];
     }
-  }
-  s2 = warp_sum(s2);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s2;
-  __syncthreads();
-  float tot = 0.f;
+    s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) sh[it][threadIdx.x >> 5] = s2;   // double-buffered: one barrier per row
+    __syncthreads();
+    float tot = 0.f;
 #pragma unroll
-  for (int i = 0; i < TPN_THREADS / 32; ++i) tot += sh[i];
-  const float inv = rsqrtf(tot / a.cols + a.eps);
+    for (int i = 0; i < TPN_THREADS / 32; ++i) tot += sh[it][i];
+    const float inv = rsqrtf(tot / a.cols + a.eps);
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int v = threadIdx.x + i * TPN_THREADS;
-    if (v < nvec) {
-      float wv[8], o[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(a.w) + v), wv);
+    for (int i = 0; i < VPT; ++i) {
+      const int v = threadIdx.x + i * TPN_THREADS;
+      if (v < nvec) {
+        float wv[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.w) + v), wv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = wv[j] * __bfloat162float(__float2bfloat16(acc[i][j] * inv));
-      const uint4 pk = pack8(o);
-      for (int d = 0; d < a.n_dst; ++d)
-        *(reinterpret_cast<uint4*>(a.dst[d] + (size_t)row * a.ld_dst) + v) = pk;
+        for (int j = 0; j < 8; ++j) o[j] = wv[j] * __bfloat162float(__float2bfloat16(acc[i][j] * inv));
+        const uint4 pk = pack8(o);
+        for (int d = 0; d < a.n_dst; ++d)
+          *(reinterpret_cast<uint4*>(a.dst[d] + (size_t)row * a.ld_dst) + v) = pk;
+      }
     }
   }
   if (a.n_signal > 0) {
@@ -196,6 +200,13 @@ int vllm_peer_close(void* ptr) {
   return e == cudaSuccess ? VLLM_OK : (int)e;
 }
 
+// CTAs (= counter arrivals per destination) of one vllm_tp_reduce_norm_bf16 launch over `rows` rows; every rank of a
+// box has the same SM count, so producer and consumer compute the same number.
+int vllm_tp_norm_ctas(int rows) {
+  const int cap = vllm_num_sms() * 4;
+  return rows < cap ? (rows > 0 ? rows : 1) : cap;
+}
+
 int vllm_tp_reduce_norm_bf16(const void* slots, int n_slots, long long slot_stride, void* x, const void* weight,
                              float eps, void* const* dst, int n_dst, long long ld_dst, const void* wait_flag,
                              unsigned wait_target, void* const* signal, int n_signal, int rows, int cols,
@@ -223,9 +234,10 @@ int vllm_tp_reduce_norm_bf16(const void* slots, int n_slots, long long slot_stri
   a.n_signal = n_signal; a.rows = rows; a.cols = cols;
   cudaStream_t st = (cudaStream_t)stream;
   const int nvec = cols / 8;
-  if (nvec <= TPN_THREADS) tp_reduce_norm_kernel<1><<<rows, TPN_THREADS, 0, st>>>(a);
-  else if (nvec <= 2 * TPN_THREADS) tp_reduce_norm_kernel<2><<<rows, TPN_THREADS, 0, st>>>(a);
-  else tp_reduce_norm_kernel<4><<<rows, TPN_THREADS, 0, st>>>(a);
+  const int grid = vllm_tp_norm_ctas(rows);
+  if (nvec <= TPN_THREADS) tp_reduce_norm_kernel<1><<<grid, TPN_THREADS, 0, st>>>(a);
+  else if (nvec <= 2 * TPN_THREADS) tp_reduce_norm_kernel<2><<<grid, TPN_THREADS, 0, st>>>(a);
+  else tp_reduce_norm_kernel<4><<<grid, TPN_THREADS, 0, st>>>(a);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
 }

@@ -79,6 +79,7 @@ class PeerComm:
         self._g0, self._r0 = g0, r0
         self.e_gather = self.e_recv = self.e_barrier = 0    # epochs (every rank advances them identically)
         self.tiles_per_pass = (self.R // 128) * ((hidden + 255) // 256) * 8   # arrivals per source and o_proj pass
+        self.push_ctas = _lib.lib().vllm_tp_norm_ctas(self.R)                # arrivals per source and norm_push
         # where my pushes land on each peer
         self._gather_dst = _ptr_array([b + g0 + rank * self.R * hidden * 2 for b in self.base])
         self._recv_dst = _ptr_array([b + r0 + rank * self.R * hidden * 2 for b in self.base])
@@ -159,7 +160,7 @@ class PeerComm:
     def gathered(self):
         """Wait for every rank's rows of the current gather epoch; returns the [M, H] buffer (a view, not a copy)."""
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().vllm_tp_wait(self._own + _GATHER_FLAG, self.e_gather * self.world * self.R,
+            _lib.check(_lib.lib().vllm_tp_wait(self._own + _GATHER_FLAG, self.e_gather * self.world * self.push_ctas,
                                                self._stream()), "vllm_tp_wait")
         return self.gather
 
