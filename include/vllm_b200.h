@@ -52,8 +52,6 @@ int vllm_msda_forward_f32(const float* value, const int64_t* spatial_shapes, con
                           const float* sampling_loc, const float* attn_weight, float* out, int batch,
                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,
                           int num_point, const int64_t* host_shapes_hint, int flags, void* stream);
-/* fp64 instance of the same operator (AT_DISPATCH_FLOATING_TYPES,
- * ms_deform_attn_cuda.cu:258); always the strict kernel. */
 /* "Fast mode" of the same operator (SURVEY 8d cfg 2b): value is bf16 [N,S,M,32] -- the bf16 value_proj output the
  * reference upcasts with .float() before calling its fp32-only kernel (modeling_ov_grounding_dino_mask_dn.py:764-766)
  * -- sampling_loc / attn_weight stay fp32, accumulation is fp32, out is fp32 or bf16 (out_bf16) [N,Lq,M*32].  Results
@@ -63,6 +61,20 @@ int vllm_msda_forward_bf16v(const void* value, const int64_t* spatial_shapes, co
                             const float* sampling_loc, const float* attn_weight, void* out, int out_bf16, int batch,
                             int spatial_size, int num_heads, int channels, int num_levels, int num_query,
                             int num_point, const int64_t* host_shapes_hint, void* stream);
+/* Paired-row fast mode: the gather is bound by L1 line fetches, not bytes -- four corner rows = four 128-byte lines
+ * in the reference layout.  vllm_msda_pack_pairs_bf16 rewrites a bf16 value [N,S,M,32] into pairs [N,S,M,2,32]
+ * (slot 1 = the pixel to the right inside the same image row, else 0; host_shapes = the [L,2] int64 level shapes on
+ * the HOST); vllm_msda_forward_pairs then fetches two lines per sample.  Same arithmetic per corner as
+ * vllm_msda_forward_bf16v (fp32 products and accumulation); num_levels*num_point even and <= 32, channels == 32,
+ * pairs 128-byte aligned. */
+int vllm_msda_pack_pairs_bf16(const void* value, void* pairs, const int64_t* host_shapes, int batch, int spatial_size,
+                              int num_heads, int channels, int num_levels, void* stream);
+int vllm_msda_forward_pairs(const void* pairs, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                            const float* sampling_loc, const float* attn_weight, void* out, int out_bf16, int batch,
+                            int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                            int num_point, const int64_t* host_shapes_hint, void* stream);
+/* fp64 instance of the same operator (AT_DISPATCH_FLOATING_TYPES,
+ * ms_deform_attn_cuda.cu:258); always the strict kernel. */
 int vllm_msda_forward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                           const double* sampling_loc, const double* attn_weight, double* out, int batch,
                           int spatial_size, int num_heads, int channels, int num_levels, int num_query,

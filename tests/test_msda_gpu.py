@@ -272,6 +272,82 @@ def test_bf16_value_matches_fp32_op_on_upcast_value(case, out_dtype):
         assert torch.equal(fast, ref.bfloat16()) or ((fast.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-5 * scale).all()
 
 
+# ---- paired-row fast mode: two line fetches per sample ----
+@pytest.mark.parametrize("case", ["enc", "dec", "oob", "points2", "generic_k"])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_pairs_mode_matches_fp32_op_on_upcast_value(case, out_dtype):
+    """pack_pairs + forward_pairs == ms_deform_attn_forward(value_bf16.float()) up to fp32 summation order, incl. samples
+    hanging over every edge (w_low = -1 re-based pair, zero partner at the right edge, rows -1 / H predicated off)."""
+    import visionllm_b200.msda as ext
+    from oracle import msda_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes_l = [(20, 27), (10, 14), (5, 7), (3, 4)]
+    L, P = {"points2": (4, 2), "generic_k": (3, 2)}.get(case, (4, 4))
+    shapes_l = shapes_l[:L]
+    shapes = torch.tensor(shapes_l, dtype=torch.int64, device="cuda")
+    lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N, M, D = 3, 8, 32
+    Lq = S if case != "dec" else 37
+    value = torch.randn(N, S, M, D, device="cuda", generator=g).bfloat16()
+    spread = 1.6 if case == "oob" else 1.05
+    loc = (torch.rand(N, Lq, M, L, P, 2, device="cuda", generator=g) - 0.5) * spread + 0.5
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, device="cuda", generator=g), -1).view(N, Lq, M, L, P).contiguous()
+    pairs = ext.ms_deform_attn_pack_pairs(value, shapes)
+    # layout contract of the pack kernel
+    assert torch.equal(pairs[:, :, :, 0], value)
+    right = torch.zeros_like(value)
+    for (H, W), st in zip(shapes_l, lsi.tolist()):
+        v = value[:, st:st + H * W].view(N, H, W, M, D)
+        r = torch.zeros_like(v); r[:, :, :-1] = v[:, :, 1:]
+        right[:, st:st + H * W] = r.view(N, H * W, M, D)
+    assert torch.equal(pairs[:, :, :, 1], right)
+    fast = ext.ms_deform_attn_forward_pairs(pairs, shapes, lsi, loc, aw, out_dtype)
+    ref = ext.ms_deform_attn_forward(value.float(), shapes, lsi, loc, aw, 64)
+    orc = torch.from_numpy(O.forward_kernel_semantics(value.float().cpu().numpy(), shapes.cpu().numpy(), lsi.cpu().numpy(),
+                                                      loc.cpu().numpy(), aw.cpu().numpy())).cuda()
+    assert fast.dtype == out_dtype and fast.shape == ref.shape
+    scale = orc.abs().max().item()
+    if out_dtype == torch.float32:
+        assert (fast - ref).abs().max().item() <= 1e-5 * scale
+        assert (fast - orc).abs().max().item() <= 1e-5 * scale
+    else:
+        assert ((fast.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-5 * scale).all()
+
+
+def test_pairs_mode_skips_out_of_map_corners_like_the_reference():
+    """A corner outside the map is never read (reference .cuh:31-58): poison everything a sample at the map border must
+    not touch with NaN and compare with the fp32 operator on the same poisoned value."""
+    import visionllm_b200.msda as ext
+    shapes = torch.tensor([[6, 5], [3, 4]], dtype=torch.int64, device="cuda")
+    lsi = torch.tensor([0, 30], dtype=torch.int64, device="cuda")
+    S, N, M, D, L, P = 42, 1, 2, 32, 2, 2
+    g = torch.Generator(device="cuda").manual_seed(3)
+    value = torch.randn(N, S, M, D, device="cuda", generator=g).bfloat16()
+    value[:, 5] = float("nan")       # pixel (1, 0) of level 0: the row-wrapped "right neighbour" of pixel (0, 4)
+    value[:, 29] = float("nan")      # last pixel of level 0
+    # queries whose samples hang over the right / top / left borders of level 0, and far outside
+    pts = torch.tensor([[[0.99, 0.05], [0.95, 0.05]], [[-0.05, 0.3], [0.3, -0.05]], [[1.15, 0.5], [0.5, 1.3]]],
+                       device="cuda")                                        # [Lq = 3, P = 2, (x, y)]
+    loc = pts.view(1, 3, 1, 1, 2, 2).expand(N, 3, M, L, 2, 2).contiguous()
+    aw = torch.full((N, 3, M, L, P), 1.0 / (L * P), device="cuda")
+    pairs = ext.ms_deform_attn_pack_pairs(value, shapes)
+    fast = ext.ms_deform_attn_forward_pairs(pairs, shapes, lsi, loc, aw, torch.float32)
+    ref = ext.ms_deform_attn_forward(value.float(), shapes, lsi, loc, aw, 64)
+    assert torch.equal(torch.isnan(fast), torch.isnan(ref))
+    ok = ~torch.isnan(ref)
+    assert (fast[ok] - ref[ok]).abs().max().item() <= 1e-5
+
+
+def test_pairs_mode_full_size_constant_field():
+    import visionllm_b200.msda as ext
+    value, shapes, lsi, loc, attw = _full_size(N=2)
+    loc = loc.clamp(0.2, 0.8).contiguous()
+    pairs = ext.ms_deform_attn_pack_pairs(torch.ones_like(value).bfloat16(), shapes)
+    out = ext.ms_deform_attn_forward_pairs(pairs, shapes, lsi, loc, attw, torch.float32)
+    assert (out - 1.0).abs().max().item() < 1e-5
+
+
 def test_bf16_value_rejects_unsupported():
     import visionllm_b200.msda as ext
     shapes = torch.tensor([[4, 4]], dtype=torch.int64, device="cuda")
