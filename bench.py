@@ -67,6 +67,15 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_T0 = time.time()
+
+
+def trace(msg):
+    """Stage timestamps on stderr (VLLM_BENCH_TRACE=1): where a multi-rank launch spends its start-up time."""
+    if os.environ.get("VLLM_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -94,13 +103,19 @@ def main():
         print(json.dumps(line), flush=True)
         return
 
+    trace("importing torch")
     import torch
     import torch.distributed as dist
+    trace("torch imported")
     torch.cuda.set_device(local_rank)
+    torch.cuda.init()
+    trace("cuda context up")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        trace("process group up")
     wl = benchlib.WORKLOADS[name](rank=rank, world=world, device=torch.device("cuda", local_rank))
     wl.setup()
+    trace("workload set up")
 
     from visionllm_b200 import _lib
 
@@ -128,6 +143,7 @@ def main():
     if rank == 0:
         sampler.start()
     ms_dev, launches = timed(wl.step_device, args.steps, args.warmup)
+    trace(f"device-resident steps timed: {ms_dev / args.steps:.2f} ms/step")
     if args.cuprof:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()

@@ -169,7 +169,7 @@ class MsdaEncoderPairsWorkload(MsdaEncoderBf16Workload):
     metric = "msda_encoder_layer_images_per_sec_bf16_value"
 
     def _run(self, value, loc, attw):
-        pairs = self.ext.ms_deform_attn_pack_pairs(value, self.shapes)
+        pairs = self.ext.ms_deform_attn_pack_pairs(value, self.shapes, self.lsi)
         return self.ext.ms_deform_attn_forward_pairs(pairs, self.shapes, self.lsi, loc, attw)
 
     def step_device(self):
@@ -182,13 +182,14 @@ class MsdaEncoderPairsWorkload(MsdaEncoderBf16Workload):
 
     def dominant_kernel_ms(self, steps):
         torch = self.torch
-        pairs = self.ext.ms_deform_attn_pack_pairs(self.value, self.shapes)
+        pairs = self.ext.ms_deform_attn_pack_pairs(self.value, self.shapes, self.lsi)
         torch.cuda.synchronize()
         evs = []
         for _ in range(steps):
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            pairs = None                       # hand the block back first: no cudaMalloc inside the timed interval
             e0.record()
-            pairs = self.ext.ms_deform_attn_pack_pairs(self.value, self.shapes)
+            pairs = self.ext.ms_deform_attn_pack_pairs(self.value, self.shapes, self.lsi)
             e1.record()
             self.ext.ms_deform_attn_forward_pairs(pairs, self.shapes, self.lsi, self.loc, self.attw)
             e2.record()

@@ -62,13 +62,14 @@ int vllm_msda_forward_bf16v(const void* value, const int64_t* spatial_shapes, co
                             int spatial_size, int num_heads, int channels, int num_levels, int num_query,
                             int num_point, const int64_t* host_shapes_hint, void* stream);
 /* Paired-row fast mode: the gather is bound by L1 line fetches, not bytes -- four corner rows = four 128-byte lines
- * in the reference layout.  vllm_msda_pack_pairs_bf16 rewrites a bf16 value [N,S,M,32] into pairs [N,S,M,2,32]
- * (slot 1 = the pixel to the right inside the same image row, else 0; host_shapes = the [L,2] int64 level shapes on
- * the HOST); vllm_msda_forward_pairs then fetches two lines per sample.  Same arithmetic per corner as
+ * in the reference layout.  vllm_msda_pack_pairs_bf16 rewrites a bf16 value [N,S,M,32] into pairs [N*S*M + 1, 2, 32]
+ * (slot 1 = the pixel to the right inside the same image row, else 0; one extra all-zero 128-byte line at the end
+ * is where corners outside the map are read from; shapes / level starts read on the device); vllm_msda_forward_pairs then fetches two lines per sample.  Same arithmetic per corner as
  * vllm_msda_forward_bf16v (fp32 products and accumulation); num_levels*num_point even and <= 32, channels == 32,
  * pairs 128-byte aligned. */
-int vllm_msda_pack_pairs_bf16(const void* value, void* pairs, const int64_t* host_shapes, int batch, int spatial_size,
-                              int num_heads, int channels, int num_levels, void* stream);
+int vllm_msda_pack_pairs_bf16(const void* value, void* pairs, const int64_t* spatial_shapes,
+                              const int64_t* level_start_index, int batch, int spatial_size, int num_heads,
+                              int channels, int num_levels, void* stream);
 int vllm_msda_forward_pairs(const void* pairs, const int64_t* spatial_shapes, const int64_t* level_start_index,
                             const float* sampling_loc, const float* attn_weight, void* out, int out_bf16, int batch,
                             int spatial_size, int num_heads, int channels, int num_levels, int num_query,

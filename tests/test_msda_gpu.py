@@ -293,15 +293,17 @@ def test_pairs_mode_matches_fp32_op_on_upcast_value(case, out_dtype):
     spread = 1.6 if case == "oob" else 1.05
     loc = (torch.rand(N, Lq, M, L, P, 2, device="cuda", generator=g) - 0.5) * spread + 0.5
     aw = torch.softmax(torch.randn(N, Lq, M, L * P, device="cuda", generator=g), -1).view(N, Lq, M, L, P).contiguous()
-    pairs = ext.ms_deform_attn_pack_pairs(value, shapes)
+    pairs = ext.ms_deform_attn_pack_pairs(value, shapes, lsi)
     # layout contract of the pack kernel
-    assert torch.equal(pairs[:, :, :, 0], value)
+    assert not pairs[-1].any()                      # the all-zero line off-map corners read
+    pairs5 = pairs[:-1].view(N, S, M, 2, D)
+    assert torch.equal(pairs5[:, :, :, 0], value)
     right = torch.zeros_like(value)
     for (H, W), st in zip(shapes_l, lsi.tolist()):
         v = value[:, st:st + H * W].view(N, H, W, M, D)
         r = torch.zeros_like(v); r[:, :, :-1] = v[:, :, 1:]
         right[:, st:st + H * W] = r.view(N, H * W, M, D)
-    assert torch.equal(pairs[:, :, :, 1], right)
+    assert torch.equal(pairs5[:, :, :, 1], right)
     fast = ext.ms_deform_attn_forward_pairs(pairs, shapes, lsi, loc, aw, out_dtype)
     ref = ext.ms_deform_attn_forward(value.float(), shapes, lsi, loc, aw, 64)
     orc = torch.from_numpy(O.forward_kernel_semantics(value.float().cpu().numpy(), shapes.cpu().numpy(), lsi.cpu().numpy(),
@@ -331,7 +333,7 @@ def test_pairs_mode_skips_out_of_map_corners_like_the_reference():
                        device="cuda")                                        # [Lq = 3, P = 2, (x, y)]
     loc = pts.view(1, 3, 1, 1, 2, 2).expand(N, 3, M, L, 2, 2).contiguous()
     aw = torch.full((N, 3, M, L, P), 1.0 / (L * P), device="cuda")
-    pairs = ext.ms_deform_attn_pack_pairs(value, shapes)
+    pairs = ext.ms_deform_attn_pack_pairs(value, shapes, lsi)
     fast = ext.ms_deform_attn_forward_pairs(pairs, shapes, lsi, loc, aw, torch.float32)
     ref = ext.ms_deform_attn_forward(value.float(), shapes, lsi, loc, aw, 64)
     assert torch.equal(torch.isnan(fast), torch.isnan(ref))
@@ -343,7 +345,7 @@ def test_pairs_mode_full_size_constant_field():
     import visionllm_b200.msda as ext
     value, shapes, lsi, loc, attw = _full_size(N=2)
     loc = loc.clamp(0.2, 0.8).contiguous()
-    pairs = ext.ms_deform_attn_pack_pairs(torch.ones_like(value).bfloat16(), shapes)
+    pairs = ext.ms_deform_attn_pack_pairs(torch.ones_like(value).bfloat16(), shapes, lsi)
     out = ext.ms_deform_attn_forward_pairs(pairs, shapes, lsi, loc, attw, torch.float32)
     assert (out - 1.0).abs().max().item() < 1e-5
 

@@ -26,7 +26,7 @@ _SIGNATURES = {
     "vllm_version": (ctypes.c_char_p, []),
     "vllm_msda_forward_f32": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
     "vllm_msda_forward_bf16v": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp]),
-    "vllm_msda_pack_pairs_bf16": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "vllm_msda_pack_pairs_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
     "vllm_msda_forward_pairs": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp]),
     "vllm_msda_forward_f64": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
     "vllm_msda_backward_f32": (ci, [vp] * 9 + [ci] * 7 + [vp]),

@@ -382,12 +382,21 @@ msda_fwd_warp_kernel(const ValT* __restrict__ value, const int64_t* __restrict__
 // costs two line fetches (rows h_low, h_low + 1) instead of four, and a warp instruction (32 x 16 B) covers two
 // samples.  Lane = (sample parity, row, column, channel octet); per-corner weights are the same products as in
 // msda_fwd_warp_kernel ((row weight * column weight) * attention weight), fp32 accumulation; corners outside the map
-// are predicated off exactly like the reference (w_low == -1 re-bases the pair on pixel 0).
+// read an all-zero line appended behind the last pixel with weight 0 (w_low == -1 re-bases the pair on pixel 0), so a
+// NaN/Inf in a pixel the reference would not touch never reaches the sum.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 msda_pack_pairs_kernel(const __nv_bfloat16* __restrict__ value, __nv_bfloat16* __restrict__ pairs, long long n_chunks,
-                       int S, int M, int L, const __grid_constant__ MsdaTiling tl) {
+                       const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi, int S, int M, int L) {
+  __shared__ int s_w[MSDA_MAX_LEVELS], s_start[MSDA_MAX_LEVELS];
+  if (threadIdx.x < L) {
+    s_w[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    s_start[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if (blockIdx.x == 0 && threadIdx.x < 8)        // the all-zero line behind the last pixel: target of every off-map corner
+    *reinterpret_cast<uint4*>(pairs + n_chunks * 8 + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += stride) {
     const int oct = (int)(i & 3), slot = (int)((i >> 2) & 1);
     const long long pm = i >> 3;               // (n*S + s)*M + m
@@ -395,24 +404,16 @@ msda_pack_pairs_kernel(const __nv_bfloat16* __restrict__ value, __nv_bfloat16* _
     const long long ns = pm / M;
     const int sidx = (int)(ns % S);
     int l = 0;
-    while (l + 1 < L && sidx >= tl.q_start[l + 1]) ++l;
-    const int w = (sidx - tl.q_start[l]) % tl.W[l];
+    while (l + 1 < L && sidx >= s_start[l + 1]) ++l;
+    const int w = (sidx - s_start[l]) % s_w[l];
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (slot == 0 || w + 1 < tl.W[l])
+    if (slot == 0 || w + 1 < s_w[l])
       v = __ldg(reinterpret_cast<const uint4*>(value + ((ns + slot) * M + m) * 32 + oct * 8));
     *reinterpret_cast<uint4*>(pairs + i * 8) = v;
   }
 }
 
-// 16-byte read-only load under a predicate (no branch): zeros when the predicate is off.
-__device__ __forceinline__ uint4 ldg_pred_u4(const void* p, int on) {
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
-               : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"(on));
-  return v;
-}
-
-constexpr int MSDA_PAIR_ROW = 32 + 2;   // int4 entries per (warp, row) slab: 32 samples + pad (row slabs on different banks)
+constexpr int MSDA_PAIR_ROW = 32 + 2;   // int2 entries per (warp, row, column) slab: 32 samples + pad (slabs on different banks)
 
 template <int TH, int TW, int NW, int KC, int PC, typename OutT>
 __global__ void __launch_bounds__(NW * 32)
@@ -425,7 +426,7 @@ msda_fwd_pair_kernel(const __nv_bfloat16* __restrict__ pairs, const int64_t* __r
   constexpr int QPW = TQ / NW;
   static_assert(TQ % NW == 0, "tile must split evenly over warps");
   __shared__ int s_h[MSDA_MAX_LEVELS], s_w[MSDA_MAX_LEVELS], s_start[MSDA_MAX_LEVELS];
-  __shared__ __align__(16) int4 s_meta[NW][2][MSDA_PAIR_ROW];   // {byte offset, weight col 0, weight col 1, valid bits}
+  __shared__ __align__(16) int2 s_meta[NW][4][MSDA_PAIR_ROW];   // [row*2 + column]: {byte offset, weight bits}; off-map corner -> zero line
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < L) {
@@ -461,13 +462,17 @@ msda_fwd_pair_kernel(const __nv_bfloat16* __restrict__ pairs, const int64_t* __r
   const char* vbl = reinterpret_cast<const char*>(pairs) + ((size_t)b * S * M + m) * 128 + (lane & 7) * 16;
   const int g1 = lane / K, s1 = lane - g1 * K;    // phase-1 role
   const int l1 = s1 / P;
+  // byte offset (relative to this CTA's (batch, head) base) of the all-zero line behind the last pixel of the tensor
+  const int zero_off = (int)(((long long)gridDim.y * S * M - ((long long)b * S * M + m)) * 128);
 
   for (int t0 = 0; t0 < QPW; t0 += G) {
     // ---- phase 1: one lane per sample -> two row entries ------------------
     int q = -1;
     if (g1 < G && t0 + g1 < QPW) q = query_of(warp * QPW + t0 + g1);
     {
-      int4 e0 = make_int4(0, 0, 0, 0), e1 = make_int4(0, 0, 0, 0);
+      int2 e[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) e[c] = make_int2(zero_off, 0);   // weight 0 x zeros: contributes exactly 0
       if (q >= 0) {
         const size_t si = (((size_t)b * Lq + q) * M + m) * K + s1;
         const float2 xy = ld_stream_f2(loc + 2 * si);
@@ -476,30 +481,32 @@ msda_fwd_pair_kernel(const __nv_bfloat16* __restrict__ pairs, const int64_t* __r
         const MsdaGeom<float> ge = msda_geom<float>(xy.x, xy.y, H, W);
         if (ge.mask & 1) {
           const float hh = 1.f - ge.lh, hw = 1.f - ge.lw;
-          // column slots: pixel w_low (slot 0) and w_low + 1 (slot 1); w_low == -1 re-bases on pixel 0
+          // column slots: pixel w_low (slot 0) and w_low + 1 (slot 1); w_low == -1 re-bases the pair on pixel 0,
+          // whose slot 0 then carries the (h, w_high) corner
           const bool left_out = ge.w_low < 0;
           const int px = left_out ? 0 : ge.w_low;
-          const int cv = left_out ? 1 : (ge.w_low + 1 <= W - 1 ? 3 : 1);     // valid column bits
+          const bool col1 = !left_out && ge.w_low + 1 <= W - 1;
           const int off0 = (s_start[l1] + ge.h_low * W + px) * pix_bytes;
+          const int off1 = off0 + W * pix_bytes;
           if (ge.h_low >= 0) {
-            const float c0 = left_out ? hh * ge.lw : hh * hw, c1 = left_out ? 0.f : hh * ge.lw;
-            e0 = make_int4(off0, __float_as_int(c0 * aw), __float_as_int(c1 * aw), cv);
+            e[0] = make_int2(off0, __float_as_int((left_out ? hh * ge.lw : hh * hw) * aw));
+            if (col1) e[1] = make_int2(off0, __float_as_int((hh * ge.lw) * aw));
           }
           if (ge.h_low + 1 <= H - 1) {
-            const float c0 = left_out ? ge.lh * ge.lw : ge.lh * hw, c1 = left_out ? 0.f : ge.lh * ge.lw;
-            e1 = make_int4(off0 + W * pix_bytes, __float_as_int(c0 * aw), __float_as_int(c1 * aw), cv);
+            e[2] = make_int2(off1, __float_as_int((left_out ? ge.lh * ge.lw : ge.lh * hw) * aw));
+            if (col1) e[3] = make_int2(off1, __float_as_int((ge.lh * ge.lw) * aw));
           }
         }
       }
-      s_meta[warp][0][lane] = e0;
-      s_meta[warp][1][lane] = e1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s_meta[warp][c][lane] = e[c];
     }
     __syncwarp();
     // ---- phase 2: 2 samples x 2 rows x 128 B per warp instruction ----------
     for (int g = 0; g < G && t0 + g < QPW; ++g) {
       const int qg = __shfl_sync(0xffffffffu, q, g * K);
       if (qg < 0) continue;  // warp-uniform
-      const int4* mp = &s_meta[warp][r][g * K + sp];
+      const int2* mp = &s_meta[warp][r * 2 + col][g * K + sp];
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -516,18 +523,18 @@ msda_fwd_pair_kernel(const __nv_bfloat16* __restrict__ pairs, const int64_t* __r
         // batches of 4 line fetches in flight per lane, branch-free (predicated loads; an off corner contributes 0)
 #pragma unroll
         for (int s0 = 0; s0 < KC / 2; s0 += 4) {
-          int4 me[4]; uint4 raw[4];
+          int2 me[4]; uint4 raw[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) me[j] = mp[2 * (s0 + j)];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) raw[j] = ldg_pred_u4(vbl + (unsigned)me[j].x, (me[j].w >> col) & 1);
+          for (int j = 0; j < 4; ++j) raw[j] = __ldg(reinterpret_cast<const uint4*>(vbl + (unsigned)me[j].x));
 #pragma unroll
-          for (int j = 0; j < 4; ++j) fma8(raw[j], __int_as_float(col ? me[j].z : me[j].y));
+          for (int j = 0; j < 4; ++j) fma8(raw[j], __int_as_float(me[j].y));
         }
       } else {
         for (int s = 0; s < K / 2; ++s) {
-          const int4 me = mp[2 * s];
-          fma8(ldg_pred_u4(vbl + (unsigned)me.x, (me.w >> col) & 1), __int_as_float(col ? me.z : me.y));
+          const int2 me = mp[2 * s];
+          fma8(__ldg(reinterpret_cast<const uint4*>(vbl + (unsigned)me.x)), __int_as_float(me.y));
         }
       }
       // reduce-scatter over the 8 lanes that hold the same channel octet: 4 + 2 + 1 shuffles
@@ -791,28 +798,21 @@ int vllm_msda_forward_bf16v(const void* value, const int64_t* spatial_shapes, co
                                                       num_query, num_point, host_shapes_hint, st);
 }
 
-int vllm_msda_pack_pairs_bf16(const void* value, void* pairs, const int64_t* host_shapes, int batch, int spatial_size,
-                              int num_heads, int channels, int num_levels, void* stream) {
+int vllm_msda_pack_pairs_bf16(const void* value, void* pairs, const int64_t* spatial_shapes,
+                              const int64_t* level_start_index, int batch, int spatial_size, int num_heads,
+                              int channels, int num_levels, void* stream) {
   if (batch < 0 || spatial_size < 0 || num_heads <= 0 || num_levels <= 0) return VLLM_EINVAL;
   if (channels != 32 || num_levels > MSDA_MAX_LEVELS) return VLLM_EUNSUPPORTED;
   const long long n_chunks = (long long)batch * spatial_size * num_heads * 8;
   if (n_chunks == 0) return VLLM_OK;
-  if (!value || !pairs || !host_shapes) return VLLM_EINVAL;
+  if (!value || !pairs || !spatial_shapes || !level_start_index) return VLLM_EINVAL;
   if (!vllm_aligned(value, 16) || !vllm_aligned(pairs, 16)) return VLLM_EALIGN;
-  MsdaTiling tl; memset(&tl, 0, sizeof(tl));
-  long long tot = 0;
-  for (int l = 0; l < num_levels; ++l) {
-    const long long H = host_shapes[2 * l], W = host_shapes[2 * l + 1];
-    if (H <= 0 || W <= 0 || H > INT_MAX || W > INT_MAX) return VLLM_EINVAL;
-    tl.H[l] = (int)H; tl.W[l] = (int)W; tl.q_start[l] = (int)tot;
-    tot += H * W;
-  }
-  if (tot != spatial_size) return VLLM_EINVAL;   // the pair layout needs the true row structure
   long long blocks = (n_chunks + 255) / 256;
   const long long cap = (long long)vllm_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   msda_pack_pairs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)value, (__nv_bfloat16*)pairs, n_chunks, spatial_size, num_heads, num_levels, tl);
+      (const __nv_bfloat16*)value, (__nv_bfloat16*)pairs, n_chunks, spatial_shapes, level_start_index, spatial_size,
+      num_heads, num_levels);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
 }
@@ -827,6 +827,7 @@ int vllm_msda_forward_pairs(const void* pairs, const int64_t* spatial_shapes, co
   if (rc) return rc;
   const int K = num_levels * num_point;
   if (channels != 32 || K > 32 || (K & 1)) return VLLM_EUNSUPPORTED;
+  if (((long long)batch * spatial_size * num_heads + 1) * 128 > INT_MAX) return VLLM_EUNSUPPORTED;  // zero line offset is int32
   if (!vllm_aligned(pairs, 128) || !vllm_aligned(sampling_loc, 8)) return VLLM_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* v = (const __nv_bfloat16*)pairs;

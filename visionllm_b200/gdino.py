@@ -105,7 +105,7 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
         if (value.dtype == torch.bfloat16 and msda_ext.PAIRS_FOR_DENSE_QUERIES and 2 * Lq >= S
                 and msda_ext.supports_pairs(D, L, P)):
             # many queries per value pixel (encoder self-attention): one pack pass buys two line fetches per sample
-            pairs = msda_ext.ms_deform_attn_pack_pairs(value.view(B, S, M, D), spatial_shapes)
+            pairs = msda_ext.ms_deform_attn_pack_pairs(value.view(B, S, M, D), spatial_shapes, level_start_index)
             out = msda_ext.ms_deform_attn_forward_pairs(pairs, spatial_shapes, level_start_index,
                                                         loc.float().contiguous(), attention_weights.float().contiguous(),
                                                         self.output_proj.weight.dtype)

@@ -163,23 +163,28 @@ def ms_deform_attn_forward_bf16(value, spatial_shapes, level_start_index, sampli
 PAIRS_FOR_DENSE_QUERIES = False
 
 
-def ms_deform_attn_pack_pairs(value, spatial_shapes):
-    """bf16 value [N,S,M,32] -> paired rows [N,S,M,2,32]: slot 0 = value(s), slot 1 = value(s+1) when pixel s+1 is in
+def ms_deform_attn_pack_pairs(value, spatial_shapes, level_start_index):
+    """bf16 value [N,S,M,32] -> paired rows [N*S*M + 1, 2, 32] (pixel-major like value): slot 0 = value(s), slot 1 = value(s+1) when pixel s+1 is in
     the same image row (else 0), so both horizontal corners of a bilinear sample sit in one aligned 128-byte line
-    (csrc/msda.cu, "paired-row fast mode").  One HBM pass: S*M*64 B read, S*M*128 B written per image."""
+    (csrc/msda.cu, "paired-row fast mode").  One HBM pass: S*M*64 B read, S*M*128 B written per image.  The level
+    geometry is read on the device (no host copy, graph-capturable)."""
     if value.dtype != torch.bfloat16 or not value.is_cuda or not value.is_contiguous() or value.dim() != 4:
         raise RuntimeError("ms_deform_attn_pack_pairs: value must be a contiguous CUDA bf16 [N,S,M,D] tensor")
     N, S, M, D = value.shape
     if D != 32:
         raise RuntimeError("ms_deform_attn_pack_pairs: D must be 32")
-    hs = _host_shapes(spatial_shapes)
-    if int(hs.prod(1).sum()) != S:
-        raise RuntimeError("spatial_shapes do not cover the value tensor")
-    pairs = torch.empty((N, S, M, 2, D), dtype=torch.bfloat16, device=value.device)
-    if pairs.numel():
+    for t in (spatial_shapes, level_start_index):
+        if t.dtype != torch.int64 or not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("spatial_shapes / level_start_index must be contiguous CUDA int64 tensors")
+    if spatial_shapes.dim() != 2 or level_start_index.numel() != spatial_shapes.shape[0]:
+        raise RuntimeError("expected spatial_shapes[L,2] and level_start_index[L]")
+    pairs = torch.empty((N * S * M + 1, 2, D), dtype=torch.bfloat16, device=value.device)   # + the all-zero line
+    pairs._b200_value_shape = (N, S, M, D)
+    if N * S * M:
         with torch.cuda.device(value.device):
-            rc = _lib.lib().vllm_msda_pack_pairs_bf16(value.data_ptr(), pairs.data_ptr(), hs.data_ptr(), N, S, M, D,
-                                                      hs.shape[0], torch.cuda.current_stream().cuda_stream)
+            rc = _lib.lib().vllm_msda_pack_pairs_bf16(value.data_ptr(), pairs.data_ptr(), spatial_shapes.data_ptr(),
+                                                      level_start_index.data_ptr(), N, S, M, D,
+                                                      spatial_shapes.shape[0], torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "ms_deform_attn_pack_pairs")
     return pairs
 
@@ -191,13 +196,16 @@ def ms_deform_attn_forward_pairs(pairs, spatial_shapes, level_start_index, sampl
                  ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)):
         if not t.is_contiguous() or not t.is_cuda:
             raise RuntimeError(f"{n} must be a contiguous CUDA tensor")
-    if pairs.dtype != torch.bfloat16 or pairs.dim() != 5 or pairs.shape[3] != 2:
-        raise RuntimeError("pairs must be bf16 [N,S,M,2,D]")
+    vs = getattr(pairs, "_b200_value_shape", None)
+    if pairs.dtype != torch.bfloat16 or pairs.dim() != 3 or pairs.shape[1] != 2 or vs is None:
+        raise RuntimeError("pairs must be the tensor returned by ms_deform_attn_pack_pairs")
     if sampling_loc.dtype != torch.float32 or attn_weight.dtype != torch.float32:
         raise RuntimeError("sampling_loc / attn_weight must be fp32")
     if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
         raise RuntimeError("spatial_shapes / level_start_index must be int64")
-    N, S, M, _, D = pairs.shape
+    N, S, M, D = vs
+    if pairs.shape[0] != N * S * M + 1 or pairs.shape[2] != D:
+        raise RuntimeError("pairs does not match its recorded value shape")
     L = spatial_shapes.shape[0]
     if sampling_loc.dim() != 6 or attn_weight.dim() != 5:
         raise RuntimeError("expected sampling_loc[N,Lq,M,L,P,2], attn_weight[N,Lq,M,L,P]")
