@@ -76,6 +76,25 @@ def trace(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries print to fd 1 (NCCL's "NCCL version ..." banner at communicator creation): park the real stdout and
+    send everything else to stderr, so that the ONE JSON line is the only thing on stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -103,6 +122,7 @@ def main():
         print(json.dumps(line), flush=True)
         return
 
+    quiet_stdout()
     trace("importing torch")
     import torch
     import torch.distributed as dist
@@ -175,8 +195,9 @@ def main():
     line.update(wl.extra())
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = benchlib.cpu_baseline(name)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
+        os.dup2(2, 1)                                  # teardown chatter stays off stdout too
         dist.destroy_process_group()
 
 
