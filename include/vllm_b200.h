@@ -177,6 +177,16 @@ int vllm_rmsnorm_bf16(const void* x, long long ldx, const void* weight, void* y,
                       int cols, float eps, void* stream);
 int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const void* bias, void* y, long long ldy,
                         long long rows, int cols, float eps, void* stream);
+/* LayerNorm followed by exact-erf GELU in one pass (the `LayerNorm -> GELU` tail of the DCNv3 module's depthwise
+ * branch, ops_dcnv3/modules/dcnv3.py:252-267). */
+int vllm_layernorm_gelu_bf16(const void* x, long long ldx, const void* weight, const void* bias, void* y,
+                             long long ldy, long long rows, int cols, float eps, void* stream);
+/* Depthwise KxK convolution (K = 3, 5, 7; stride 1, padding K/2) over a channels-last bf16 map x[batch,H,W,C] with
+ * fp32 accumulation: the `nn.Conv2d(C, C, k, padding=(k-1)//2, groups=C)` at the head of the DCNv3 module
+ * (ops_dcnv3/modules/dcnv3.py:252-259; InternImage-H: k = 5).  weight_taps is the conv weight repacked tap-major
+ * [K*K][C] bf16, bias [C] bf16 or NULL, C % 8 == 0. */
+int vllm_dwconv_nhwc_bf16(const void* x, const void* weight_taps, const void* bias, void* y, int batch, int height,
+                          int width, int channels, int kernel, void* stream);
 /* GroupNorm over channels-last rows x[batch, hw, channels] (bf16, fp32 statistics, optional fused ReLU): the
  * nn.GroupNorm(32, d_model) after each Grounding-DINO input projection
  * (grounding_dino/modeling_ov_grounding_dino_mask_dn.py:2085-2110, :2393-2405) and the detectron2

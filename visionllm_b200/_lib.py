@@ -41,6 +41,8 @@ _SIGNATURES = {
     "vllm_gemm_set_group_m": (ci, [ci]),
     "vllm_rmsnorm_bf16": (ci, [vp, cll, vp, vp, cll, cll, ci, cf, vp]),
     "vllm_layernorm_bf16": (ci, [vp, cll, vp, vp, vp, cll, cll, ci, cf, vp]),
+    "vllm_layernorm_gelu_bf16": (ci, [vp, cll, vp, vp, vp, cll, cll, ci, cf, vp]),
+    "vllm_dwconv_nhwc_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
     "vllm_rope_bf16": (ci, [vp, cll, vp, vp, cll, ci, ci, vp]),
     "vllm_groupnorm_workspace_bytes": (cll, [ci, ci]),
     "vllm_groupnorm_nhwc_bf16": (ci, [vp, vp, vp, vp, ci, cll, ci, ci, cf, ci, vp, cll, vp]),

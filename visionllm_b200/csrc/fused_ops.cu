@@ -56,7 +56,7 @@ template <int MODE, int VPT, int TPR>
 __global__ void __launch_bounds__(NT)
 norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __restrict__ w,
                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* y, long long ldy, long long rows,
-                 int cols, float eps) {
+                 int cols, float eps, int act) {
   __shared__ float sh[NT / 32];
   constexpr int RPC = NT / TPR;
   const int tr = threadIdx.x % TPR;
@@ -105,6 +105,10 @@ norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __r
         float bv[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(b) + v), bv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * inv * wv[j] + bv[j];
+        if (act == 1) {                                  // exact-erf GELU on the normalised row (LN -> GELU chains)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = 0.5f * o[j] * (1.f + erff(o[j] * 0.70710678118654752f));
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -120,7 +124,7 @@ norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __r
 
 template <int MODE>
 int launch_norm(const void* x, long long ldx, const void* w, const void* b, void* y, long long ldy, long long rows,
-                int cols, float eps, cudaStream_t st) {
+                int cols, float eps, cudaStream_t st, int act = 0) {
   const int nvec = cols / 8;
   auto go = [&](auto vpt, auto tpr) -> int {
     constexpr int VPT = decltype(vpt)::value, TPR = decltype(tpr)::value;
@@ -128,7 +132,7 @@ int launch_norm(const void* x, long long ldx, const void* w, const void* b, void
     if (blocks > 2147483647LL) return VLLM_EUNSUPPORTED;
     norm_rows_kernel<MODE, VPT, TPR><<<(unsigned)blocks, NT, 0, st>>>(
         (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, rows,
-        cols, eps);
+        cols, eps, act);
     VLLM_CHECK_LAUNCH();
     return VLLM_OK;
   };
@@ -239,6 +243,15 @@ int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const 
   if (rc) return rc;
   if (!weight || !bias || !vllm_aligned(weight, 16) || !vllm_aligned(bias, 16)) return VLLM_EINVAL;
   return launch_norm<1>(x, ldx, weight, bias, y, ldy, rows, cols, eps, (cudaStream_t)stream);
+}
+
+int vllm_layernorm_gelu_bf16(const void* x, long long ldx, const void* weight, const void* bias, void* y,
+                             long long ldy, long long rows, int cols, float eps, void* stream) {
+  int rc = check_rows(x, ldx, y, ldy, rows, cols);
+  if (rc == 1000) return VLLM_OK;
+  if (rc) return rc;
+  if (!weight || !bias || !vllm_aligned(weight, 16) || !vllm_aligned(bias, 16)) return VLLM_EINVAL;
+  return launch_norm<1>(x, ldx, weight, bias, y, ldy, rows, cols, eps, (cudaStream_t)stream, 1);
 }
 
 int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long long tokens, int heads,

@@ -186,10 +186,16 @@ class B200GroundingDinoModel(nn.Module):
         super().__init__()
         self.config = config
         if backbone_model is None:
-            if config.backbone_config.model_type != "swin":
-                raise NotImplementedError("only the Swin backbone preset is wired (InternImage-H: visionllm_b200.dcnv3 op only)")
-            from transformers import AutoBackbone
-            backbone_model = AutoBackbone.from_config(config.backbone_config)
+            bc = config.backbone_config
+            mtype = bc.get("model_type") if isinstance(bc, dict) else getattr(bc, "model_type", None)
+            if mtype == "internimage-H":                 # gd.py:2073-2074 / 5186-5195: a plain dict of overrides
+                from .internimage import build_internimage_h
+                backbone_model = build_internimage_h({k: v for k, v in bc.items() if k != "model_type"})
+            elif mtype == "swin":
+                from transformers import AutoBackbone
+                backbone_model = AutoBackbone.from_config(bc)
+            else:
+                raise NotImplementedError(f"backbone model_type={mtype!r} (the reference wires 'swin' and 'internimage-H')")
         enc = _ConvEncoder(backbone_model)
         self.backbone = _ConvModel(enc, GroundingDinoSinePositionEmbedding(
             config.d_model // 2, config.positional_embedding_temperature, normalize=True))

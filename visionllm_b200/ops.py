@@ -144,17 +144,39 @@ def rmsnorm(x, weight, eps, out=None):
     return out
 
 
-def layernorm(x, weight, bias, eps, out=None):
+def layernorm(x, weight, bias, eps, out=None, gelu=False):
+    """nn.LayerNorm over the last dim (bf16 rows, fp32 statistics); gelu=True appends exact-erf GELU in the same pass."""
     xv, rows, ldx = _rows(x, "x")
     cols = x.shape[-1]
     if out is None:
         out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
     ov, _, ldy = _rows(out, "out")
+    fn = _lib.lib().vllm_layernorm_gelu_bf16 if gelu else _lib.lib().vllm_layernorm_bf16
     with torch.cuda.device(x.device), _Prof("layernorm", 0.0, 4.0 * rows * cols):
-        rc = _lib.lib().vllm_layernorm_bf16(xv.data_ptr(), ldx, weight.data_ptr(), bias.data_ptr(), ov.data_ptr(),
-                                            ldy, rows, cols, float(eps), _stream())
+        rc = fn(xv.data_ptr(), ldx, weight.data_ptr(), bias.data_ptr(), ov.data_ptr(), ldy, rows, cols, float(eps),
+                _stream())
     _lib.check(rc, "vllm_layernorm_bf16")
     return out
+
+
+def dwconv_nhwc(x, weight_taps, bias, kernel):
+    """Depthwise KxK conv (stride 1, padding K//2) of a channels-last map x [B, H, W, C] bf16; weight_taps [K*K, C]
+    (the Conv2d weight [C, 1, K, K] repacked tap-major), bias [C] or None.  One launch, fp32 accumulation."""
+    if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_cuda or not x.is_contiguous():
+        raise RuntimeError("dwconv_nhwc: x must be a contiguous CUDA bf16 [B, H, W, C] tensor")
+    B, Hh, W, C = x.shape
+    k = int(kernel)
+    if weight_taps.shape != (k * k, C) or weight_taps.dtype != torch.bfloat16 or not weight_taps.is_contiguous():
+        raise RuntimeError("dwconv_nhwc: weight_taps must be contiguous bf16 [K*K, C]")
+    if bias is not None and (bias.dtype != torch.bfloat16 or bias.numel() != C or not bias.is_contiguous()):
+        raise RuntimeError("dwconv_nhwc: bias must be contiguous bf16 [C]")
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device), _Prof("dwconv", 2.0 * x.numel() * k * k, 4.0 * x.numel()):
+        rc = _lib.lib().vllm_dwconv_nhwc_bf16(x.data_ptr(), weight_taps.data_ptr(),
+                                              bias.data_ptr() if bias is not None else None, y.data_ptr(), B, Hh, W, C,
+                                              k, _stream())
+    _lib.check(rc, "vllm_dwconv_nhwc_bf16")
+    return y
 
 
 _GN_WS = {}
