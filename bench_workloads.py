@@ -672,10 +672,74 @@ class LlmTpWorkload(PairForwardWorkload):
         return {"kernel_breakdown": self.breakdown, "scaling": "strong"}
 
 
+class InternImageHWorkload(PairForwardWorkload):
+    """The alternative GDINO backbone of BASELINE cfg 4: InternImage-H (gd.py:5154-5170: 320 channels,
+    depths [6, 6, 32, 6], groups [10, 20, 40, 80], 5x5 depthwise branch, DCNv3 core, centre-feature scale), random init,
+    bf16, 4 images of 1024^2 per GPU per step through `visionllm_b200.internimage.build_internimage_h`, all four level
+    maps returned."""
+    metric = "internimage_h_backbone_images_per_sec_1024px"
+    unit = "images/s"
+    dtype = "bf16 (DCNv3 core fp32)"
+    IMAGES = 4
+
+    def setup(self):
+        import torch
+        from visionllm_b200.internimage import build_internimage_h
+        self.torch = torch
+        with torch.device("meta"):
+            m = build_internimage_h()
+        m = m.to_empty(device=self.device).to(torch.bfloat16)
+        g = torch.Generator(device=self.device).manual_seed(0)
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                last = name.split(".")[-1]
+                if p.dim() <= 1:
+                    p.fill_(1.0) if (last == "weight") else p.zero_()
+                else:
+                    fan_in = p[0].numel()
+                    p.copy_(torch.randn(p.shape, device=self.device, generator=g, dtype=torch.float32) / fan_in ** 0.5)
+        self.model = m.eval()
+        gi = torch.Generator(device=self.device).manual_seed(1234 + self.rank)
+        self.images = torch.randn(self.IMAGES, 3, 1024, 1024, device=self.device, generator=gi).bfloat16()
+        self.h_images = self.images.cpu().pin_memory()
+        self.d_images = torch.empty_like(self.images)
+        self.h_out = torch.empty((self.IMAGES, 32, 32, 2560), dtype=torch.bfloat16).pin_memory()
+        self.h2d_bytes = self.images.numel() * 2
+        self.d2h_bytes = self.h_out.numel() * 2
+        from visionllm_b200.graphs import GraphedForward
+        self.fwd = GraphedForward(lambda x: tuple(self.model(x)))     # ~2500 launches per step: replay, not Python
+        self.eager = False
+
+    def step_device(self):
+        self.out = self.model(self.images) if self.eager else self.fwd(self.images)
+
+    def step_e2e(self):
+        self.d_images.copy_(self.h_images, non_blocking=True)
+        out = self.fwd(self.d_images)
+        self.h_out.copy_(out[-1], non_blocking=True)
+
+    def units_per_step(self):
+        return self.IMAGES
+
+    def dominant_kernel_ms(self, steps):
+        self.eager = True                       # per-launch CUDA events need the eager launches
+        try:
+            return super().dominant_kernel_ms(steps)
+        finally:
+            self.eager = False
+
+    def config(self):
+        return {"workload": "InternImage-H backbone forward (GDINO backbone option of BASELINE cfg 4): 4 x 1024^2 images, "
+                            "strides 4/8/16/32 maps of 320/640/1280/2560 channels",
+                "images_per_gpu_per_step": self.IMAGES, "launch": "CUDA graph replay",
+                "l2_policy": "inputs_exceed_l2 (weights 2.2 GB, level-0 activations 168 MB per tensor > 126 MB L2)",
+                "parallelism": f"dp{self.world} (batch shard, no forward collective)"}
+
+
 WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "msda_encoder_bf16": MsdaEncoderBf16Workload,
              "msda_encoder_pairs": MsdaEncoderPairsWorkload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
              "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload,
-             "llm_tp": LlmTpWorkload}
+             "llm_tp": LlmTpWorkload, "internimage_h": InternImageHWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
 
@@ -777,9 +841,51 @@ def _cpu_llm_tp(steps, warmup):
             "ms_per_step": 8 * seq_s * 1e3}
 
 
+def _cpu_internimage_h(steps, warmup):
+    """Reference CPU path of the InternImage-H backbone, bounded sample: ONE level-0 layer (320 channels, 10 groups,
+    5x5 depthwise branch, DCNv3 core through the C oracle = the reference CUDA kernel's arithmetic restated, fp32 torch
+    for the projections / MLP / norms) on one 256x256 map; an image is extrapolated as 50 such layers (every level's
+    layer costs the same FLOPs: a quarter of the pixels at twice the width), stem and downsampling left out."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from oracle import dcnv3_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    C, G, K, Hh = 320, 10, 9, 256
+    r = lambda *s: torch.randn(*s, generator=g) * 0.02  # noqa: E731
+    x = torch.randn(1, Hh, Hh, C, generator=g)
+    w_in, w_out, w_dw, w_off, w_mask = r(C, C), r(C, C), r(C, 1, 5, 5), r(G * K * 2, C), r(G * K, C)
+    w1, w2 = r(4 * C, C), r(C, 4 * C)
+
+    def once():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            h = F.layer_norm(x, (C,))
+            xp = F.linear(h, w_in)
+            x1 = F.gelu(F.layer_norm(F.conv2d(h.permute(0, 3, 1, 2), w_dw, padding=2, groups=C).permute(0, 2, 3, 1), (C,)))
+            off = F.linear(x1, w_off).contiguous()
+            msk = F.softmax(F.linear(x1, w_mask).view(1, Hh, Hh, G, K), -1).reshape(1, Hh, Hh, G * K).contiguous()
+            core = torch.from_numpy(np.asarray(O.forward(xp.numpy(), off.numpy(), msk.numpy(), 3, 3, 1, 1, 1, 1, 1, 1, G,
+                                                         C // G, 1.0), dtype=np.float32))
+            y = x + F.layer_norm(F.linear(core, w_out), (C,))
+            y = y + F.layer_norm(F.linear(F.gelu(F.linear(F.layer_norm(y, (C,)), w1)), w2), (C,))
+        return time.perf_counter() - t0
+
+    for _ in range(warmup):
+        once()
+    tl = sum(once() for _ in range(steps)) / steps
+    img_s = 50 * tl
+    return {"value": 1.0 / img_s, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"1 level-0 InternImage-H layer on one 256x256x320 map ({tl * 1e3:.0f} ms; DCNv3 core = C oracle, "
+                      "projections fp32 torch); image = 50 x layer (extrapolated)",
+            "ms_per_step": 4 * img_s * 1e3}
+
+
 _CPU = {"msda_encoder": _cpu_msda_encoder, "msda_encoder_bf16": _cpu_msda_encoder, "msda_encoder_pairs": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
         "gdino_stage": _cpu_msda_encoder,
-        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp}
+        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp, "internimage_h": _cpu_internimage_h}
 
 
 def cpu_baseline(name):

@@ -40,7 +40,9 @@ def dcnv3_forward(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, p
     out = torch.empty((N, H_out, W_out, C), dtype=torch.float32, device=input.device)
     if out.numel() == 0:
         return out
-    with torch.cuda.device(input.device):
+    from . import ops
+    with torch.cuda.device(input.device), ops._Prof("dcnv3", 0.0, 4.0 * (input.numel() + offset.numel() + mask.numel()
+                                                                          + out.numel())):
         rc = _lib.lib().vllm_dcnv3_forward_f32(
             input.data_ptr(), offset.data_ptr(), mask.data_ptr(), out.data_ptr(), N, H_in, W_in, H_out, W_out, group,
             group_channels, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
