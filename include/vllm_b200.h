@@ -181,6 +181,20 @@ int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const 
  * branch, ops_dcnv3/modules/dcnv3.py:252-267). */
 int vllm_layernorm_gelu_bf16(const void* x, long long ldx, const void* weight, const void* bias, void* y,
                              long long ldy, long long rows, int cols, float eps, void* stream);
+/* y = residual + LayerNorm(x): the post-norm residual of InternImage-H (`x + res_post_norm(dcn(norm(x)))`,
+ * grounding_dino/modeling_ov_grounding_dino_mask_dn.py:4866-4868) in one pass. */
+int vllm_layernorm_residual_bf16(const void* x, long long ldx, const void* weight, const void* bias,
+                                 const void* residual, long long ldr, void* y, long long ldy, long long rows, int cols,
+                                 float eps, void* stream);
+/* Elementwise companions of the DCNv3 module (ops_dcnv3/modules/dcnv3.py:318-349), fp32:
+ * prep: packed[row, :] = [offset (group*taps*2) | mask logits (group*taps) | centre-scale logit (group, only read when
+ *       scale != NULL)] with row pitch ld -> contiguous offset, mask = softmax over the taps of each group, scale =
+ *       sigmoid(logit); taps = 9 or 25.
+ * blend: out = bf16(core * (1 - s) + xproj * s), s = scale[row, channel / group_channels] (scale == NULL: plain cast). */
+int vllm_dcnv3_prep_f32(const void* packed, long long ld, void* offset, void* mask, void* scale, long long rows,
+                        int group, int taps, void* stream);
+int vllm_dcnv3_blend_bf16(const void* core, const void* xproj, const void* scale, void* out, long long rows,
+                          int channels, int group_channels, void* stream);
 /* Depthwise KxK convolution (K = 3, 5, 7; stride 1, padding K/2) over a channels-last bf16 map x[batch,H,W,C] with
  * fp32 accumulation: the `nn.Conv2d(C, C, k, padding=(k-1)//2, groups=C)` at the head of the DCNv3 module
  * (ops_dcnv3/modules/dcnv3.py:252-259; InternImage-H: k = 5).  weight_taps is the conv weight repacked tap-major

@@ -83,3 +83,42 @@ def test_internimage_matches_reference(golden_dir):
     nchw.load_state_dict(seeded_state_dict(nchw, 303))
     o2 = nchw.to("cuda", torch.bfloat16).eval()(x)
     assert all(torch.equal(a, b.permute(0, 3, 1, 2)) for a, b in zip(o2, outs))
+
+
+@pytest.mark.parametrize("G,K,with_scale,pad", [(10, 9, True, 0), (2, 9, False, 2), (4, 25, True, 0)])
+def test_dcnv3_prep_and_blend_match_torch(G, K, with_scale, pad):
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(G * K)
+    cols = G * K * 3 + (G if with_scale else 0) + pad
+    om = torch.randn(2, 5, 7, cols, device="cuda", generator=g) * 3
+    off, mask, sc = ops.dcnv3_prep(om, G, K, with_scale)
+    assert torch.equal(off, om[..., :G * K * 2])
+    want = F.softmax(om[..., G * K * 2:G * K * 3].reshape(2, 5, 7, G, K), -1).reshape(2, 5, 7, G * K)
+    assert (mask - want).abs().max().item() < 1e-6
+    assert (mask.reshape(2, 5, 7, G, K).sum(-1) - 1).abs().max().item() < 1e-5
+    if with_scale:
+        assert (sc - om[..., G * K * 3:G * K * 3 + G].sigmoid()).abs().max().item() < 1e-6
+    else:
+        assert sc is None
+    gc = 32
+    core = torch.randn(2, 5, 7, G * gc, device="cuda", generator=g)
+    xp = torch.randn(2, 5, 7, G * gc, device="cuda", generator=g)
+    out = ops.dcnv3_blend(core, xp, sc, gc)
+    if with_scale:
+        s_ = sc[..., None].expand(2, 5, 7, G, gc).reshape(core.shape)
+        ref = core * (1 - s_) + xp * s_
+    else:
+        ref = core
+    assert out.dtype == torch.bfloat16 and torch.equal(out, ref.bfloat16()) or (out.float() - ref).abs().max() < 2e-2
+
+
+def test_layernorm_residual_matches_fp32():
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = (torch.randn(3, 11, 640, device="cuda", generator=g) * 2).bfloat16()
+    r = torch.randn(3, 11, 640, device="cuda", generator=g).bfloat16()
+    w = (1 + 0.1 * torch.randn(640, device="cuda", generator=g)).bfloat16()
+    b = (0.1 * torch.randn(640, device="cuda", generator=g)).bfloat16()
+    y = ops.layernorm(x, w, b, 1e-6, residual=r)
+    ref = r.float() + F.layer_norm(x.float(), (640,), w.float(), b.float(), 1e-6)
+    assert ((y.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 2e-3).all()

@@ -56,7 +56,7 @@ template <int MODE, int VPT, int TPR>
 __global__ void __launch_bounds__(NT)
 norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __restrict__ w,
                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* y, long long ldy, long long rows,
-                 int cols, float eps, int act) {
+                 int cols, float eps, int act, const __nv_bfloat16* __restrict__ res, long long ldr) {
   __shared__ float sh[NT / 32];
   constexpr int RPC = NT / TPR;
   const int tr = threadIdx.x % TPR;
@@ -109,6 +109,11 @@ norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __r
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = 0.5f * o[j] * (1.f + erff(o[j] * 0.70710678118654752f));
         }
+        if (res) {                                       // y = residual + LN(x): the post-norm residual of InternImage-H
+          float rv[8]; unpack8(*(reinterpret_cast<const uint4*>(res + row * ldr) + v), rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -124,7 +129,7 @@ norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __r
 
 template <int MODE>
 int launch_norm(const void* x, long long ldx, const void* w, const void* b, void* y, long long ldy, long long rows,
-                int cols, float eps, cudaStream_t st, int act = 0) {
+                int cols, float eps, cudaStream_t st, int act = 0, const void* res = nullptr, long long ldr = 0) {
   const int nvec = cols / 8;
   auto go = [&](auto vpt, auto tpr) -> int {
     constexpr int VPT = decltype(vpt)::value, TPR = decltype(tpr)::value;
@@ -132,7 +137,7 @@ int launch_norm(const void* x, long long ldx, const void* w, const void* b, void
     if (blocks > 2147483647LL) return VLLM_EUNSUPPORTED;
     norm_rows_kernel<MODE, VPT, TPR><<<(unsigned)blocks, NT, 0, st>>>(
         (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, rows,
-        cols, eps, act);
+        cols, eps, act, (const __nv_bfloat16*)res, ldr);
     VLLM_CHECK_LAUNCH();
     return VLLM_OK;
   };
@@ -252,6 +257,17 @@ int vllm_layernorm_gelu_bf16(const void* x, long long ldx, const void* weight, c
   if (rc) return rc;
   if (!weight || !bias || !vllm_aligned(weight, 16) || !vllm_aligned(bias, 16)) return VLLM_EINVAL;
   return launch_norm<1>(x, ldx, weight, bias, y, ldy, rows, cols, eps, (cudaStream_t)stream, 1);
+}
+
+int vllm_layernorm_residual_bf16(const void* x, long long ldx, const void* weight, const void* bias,
+                                 const void* residual, long long ldr, void* y, long long ldy, long long rows, int cols,
+                                 float eps, void* stream) {
+  int rc = check_rows(x, ldx, y, ldy, rows, cols);
+  if (rc == 1000) return VLLM_OK;
+  if (rc) return rc;
+  if (!weight || !bias || !residual || !vllm_aligned(weight, 16) || !vllm_aligned(bias, 16)) return VLLM_EINVAL;
+  if (!vllm_aligned(residual, 16) || ldr % 8) return VLLM_EALIGN;
+  return launch_norm<1>(x, ldx, weight, bias, y, ldy, rows, cols, eps, (cudaStream_t)stream, 0, residual, ldr);
 }
 
 int vllm_rope_bf16(void* x, long long ld, const void* cos, const void* sin, long long tokens, int heads,

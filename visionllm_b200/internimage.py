@@ -15,7 +15,9 @@ Execution on our kernels, channels-last throughout (the reference permutes to NC
   offset | mask | centre-scale     ONE packed GEMM -> fp32 (the reference issues three)
   DCNv3 core                       csrc/dcnv3.cu through visionllm_b200.dcnv3.dcnv3_forward
   output_proj, MLP fc1(+GELU)/fc2  GEMM epilogues
-The 9-way mask softmax, the sigmoid centre-feature blend and the residual adds are torch elementwise glue.
+  slices / 9-way mask softmax / sigmoid            ONE pass over the packed projection  ops.dcnv3_prep
+  centre-feature blend + bf16 cast                 ONE pass                              ops.dcnv3_blend
+  post-norm residual  x + LN(.)                    inside the LayerNorm pass
 Forward only (the GDINO stage of the eval path); DropPath / dropout are identities at eval like in the reference.
 """
 import torch
@@ -51,9 +53,9 @@ def _ln(seq):
     raise RuntimeError("no LayerNorm in container")
 
 
-def _apply_ln(seq, x, gelu=False):
+def _apply_ln(seq, x, gelu=False, residual=None):
     ln = _ln(seq)
-    return ops.layernorm(x, ln.weight, ln.bias, ln.eps, gelu=gelu)
+    return ops.layernorm(x, ln.weight, ln.bias, ln.eps, gelu=gelu, residual=residual)
 
 
 class _Cache:
@@ -211,16 +213,12 @@ class DCNv3(nn.Module):
         x1 = _apply_ln(self.dw_conv[1], x1, gelu=True)
         wq, bq = self._query_proj(input.dtype)
         om = ops.linear(x1, wq, bias=bq, out_dtype=torch.float32)          # [N, H, W, G*K*2 | G*K | G]
-        offset = om[..., :G * K * 2].contiguous()
-        mask = F.softmax(om[..., G * K * 2:G * K * 3].reshape(N, Hh, W, G, K), -1).reshape(N, Hh, W, G * K).contiguous()
+        offset, mask, cfs = ops.dcnv3_prep(om, G, K, self.center_feature_scale)   # slices, 9-way softmax, sigmoid
         x = dcn_ext.dcnv3_forward(x32.view(N, Hh, W, C), offset, mask, self.kernel_size, self.kernel_size, self.stride,
                                   self.stride, self.pad, self.pad, self.dilation, self.dilation, G, self.group_channels,
                                   self.offset_scale, 256)
-        if self.center_feature_scale:
-            cfs = om[..., G * K * 3:].sigmoid()                             # [N, H, W, G]
-            cfs = cfs[..., None].expand(N, Hh, W, G, self.group_channels).reshape(N, Hh, W, C)
-            x = x * (1 - cfs) + x32.view(N, Hh, W, C) * cfs
-        return ops.linear(x.to(input.dtype), self.output_proj.weight, bias=self.output_proj.bias)
+        x = ops.dcnv3_blend(x, x32.view(N, Hh, W, C), cfs, self.group_channels)    # centre-feature blend + bf16 cast
+        return ops.linear(x, self.output_proj.weight, bias=self.output_proj.bias)
 
 
 class InternImageLayer(nn.Module):
@@ -255,8 +253,8 @@ class InternImageLayer(nn.Module):
                 x = x + n1(self.dcn(x))
                 return x + n2(self.mlp(x))
             if self.res_post_norm:
-                x = x + _apply_ln(self.res_post_norm1, self.dcn(n1(x)))
-                return x + _apply_ln(self.res_post_norm2, self.mlp(n2(x)))
+                x = _apply_ln(self.res_post_norm1, self.dcn(n1(x)), residual=x)
+                return _apply_ln(self.res_post_norm2, self.mlp(n2(x)), residual=x)
             x = x + self.dcn(n1(x))
             return x + self.mlp(n2(x))
         g1, g2 = self.gamma1.to(x.dtype), self.gamma2.to(x.dtype)

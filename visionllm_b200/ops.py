@@ -144,18 +144,65 @@ def rmsnorm(x, weight, eps, out=None):
     return out
 
 
-def layernorm(x, weight, bias, eps, out=None, gelu=False):
-    """nn.LayerNorm over the last dim (bf16 rows, fp32 statistics); gelu=True appends exact-erf GELU in the same pass."""
+def layernorm(x, weight, bias, eps, out=None, gelu=False, residual=None):
+    """nn.LayerNorm over the last dim (bf16 rows, fp32 statistics); gelu=True appends exact-erf GELU in the same pass;
+    residual (same shape) returns residual + LN(x) in the same pass."""
     xv, rows, ldx = _rows(x, "x")
     cols = x.shape[-1]
     if out is None:
         out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
     ov, _, ldy = _rows(out, "out")
+    if residual is not None:
+        if gelu:
+            raise RuntimeError("layernorm: gelu and residual are separate fusions")
+        if residual.shape != x.shape:
+            raise RuntimeError("layernorm: residual shape mismatch")
+        rv, _, ldr = _rows(residual, "residual")
+        with torch.cuda.device(x.device), _Prof("layernorm", 0.0, 6.0 * rows * cols):
+            rc = _lib.lib().vllm_layernorm_residual_bf16(xv.data_ptr(), ldx, weight.data_ptr(), bias.data_ptr(),
+                                                         rv.data_ptr(), ldr, ov.data_ptr(), ldy, rows, cols, float(eps),
+                                                         _stream())
+        _lib.check(rc, "vllm_layernorm_residual_bf16")
+        return out
     fn = _lib.lib().vllm_layernorm_gelu_bf16 if gelu else _lib.lib().vllm_layernorm_bf16
     with torch.cuda.device(x.device), _Prof("layernorm", 0.0, 4.0 * rows * cols):
         rc = fn(xv.data_ptr(), ldx, weight.data_ptr(), bias.data_ptr(), ov.data_ptr(), ldy, rows, cols, float(eps),
                 _stream())
     _lib.check(rc, "vllm_layernorm_bf16")
+    return out
+
+
+def dcnv3_prep(packed, group, taps, with_scale):
+    """packed [..., >= G*K*3 (+G)] fp32 rows (one GEMM output) -> (offset [..., G*K*2], mask [..., G*K] = softmax over
+    the K taps of each group, scale [..., G] = sigmoid(logit) or None), contiguous fp32.  One launch."""
+    if packed.dtype != torch.float32 or not packed.is_cuda or packed.stride(-1) != 1:
+        raise RuntimeError("dcnv3_prep: packed must be CUDA fp32 with unit inner stride")
+    lead = packed.shape[:-1]
+    p2 = packed.reshape(-1, packed.shape[-1])
+    rows = p2.shape[0]
+    offset = torch.empty((*lead, group * taps * 2), dtype=torch.float32, device=packed.device)
+    mask = torch.empty((*lead, group * taps), dtype=torch.float32, device=packed.device)
+    scale = torch.empty((*lead, group), dtype=torch.float32, device=packed.device) if with_scale else None
+    with torch.cuda.device(packed.device), _Prof("dcn_glue", 0.0, 4.0 * rows * group * taps * 6):
+        rc = _lib.lib().vllm_dcnv3_prep_f32(p2.data_ptr(), p2.stride(0), offset.data_ptr(), mask.data_ptr(),
+                                            scale.data_ptr() if with_scale else None, rows, group, taps, _stream())
+    _lib.check(rc, "vllm_dcnv3_prep_f32")
+    return offset, mask, scale
+
+
+def dcnv3_blend(core, xproj, scale, group_channels):
+    """bf16(core * (1 - s) + xproj * s) with s [..., G] broadcast over each group's channels (scale None: plain cast)."""
+    for t in (core,) + ((xproj, scale) if scale is not None else ()):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("dcnv3_blend: fp32 contiguous CUDA tensors expected")
+    C = core.shape[-1]
+    rows = core.numel() // C
+    out = torch.empty(core.shape, dtype=torch.bfloat16, device=core.device)
+    with torch.cuda.device(core.device), _Prof("dcn_glue", 0.0, 10.0 * rows * C):
+        rc = _lib.lib().vllm_dcnv3_blend_bf16(core.data_ptr(), xproj.data_ptr() if scale is not None else None,
+                                              scale.data_ptr() if scale is not None else None, out.data_ptr(), rows, C,
+                                              int(group_channels), _stream())
+    _lib.check(rc, "vllm_dcnv3_blend_bf16")
     return out
 
 
