@@ -5,10 +5,8 @@ CUDA-backed `DCNv3`, whose extension cannot run here).  A scaled-down InternImag
 (dw_kernel_size=5, res_post_norm, level2_post_norm, center_feature_scale).  Stored: bf16-representable input, fp32
 outputs of all four levels, the reference's own bf16 run, and the state-dict key/shape list."""
 import json
-import logging
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -25,22 +23,7 @@ CFG = dict(core_op="DCNv3_pytorch", channels=32, depths=[1, 1, 6, 1], groups=[2,
 
 
 def load_reference():
-    cfgm, gd = ref_shim.load_gdino()
-    # the DCNv3 module package: stub the compiled extension its functions file imports (dcnv3_func.py:16)
-    sys.modules["DCNv3"] = types.ModuleType("DCNv3")
-    base = f"{ref_shim.REF}/ops_dcnv3"
-    pkg = types.ModuleType("refpkg_dcnv3"); pkg.__path__ = [base]; sys.modules["refpkg_dcnv3"] = pkg
-    fpk = types.ModuleType("refpkg_dcnv3.functions"); fpk.__path__ = [base + "/functions"]
-    sys.modules["refpkg_dcnv3.functions"] = fpk
-    ff = ref_shim.load_file("refpkg_dcnv3.functions", "dcnv3_func", base + "/functions/dcnv3_func.py")
-    fpk.DCNv3Function, fpk.dcnv3_core_pytorch = ff.DCNv3Function, ff.dcnv3_core_pytorch
-    mpk = types.ModuleType("refpkg_dcnv3.modules"); mpk.__path__ = [base + "/modules"]
-    sys.modules["refpkg_dcnv3.modules"] = mpk
-    mm = ref_shim.load_file("refpkg_dcnv3.modules", "dcnv3", base + "/modules/dcnv3.py")
-    mpk.DCNv3, mpk.DCNv3_pytorch = mm.DCNv3, mm.DCNv3_pytorch
-    gd.opsm = mpk
-    gd.get_root_logger = lambda *a, **k: logging.getLogger("ref")
-    return gd
+    return ref_shim.load_gdino_with_dcnv3()[1]
 
 
 def main():

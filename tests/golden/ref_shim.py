@@ -130,3 +130,26 @@ def load_internlm2():
     cfg = load_file(pkg, "configuration_internlm2", f"{REF}/internlm2/configuration_internlm2.py")
     mod = load_file(pkg, "modeling_internlm2", f"{REF}/internlm2/modeling_internlm2.py")
     return cfg, mod
+
+
+def load_gdino_with_dcnv3():
+    """`load_gdino()` plus the reference's DCNv3 module package bound to `gd.opsm` (gd.py:64-67 imports it relatively,
+    which fails under the shim's flat package): lets `InternImage(core_op='DCNv3_pytorch')` -- the pure-PyTorch core,
+    ops_dcnv3/modules/dcnv3.py:86-208 -- run on CPU.  The compiled `DCNv3` extension its functions file imports
+    (dcnv3_func.py:16) is stubbed."""
+    import logging
+    cfgm, gd = load_gdino()
+    sys.modules.setdefault("DCNv3", types.ModuleType("DCNv3"))
+    base = f"{REF}/ops_dcnv3"
+    pkg = types.ModuleType("refpkg_dcnv3"); pkg.__path__ = [base]; sys.modules["refpkg_dcnv3"] = pkg
+    fpk = types.ModuleType("refpkg_dcnv3.functions"); fpk.__path__ = [base + "/functions"]
+    sys.modules["refpkg_dcnv3.functions"] = fpk
+    ff = load_file("refpkg_dcnv3.functions", "dcnv3_func", base + "/functions/dcnv3_func.py")
+    fpk.DCNv3Function, fpk.dcnv3_core_pytorch = ff.DCNv3Function, ff.dcnv3_core_pytorch
+    mpk = types.ModuleType("refpkg_dcnv3.modules"); mpk.__path__ = [base + "/modules"]
+    sys.modules["refpkg_dcnv3.modules"] = mpk
+    mm = load_file("refpkg_dcnv3.modules", "dcnv3", base + "/modules/dcnv3.py")
+    mpk.DCNv3, mpk.DCNv3_pytorch = mm.DCNv3, mm.DCNv3_pytorch
+    gd.opsm = mpk
+    gd.get_root_logger = lambda *a, **k: logging.getLogger("ref")
+    return cfgm, gd

@@ -113,3 +113,85 @@ def test_neck_integer_outputs_match_reference(gn_kernel):
     assert torch.equal(vr, cap["valid_ratios"])
     assert (src - cap["vision_features"]).abs().max() < 1e-4
     assert (pos - cap["vision_position_embedding"]).abs().max() < 1e-5
+
+
+def test_whole_stage_with_internimage_backbone_matches_reference(gn_kernel, monkeypatch):
+    """`backbone_config = {'model_type': 'internimage-H', ...}` (gd.py:2073-2074, 5154-5195): the reference builds
+    `GroundingDinoInternImageBackbone`, we build `visionllm_b200.internimage` from the same dict; same state dict, same
+    forward_test outputs.  The reference runs its pure-PyTorch core op; ours runs the C oracle of the CUDA core."""
+    import numpy as np
+    import ref_shim
+    from weights_util import seeded_state_dict
+    import visionllm_b200.dcnv3 as dcn
+    import visionllm_b200.ops as ops
+    from oracle import dcnv3_oracle as O
+    from visionllm_b200.gdino_model import B200GroundingDinoForObjectDetection
+
+    def layernorm(x, w, b, eps, out=None, gelu=False, residual=None):
+        y = F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), eps)
+        if residual is not None:
+            y = y + residual.float()
+        return F.gelu(y) if gelu else y
+
+    def dwconv_nhwc(x, wt, bias, k):
+        C = x.shape[-1]
+        return F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().t().reshape(C, 1, k, k), bias.float(), padding=k // 2,
+                        groups=C).permute(0, 2, 3, 1).contiguous()
+
+    def dcnv3_prep(packed, G, K, with_scale):
+        lead = packed.shape[:-1]
+        mask = F.softmax(packed[..., G * K * 2:G * K * 3].reshape(*lead, G, K), -1).reshape(*lead, G * K).contiguous()
+        return (packed[..., :G * K * 2].contiguous(), mask,
+                packed[..., G * K * 3:G * K * 3 + G].sigmoid() if with_scale else None)
+
+    def dcnv3_blend(core, xproj, scale, gc):
+        if scale is None:
+            return core
+        s_ = scale[..., None].expand(*scale.shape, gc).reshape(core.shape)
+        return core * (1 - s_) + xproj * s_
+
+    def dcnv3_forward(inp, offset, mask, kh, kw, sh, sw, ph, pw, dh, dw, group, gc, offset_scale, step=256, **kw_):
+        return torch.from_numpy(np.asarray(O.forward(inp.float().numpy(), offset.float().numpy(), mask.float().numpy(),
+                                                     kh, kw, sh, sw, ph, pw, dh, dw, group, gc, offset_scale),
+                                           dtype=np.float32))
+
+    for name, fn in (("layernorm", layernorm), ("dwconv_nhwc", dwconv_nhwc),
+                     ("dcnv3_prep", dcnv3_prep), ("dcnv3_blend", dcnv3_blend)):
+        monkeypatch.setattr(ops, name, fn)
+    monkeypatch.setattr(dcn, "dcnv3_forward", dcnv3_forward)
+
+    cfgm, gd = ref_shim.load_gdino_with_dcnv3()
+    # H width (the reference hard-codes the neck's input widths to 320..2560, gd.py:5183), one layer per level
+    bc = dict(model_type="internimage-H", core_op="DCNv3_pytorch", depths=[1, 1, 1, 1], level2_post_norm_block_ids=[0],
+              with_cp=False)
+    cfg = cfgm.GroundingDinoConfig(
+        backbone_config=bc, d_model=256, encoder_layers=1, decoder_layers=1, encoder_ffn_dim=256, decoder_ffn_dim=256,
+        num_queries=12, num_feature_levels=4, dropout=0., attention_dropout=0., activation_dropout=0., fusion_dropout=0.,
+        fusion_droppath=0., text_enhancer_dropout=0., disable_custom_kernels=True, mask_dim=256, norm="GN",
+        l_hidden_size=64)
+    ref = gd.OVGroundingDinoForObjectDetection(cfg).eval()
+    sd = seeded_state_dict(ref, 21)
+    for k in sd:
+        if k.endswith("vision_param") or k.endswith("text_param"):
+            sd[k] = sd[k] * 0 + 0.5
+    ref.load_state_dict(sd)
+    cfg.activation_function = "relu"
+    ours = B200GroundingDinoForObjectDetection(cfg).eval()
+    assert type(ours.model.backbone.conv_encoder.model).__name__ == "B200InternImage"
+    missing, unexpected = ours.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    g = torch.Generator().manual_seed(6)
+    B, Hh, W = 2, 64, 96
+    x = torch.randn(B, 3, Hh, W, generator=g)
+    pm = torch.ones(B, Hh, W, dtype=torch.long)
+    pm[1, 32:, :] = 0
+    tq = torch.randn(B, 4, 4, cfg.l_hidden_size, generator=g)
+    tm = torch.ones(B, 4, dtype=torch.bool)
+    with torch.no_grad():
+        a = ref.forward_test(pixel_values=x, pixel_mask=pm, text_query=tq, text_query_masks=tm, return_dict=True)
+        b = ours.forward_test(x, pixel_mask=pm, text_query=tq, text_query_masks=tm)
+    finite = torch.isfinite(a.logits)
+    assert torch.equal(finite, torch.isfinite(b.logits))
+    assert (a.logits[finite] - b.logits[finite]).abs().max() < 2e-3
+    assert (a.pred_boxes - b.pred_boxes).abs().max() < 1e-4
+    assert (a.pred_masks - b.pred_masks).abs().max() < 2e-2 * a.pred_masks.abs().max().clamp(min=1)

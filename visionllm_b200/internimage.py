@@ -361,4 +361,8 @@ def build_internimage_h(cfg_hf=None, **kw):
         cfg.update(cfg_hf)
     cfg.pop("load_path", None)
     cfg.update(kw)
-    return B200InternImage(**cfg)
+    backbone = B200InternImage(**cfg)
+    # the reference pins the neck's input widths to the H preset whatever the overrides say (gd.py:5183)
+    backbone.num_features = [320, 640, 1280, 2560]
+    backbone.channels = list(backbone.num_features)
+    return backbone
