@@ -48,7 +48,9 @@ def _host_shapes(spatial_shapes):
     hs = getattr(spatial_shapes, "_b200_host", None)
     if hs is not None:
         return hs
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.device.index)
+    # The caching allocator recycles addresses: a new tensor can reuse a dead one's (ptr, version).  The hint only
+    # orders work (the kernels read the geometry on the device), but its LENGTH must match, so the shape is in the key.
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.device.index, tuple(spatial_shapes.shape))
     hit = _shape_cache.get(key)
     if hit is None:
         if len(_shape_cache) > 64:
