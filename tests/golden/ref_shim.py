@@ -153,3 +153,22 @@ def load_gdino_with_dcnv3():
     gd.opsm = mpk
     gd.get_root_logger = lambda *a, **k: logging.getLogger("ref")
     return cfgm, gd
+
+
+def load_unipose():
+    """The reference's UniPose model file as a package by path (relative imports of .utils / .ops resolve through the
+    import system).  The compiled `MultiScaleDeformableAttention` extension its functions file imports
+    (unipose/ops/functions/ms_deform_attn_func.py:19) is stubbed by a module whose forward is the reference's OWN
+    pure-PyTorch core (`ms_deform_attn_core_pytorch`, same file :41-61), bound after the functions module loads."""
+    import importlib
+    install_stubs()
+    ext = types.ModuleType("MultiScaleDeformableAttention")
+    sys.modules["MultiScaleDeformableAttention"] = ext
+    pkg = types.ModuleType("refpkg_unipose"); pkg.__path__ = [f"{REF}/unipose"]
+    pkg.__spec__ = importlib.util.spec_from_loader("refpkg_unipose", loader=None, is_package=True)
+    sys.modules["refpkg_unipose"] = pkg
+    # gd-style relative import of ..ops_dcnv3 fails harmlessly (guarded by try/except in the file)
+    fn = importlib.import_module("refpkg_unipose.ops.functions.ms_deform_attn_func")
+    ext.ms_deform_attn_forward = lambda v, shapes, lsi, loc, w, step: fn.ms_deform_attn_core_pytorch(
+        v, [(int(h), int(ww)) for h, ww in shapes.tolist()], loc, w)
+    return importlib.import_module("refpkg_unipose.modeling_unipose")

@@ -1,0 +1,26 @@
+"""Deterministic inputs of the UniPose layer parity tests (CPU generator, bf16-representable), shared by the golden
+generator (build container) and the tests (GPU box) so the golden file only carries outputs."""
+import torch
+
+SHAPES = [(12, 16), (6, 8), (3, 4), (2, 2)]
+
+
+def inputs():
+    g = torch.Generator().manual_seed(9)
+    r = lambda *s: (torch.randn(*s, generator=g) * 0.5).to(torch.bfloat16).float()  # noqa: E731
+    S = sum(h * w for h, w in SHAPES)
+    bs, nq, ntok, d = 2, 19, 7, 256
+    shapes = torch.tensor(SHAPES, dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    pad = torch.zeros(bs, S, dtype=torch.bool)
+    pad[1, 150:192] = True
+    ref2 = torch.rand(bs, S, 4, 2, generator=g)
+    ref4 = torch.cat((torch.rand(nq, bs, 4, 2, generator=g), torch.rand(nq, bs, 4, 2, generator=g) * 0.4 + 0.05), -1)
+    attn_mask = torch.zeros(nq, nq, dtype=torch.bool)
+    attn_mask[:9, 9:] = True
+    attn_mask[9:, :9] = True
+    text_mask = torch.zeros(bs, ntok, dtype=torch.bool)
+    text_mask[1, 5:] = True
+    return dict(src=r(bs, S, d), pos=r(bs, S, d), ref2=ref2, shapes=shapes, lsi=lsi, pad=pad, tgt=r(nq, bs, d),
+                qpos=r(nq, bs, d), ref4=ref4, memory=r(S, bs, d), memory_text=r(bs, ntok, d), text_mask=text_mask,
+                attn_mask=attn_mask)
