@@ -21,6 +21,19 @@ carries the 64-byte handles at setup).  `PeerComm.virtual(W, ...)` builds W rank
 cross-reference each other, and `run_lockstep` advances their forwards phase by phase on one stream -- the multi-rank
 protocol (pointer tables, slots, counters, epochs) is then testable on a single GPU.
 
+Why single buffers and ever-growing counters are safe (no per-layer barrier):
+  * gather buffer: rank j writes its rows of epoch e+1 into rank i's gather buffer only after its reduce(e) kernel
+    finished (stream order), which needed rank i's o_proj partials of epoch e, which rank i's stream issued after its
+    QKV GEMM -- the last reader of the epoch-e gather buffer -- completed.  So nobody overwrites rows a peer still reads.
+  * receive slots: rank i's o_proj of epoch e+1 runs after its wait for gather(e+1), i.e. after rank j's norm_push(e+1),
+    which rank j's stream issued after its reduce(e) -- the last reader of its epoch-e slots -- completed.
+  * counters: an arrival of epoch e+1 can only be produced by a rank that has consumed every peer's epoch-e arrivals
+    (same two chains), so "count >= e * arrivals_per_epoch" can never be satisfied by a mix of a fast rank's e+1 and a
+    slow rank's missing e arrivals.  Comparisons are wrap-safe (signed difference).
+  * across forwards the chain is broken (the final gather is read by host-ordered torch ops), hence the counter barrier
+    at the top of `phases`.
+A waiter that never sees its arrivals traps after 20 s (csrc/peer.cu) instead of hanging the GPU.
+
 Forward only.  No CPU path: the collectives ARE the CUDA kernels; tests that run on CPU substitute a gloo-backed
 double for the comm object (tests/test_tp_cpu.py).
 """
