@@ -40,3 +40,12 @@ def test_pixel_shuffle_is_space_to_depth():
     n, w, h, c = x.shape
     r = x.view(n, w, h // 2, c * 2).permute(0, 2, 1, 3).contiguous().view(n, h // 2, w // 2, c * 4).permute(0, 2, 1, 3)
     assert torch.equal(y, r.contiguous())
+
+
+def test_vl_bridge_state_dict_keys_match_reference_layouts():
+    """modeling_visionllmv2.py:162-184: 'linear' is a bare nn.Linear, the others nn.Sequential with GELU placeholders."""
+    from visionllm_b200.modeling import build_vl_bridge
+    assert sorted(build_vl_bridge("linear", 8, 16).state_dict()) == ["bias", "weight"]
+    assert sorted(build_vl_bridge("mlp2x_gelu", 8, 16).state_dict()) == ["0.bias", "0.weight", "2.bias", "2.weight"]
+    assert sorted(build_vl_bridge("internvl_mlp", 8, 16).state_dict()) == ["0.bias", "0.weight", "1.bias", "1.weight",
+                                                                           "3.bias", "3.weight"]

@@ -53,7 +53,7 @@ class VLBridge(nn.Sequential):
 
 def build_vl_bridge(vl_bridge_type, v_hidden, l_hidden):
     if vl_bridge_type == "linear":
-        return VLBridge(BridgeLinear(v_hidden, l_hidden))
+        return BridgeLinear(v_hidden, l_hidden)          # a bare nn.Linear in the reference: keys `vl_bridge.weight/bias`
     if vl_bridge_type in ("internvl_mlp", "internvl"):
         return VLBridge(BridgeLayerNorm(v_hidden), BridgeLinear(v_hidden, l_hidden), nn.GELU(),
                         BridgeLinear(l_hidden, l_hidden))
