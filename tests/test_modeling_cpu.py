@@ -49,3 +49,46 @@ def test_vl_bridge_state_dict_keys_match_reference_layouts():
     assert sorted(build_vl_bridge("mlp2x_gelu", 8, 16).state_dict()) == ["0.bias", "0.weight", "2.bias", "2.weight"]
     assert sorted(build_vl_bridge("internvl_mlp", 8, 16).state_dict()) == ["0.bias", "0.weight", "1.bias", "1.weight",
                                                                            "3.bias", "3.weight"]
+
+
+def _views(tag, n):
+    return torch.arange(n, dtype=torch.float32)[:, None, None, None] + torch.zeros(n, 3, 4, 4) + {"a": 0, "b": 100, "c": 200}[tag]
+
+
+def test_region_encoder_inputs_pair_regions_with_the_global_view():
+    """mv2.py:609-687: anyres -> last tile of the sample; pad -> the sample's image; mmic (num_splits) -> the last tile
+    of the r-th image for the r-th region; features = patch tokens (CLS dropped) of that view, last three levels."""
+    from visionllm_b200.modeling import region_encoder_inputs
+    regions = [torch.ones(2, 4, 4), torch.zeros(0, 4, 4), torch.ones(1, 4, 4) * 2]
+    # anyres: 3 samples with 3 / 1 / 2 tiles -> ViT batch rows 0-2 | 3 | 4-5
+    images = [_views("a", 3), _views("b", 1), _views("c", 2)]
+    hs = [torch.arange(6, dtype=torch.float32)[:, None, None].expand(6, 5, 2) + 10 * lv for lv in range(4)]
+    ai, ar, af = region_encoder_inputs(images, regions, hs, [3, 1, 2])
+    assert ai.shape == (3, 3, 4, 4) and ar.shape == (3, 1, 4, 4) and len(af) == 3
+    assert ai[:, 0, 0, 0].tolist() == [2.0, 2.0, 201.0]                 # last tile of sample 0 twice, of sample 2 once
+    assert ar[:, 0, 0, 0].tolist() == [1.0, 1.0, 2.0]
+    for lv, f in enumerate(af):                                         # hidden_states[-3:] = levels 1, 2, 3
+        assert f.shape == (3, 4, 2) and f[:, 0, 0].tolist() == [2 + 10 * (lv + 1), 2 + 10 * (lv + 1), 5 + 10 * (lv + 1)]
+    # pad: one image per sample
+    pad = torch.cat([_views("a", 1), _views("b", 1), _views("c", 1)])
+    hs3 = [h[:3] for h in hs]
+    ai, _, af = region_encoder_inputs(pad, regions, hs3, None)
+    assert ai[:, 0, 0, 0].tolist() == [0.0, 0.0, 200.0] and af[0][:, 0, 0].tolist() == [10.0, 10.0, 12.0]
+    # mmic: sample 0 holds two images of 2 + 1 tiles, its two regions go to image 0 and image 1
+    ai, _, af = region_encoder_inputs([_views("a", 3), _views("b", 1), _views("c", 2)], regions, hs, [3, 1, 2],
+                                      num_splits=[[2, 1], [1], [2]])
+    assert ai[:, 0, 0, 0].tolist() == [1.0, 2.0, 201.0]
+    assert af[2][:, 0, 0].tolist() == [31.0, 32.0, 35.0]
+
+
+def test_scatter_region_tokens_in_order():
+    from visionllm_b200.modeling import scatter_region_tokens
+    ids = torch.tensor([[1, 9, 2, 9], [9, 3, 4, 5]])
+    emb = torch.zeros(2, 4, 3)
+    feats = torch.tensor([[1., 1, 1], [2, 2, 2], [3, 3, 3]])
+    out = scatter_region_tokens(ids, emb, feats, 9)
+    assert out[0, 1].tolist() == [1, 1, 1] and out[0, 3].tolist() == [2, 2, 2] and out[1, 0].tolist() == [3, 3, 3]
+    assert out.sum().item() == 18 and emb.sum().item() == 0            # input untouched
+    import pytest
+    with pytest.raises(RuntimeError):
+        scatter_region_tokens(ids, emb, feats[:2], 9)

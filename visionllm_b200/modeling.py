@@ -87,8 +87,60 @@ def emb_overwrite_indices(input_ids, tool_ids, num_embs):
     return b[:, None].expand_as(pos).reshape(-1), pos.reshape(-1), j[None, :].expand_as(pos).reshape(-1)
 
 
+def region_encoder_inputs(images, regions, vit_hidden_states, split_sizes, num_splits=None):
+    """The tensors the reference hands its region encoder (mv2.py:609-687), vectorised: every region of a sample is
+    paired with the sample's GLOBAL view -- the image itself ('pad': `images` a [bs,3,h,w] tensor), the last tile
+    ('anyres': a list of [n_tiles,3,h,w]), or, for multi-image in-context samples (`num_splits`: per sample the tile
+    count of each image), the last tile of the r-th image for the r-th region -- and with the patch tokens (CLS
+    dropped) of that view in the last three ViT hidden states.
+
+    regions: list of [n_region_i, h, w] 0/1 masks.  Returns (all_images [R,3,h,w], all_regions [R,1,h,w],
+    [3 x all_image_features [R, n_tokens, C]])."""
+    num_regions = [len(r) for r in regions]
+    all_regions = torch.cat([r[:, None] for r in regions], dim=0)
+    dev = all_regions.device
+    if torch.is_tensor(images):                                     # 'pad': one view per sample, row b of the ViT batch
+        view_rows = [torch.full((n,), b, dtype=torch.long, device=dev) for b, n in enumerate(num_regions)]
+        flat_images = images
+    else:
+        images = [x.unsqueeze(0) if x.ndim == 3 else x for x in images]
+        sizes = split_sizes if split_sizes is not None else [im.shape[0] for im in images]
+        starts = [0]
+        for n in sizes[:-1]:
+            starts.append(starts[-1] + n)
+        view_rows = []
+        for b, n in enumerate(num_regions):
+            if num_splits is not None:                              # r-th region <-> last tile of the r-th image
+                ends, acc = [], 0
+                for k in num_splits[b]:
+                    acc += k
+                    ends.append(acc - 1)
+                rows = torch.as_tensor(ends[:n], dtype=torch.long, device=dev) + starts[b]
+                if len(rows) != n:
+                    raise RuntimeError("mmic sample with more regions than images (mv2.py:634 would mis-pair them)")
+            else:                                                   # all regions <-> the last (global) tile
+                rows = torch.full((n,), starts[b] + sizes[b] - 1, dtype=torch.long, device=dev)
+            view_rows.append(rows)
+        flat_images = torch.cat(list(images), dim=0)
+    rows = torch.cat(view_rows) if view_rows else torch.zeros(0, dtype=torch.long, device=dev)
+    all_images = flat_images[rows]
+    feats = [h[rows, 1:] for h in vit_hidden_states[-3:]]
+    return all_images, all_regions, feats
+
+
+def scatter_region_tokens(input_ids, inputs_embeds, region_features, reg_token_id):
+    """mv2.py:690-698: the k-th `<region>` token of the flattened batch takes the k-th region feature."""
+    B, L, C = inputs_embeds.shape
+    mask = (input_ids == reg_token_id).reshape(-1)
+    if int(mask.sum()) != region_features.shape[0]:
+        raise RuntimeError(f"{int(mask.sum())} <region> tokens vs {region_features.shape[0]} region features")
+    flat = inputs_embeds.reshape(B * L, C).clone()
+    flat[mask] = region_features.to(flat.dtype)
+    return flat.reshape(B, L, C)
+
+
 class B200VisionLLMv2Model(nn.Module):
-    def __init__(self, config, vis_encoder, llm, gdino=None):
+    def __init__(self, config, vis_encoder, llm, gdino=None, region_encoder=None):
         super().__init__()
         self.config = config
         self.vis_encoder = vis_encoder
@@ -101,11 +153,15 @@ class B200VisionLLMv2Model(nn.Module):
         self.use_gdino = gdino is not None
         if gdino is not None:
             self.gdino = gdino
+        self.use_region_encoder = region_encoder is not None
+        if region_encoder is not None:
+            self.region_encoder = region_encoder
         self.num_embs = int(getattr(config, "num_embs", 4))
         self.emb_embeddings_det = nn.Embedding(self.num_embs, self.l_hidden_size)
         self.emb_embeddings_pose = nn.Embedding(self.num_embs, self.l_hidden_size)
         # special-token ids are assigned by init_special_token_ids (mv2.py:281-353)
-        for k in ("imp_token_id", "emb_token_id", "det_tool_id", "seg_tool_id", "grd_tool_id", "pose_tool_id"):
+        for k in ("imp_token_id", "emb_token_id", "det_tool_id", "seg_tool_id", "grd_tool_id", "pose_tool_id",
+                  "reg_token_id"):
             setattr(self, k, getattr(config, k, -1))
 
     # ---- pieces ------------------------------------------------------------------------------
@@ -184,7 +240,8 @@ class B200VisionLLMv2Model(nn.Module):
     @torch.no_grad()
     def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, images=None, images_aug=None,
                 img_metas=None, targets=None, labels=None, past_key_values=None, use_cache=False,
-                output_attentions=False, output_hidden_states=False, return_dict=True, **unused):
+                output_attentions=False, output_hidden_states=False, return_dict=True, regions=None, num_splits=None,
+                region_sample_points=None, **unused):
         if past_key_values is not None or use_cache:
             raise NotImplementedError("generation with KV cache is outside the forward hot path")
         if labels is not None or targets is not None:
@@ -197,6 +254,10 @@ class B200VisionLLMv2Model(nn.Module):
             feats, split_sizes, vit_out = self.encode_images(images)
             inputs_embeds = self.scatter_image_tokens(input_ids, inputs_embeds, feats.to(inputs_embeds.dtype),
                                                       split_sizes)
+            if self.use_region_encoder and regions is not None:                              # mv2.py:607-698
+                ri, rm, rf = region_encoder_inputs(images, regions, vit_out.hidden_states, split_sizes, num_splits)
+                rfeat = self.region_encoder(ri, rm, rf, sample_points=region_sample_points)
+                inputs_embeds = scatter_region_tokens(input_ids, inputs_embeds, rfeat, self.reg_token_id)
         out = self.llm(attention_mask=attention_mask, inputs_embeds=inputs_embeds, output_hidden_states=True)
         hidden = out.hidden_states[-1]
         gdino_outputs = None
