@@ -22,6 +22,24 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_dram_bytes(profile_name, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes, per launch) of a kernel from a committed `ncu --set full`
+    summary under profiles/ (tools/ncu_summary.py), or None -- the `traffic` field of the roofline object."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", profile_name)))
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for launch in d.get("launches", []):
+            if kernel_substr in launch.get("kernel", ""):
+                tot = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    val, u = launch[key].split()
+                    tot += float(val) * unit[u]
+                return tot
+    except Exception:
+        pass
+    return None
+
+
 def shard_range(total, rank, world):
     """Contiguous batch shard of SURVEY 8e: rank r owns units [r*total/world, (r+1)*total/world)."""
     if total % world:
@@ -116,8 +134,13 @@ class MsdaEncoderWorkload:
     def roofline(self, kern_ms, peaks):
         ach = self.alg_bytes_per_image * self.N / (kern_ms * 1e-3) / 1e9
         return {"kernel": "msda_fwd_warp_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
-                "peak_source": peaks["source"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
-                "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": self.alg_bytes_per_image * self.N}
+                "peak_source": peaks["source"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                "traffic": self.ncu_traffic(), "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": self.alg_bytes_per_image * self.N}
+
+    def ncu_traffic(self):
+        # DRAM bytes per launch of the same kernel at the same shape, from the committed ncu capture
+        return ncu_dram_bytes("r1_msda_warp_ncu.json", "msda_fwd_warp_kernel<8, 16, 16, 16, 4, float>")
 
     def config(self):
         return {"workload": "msda_fwd encoder shape (BASELINE cfg 2b): N=8 S=Lq=21760 M=8 D=32 L=4 P=4 fp32",
@@ -145,6 +168,9 @@ class MsdaEncoderBf16Workload(MsdaEncoderWorkload):
         self.d2h_bytes = self.h_out.numel() * 2
         self.alg_bytes_per_image = (self.value[0].numel() * 2 + self.loc[0].numel() * 4 + self.attw[0].numel() * 4
                                     + S * 256 * 2)
+
+    def ncu_traffic(self):
+        return None                                     # no ncu capture committed for the in-place bf16 instantiation
 
     def step_device(self):
         self.out = self.ext.ms_deform_attn_forward_bf16(self.value, self.shapes, self.lsi, self.loc, self.attw)
@@ -198,6 +224,9 @@ class MsdaEncoderPairsWorkload(MsdaEncoderBf16Workload):
         self.pack_ms = sum(a.elapsed_time(b) for a, b, _ in evs) / steps
         self.gather_ms = sum(b.elapsed_time(c) for _, b, c in evs) / steps
         return self.pack_ms + self.gather_ms
+
+    def ncu_traffic(self):
+        return ncu_dram_bytes("r1_msda_pair_ncu.json", "msda_fwd_pair_kernel")     # the gather launch only
 
     def roofline(self, kern_ms, peaks):
         r = super().roofline(kern_ms, peaks)
