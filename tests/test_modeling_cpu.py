@@ -92,3 +92,68 @@ def test_scatter_region_tokens_in_order():
     import pytest
     with pytest.raises(RuntimeError):
         scatter_region_tokens(ids, emb, feats[:2], 9)
+
+
+def test_composite_forward_region_path_end_to_end(monkeypatch):
+    """B200VisionLLMv2Model.forward with `regions`: the region encoder is called with the global view of every sample
+    (anyres list input) and its outputs replace the `<region>` tokens in order, after the image tokens were scattered
+    (mv2.py:582-698).  Sub-models are torch stand-ins; only the composite's own glue runs."""
+    from types import SimpleNamespace
+    import torch.nn as nn
+    import torch.nn.functional as F
+    import visionllm_b200.ops as ops
+    from visionllm_b200.modeling import B200VisionLLMv2Model
+    monkeypatch.setattr(ops, "linear", lambda x, w, bias=None, act=None, **kw: F.linear(x, w, bias))
+    C = 8
+
+    class FakeViT(nn.Module):
+        config = SimpleNamespace(hidden_size=C, patch_size=14)
+
+        def forward(self, x, output_hidden_states=True):
+            n = x.shape[0]
+            tok = x[:, 0, 0, 0].view(n, 1, 1).expand(n, 1 + 4, C)              # every token carries its tile's marker
+            return SimpleNamespace(hidden_states=[tok + 0.1 * i for i in range(4)])
+
+    class FakeLLM(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.config = SimpleNamespace(hidden_size=C, vocab_size=50)
+            self.emb = nn.Embedding(50, C)
+            self.dtype = torch.float32
+
+        def get_input_embeddings(self):
+            return self.emb
+
+        def forward(self, attention_mask=None, inputs_embeds=None, output_hidden_states=True):
+            return SimpleNamespace(hidden_states=(inputs_embeds,), logits=None)
+
+    seen = {}
+
+    class FakeRegionEncoder(nn.Module):
+        def forward(self, images, masks, feats, sample_points=None):
+            seen.update(images=images, masks=masks, feats=feats)
+            return masks.flatten(1).sum(1, keepdim=True).expand(-1, C) * 1000.0   # one marker row per region
+
+    IMP, REG = 40, 41
+    cfg = SimpleNamespace(use_pixelshuffle=False, vl_bridge_type="linear", vis_output_layer=-1, num_embs=4,
+                          imp_token_id=IMP, emb_token_id=45, det_tool_id=-1, seg_tool_id=-1, grd_tool_id=-1,
+                          pose_tool_id=-1, reg_token_id=REG)
+    m = B200VisionLLMv2Model(cfg, FakeViT(), FakeLLM(), region_encoder=FakeRegionEncoder()).eval()
+    with torch.no_grad():
+        m.vl_bridge.weight.copy_(torch.eye(C)); m.vl_bridge.bias.zero_()
+    ids = torch.randint(0, 30, (2, 12))
+    ids[0, :8] = IMP                                          # sample 0: 2 tiles x 4 tokens
+    ids[1, :4] = IMP                                          # sample 1: 1 tile
+    ids[0, 9] = REG; ids[0, 11] = REG; ids[1, 6] = REG
+    images = [torch.full((2, 3, 4, 4), 5.0), torch.full((1, 3, 4, 4), 7.0)]
+    images[0][1] = 6.0                                        # sample 0's LAST tile (the global view) is marked 6
+    regions = [torch.ones(2, 4, 4), torch.ones(1, 4, 4)]
+    regions[0][1, :2] = 0                                     # second region of sample 0 covers 8 pixels
+    out = m(input_ids=ids, images=images, regions=regions)
+    assert seen["images"][:, 0, 0, 0].tolist() == [6.0, 6.0, 7.0]
+    want = torch.tensor([[6.1, 6.1, 7.1], [6.2, 6.2, 7.2], [6.3, 6.3, 7.3]])
+    assert torch.allclose(torch.stack([f[:, 0, 0] for f in seen["feats"]]), want) and seen["feats"][0].shape == (3, 4, C)
+    h = out.last_hidden_state
+    assert h[0, 9, 0].item() == 16000.0 and h[0, 11, 0].item() == 8000.0 and h[1, 6, 0].item() == 16000.0
+    assert torch.allclose(h[0, :4], torch.full((4, C), 5.3)) and torch.allclose(h[0, 4:8], torch.full((4, C), 6.3))
+    assert torch.allclose(h[1, :4], torch.full((4, C), 7.3))
