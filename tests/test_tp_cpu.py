@@ -157,3 +157,47 @@ def test_shard_rejects_indivisible_heads():
 def test_exchange_layout():
     from visionllm_b200 import tp
     assert tp.exchange_bytes(4096, 4096, 8) == 4096 + 2 * 4096 * 4096 * 2
+
+
+def test_internlm2_shards_equal_llama_shards_of_the_unfused_weights():
+    """The reference's fused InternLM2 `wqkv` ((G q heads, k, v) per KV head, internlm2/modeling_internlm2.py:337-349)
+    un-fused into HF-Llama q/k/v projections must shard to exactly the same per-rank tensors: GQA groups stay
+    rank-local and the rank's query heads are the contiguous block `wo` is ordered by."""
+    from types import SimpleNamespace
+    from visionllm_b200 import tp
+    nq, nkv, D, H, I, L, V = 8, 4, 4, 32, 24, 2, 11
+    G = nq // nkv
+    cfg = SimpleNamespace(num_attention_heads=nq, num_key_value_heads=nkv, hidden_size=H, num_hidden_layers=L)
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    il, ll = {"model.tok_embeddings.weight": r(V, H), "model.norm.weight": r(H), "output.weight": r(V, H)}, {}
+    ll.update({"model.embed_tokens.weight": il["model.tok_embeddings.weight"], "model.norm.weight": il["model.norm.weight"],
+               "lm_head.weight": il["output.weight"]})
+    for i in range(L):
+        q, k, v = r(nq * D, H), r(nkv * D, H), r(nkv * D, H)
+        fused = torch.cat([torch.cat([q.view(nkv, G * D, H)[j], k.view(nkv, D, H)[j], v.view(nkv, D, H)[j]], 0)
+                           for j in range(nkv)], 0)
+        p, pl = f"model.layers.{i}.", f"model.layers.{i}."
+        il.update({p + "attention.wqkv.weight": fused, p + "attention.wo.weight": r(H, nq * D),
+                   p + "feed_forward.w1.weight": r(I, H), p + "feed_forward.w3.weight": r(I, H),
+                   p + "feed_forward.w2.weight": r(H, I), p + "attention_norm.weight": r(H), p + "ffn_norm.weight": r(H)})
+        ll.update({pl + "self_attn.q_proj.weight": q, pl + "self_attn.k_proj.weight": k, pl + "self_attn.v_proj.weight": v,
+                   pl + "self_attn.o_proj.weight": il[p + "attention.wo.weight"],
+                   pl + "mlp.gate_proj.weight": il[p + "feed_forward.w1.weight"],
+                   pl + "mlp.up_proj.weight": il[p + "feed_forward.w3.weight"],
+                   pl + "mlp.down_proj.weight": il[p + "feed_forward.w2.weight"],
+                   pl + "input_layernorm.weight": il[p + "attention_norm.weight"],
+                   pl + "post_attention_layernorm.weight": il[p + "ffn_norm.weight"]})
+    for world in (1, 2, 4):
+        for rank in range(world):
+            a = tp.shard_internlm2_state_dict(il, cfg, rank, world)
+            b = tp.shard_llama_state_dict(ll, cfg, rank, world)
+            for key in ("embed", "final_norm", "lm_head"):
+                assert torch.equal(a[key], b[key])
+            for la, lb in zip(a["layers"], b["layers"]):
+                assert la.keys() == lb.keys()
+                for key in la:
+                    assert torch.equal(la[key], lb[key]), (world, rank, key)
+    import pytest
+    with pytest.raises(ValueError):
+        tp.shard_internlm2_state_dict(il, cfg, 0, 8)            # 4 KV heads over 8 ranks

@@ -256,6 +256,39 @@ def shard_llama_state_dict(sd, config, rank, world):
     return out
 
 
+def shard_internlm2_state_dict(sd, config, rank, world):
+    """The same shards from the reference's InternLM2 names (internlm2/modeling_internlm2.py: model.tok_embeddings,
+    layers.N.attention.{wqkv,wo}, feed_forward.{w1,w2,w3}, attention_norm, ffn_norm, model.norm, output) -- the 26B
+    preset's LLM.  `wqkv` interleaves, per KV head, (G query heads, k, v) along its rows (:337-349): rank r takes KV
+    heads [r*nkv/W, (r+1)*nkv/W) WITH their G query heads each, so grouped-query attention stays rank-local and the
+    rank's query heads are the contiguous global heads [r*nq/W, (r+1)*nq/W) that `wo`'s columns are ordered by."""
+    nq = config.num_attention_heads
+    nkv = getattr(config, "num_key_value_heads", None) or nq
+    D = config.hidden_size // nq
+    if nq % world or nkv % world:
+        raise ValueError(f"heads ({nq} q / {nkv} kv) must divide over {world} ranks")
+    if getattr(config, "bias", False):
+        raise NotImplementedError("TP path: InternLM2 with projection biases")
+    G, kvl = nq // nkv, nkv // world
+    ql = kvl * G * D
+    out = {"embed": sd["model.tok_embeddings.weight"], "final_norm": sd["model.norm.weight"],
+           "lm_head": sd["output.weight"], "layers": []}
+    for i in range(config.num_hidden_layers):
+        p = f"model.layers.{i}."
+        w = sd[p + "attention.wqkv.weight"]
+        blk = w.view(nkv, G + 2, D, w.shape[1])[rank * kvl:(rank + 1) * kvl]           # this rank's KV-head groups
+        g, u = sd[p + "feed_forward.w1.weight"], sd[p + "feed_forward.w3.weight"]
+        out["layers"].append({
+            "wqkv": torch.cat([blk[:, :G].reshape(-1, w.shape[1]), blk[:, G].reshape(-1, w.shape[1]),
+                               blk[:, G + 1].reshape(-1, w.shape[1])], 0).contiguous(),
+            "wo": sd[p + "attention.wo.weight"][:, rank * ql:(rank + 1) * ql].contiguous(),
+            "w_gate_up": torch.stack([g, u], 1).reshape(2 * g.shape[0], g.shape[1]).contiguous(),
+            "w_down": sd[p + "feed_forward.w2.weight"],
+            "ln1": sd[p + "attention_norm.weight"], "ln2": sd[p + "ffn_norm.weight"],
+        })
+    return out
+
+
 class TPLlamaForCausalLM(nn.Module):
     """One rank of the tensor-parallel `B200LlamaForCausalLM`.  `comm` is a `PeerComm` (or, in CPU tests, a double
     with the same five methods)."""
@@ -269,8 +302,8 @@ class TPLlamaForCausalLM(nn.Module):
         W = comm.world
         if self.nq % W or self.nkv % W:
             raise ValueError(f"heads ({self.nq} q / {self.nkv} kv) must divide over {W} ranks")
-        if getattr(config, "attention_bias", False):
-            raise NotImplementedError("TP path: attention_bias")
+        if getattr(config, "attention_bias", False) or getattr(config, "bias", False):
+            raise NotImplementedError("TP path: projection biases")
         self.eps = config.rms_norm_eps
         theta = getattr(config, "rope_theta", None)
         if theta is None:
@@ -289,7 +322,9 @@ class TPLlamaForCausalLM(nn.Module):
 
     @classmethod
     def from_full_state_dict(cls, config, comm, sd, device=None, dtype=torch.bfloat16):
-        return cls(config, comm, shard_llama_state_dict(sd, config, comm.rank, comm.world), device, dtype)
+        """HF Llama names (Vicuna, 7B preset) or the reference's InternLM2 names (26B preset), told apart by the keys."""
+        shard = shard_internlm2_state_dict if "model.tok_embeddings.weight" in sd else shard_llama_state_dict
+        return cls(config, comm, shard(sd, config, comm.rank, comm.world), device, dtype)
 
     @classmethod
     def random_init(cls, config, comm, device, seed=0, std=0.02):
