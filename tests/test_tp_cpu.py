@@ -115,7 +115,9 @@ def _worker(rank, world, port, q):
         want = ref(inputs_embeds=emb, attention_mask=am, output_hidden_states=True)
     comm = GlooComm(rank, world, B * T, H)
     model = tp.TPLlamaForCausalLM.from_full_state_dict(cfg, comm, ref.state_dict(), dtype=torch.float32)
-    out = model(inputs_embeds=emb, attention_mask=am)
+    out = model(inputs_embeds=emb, attention_mask=am, output_hidden_states=True, use_cache=False)   # HF-style call
+    assert out.hidden_states[-1] is out.last_hidden_state and out.logits is None
+    assert model.dtype == torch.float32 and model.get_input_embeddings()(torch.tensor([[1, 2]])).shape == (1, 2, H)
     lo, hi = out.row_range
     valid = am.bool().reshape(-1)                            # padded query rows are don't-care in both
     err_h = (out.last_hidden_state.reshape(B * T, H) - want.hidden_states[-1].reshape(B * T, H))[valid].abs().max()

@@ -397,11 +397,25 @@ class TPLlamaForCausalLM(nn.Module):
             buf = torch.empty((R, Vp), dtype=torch.float32, device=dev)
             ops.linear(last.view(M, H)[r * R:(r + 1) * R], S["lm_head"], out=buf[:, :V])
             logits = buf[:, :V]
-        self.result = SimpleNamespace(last_hidden_state=last, logits_local=logits, row_range=(r * R, (r + 1) * R))
+        # `hidden_states[-1]` / `logits` are what the composite forward reads (modeling_visionllmv2.py:733-751); the full
+        # [B, T, V] logits are never materialised here -- each rank keeps the rows it owns.
+        self.result = SimpleNamespace(last_hidden_state=last, hidden_states=(last,), logits=None, logits_local=logits,
+                                      row_range=(r * R, (r + 1) * R), past_key_values=None, attentions=None)
+
+    # ---- the parts of the HF interface the composite model touches (modeling_visionllmv2.py:420,571,724-751) -------
+    @property
+    def dtype(self):
+        return self.shards["lm_head"].dtype
+
+    def get_input_embeddings(self):
+        return lambda ids: torch.nn.functional.embedding(ids, self.shards["embed"])
 
     @torch.no_grad()
     def forward(self, inputs_embeds=None, input_ids=None, attention_mask=None, position_ids=None,
-                compute_logits=True):
+                compute_logits=True, past_key_values=None, use_cache=False, output_attentions=False,
+                output_hidden_states=True, return_dict=True):
+        if past_key_values is not None or use_cache:
+            raise NotImplementedError("KV-cache decoding is outside the forward hot path (SURVEY 3.4)")
         if inputs_embeds is None:
             inputs_embeds = torch.nn.functional.embedding(input_ids, self.shards["embed"])
         for _ in self.phases(inputs_embeds, attention_mask, position_ids, compute_logits):
