@@ -101,7 +101,8 @@ int vllm_msda_backward_f64(const double* value, const int64_t* spatial_shapes, c
  * h_low/w_low are 0 when bit0 is clear. */
 int vllm_msda_sample_indices_f32(const int64_t* spatial_shapes, const float* sampling_loc, int32_t* out_hwm,
                                  long long n_samples, int num_levels, int num_point, void* stream);
-/* Tuning knob for bench sweeps (process-global, not part of the drop-in API). */
+/* Tuning knob for bench sweeps (process-global, not part of the drop-in API): 0 default; 1-4 tile shapes of the fp32
+ * warp-gather kernel; 16 = experimental FHFMA.BF16 form of vllm_msda_forward_pairs (bf16 corner weights). */
 int vllm_msda_set_variant(int variant);
 
 /* ---- DCNv3 forward (InternImage core op) ------------------------------------------
