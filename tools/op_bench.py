@@ -100,6 +100,36 @@ attn("attn_swin_s1_10952win_49_h3d32", 8 * 1369, 49, 49, 3, 32, bias_nb=1369)
 attn("attn_swin_s2_2888win_49_h6d32", 8 * 361, 49, 49, 6, 32, bias_nb=361)
 attn("attn_swin_s3_800win_49_h12d32", 8 * 100, 49, 49, 12, 32, bias_nb=100)
 
+# ---- InternImage-H depthwise branch and DCNv3-module glue (variant 1 of the depthwise kernel = experimental FHFMA.BF16) --
+from visionllm_b200 import _lib  # noqa: E402
+for name, (N, Hh, W, C) in {"dwconv5_s1_4x256x256x320": (4, 256, 256, 320), "dwconv5_s3_4x64x64x1280": (4, 64, 64, 1280)}.items():
+    x = torch.randn(N, Hh, W, C, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(25, C, device="cuda", generator=g) / 5).bfloat16()
+    b = torch.randn(C, device="cuda", generator=g).bfloat16()
+    for variant in (0, 1):
+        _lib.lib().vllm_dwconv_set_variant(variant)
+        rec(f"{name}_v{variant}", timeit(lambda: ops.dwconv_nhwc(x, wt, b, 5)), x.numel() * 4, note="in read + out written (bf16)")
+    _lib.lib().vllm_dwconv_set_variant(0)
+    lw, lb = torch.ones(C, device="cuda").bfloat16(), torch.zeros(C, device="cuda").bfloat16()
+    rec(name.replace("dwconv5", "ln_gelu"), timeit(lambda: ops.layernorm(x, lw, lb, 1e-6, gelu=True)), x.numel() * 4)
+    rec(name.replace("dwconv5", "ln_residual"), timeit(lambda: ops.layernorm(x, lw, lb, 1e-6, residual=x)), x.numel() * 6)
+    G = C // 32
+    om = torch.randn(N, Hh, W, G * 28, device="cuda", generator=g)
+    rec(name.replace("dwconv5", "dcn_prep"), timeit(lambda: ops.dcnv3_prep(om, G, 9, True)), om.numel() * 8)
+    core, xp = torch.randn(N, Hh, W, C, device="cuda", generator=g), torch.randn(N, Hh, W, C, device="cuda", generator=g)
+    sc = torch.rand(N, Hh, W, G, device="cuda", generator=g)
+    rec(name.replace("dwconv5", "dcn_blend"), timeit(lambda: ops.dcnv3_blend(core, xp, sc, 32)), core.numel() * 10)
+
+# ---- MSDA paired-row mode: default vs the experimental FHFMA.BF16 variant (vllm_msda_set_variant(16)) ----
+import bench_workloads as BW  # noqa: E402
+value, shapes, lsi, loc, attw = BW.msda_encoder_inputs(torch, 8, torch.device("cuda"), 1234)
+pairs = msda.ms_deform_attn_pack_pairs(value.bfloat16(), shapes, lsi)
+alg = value.numel() * 2 + loc.numel() * 4 + attw.numel() * 4 + value.numel() * 2
+for variant in (0, 16):
+    _lib.lib().vllm_msda_set_variant(variant)
+    rec(f"msda_pairs_gather_v{variant}", timeit(lambda: msda.ms_deform_attn_forward_pairs(pairs, shapes, lsi, loc, attw)), alg)
+_lib.lib().vllm_msda_set_variant(0)
+
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({"peaks": {k: PEAKS[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained")}, "results": res},
           open("gpurun_out/op_bench.json", "w"), indent=1)
