@@ -613,6 +613,7 @@ class PairForwardGdinoWorkload(PairForwardWorkload):
         self.model.use_gdino = True
         self.aug = torch.randn(self.PAIRS, 3, 1024, 1024, device=self.device).bfloat16()   # mmdet-normalised images_aug
         self.h_aug = self.aug.cpu().pin_memory()
+        self.metas = [{"task": "det"} for _ in range(self.PAIRS)]        # the eval loop's img_metas (mv2.py:755-763)
         self.d_aug = torch.empty_like(self.aug)
         self.h2d_bytes = sum(t.numel() * 2 for t in self.h_images) + self.ids.numel() * 8 + self.aug.numel() * 2
         self.h_out = torch.empty((self.PAIRS, 100, 6), dtype=torch.float32).pin_memory()
@@ -627,14 +628,16 @@ class PairForwardGdinoWorkload(PairForwardWorkload):
                                  for r in res])
 
     def step_device(self):
-        self.out = self._post(self.model(input_ids=self.ids, attention_mask=None, images=self.images, images_aug=self.aug))
+        self.out = self._post(self.model(input_ids=self.ids, attention_mask=None, images=self.images, images_aug=self.aug,
+                                         img_metas=self.metas))
 
     def step_e2e(self):
         for d, h in zip(self.d_images, self.h_images):
             d.copy_(h, non_blocking=True)
         self.d_ids.copy_(self.h_ids, non_blocking=True)
         self.d_aug.copy_(self.h_aug, non_blocking=True)
-        out = self._post(self.model(input_ids=self.d_ids, attention_mask=None, images=self.d_images, images_aug=self.d_aug))
+        out = self._post(self.model(input_ids=self.d_ids, attention_mask=None, images=self.d_images, images_aug=self.d_aug,
+                                    img_metas=self.metas))
         self.h_out.copy_(out, non_blocking=True)                     # boxes, scores, labels of the top-100 detections
 
     def config(self):

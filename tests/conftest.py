@@ -15,3 +15,19 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device AND the in-tree library: skip (not fail) them elsewhere, so that a plain
+    `pytest tests` on the build box is green; on a GPU box a missing library is still a hard error inside the tests."""
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+    except Exception:
+        has_cuda = False
+    if has_cuda:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run under gpurun)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -157,3 +157,106 @@ def test_composite_forward_region_path_end_to_end(monkeypatch):
     assert h[0, 9, 0].item() == 16000.0 and h[0, 11, 0].item() == 8000.0 and h[1, 6, 0].item() == 16000.0
     assert torch.allclose(h[0, :4], torch.full((4, C), 5.3)) and torch.allclose(h[0, 4:8], torch.full((4, C), 6.3))
     assert torch.allclose(h[1, :4], torch.full((4, C), 7.3))
+
+
+def _ref_nested_tensor(tensor_list, size_divisibility):
+    """util/misc.py:288-316 restated as the reference's loop (split into 3-channel images, zero-pad to the max size
+    rounded up to the divisibility)."""
+    tensor_list = [piece for t in tensor_list for piece in t.split(3, dim=0)]
+    max_size = [max(s) for s in zip(*[list(img.shape) for img in tensor_list])]
+    max_size[-2] = (max_size[-2] + size_divisibility - 1) // size_divisibility * size_divisibility
+    max_size[-1] = (max_size[-1] + size_divisibility - 1) // size_divisibility * size_divisibility
+    tensor = torch.zeros([len(tensor_list)] + max_size, dtype=tensor_list[0].dtype)
+    for img, pad_img in zip(tensor_list, tensor):
+        pad_img[: img.shape[0], : img.shape[1], : img.shape[2]].copy_(img)
+    return tensor
+
+
+def test_pad_images_aug_matches_reference_nested_tensor():
+    """ragged, non-/32 images_aug must reach the GDINO stage zero-padded like mv2.py:771."""
+    from visionllm_b200.modeling import pad_images_aug
+    g = torch.Generator().manual_seed(0)
+    ragged = [torch.randn(3, 50, 67, generator=g), torch.randn(3, 64, 40, generator=g), torch.randn(3, 33, 96, generator=g)]
+    got = pad_images_aug(ragged, 32)
+    ref = _ref_nested_tensor(ragged, 32)
+    assert got.shape == (3, 3, 64, 96) and torch.equal(got, ref)
+    same = torch.randn(2, 3, 64, 96, generator=g)              # already aligned: a plain stack, values untouched
+    assert torch.equal(pad_images_aug(same, 32), same) and torch.equal(pad_images_aug(list(same), 32), same)
+    odd = torch.randn(2, 3, 50, 70, generator=g)                # a tensor whose H/W is not a multiple of 32
+    assert torch.equal(pad_images_aug(odd, 32), _ref_nested_tensor(list(odd), 32))
+    mask = pad_images_aug(ragged, 32)[:, 0] != 0                # mv2.py:773: the padding is what the mask sees
+    assert not mask[0, 50:, :].any() and not mask[0, :, 67:].any() and mask[0, :50, :67].all()
+
+
+def _tiny_composite(gdino=None, **ids):
+    from types import SimpleNamespace
+    import torch.nn as nn
+    from visionllm_b200.modeling import B200VisionLLMv2Model
+    C = 8
+
+    class FakeViT(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.config = SimpleNamespace(hidden_size=C, patch_size=2)
+
+        def forward(self, x, output_hidden_states=True):
+            t = torch.zeros(x.shape[0], 5, C)
+            return SimpleNamespace(hidden_states=(t, t, t))
+
+    class FakeLLM(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.config = SimpleNamespace(hidden_size=C, vocab_size=64)
+            self.emb = nn.Embedding(64, C)
+            self.dtype = torch.float32
+
+        def get_input_embeddings(self):
+            return self.emb
+
+        def forward(self, attention_mask=None, inputs_embeds=None, output_hidden_states=True):
+            return SimpleNamespace(hidden_states=(inputs_embeds,), logits=None)
+
+    cfg = SimpleNamespace(use_pixelshuffle=False, vl_bridge_type="linear", vis_output_layer=-1, num_embs=4,
+                          imp_token_id=40, emb_token_id=45, det_tool_id=50, seg_tool_id=-1, grd_tool_id=-1,
+                          pose_tool_id=51)
+    return B200VisionLLMv2Model(cfg, FakeViT(), FakeLLM(), gdino=gdino).eval()
+
+
+def test_inject_emb_refuses_to_clobber_real_tokens():
+    """a tool token whose following slots are NOT pre-placed [EMB] ids is the reference's insert form
+    (mv2.py:428-431, gap_len = 0); the overwrite form must not silently eat the next num_embs tokens."""
+    import pytest
+    m = _tiny_composite()
+    ids = torch.randint(0, 30, (1, 16))
+    ids[0, 3] = 50                                             # [DET] followed by ordinary tokens
+    with pytest.raises(NotImplementedError):
+        m(input_ids=ids)
+    ids[0, 4:8] = 45                                           # collator form: [EMB] x 4 placeholders after the tool
+    out = m(input_ids=ids)
+    assert out.input_ids[0, 4:8].tolist() == [45, 46, 47, 48]
+    ids2 = ids.clone(); ids2[0, 15] = 50                       # tool token at the very end: slots run past the row
+    with pytest.raises(NotImplementedError):
+        m(input_ids=ids2)
+
+
+def test_gdino_task_gate_follows_reference():
+    """mv2.py:755-770: gdino runs only for det/det_cap/grd/seg/count_*/interactive/ic_mask; 'pose' is not wired."""
+    import pytest
+    from types import SimpleNamespace
+    import torch.nn as nn
+    calls = []
+
+    class FakeGdino(nn.Module):
+        def forward(self, pixel_values, pixel_mask=None, text_query=None, text_query_masks=None, **kw):
+            calls.append(tuple(pixel_values.shape))
+            return SimpleNamespace(logits=None)
+
+    m = _tiny_composite(gdino=FakeGdino())
+    ids = torch.randint(0, 30, (1, 16)); ids[0, 3] = 50; ids[0, 4:8] = 45
+    aug = [torch.ones(3, 40, 50)]
+    assert m(input_ids=ids, images_aug=aug).gdino_outputs is None and not calls                # no img_metas -> task None
+    assert m(input_ids=ids, images_aug=aug, img_metas=[{"task": "vqa"}]).gdino_outputs is None and not calls
+    assert m(input_ids=ids, images_aug=aug, img_metas=[{"task": "seg"}]).gdino_outputs is not None
+    assert calls == [(1, 3, 64, 64)]                                                            # padded to /32
+    with pytest.raises(NotImplementedError):
+        m(input_ids=ids, images_aug=aug, img_metas=[{"task": "pose"}])

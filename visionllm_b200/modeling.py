@@ -87,6 +87,35 @@ def emb_overwrite_indices(input_ids, tool_ids, num_embs):
     return b[:, None].expand_as(pos).reshape(-1), pos.reshape(-1), j[None, :].expand_as(pos).reshape(-1)
 
 
+GDINO_TASKS = ("det", "det_cap", "grd", "seg", "count_text", "count_visual", "interactive", "ic_mask")   # mv2.py:763
+
+
+def pad_images_aug(images_aug, size_divisibility=32):
+    """`nested_tensor_from_tensor_list(images_aug, size_divisibility=32).tensors` (util/misc.py:288-316, called at
+    mv2.py:771): every [3k, H, W] entry is split into 3-channel images, the batch is zero-padded bottom/right to the
+    per-axis maximum rounded UP to a multiple of `size_divisibility`.  (The NestedTensor's own mask is discarded by
+    the caller -- mv2.py:773 re-derives pixel_mask from the red channel -- so only the tensor is built.)"""
+    if torch.is_tensor(images_aug):
+        if images_aug.ndim != 4:
+            raise ValueError("not supported")
+        images_aug = list(images_aug)
+    imgs = [piece for t in images_aug for piece in t.split(3, dim=0)]
+    if imgs[0].ndim != 3:
+        raise ValueError("not supported")
+    c = max(im.shape[0] for im in imgs)
+    h = max(im.shape[1] for im in imgs)
+    w = max(im.shape[2] for im in imgs)
+    if size_divisibility > 1:
+        h = (h + size_divisibility - 1) // size_divisibility * size_divisibility
+        w = (w + size_divisibility - 1) // size_divisibility * size_divisibility
+    if all(tuple(im.shape) == (c, h, w) for im in imgs):
+        return torch.stack(imgs)
+    out = torch.zeros((len(imgs), c, h, w), dtype=imgs[0].dtype, device=imgs[0].device)
+    for im, dst in zip(imgs, out):
+        dst[: im.shape[0], : im.shape[1], : im.shape[2]].copy_(im)
+    return out
+
+
 def region_encoder_inputs(images, regions, vit_hidden_states, split_sizes, num_splits=None):
     """The tensors the reference hands its region encoder (mv2.py:609-687), vectorised: every region of a sample is
     paired with the sample's GLOBAL view -- the image itself ('pad': `images` a [bs,3,h,w] tensor), the last tile
@@ -177,8 +206,15 @@ class B200VisionLLMv2Model(nn.Module):
             b, p, j = emb_overwrite_indices(ids, tools, self.num_embs)
             if b.numel() == 0:
                 continue
-            if int(p.max()) >= L:
-                raise NotImplementedError("tool token without its [EMB] slots: generation-time insertion "
+            # The reference takes the overwrite form (gap_len == num_embs) only when [EMB] ids are already present in
+            # the FIRST row (mv2.py:426-431); otherwise it INSERTS (gap_len == 0, generation).  Refuse instead of
+            # clobbering real tokens: every target slot must already hold an [EMB] id.
+            in_range = p < L
+            slots = ids[b[in_range], p[in_range]]
+            ok = bool(in_range.all()) and bool(((slots >= self.emb_token_id)
+                                                & (slots < self.emb_token_id + self.num_embs)).all())
+            if not ok:
+                raise NotImplementedError("tool token without its pre-placed [EMB] slots: generation-time insertion "
                                           "(mv2.py:428-429, gap_len == 0) is outside the forward hot path")
             ids[b, p] = self.emb_token_id + j
             emb = emb.clone() if emb is inputs_embeds else emb
@@ -261,10 +297,15 @@ class B200VisionLLMv2Model(nn.Module):
         out = self.llm(attention_mask=attention_mask, inputs_embeds=inputs_embeds, output_hidden_states=True)
         hidden = out.hidden_states[-1]
         gdino_outputs = None
-        if self.use_gdino and images_aug is not None:
+        task = img_metas[0]["task"] if img_metas is not None else None                       # mv2.py:755-758
+        if task == "pose":
+            raise NotImplementedError("task 'pose' routes the [EMB] states to UniPose (mv2.py:795-), which is not "
+                                      "wired into this composite")
+        # mv2.py:762-763: the region decoder runs only for these tasks (no img_metas -> task None -> no gdino_outputs)
+        if self.use_gdino and images_aug is not None and task in GDINO_TASKS:
             tq, tm = self.gather_text_query(input_ids, hidden)
             if tq is not None:
-                pixel_values = images_aug if torch.is_tensor(images_aug) else torch.stack(list(images_aug))
+                pixel_values = pad_images_aug(images_aug, 32)                               # mv2.py:771-772
                 pixel_mask = pixel_values[:, 0, :, :] != 0                                  # mv2.py:773
                 gdino_outputs = self.gdino(pixel_values, pixel_mask=pixel_mask, text_query=tq,
                                            text_query_masks=tm, img_metas=img_metas, labels=None)

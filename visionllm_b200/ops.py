@@ -226,7 +226,11 @@ def dwconv_nhwc(x, weight_taps, bias, kernel):
     return y
 
 
-_GN_WS = {}
+_GN_WS = {}            # (device, stream) -> scratch: two streams running GroupNorm concurrently never share a buffer
+
+
+def _ws_key(device):
+    return (device.index, torch.cuda.current_stream(device).cuda_stream)
 
 
 def groupnorm_nhwc(x, weight, bias, groups, eps, relu=False):
@@ -238,9 +242,10 @@ def groupnorm_nhwc(x, weight, bias, groups, eps, relu=False):
     if weight.dtype != torch.bfloat16 or bias.dtype != torch.bfloat16 or weight.numel() != c or bias.numel() != c:
         raise RuntimeError("groupnorm_nhwc: weight/bias must be bf16 [channels]")
     need = _lib.lib().vllm_groupnorm_workspace_bytes(n, groups)
-    ws = _GN_WS.get(x.device)
+    key = _ws_key(x.device)
+    ws = _GN_WS.get(key)
     if ws is None or ws.numel() < need:
-        ws = _GN_WS[x.device] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=x.device)
+        ws = _GN_WS[key] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=x.device)
     out = torch.empty_like(x)
     with torch.cuda.device(x.device), _Prof("groupnorm", 0.0, 6.0 * n * hw * c):
         rc = _lib.lib().vllm_groupnorm_nhwc_bf16(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(), n, hw, c,
@@ -265,14 +270,15 @@ def rope_(x, cos, sin, heads, head_dim):
     return x
 
 
-_ATTN_WS = {}          # per-device split-KV scratch (grow-only), see vllm_attention_bf16
+_ATTN_WS = {}          # (device, stream) -> split-KV scratch (grow-only), see vllm_attention_bf16
 
 
 def _attn_workspace(device, nbytes):
-    ws = _ATTN_WS.get(device.index)
+    key = _ws_key(device)
+    ws = _ATTN_WS.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _ATTN_WS[device.index] = ws
+        _ATTN_WS[key] = ws
     return ws
 
 

@@ -131,6 +131,13 @@ class PeerComm:
             _lib.check(L.vllm_peer_export(own, buf), "vllm_peer_export")
             handles = [None] * world
             dist.all_gather_object(handles, bytes(buf.raw), group=group)
+            # the arrival counts of the protocol assume every rank launches the norm/push kernel with the same CTA
+            # count (peer.cu: min(rows, 4 x SMs)); MIG / MPS SM limits would break that silently -- check it
+            ctas = [None] * world
+            dist.all_gather_object(ctas, int(L.vllm_tp_norm_ctas(rows_total // world)), group=group)
+            if len(set(ctas)) != 1:
+                raise RuntimeError(f"tensor-parallel ranks disagree on the norm/push CTA count {ctas}: "
+                                   "the GPUs of the group expose different SM counts")
             ptrs, opened = [], []
             for j in range(world):
                 if j == rank:
