@@ -8,7 +8,8 @@ LIB := visionllm_b200/lib/libvllm_b200.so
 
 all: $(LIB) oracle
 
-build/%.o: visionllm_b200/csrc/%.cu visionllm_b200/csrc/common.cuh include/vllm_b200.h
+HDRS := $(wildcard visionllm_b200/csrc/*.cuh) include/vllm_b200.h
+build/%.o: visionllm_b200/csrc/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 

@@ -173,6 +173,12 @@ def main():
     kern = wl.dominant_kernel_ms(args.steps)            # live CUDA-event time of the dominant kernel
     ms_e2e, _ = timed(wl.step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    tp_obj = None
+    if world > 1 and name == benchlib.DEFAULT_WORKLOAD and not os.environ.get("VLLM_BENCH_NO_EXTRAS"):
+        try:                                               # cfg 5 under the same launch (all ranks take part)
+            tp_obj = benchlib.tp_extra(rank, world, torch.device("cuda", local_rank))
+        except Exception as e:
+            tp_obj = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -193,6 +199,13 @@ def main():
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
     }
     line.update(wl.extra())
+    if tp_obj is not None:
+        line["tp"] = tp_obj
+    if name == benchlib.DEFAULT_WORKLOAD and not os.environ.get("VLLM_BENCH_NO_EXTRAS"):
+        try:                                               # the "deform-attn HBM GB/s" half of BASELINE.json's metric
+            line["msda"] = benchlib.msda_extra(torch.device("cuda", local_rank))
+        except Exception as e:
+            line["msda"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = benchlib.cpu_baseline(name)
     emit(line)

@@ -104,6 +104,14 @@ int vllm_msda_sample_indices_f32(const int64_t* spatial_shapes, const float* sam
 /* Tuning knob for bench sweeps (process-global, not part of the drop-in API): 0 default; 1-4 tile shapes of the fp32
  * warp-gather kernel; 16 = experimental FHFMA.BF16 form of vllm_msda_forward_pairs (bf16 corner weights). */
 int vllm_msda_set_variant(int variant);
+/* Encoder shape (num_query == spatial_size, host_shapes_hint given, <= 4 levels, channels == 32): vllm_msda_forward_f32
+ * (non-strict) and vllm_msda_forward_bf16v run the TMA-staged window kernel (csrc/msda_win.cu): one CTA per (image
+ * region, head) loads the bounded value window of every level into shared memory with cp.async.bulk.tensor (zero fill
+ * outside the map = the operator's zero padding) and gathers from there; a (query, head) with a sample outside its
+ * window falls back to the global-memory path inside the same kernel (bit-identical sums).  Variant 32 disables the
+ * window path for bf16 values, variants 1-4 for fp32.  vllm_msda_set_window: tuning knob (process-global) -- level-0
+ * patch height / width in pixels and level-0 halo; 0 = default (8 x 16, halo 8 for bf16 rows; 8 x 8, halo 6 for fp32). */
+int vllm_msda_set_window(int patch_h, int patch_w, int halo0);
 
 /* ---- DCNv3 forward (InternImage core op) ------------------------------------------
  * Replaces `dcnv3_forward` of the reference extension module `DCNv3`

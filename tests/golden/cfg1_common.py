@@ -47,3 +47,41 @@ def bridge_module():
     """mv2.py:174-182 `mlp2x_gelu`: Linear(768 -> 512) + GELU + Linear(512 -> 512) (a plain nn.Sequential)."""
     import torch.nn as nn
     return nn.Sequential(nn.Linear(VIT["hidden_size"], L_HIDDEN), nn.GELU(), nn.Linear(L_HIDDEN, L_HIDDEN))
+
+
+def build_b200_model(g=None, device="cuda", dtype=torch.bfloat16):
+    """The cfg-1 composite on our modules, weights regenerated from the generator's seeds (key lists checked)."""
+    import json
+    from types import SimpleNamespace
+    from transformers import LlamaConfig
+    from weights_util import key_shapes, seeded_state_dict
+    from visionllm_b200.gdino_model import B200GroundingDinoForObjectDetection
+    from visionllm_b200.internvit import B200InternVisionModel, InternVisionConfig
+    from visionllm_b200.llama import B200LlamaForCausalLM
+    from visionllm_b200.modeling import B200VisionLLMv2Model
+    from visionllm_b200.swin import B200SwinBackbone
+    vit = B200InternVisionModel(InternVisionConfig(**VIT))
+    llm = B200LlamaForCausalLM(LlamaConfig(**LLM))
+    gcfg = SimpleNamespace(backbone_config=swin_config(), activation_function="relu", max_text_len=256, query_dim=4,
+                           two_stage=True, embedding_init_target=True, two_stage_bbox_embed_share=False,
+                           decoder_bbox_embed_share=True, position_embedding_type="sine",
+                           positional_embedding_temperature=20, **GDINO)
+    gdino = B200GroundingDinoForObjectDetection(gcfg, backbone_model=B200SwinBackbone(gcfg.backbone_config))
+    if g is not None:
+        for mod, key in ((vit, "keys_vit"), (llm, "keys_llm"), (gdino, "keys_gdino")):
+            assert json.loads(str(g[key])) == [list(k) for k in key_shapes(mod)], f"{key}: state-dict keys differ"
+    vit.load_state_dict(seeded_state_dict(vit, SEEDS["vit"]))
+    llm.load_state_dict(seeded_state_dict(llm, SEEDS["llm"]))
+    sd = seeded_state_dict(gdino, SEEDS["gdino"])
+    for k in sd:
+        if k.endswith("vision_param") or k.endswith("text_param"):
+            sd[k] = sd[k] * 0 + 0.5
+    gdino.load_state_dict(sd)
+    cfg = SimpleNamespace(use_pixelshuffle=False, vl_bridge_type="mlp2x_gelu", vis_output_layer=-1, num_embs=NUM_EMBS,
+                          imp_token_id=IMP, emb_token_id=EMB, det_tool_id=DET, seg_tool_id=-1, grd_tool_id=-1,
+                          pose_tool_id=-1)
+    model = B200VisionLLMv2Model(cfg, vit, llm, gdino=gdino)
+    ref_bridge = bridge_module()
+    model.vl_bridge.load_state_dict(seeded_state_dict(ref_bridge, SEEDS["bridge"]))      # same keys as nn.Sequential
+    model.emb_embeddings_det.load_state_dict(seeded_state_dict(torch.nn.Embedding(NUM_EMBS, L_HIDDEN), SEEDS["emb"]))
+    return model.to(device, dtype).eval()

@@ -30,38 +30,7 @@ def rel(a, b):
 
 
 def build_cfg1_model(g=None):
-    """The cfg-1 composite on our modules, weights regenerated from the generator's seeds (key lists checked)."""
-    from transformers import LlamaConfig
-    from visionllm_b200.gdino_model import B200GroundingDinoForObjectDetection
-    from visionllm_b200.internvit import B200InternVisionModel, InternVisionConfig
-    from visionllm_b200.llama import B200LlamaForCausalLM
-    from visionllm_b200.modeling import B200VisionLLMv2Model
-    from visionllm_b200.swin import B200SwinBackbone
-    vit = B200InternVisionModel(InternVisionConfig(**C.VIT))
-    llm = B200LlamaForCausalLM(LlamaConfig(**C.LLM))
-    gcfg = SimpleNamespace(backbone_config=C.swin_config(), activation_function="relu", max_text_len=256, query_dim=4,
-                           two_stage=True, embedding_init_target=True, two_stage_bbox_embed_share=False,
-                           decoder_bbox_embed_share=True, position_embedding_type="sine",
-                           positional_embedding_temperature=20, **C.GDINO)
-    gdino = B200GroundingDinoForObjectDetection(gcfg, backbone_model=B200SwinBackbone(gcfg.backbone_config))
-    if g is not None:
-        for mod, key in ((vit, "keys_vit"), (llm, "keys_llm"), (gdino, "keys_gdino")):
-            assert json.loads(str(g[key])) == [list(k) for k in key_shapes(mod)], f"{key}: state-dict keys differ"
-    vit.load_state_dict(seeded_state_dict(vit, C.SEEDS["vit"]))
-    llm.load_state_dict(seeded_state_dict(llm, C.SEEDS["llm"]))
-    sd = seeded_state_dict(gdino, C.SEEDS["gdino"])
-    for k in sd:
-        if k.endswith("vision_param") or k.endswith("text_param"):
-            sd[k] = sd[k] * 0 + 0.5
-    gdino.load_state_dict(sd)
-    cfg = SimpleNamespace(use_pixelshuffle=False, vl_bridge_type="mlp2x_gelu", vis_output_layer=-1, num_embs=C.NUM_EMBS,
-                          imp_token_id=C.IMP, emb_token_id=C.EMB, det_tool_id=C.DET, seg_tool_id=-1, grd_tool_id=-1,
-                          pose_tool_id=-1)
-    model = B200VisionLLMv2Model(cfg, vit, llm, gdino=gdino)
-    ref_bridge = C.bridge_module()
-    model.vl_bridge.load_state_dict(seeded_state_dict(ref_bridge, C.SEEDS["bridge"]))      # same keys as nn.Sequential
-    model.emb_embeddings_det.load_state_dict(seeded_state_dict(torch.nn.Embedding(C.NUM_EMBS, C.L_HIDDEN), C.SEEDS["emb"]))
-    return model.to("cuda", torch.bfloat16).eval()
+    return C.build_b200_model(g, device="cuda", dtype=torch.bfloat16)
 
 
 @pytest.fixture(scope="module")

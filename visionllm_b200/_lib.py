@@ -33,6 +33,7 @@ _SIGNATURES = {
     "vllm_msda_backward_f64": (ci, [vp] * 9 + [ci] * 7 + [vp]),
     "vllm_msda_sample_indices_f32": (ci, [vp, vp, vp, cll, ci, ci, vp]),
     "vllm_msda_set_variant": (ci, [ci]),
+    "vllm_msda_set_window": (ci, [ci, ci, ci]),
     "vllm_dcnv3_forward_f32": (ci, [vp, vp, vp, vp] + [ci] * 15 + [cf, ci, vp]),
     "vllm_dcnv3_backward_f32": (ci, [vp] * 7 + [ci] * 15 + [cf, vp]),
     "vllm_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp]),

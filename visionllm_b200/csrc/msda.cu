@@ -35,59 +35,7 @@
 // product is rounded to fp32 BEFORE the subtraction; nvcc must not contract it
 // into an FMA.  msda_geom() uses __fmul_rn/__fsub_rn and is shared by both
 // kernels and by the index-dump entry point the parity tests use.
-#include "common.cuh"
-#include <limits.h>
-
-#define MSDA_MAX_LEVELS 8
-
-struct MsdaTiling {
-  int mode;                          // 0: tiles of consecutive queries; 1: 2-D pixel patches
-  int n_tiles;                       // tiles per (batch, head)
-  int tile_start[MSDA_MAX_LEVELS + 1];
-  int H[MSDA_MAX_LEVELS], W[MSDA_MAX_LEVELS];
-  int q_start[MSDA_MAX_LEVELS];
-  int tiles_w[MSDA_MAX_LEVELS];
-};
-
-// ---------------------------------------------------------------------------
-// Index arithmetic shared by every path (reference .cuh:238-241 and :22-29).
-// ---------------------------------------------------------------------------
-template <typename T> struct MsdaGeom {
-  int h_low, w_low;
-  T lh, lw;
-  int mask;  // bit0: sample in range; bits1..4: corner (ll, lh, hl, hh) in bounds
-};
-
-__device__ __forceinline__ float msda_mul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float msda_sub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float msda_add(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double msda_mul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double msda_sub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double msda_add(double a, double b) { return __dadd_rn(a, b); }
-
-template <typename T>
-__device__ __forceinline__ MsdaGeom<T> msda_geom(T loc_w, T loc_h, int H, int W) {
-  MsdaGeom<T> g;
-  const T h_im = msda_sub(msda_mul(loc_h, (T)H), (T)0.5);
-  const T w_im = msda_sub(msda_mul(loc_w, (T)W), (T)0.5);
-  g.mask = 0; g.h_low = 0; g.w_low = 0; g.lh = 0; g.lw = 0;
-  if (h_im > (T)-1 && w_im > (T)-1 && h_im < (T)H && w_im < (T)W) {
-    // The reference calls floorf() for every scalar type (kernel.cuh:22-23).
-    const int h_low = (int)floorf((float)h_im);
-    const int w_low = (int)floorf((float)w_im);
-    g.h_low = h_low; g.w_low = w_low;
-    g.lh = msda_sub(h_im, (T)h_low);
-    g.lw = msda_sub(w_im, (T)w_low);
-    const int h_high = h_low + 1, w_high = w_low + 1;
-    int m = 1;
-    if (h_low >= 0 && w_low >= 0) m |= 2;
-    if (h_low >= 0 && w_high <= W - 1) m |= 4;
-    if (h_high <= H - 1 && w_low >= 0) m |= 8;
-    if (h_high <= H - 1 && w_high <= W - 1) m |= 16;
-    g.mask = m;
-  }
-  return g;
-}
+#include "msda_common.cuh"
 
 // ---------------------------------------------------------------------------
 // Strict kernel: reference mapping, reference order, no contraction.
@@ -163,17 +111,6 @@ __global__ void msda_index_dump_kernel(long long n_samples, const int64_t* __res
 // ---------------------------------------------------------------------------
 // Fast warp kernel (fp32, D == 32, L*P <= 32).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float2 ld_stream_f2(const float* p) {
-  float2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float ld_stream_f1(const float* p) {
-  float r;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-  return r;
-}
-
 // TH x TW query tile per CTA, NW warps; each warp owns TH*TW/NW queries.
 // KC > 0: compile-time K = L*P (and PC = P) for the common GDINO shape; KC == 0: runtime.
 // s_meta layout: [warp][corner][sample] of {byte offset, weight bits}, corner rows padded
@@ -304,24 +241,28 @@ msda_fwd_warp_kernel(const ValT* __restrict__ value, const int64_t* __restrict__
             if (me.x >= 0) fma8(__ldg(reinterpret_cast<const uint4*>(vbl + (unsigned)me.x)), __int_as_float(me.y));
           }
         }
+        // reduce-scatter over the 8 lanes holding the same 16-byte chunk (sample slot x corner): 4 + 2 + 1 shuffles
+        // (same association order as msda_fwd_win_kernel, so both paths give bit-identical sums)
+        float k4[4], k2[2];
 #pragma unroll
-        for (int o = 4; o <= 16; o <<= 1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        for (int j = 0; j < 4; ++j) {
+          const float send = sp ? acc[j] : acc[j + 4];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+          k4[j] = (sp ? acc[j + 4] : acc[j]) + recv;
         }
-        if (lane < 4) {
-          OutT* op = out + (((size_t)b * Lq + qg) * M + m) * D + cq * 8;
-          if constexpr (sizeof(OutT) == 4) {
-            __stcs(reinterpret_cast<float4*>(op), make_float4(acc[0], acc[1], acc[2], acc[3]));
-            __stcs(reinterpret_cast<float4*>(op) + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
-          } else {
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+        const int cb1 = corner >> 1, cb0 = corner & 1;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-            *reinterpret_cast<uint4*>(op) = pk;
-          }
+        for (int j = 0; j < 2; ++j) {
+          const float send = cb1 ? k4[j] : k4[j + 2];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+          k2[j] = (cb1 ? k4[j + 2] : k4[j]) + recv;
         }
+        const float send = cb0 ? k2[0] : k2[1];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        const float res = (cb0 ? k2[1] : k2[0]) + recv;
+        OutT* op = out + (((size_t)b * Lq + qg) * M + m) * D + cq * 8 + sp * 4 + cb1 * 2 + cb0;
+        if constexpr (sizeof(OutT) == 4) *op = res;
+        else *op = __float2bfloat16(res);
         continue;
       }
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -350,23 +291,21 @@ msda_fwd_warp_kernel(const ValT* __restrict__ value, const int64_t* __restrict__
           acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
         }
       }
-#pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      // reduce-scatter over the 4 corner groups: 2 + 1 shuffles, one channel per lane (same order as msda_win.cu)
+      const int cb1 = corner >> 1, cb0 = corner & 1;
+      float k2[2];
+      {
+        const float s0 = cb1 ? acc.x : acc.z, s1 = cb1 ? acc.y : acc.w;
+        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+        k2[0] = (cb1 ? acc.z : acc.x) + r0;
+        k2[1] = (cb1 ? acc.w : acc.y) + r1;
       }
-      if (corner == 0) {
-        OutT* op = out + (((size_t)b * Lq + qg) * M + m) * D + cq * 4;
-        if constexpr (sizeof(OutT) == 4) {
-          __stcs(reinterpret_cast<float4*>(op), acc);
-        } else {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
-          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(op) = pk;
-        }
-      }
+      const float send = cb0 ? k2[0] : k2[1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+      const float res = (cb0 ? k2[1] : k2[0]) + recv;
+      OutT* op = out + (((size_t)b * Lq + qg) * M + m) * D + cq * 4 + cb1 * 2 + cb0;
+      if constexpr (sizeof(OutT) == 4) *op = res;
+      else *op = __float2bfloat16(res);
     }
     __syncwarp();
   }
@@ -668,6 +607,11 @@ static int launch_bwd(const T* value, const int64_t* shapes, const int64_t* lsi,
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
+// msda_win.cu: TMA-staged window kernel for the encoder shape; returns 1 when it does not apply.
+template <typename ValT, typename OutT>
+int msda_launch_window(const ValT* value, const int64_t* lsi, const float* loc, const float* attw, OutT* out, int N, int S,
+                       int M, int L, int Lq, int P, const int64_t* host_shapes, cudaStream_t st);
+
 static int g_msda_variant = 0;  // bench/tuning knob, see vllm_msda_set_variant
 
 static bool build_tiling(MsdaTiling& tl, const int64_t* host_shapes, int L, int Lq, int S, int TH, int TW) {
@@ -771,6 +715,12 @@ int vllm_msda_forward_f32(const float* value, const int64_t* spatial_shapes, con
   const int K = num_levels * num_point;
   if (!strict && channels == 32 && K <= 32 && vllm_aligned(value, 16) && vllm_aligned(out, 16) &&
       vllm_aligned(sampling_loc, 8)) {
+    if (g_msda_variant == 0 || g_msda_variant == 33) {   // encoder shape: TMA-staged windows (msda_win.cu)
+      const int r = msda_launch_window<float, float>(value, level_start_index, sampling_loc, attn_weight, out, batch,
+                                                     spatial_size, num_heads, num_levels, num_query, num_point,
+                                                     host_shapes_hint, st);
+      if (r != 1) return r;
+    }
     switch (g_msda_variant) {
       case 1: return launch_warp<8, 8, 8, float>(value, spatial_shapes, level_start_index, sampling_loc,
                                                  attn_weight, out, batch, spatial_size, num_heads, num_levels,
@@ -784,9 +734,17 @@ int vllm_msda_forward_f32(const float* value, const int64_t* spatial_shapes, con
       case 4: return launch_warp<8, 8, 8, float>(value, spatial_shapes, level_start_index, sampling_loc,
                                                  attn_weight, out, batch, spatial_size, num_heads, num_levels,
                                                  num_query, num_point, nullptr, st);
-      default: return launch_warp<8, 16, 16, float>(value, spatial_shapes, level_start_index, sampling_loc,
-                                                    attn_weight, out, batch, spatial_size, num_heads, num_levels,
-                                                    num_query, num_point, host_shapes_hint, st);
+      default:
+        // few queries (decoder: 100 / 900 object queries): 128-query tiles leave most SMs idle and make every warp
+        // walk 8 queries one HBM latency after the other -- 16-query tiles, 2 queries per warp, one pass
+        if (num_query != spatial_size &&
+            (long long)((num_query + 127) / 128) * num_heads * batch < 4ll * vllm_num_sms())
+          return launch_warp<4, 4, 8, float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out,
+                                             batch, spatial_size, num_heads, num_levels, num_query, num_point, nullptr,
+                                             st);
+        return launch_warp<8, 16, 16, float>(value, spatial_shapes, level_start_index, sampling_loc,
+                                             attn_weight, out, batch, spatial_size, num_heads, num_levels,
+                                             num_query, num_point, host_shapes_hint, st);
     }
   }
   return launch_strict<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, batch,
@@ -805,6 +763,26 @@ int vllm_msda_forward_bf16v(const void* value, const int64_t* spatial_shapes, co
   if (!vllm_aligned(value, 16) || !vllm_aligned(out, 16) || !vllm_aligned(sampling_loc, 8)) return VLLM_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* v = (const __nv_bfloat16*)value;
+  if (g_msda_variant != 32) {                             // encoder shape: TMA-staged windows (msda_win.cu)
+    const int r = out_bf16
+        ? msda_launch_window<__nv_bfloat16, __nv_bfloat16>(v, level_start_index, sampling_loc, attn_weight,
+                                                           (__nv_bfloat16*)out, batch, spatial_size, num_heads,
+                                                           num_levels, num_query, num_point, host_shapes_hint, st)
+        : msda_launch_window<__nv_bfloat16, float>(v, level_start_index, sampling_loc, attn_weight, (float*)out, batch,
+                                                   spatial_size, num_heads, num_levels, num_query, num_point,
+                                                   host_shapes_hint, st);
+    if (r != 1) return r;
+  }
+  const bool few = num_query != spatial_size &&
+                   (long long)((num_query + 127) / 128) * num_heads * batch < 4ll * vllm_num_sms();
+  if (few && out_bf16)
+    return launch_warp<4, 4, 8, __nv_bfloat16, __nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc,
+                                                              attn_weight, (__nv_bfloat16*)out, batch, spatial_size,
+                                                              num_heads, num_levels, num_query, num_point, nullptr, st);
+  if (few)
+    return launch_warp<4, 4, 8, float, __nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                                      (float*)out, batch, spatial_size, num_heads, num_levels,
+                                                      num_query, num_point, nullptr, st);
   if (out_bf16)
     return launch_warp<8, 16, 16, __nv_bfloat16, __nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc,
                                                                 attn_weight, (__nv_bfloat16*)out, batch, spatial_size,

@@ -16,10 +16,10 @@ PROFILE = None
 
 
 class _Prof:
-    __slots__ = ("name", "flops", "bytes", "e0")
+    __slots__ = ("name", "flops", "bytes", "e0", "tag")
 
-    def __init__(self, name, flops=0.0, nbytes=0.0):
-        self.name, self.flops, self.bytes = name, flops, nbytes
+    def __init__(self, name, flops=0.0, nbytes=0.0, tag=None):
+        self.name, self.flops, self.bytes, self.tag = name, flops, nbytes, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -31,7 +31,7 @@ class _Prof:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1, self.tag))
         return False
 
 
@@ -81,7 +81,7 @@ def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dty
         if v is not None and (v.dtype != torch.bfloat16 or v.numel() != N or not v.is_contiguous()):
             raise RuntimeError(f"linear: {nm} must be contiguous bf16 [N]")
     with torch.cuda.device(x.device), _Prof("gemm", 2.0 * M * N * K,
-                                            2.0 * (M * K + N * K) + out.element_size() * M * n_out):
+                                            2.0 * (M * K + N * K) + out.element_size() * M * n_out, f"{M}x{N}x{K}"):
         rc = _lib.lib().vllm_gemm_bf16(
             x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(), out.stride(0),
             M, N, K, bias.data_ptr() if bias is not None else None,
