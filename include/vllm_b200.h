@@ -297,6 +297,58 @@ int vllm_tp_norm_ctas(int rows); /* counter arrivals per destination of one vllm
 int vllm_tp_wait(const void* flag, unsigned target, void* stream);
 int vllm_tp_signal(void* const* signal, int n_signal, unsigned add, void* stream);
 
+/* ---- Grounding-DINO post-processing (csrc/postproc.cu) -------------------------------------
+ * vllm_det_postprocess_f32 replaces post_process_det_gdino (visionllmv2/eval/eval_det.py:18-56): per image
+ * sigmoid(logits[:, :num_classes]) -> top-k over the flattened (query, class) grid -> box_idx = idx // K, label =
+ * idx % K (int64) -> gather pred_boxes, cxcywh -> xyxy (util/box_ops.py:16-22), scale by (w, h, w, h).  logits
+ * [batch, num_queries, logits_ld] fp32 (only the first num_classes columns of a row are scored), pred_boxes
+ * [batch, num_queries, 4] fp32, sizes_hw [batch, 2] fp32 = (img_h, img_w).  Outputs [batch, topk]: scores fp32,
+ * topk_indexes / box_idx / labels int64, boxes [batch, topk, 4] fp32.  topk <= min(1024, num_queries*num_classes).
+ * Order: probability descending; equal probabilities by ascending flat index (torch leaves ties unspecified). */
+int vllm_det_postprocess_f32(const float* logits, const float* pred_boxes, const float* sizes_hw, int batch, int num_queries,
+                             int num_classes, int logits_ld, int topk, float* scores, int64_t* topk_indexes,
+                             int64_t* box_idx, int64_t* labels, float* boxes, void* stream);
+/* vllm_mask_postprocess_f32 replaces the mask branch of post_process_instseg_gdino (eval_det.py:88-99) for ONE image:
+ * masks [num_queries, mask_h, mask_w] fp32, box_idx [num_det] int64 -> out [num_det, out_h, out_w] uint8 (0/1) =
+ * sigmoid(bilinear(crop(bilinear(masks[box_idx], x mask_stride))[:crop_h, :crop_w] -> (out_h, out_w))) > 0.5, both
+ * interpolations with ATen's align_corners=False arithmetic, evaluated analytically (no intermediate tensors). */
+int vllm_mask_postprocess_f32(const float* masks, const int64_t* box_idx, int num_det, int mask_h, int mask_w, int mask_stride,
+                              int crop_h, int crop_w, int out_h, int out_w, unsigned char* out, void* stream);
+
+/* ---- sequence assembly of VisionLLMv2Model.forward (csrc/seqglue.cu) -----------------
+ * vllm_seq_index: ONE pass over input_ids [batch, seq_len] (int64, device) producing
+ *   new_ids   the ids with [EMB] .. [EMB+num_embs-1] written after every tool token (modeling_visionllmv2.py:447-486,
+ *             overwrite form; tool_ids / tool_tables are HOST arrays: table 0 = emb_embeddings_det (det/seg/grd tools),
+ *             1 = emb_embeddings_pose),
+ *   kind/row  per position where its embedding row comes from: 0 token embedding (row = original id), 1 / 2 the det /
+ *             pose [EMB] table (row = j), 3 image feature (row = k-th ViT token of the samples that own <im_patch> tokens,
+ *             :582-605; tile_start / tile_count [batch] int32 device arrays give each sample's tile rows, NULL = no images),
+ *   emb_pos   [batch, seq_len] int32: positions of the [EMB] tokens of each row in order, emb_count [batch] their number
+ *             (:776-787),
+ *   status    int32, OR-ed: 1 = a tool token without its pre-placed [EMB] slots (the generation-time insert form, refused),
+ *             2 = <im_patch> slots != ViT tokens.  The caller zeroes it first and reads it back.
+ * vllm_assemble_embeds_bf16: inputs_embeds [rows, hidden] from kind/row and the four sources (base_embeds, if given,
+ * replaces the token-embedding lookup: the caller passed inputs_embeds).  vllm_text_query_gather_bf16: text_query
+ * [batch, max_patches, num_embs, hidden] zero padded + masks [batch, max_patches] (uint8).  vllm_gather_rows_bf16:
+ * dst[i] = src[idx[i]] (negative idx counts from src_rows).  vllm_pixel_shuffle_rows_bf16: :381-392 + the [:, 1:] CLS
+ * slice + optionally the LayerNorm(4C) opening the internvl_mlp bridge in one pass: x = ViT hidden state [tiles,
+ * skip_tokens + grid_w*grid_h, C] (pitches ld_tile / ld_token), y = [tiles * grid_w/2 * grid_h/2, 4C]. */
+int vllm_seq_index(const int64_t* input_ids, int batch, int seq_len, const int64_t* tool_ids, const int* tool_tables,
+                   int num_tools, int64_t emb_token_id, int num_embs, int64_t imp_token_id, const int* tile_start,
+                   const int* tile_count, int tokens_per_tile, int64_t* new_ids, unsigned char* kind, int* row, int* emb_pos,
+                   int* emb_count, int* status, void* stream);
+int vllm_assemble_embeds_bf16(const unsigned char* kind, const int* row, const void* embed_tokens, const void* emb_det,
+                              const void* emb_pose, const void* image_features, const void* base_embeds, void* out,
+                              long long rows, int hidden, void* stream);
+int vllm_text_query_gather_bf16(const void* hidden, const int* emb_pos, const int* emb_count, int batch, int seq_len,
+                                int hidden_size, int num_embs, int max_patches, void* text_query, unsigned char* masks,
+                                void* stream);
+int vllm_gather_rows_bf16(const void* src, long long src_ld, long long src_rows, const int64_t* idx, long long n, int cols,
+                          void* dst, void* stream);
+int vllm_pixel_shuffle_rows_bf16(const void* x, long long ld_tile, long long ld_token, int skip_tokens, int tiles, int grid_w,
+                                 int grid_h, int channels, const void* ln_weight, const void* ln_bias, float eps, void* y,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

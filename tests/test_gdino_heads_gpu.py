@@ -112,3 +112,87 @@ def test_patch2query_mean(g):
         if i < 2:
             ref = torch.relu(ref)
     close(out, ref.mean(-2), extra=2e-2)
+
+
+# ---- fused post-processing kernels (csrc/postproc.cu) vs the reference's torch primitives on the GPU ----
+def _ref_det(logits, boxes, tsz, K, topk):
+    """eval_det.py:26-46 with the reference's own torch calls (on the GPU, like the eval loop)."""
+    from visionllm_b200.gdino_heads import box_cxcywh_to_xyxy
+    lg = logits[:, :, :K]
+    prob = lg.sigmoid().view(lg.shape[0], -1)
+    k = min(topk, prob.size(1))
+    tv, ti = torch.topk(prob, k, dim=1)
+    tb = torch.div(ti, lg.shape[2], rounding_mode="floor")
+    bx = torch.gather(box_cxcywh_to_xyxy(boxes), 1, tb.unsqueeze(-1).repeat(1, 1, 4))
+    img_h = torch.Tensor([i[0] for i in tsz]); img_w = torch.Tensor([i[1] for i in tsz])
+    bx = bx * torch.stack([img_w, img_h, img_w, img_h], dim=1).to(bx.device)[:, None, :]
+    return tv, ti, tb, ti % lg.shape[2], bx
+
+
+@pytest.mark.parametrize("Q,K,ld,topk", [(100, 80, 256, 100), (900, 80, 256, 300), (20, 16, 16, 25), (7, 3, 8, 100), (300, 256, 256, 1000)])
+def test_fused_det_topk_equals_torch_primitives(Q, K, ld, topk):
+    from visionllm_b200 import gdino_heads as H
+    g = torch.Generator(device="cuda").manual_seed(Q + K)
+    B = 3
+    logits = torch.randn(B, Q, ld, device="cuda", generator=g) * 3 - 2
+    logits[:, :, K:] = float("-inf")                      # the -inf class padding of the contrastive head (gd.py:1415-1428)
+    boxes = torch.rand(B, Q, 4, device="cuda", generator=g)
+    tsz = [(480, 640), (1024, 1024), (333, 500)]
+    tv, ti, tb, tl, bx = _ref_det(logits, boxes, tsz, K, topk)
+    scores, labels, fboxes, idx, box_idx = H.det_topk_fused(logits, boxes, tsz, K, topk)
+    assert torch.equal(scores, tv), (scores - tv).abs().max()        # sigmoid bit-identical to torch's, same order
+    assert torch.equal(idx, ti) and torch.equal(box_idx, tb) and torch.equal(labels, tl)
+    assert idx.dtype == torch.int64 and torch.equal(fboxes, bx)
+
+
+def test_fused_det_topk_ties_take_the_lowest_index_first():
+    from visionllm_b200 import gdino_heads as H
+    logits = torch.zeros(1, 10, 4, device="cuda")
+    logits[0, 3, 1] = 5.0; logits[0, 7, 2] = 5.0; logits[0, 2, 0] = 9.0
+    boxes = torch.rand(1, 10, 4, device="cuda")
+    scores, labels, _, idx, box_idx = H.det_topk_fused(logits, boxes, [(10, 10)], 4, 6)
+    assert idx[0].tolist() == [8, 13, 30, 0, 1, 2]                   # 9.0; the two 5.0 by index; then the zeros by index
+    assert box_idx[0].tolist() == [2, 3, 7, 0, 0, 0] and labels[0].tolist() == [0, 1, 2, 0, 1, 2]
+    assert scores[0, 3:].eq(0.5).all()
+
+
+@pytest.mark.parametrize("case", [(64, 64, 4, (250, 256), (480, 517)), (32, 40, 4, (128, 160), (128, 160)),
+                                  (56, 56, 4, (200, 224), (1000, 1333)), (16, 24, 2, (31, 47), (97, 61))])
+def test_fused_mask_chain_equals_torch_interpolate_chain(case):
+    """masks[box_idx] -> F.interpolate x stride -> crop -> F.interpolate to the original size -> sigmoid() > 0.5 (eval_det.py
+    :88-99) vs the single fused kernel.  The boolean masks agree except where the pre-threshold value is within fp32
+    rounding of 0 (FMA contraction inside ATen's kernel is the compiler's choice): < 1e-5 of the pixels, and never where
+    |value| > 1e-5."""
+    import torch.nn.functional as F
+    from visionllm_b200 import gdino_heads as H
+    Hm, Wm, stride, isz, tsz = case
+    g = torch.Generator(device="cuda").manual_seed(Hm * 7 + Wm)
+    Q, k = 20, 9
+    masks = torch.randn(Q, Hm, Wm, device="cuda", generator=g) * 4
+    bi = torch.randint(0, Q, (k,), device="cuda", generator=g)
+    m = F.interpolate(masks[bi][:, None], size=(Hm * stride, Wm * stride), mode="bilinear", align_corners=False)
+    m = m[:, :, :isz[0], :isz[1]]
+    pre = F.interpolate(m, size=tsz, mode="bilinear", align_corners=False)[:, 0]
+    ref = pre.sigmoid() > 0.5
+    got = H.mask_chain_fused(masks, bi, isz, tsz, stride)
+    assert got.dtype == torch.bool and got.shape == ref.shape
+    diff = got != ref
+    assert diff.float().mean().item() < 1e-5, diff.float().mean().item()
+    assert (pre[diff].abs() < 1e-5).all()
+
+
+def test_fused_instseg_path_matches_torch_path(g):
+    from visionllm_b200 import gdino_heads as H
+    logits, boxes, masks = t(g, "pp_logits"), t(g, "pp_boxes"), t(g, "pp_masks")
+    tsz = [tuple(int(v) for v in r) for r in g["pp_tsz"]]
+    isz = [tuple(int(v) for v in r) for r in g["pp_isz"]]
+    fused = H.post_process_instseg_gdino(logits, boxes, masks, tsz, isz, num_classes=16, topk=10, mask_stride=4)
+    H.FUSED_POSTPROCESS = False
+    try:
+        eager = H.post_process_instseg_gdino(logits, boxes, masks, tsz, isz, num_classes=16, topk=10, mask_stride=4)
+    finally:
+        H.FUSED_POSTPROCESS = True
+    for a, b in zip(fused, eager):
+        assert torch.equal(a["topk_indexes"], b["topk_indexes"]) and torch.equal(a["labels"], b["labels"])
+        assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["boxes"], b["boxes"])
+        assert (a["masks"] != b["masks"]).float().mean().item() < 1e-5

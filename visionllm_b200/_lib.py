@@ -34,6 +34,13 @@ _SIGNATURES = {
     "vllm_msda_sample_indices_f32": (ci, [vp, vp, vp, cll, ci, ci, vp]),
     "vllm_msda_set_variant": (ci, [ci]),
     "vllm_msda_set_window": (ci, [ci, ci, ci]),
+    "vllm_seq_index": (ci, [vp, ci, ci, vp, vp, ci, cll, ci, cll, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]),
+    "vllm_assemble_embeds_bf16": (ci, [vp] * 8 + [cll, ci, vp]),
+    "vllm_text_query_gather_bf16": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]),
+    "vllm_gather_rows_bf16": (ci, [vp, cll, cll, vp, cll, ci, vp, vp]),
+    "vllm_pixel_shuffle_rows_bf16": (ci, [vp, cll, cll, ci, ci, ci, ci, ci, vp, vp, cf, vp, vp]),
+    "vllm_det_postprocess_f32": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
+    "vllm_mask_postprocess_f32": (ci, [vp, vp] + [ci] * 8 + [vp, vp]),
     "vllm_dcnv3_forward_f32": (ci, [vp, vp, vp, vp] + [ci] * 15 + [cf, ci, vp]),
     "vllm_dcnv3_backward_f32": (ci, [vp] * 7 + [ci] * 15 + [cf, vp]),
     "vllm_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp]),

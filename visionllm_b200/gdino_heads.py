@@ -143,9 +143,81 @@ def box_cxcywh_to_xyxy(x):
     return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
 
 
+def _sizes_hw(target_sizes, device):
+    if torch.is_tensor(target_sizes):
+        return target_sizes.to(device=device, dtype=torch.float32)[:, :2].contiguous()
+    return torch.tensor([[float(t[0]), float(t[1])] for t in target_sizes], dtype=torch.float32, device=device)
+
+
+def det_topk_fused(logits, pred_boxes, target_sizes, num_classes, topk):
+    """ONE kernel (csrc/postproc.cu `det_topk_kernel`) for eval_det.py:28-46: sigmoid, top-k over the flattened
+    (query, class) grid, `//`, `%`, box gather, cxcywh -> xyxy, (w, h, w, h) scale.  Returns scores [B, k] fp32, labels /
+    topk_indexes / box_idx [B, k] int64, boxes [B, k, 4] fp32."""
+    from . import _lib
+    if logits.dtype != torch.float32 or pred_boxes.dtype != torch.float32 or not logits.is_cuda:
+        raise RuntimeError("det_topk_fused: logits / pred_boxes must be CUDA fp32 tensors (the stage's head outputs)")
+    B, Q, ld = logits.shape
+    if logits.stride(2) != 1 or logits.stride(1) != ld or logits.stride(0) != Q * ld:
+        logits = logits.contiguous()
+    pred_boxes = pred_boxes.contiguous()
+    K = min(int(num_classes), ld)
+    k = min(int(topk), Q * K)
+    dev = logits.device
+    scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    idx, box_idx, labels = (torch.empty((B, k), dtype=torch.int64, device=dev) for _ in range(3))
+    boxes = torch.empty((B, k, 4), dtype=torch.float32, device=dev)
+    sizes = _sizes_hw(target_sizes, dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().vllm_det_postprocess_f32(logits.data_ptr(), pred_boxes.data_ptr(), sizes.data_ptr(), B, Q, K, ld, k,
+                                                 scores.data_ptr(), idx.data_ptr(), box_idx.data_ptr(), labels.data_ptr(),
+                                                 boxes.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "vllm_det_postprocess_f32")
+    return scores, labels, boxes, idx, box_idx
+
+
+def mask_chain_fused(pred_masks_i, box_idx_i, image_size, target_size, mask_stride=4):
+    """ONE kernel (`mask_chain_kernel`) for eval_det.py:88-99 of one image: masks[box_idx] -> x mask_stride bilinear ->
+    crop to image_size -> bilinear to target_size -> sigmoid() > 0.5, without the two full-resolution intermediates."""
+    from . import _lib
+    if pred_masks_i.dtype != torch.float32 or not pred_masks_i.is_cuda or pred_masks_i.dim() != 3:
+        raise RuntimeError("mask_chain_fused: pred_masks of one image must be a CUDA fp32 [Q, H, W] tensor")
+    m = pred_masks_i.contiguous()
+    bi = box_idx_i.to(torch.int64).contiguous()
+    Q, H, W = m.shape
+    oh, ow = int(target_size[0]), int(target_size[1])
+    ch, cw = min(int(image_size[0]), H * mask_stride), min(int(image_size[1]), W * mask_stride)
+    out = torch.empty((bi.numel(), oh, ow), dtype=torch.bool, device=m.device)
+    with torch.cuda.device(m.device):
+        rc = _lib.lib().vllm_mask_postprocess_f32(m.data_ptr(), bi.data_ptr(), bi.numel(), H, W, int(mask_stride), ch, cw, oh,
+                                                  ow, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "vllm_mask_postprocess_f32")
+    return out
+
+
+FUSED_POSTPROCESS = True      # CUDA fp32 head outputs with topk <= 1024 take the fused kernels; False = torch primitives
+
+
+def _can_fuse(logits, pred_boxes, topk):
+    return (FUSED_POSTPROCESS and logits.is_cuda and logits.dtype == torch.float32 and pred_boxes.dtype == torch.float32
+            and min(int(topk), logits.shape[1] * logits.shape[2]) <= 1024)
+
+
 @torch.no_grad()
 def post_process_det_gdino(logits, pred_boxes, target_sizes, num_classes, threshold=0.0, topk=100):
     """eval_det.py:18-56.  Returns per-image dicts (scores, labels, boxes) plus the raw index tensors."""
+    if _can_fuse(logits, pred_boxes, topk):
+        scores, labels, boxes, idx, box_idx = det_topk_fused(logits, pred_boxes, target_sizes, num_classes, topk)
+        res = []
+        for s, l, bx in zip(scores, labels, boxes):
+            if threshold > 0.0:                            # the reference's boolean filter (eval_det.py:50-54)
+                keep = s > threshold
+                s, l, bx = s[keep], l[keep], bx[keep]
+            # threshold == 0 (the eval default): sigmoid outputs in (0, 1] all pass except an exact 0, dropped like the reference
+            elif bool((s <= 0).any()):
+                keep = s > threshold
+                s, l, bx = s[keep], l[keep], bx[keep]
+            res.append({"scores": s, "labels": l, "boxes": bx})
+        return res, idx, box_idx
     logits = logits[:, :, :num_classes]
     B, Q, K = logits.shape
     prob = logits.sigmoid().view(B, -1)
@@ -168,6 +240,11 @@ def post_process_det_gdino(logits, pred_boxes, target_sizes, num_classes, thresh
 def post_process_instseg_gdino(logits, pred_boxes, pred_masks, target_sizes, image_sizes, num_classes=80, topk=100,
                                mask_stride=4):
     """eval_det.py:59-104: per image top-k, box scale, mask 4x bilinear -> crop -> resize -> sigmoid > 0.5."""
+    if _can_fuse(logits, pred_boxes, topk) and pred_masks.dtype == torch.float32:
+        scores, labels, boxes, idx, box_idx = det_topk_fused(logits, pred_boxes, target_sizes, num_classes, topk)
+        return [{"scores": scores[i], "labels": labels[i], "boxes": boxes[i],
+                 "masks": mask_chain_fused(pred_masks[i], box_idx[i], image_sizes[i], target_sizes[i], mask_stride),
+                 "topk_indexes": idx[i], "topk_boxes": box_idx[i]} for i in range(logits.shape[0])]
     logits = logits[:, :, :num_classes]
     res = []
     for i in range(logits.shape[0]):

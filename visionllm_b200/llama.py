@@ -188,14 +188,25 @@ class B200LlamaForCausalLM(nn.Module):
     @torch.no_grad()
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
                 inputs_embeds=None, use_cache=False, output_attentions=False, output_hidden_states=False,
-                return_dict=True, compute_logits=True):
+                return_dict=True, compute_logits=True, logits_rows=None):
         if past_key_values is not None or use_cache:
             raise NotImplementedError("KV-cache decoding is outside the forward hot path (SURVEY 3.4)")
         if inputs_embeds is None:
             inputs_embeds = self.model.embed_tokens(input_ids)
         out = self.model(inputs_embeds, attention_mask, position_ids, output_hidden_states)
         logits = None
-        if compute_logits:
+        if logits_rows is not None:
+            # lm_head on the requested rows only: logits_rows int64 [n] indexes the flattened [B*T]
+            # positions (negative = from the end); returns fp32 [n, V].  The all-positions form below stays the default
+            # (what mv2.py:733-738 computes); eval loops that only read a few rows skip a ~400 MB fp32 write per batch.
+            B, T, H = out.last_hidden_state.shape
+            V = self.config.vocab_size
+            Vp = (V + 3) // 4 * 4
+            rows = ops.gather_rows(out.last_hidden_state.view(B * T, H), logits_rows.to(torch.int64).contiguous())
+            buf = torch.empty((rows.shape[0], Vp), dtype=torch.float32, device=rows.device)
+            ops.linear(rows, self.lm_head.weight, out=buf[:, :V])
+            logits = buf[:, :V]
+        elif compute_logits:
             # fp32 logits for every position, like `logits = self.llm.lm_head(hidden); logits.float()` (mv2.py:733-738);
             # the fp32 convert is the GEMM's store format, not a second pass.  Row pitch padded to 16 bytes.
             B, T, H = out.last_hidden_state.shape

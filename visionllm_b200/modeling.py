@@ -36,9 +36,9 @@ class VLBridge(nn.Sequential):
     """Same module indices / state-dict keys as the reference nn.Sequential (mv2.py:162-184); GELU modules
     are kept as placeholders (so indices match) and fused into the preceding GEMM's epilogue."""
 
-    def forward(self, x):
+    def forward(self, x, start=0):
         mods = list(self)
-        i = 0
+        i = start
         while i < len(mods):
             m = mods[i]
             if isinstance(m, BridgeLinear):
@@ -86,6 +86,11 @@ def emb_overwrite_indices(input_ids, tool_ids, num_embs):
     pos = p[:, None] + 1 + j[None, :]
     return b[:, None].expand_as(pos).reshape(-1), pos.reshape(-1), j[None, :].expand_as(pos).reshape(-1)
 
+
+# CUDA bf16 batches take the sequence-assembly kernels (csrc/seqglue.cu) instead of the vectorised torch indexing below;
+# both produce the same ids / embeddings / text_query (tests/test_seqglue_gpu.py).  The torch form stays as the host
+# logic that the CPU tests pin against the reference's python loops.
+FUSED_SEQUENCE = True
 
 GDINO_TASKS = ("det", "det_cap", "grd", "seg", "count_text", "count_visual", "interactive", "ic_mask")   # mv2.py:763
 
@@ -229,7 +234,16 @@ class B200VisionLLMv2Model(nn.Module):
         else:
             split_sizes, concat = None, images
         outs = self.vis_encoder(concat, output_hidden_states=True)
-        feats = outs.hidden_states[getattr(self.config, "vis_output_layer", -2)][:, 1:].to(self.llm.dtype)
+        hs = outs.hidden_states[getattr(self.config, "vis_output_layer", -2)]
+        if (self.use_pixelshuffle and FUSED_SEQUENCE and hs.is_cuda and hs.dtype == torch.bfloat16
+                and self.llm.dtype == torch.bfloat16 and hs.stride(2) == 1):
+            # CLS slice + pixel shuffle (+ the LayerNorm that opens internvl_mlp) in ONE pass: the projector's A operand
+            mods = list(self.vl_bridge) if isinstance(self.vl_bridge, VLBridge) else None
+            if mods and isinstance(mods[0], BridgeLayerNorm):
+                x = ops.pixel_shuffle_rows(hs, 1, mods[0].weight, mods[0].bias, mods[0].eps)
+                return self.vl_bridge(x, start=1), split_sizes, outs
+            return self.vl_bridge(ops.pixel_shuffle_rows(hs, 1)), split_sizes, outs
+        feats = hs[:, 1:].to(self.llm.dtype)
         if self.use_pixelshuffle:
             h = w = int(feats.shape[1] ** 0.5)
             feats = pixel_shuffle(feats.reshape(feats.shape[0], h, w, -1), 0.5)
@@ -277,24 +291,47 @@ class B200VisionLLMv2Model(nn.Module):
     def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, images=None, images_aug=None,
                 img_metas=None, targets=None, labels=None, past_key_values=None, use_cache=False,
                 output_attentions=False, output_hidden_states=False, return_dict=True, regions=None, num_splits=None,
-                region_sample_points=None, **unused):
+                region_sample_points=None, logits_rows=None, **unused):
         if past_key_values is not None or use_cache:
             raise NotImplementedError("generation with KV cache is outside the forward hot path")
         if labels is not None or targets is not None:
             raise NotImplementedError("training losses are outside the forward hot path (SURVEY 8f)")
-        if inputs_embeds is None:
-            inputs_embeds = self.llm.get_input_embeddings()(input_ids)
-        input_ids, inputs_embeds = self.inject_emb(input_ids, inputs_embeds)
-        vit_out = None
+        embed_w = self.llm.get_input_embeddings().weight
+        fused = (FUSED_SEQUENCE and input_ids is not None and input_ids.is_cuda and embed_w.dtype == torch.bfloat16
+                 and (inputs_embeds is None or (inputs_embeds.dtype == torch.bfloat16 and inputs_embeds.is_contiguous())))
+        vit_out, plan, feats, split_sizes = None, None, None, False
         if images is not None:
             feats, split_sizes, vit_out = self.encode_images(images)
-            inputs_embeds = self.scatter_image_tokens(input_ids, inputs_embeds, feats.to(inputs_embeds.dtype),
-                                                      split_sizes)
+        if fused:
+            plan = ops.seq_index(input_ids, (self.det_tool_id, self.seg_tool_id, self.grd_tool_id), (self.pose_tool_id,),
+                                 self.emb_token_id, self.num_embs, self.imp_token_id,
+                                 split_sizes if images is not None else False, feats.shape[1] if feats is not None else 0)
+            status = int(plan.status.item())
+            if status & 1:
+                raise NotImplementedError("tool token without its pre-placed [EMB] slots: generation-time insertion "
+                                          "(mv2.py:428-429, gap_len == 0) is outside the forward hot path")
+            if status & 2:
+                raise RuntimeError("image token count mismatch between the <im_patch> slots and the ViT tokens (the "
+                                   "reference tiles/trims and zeroes the loss here, mv2.py:591-604; this drop-in refuses)")
+            inputs_embeds = ops.assemble_embeds(
+                plan, embed_w, self.emb_embeddings_det.weight, self.emb_embeddings_pose.weight,
+                feats.reshape(-1, feats.shape[-1]).contiguous() if feats is not None else None, base_embeds=inputs_embeds)
+            input_ids = plan.new_ids
+        else:
+            if inputs_embeds is None:
+                inputs_embeds = self.llm.get_input_embeddings()(input_ids)
+            input_ids, inputs_embeds = self.inject_emb(input_ids, inputs_embeds)
+            if images is not None:
+                inputs_embeds = self.scatter_image_tokens(input_ids, inputs_embeds, feats.to(inputs_embeds.dtype),
+                                                          split_sizes)
+        if images is not None:
             if self.use_region_encoder and regions is not None:                              # mv2.py:607-698
                 ri, rm, rf = region_encoder_inputs(images, regions, vit_out.hidden_states, split_sizes, num_splits)
                 rfeat = self.region_encoder(ri, rm, rf, sample_points=region_sample_points)
                 inputs_embeds = scatter_region_tokens(input_ids, inputs_embeds, rfeat, self.reg_token_id)
-        out = self.llm(attention_mask=attention_mask, inputs_embeds=inputs_embeds, output_hidden_states=True)
+        # logits_rows (extension): lm_head on those flattened [B*L] positions only -> out.logits is fp32 [n, V]
+        head_kw = {} if logits_rows is None else {"logits_rows": logits_rows}
+        out = self.llm(attention_mask=attention_mask, inputs_embeds=inputs_embeds, output_hidden_states=True, **head_kw)
         hidden = out.hidden_states[-1]
         gdino_outputs = None
         task = img_metas[0]["task"] if img_metas is not None else None                       # mv2.py:755-758
@@ -303,7 +340,11 @@ class B200VisionLLMv2Model(nn.Module):
                                       "wired into this composite")
         # mv2.py:762-763: the region decoder runs only for these tasks (no img_metas -> task None -> no gdino_outputs)
         if self.use_gdino and images_aug is not None and task in GDINO_TASKS:
-            tq, tm = self.gather_text_query(input_ids, hidden)
+            if plan is not None and hidden.dtype == torch.bfloat16 and hidden.is_contiguous():
+                mx = int((plan.emb_count // self.num_embs).max()) if plan.B else 0
+                tq, tm = ops.text_query_gather(plan, hidden, self.num_embs, mx) if mx > 0 else (None, None)
+            else:
+                tq, tm = self.gather_text_query(input_ids, hidden)
             if tq is not None:
                 pixel_values = pad_images_aug(images_aug, 32)                               # mv2.py:771-772
                 pixel_mask = pixel_values[:, 0, :, :] != 0                                  # mv2.py:773

@@ -336,3 +336,117 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
             out.stride(0), out.stride(1), sl, km, amp, abp, nb, 1 if causal else 0, float(scale), ws_ptr, ws_bytes, _stream())
     _lib.check(rc, "vllm_attention_bf16")
     return out
+
+
+# ---- sequence assembly (csrc/seqglue.cu): integer index work of VisionLLMv2Model.forward as kernels -----------------
+class SeqPlan:
+    """Device-side result of `seq_index`: rewritten ids, per-position embedding source, [EMB] position lists."""
+    __slots__ = ("new_ids", "kind", "row", "emb_pos", "emb_count", "status", "B", "L")
+
+
+def seq_index(input_ids, det_tools, pose_tools, emb_token_id, num_embs, imp_token_id, split_sizes=None, tokens_per_tile=0):
+    """modeling_visionllmv2.py:426-486 ([EMB] overwrite), :582-605 (<im_patch> -> ViT token map), :776-787 ([EMB] position
+    lists) from ONE kernel over input_ids [B, L] (CUDA int64).  split_sizes: tiles per sample (None = one per sample) when
+    image features will be scattered, or `False` for text-only."""
+    if input_ids.dtype != torch.int64 or not input_ids.is_cuda or input_ids.dim() != 2:
+        raise RuntimeError("seq_index: input_ids must be a CUDA int64 [B, L] tensor")
+    ids = input_ids.contiguous()
+    B, L = ids.shape
+    dev = ids.device
+    tools = [(int(t), 0) for t in det_tools if t is not None and t >= 0] + \
+            [(int(t), 1) for t in pose_tools if t is not None and t >= 0]
+    import ctypes
+    tid = (ctypes.c_int64 * max(1, len(tools)))(*[t for t, _ in tools])
+    ttb = (ctypes.c_int * max(1, len(tools)))(*[k for _, k in tools])
+    p = SeqPlan()
+    p.B, p.L = B, L
+    p.new_ids = torch.empty_like(ids)
+    p.kind = torch.empty((B, L), dtype=torch.uint8, device=dev)
+    p.row = torch.empty((B, L), dtype=torch.int32, device=dev)
+    p.emb_pos = torch.empty((B, L), dtype=torch.int32, device=dev)
+    p.emb_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    p.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ts = tc = None
+    if split_sizes is not False:
+        sizes = [1] * B if split_sizes is None else [int(s) for s in split_sizes]
+        starts = [0]
+        for s in sizes[:-1]:
+            starts.append(starts[-1] + s)
+        meta = torch.tensor([starts, sizes], dtype=torch.int32).to(dev, non_blocking=True)
+        ts, tc = meta[0], meta[1]
+    with torch.cuda.device(dev):
+        rc = _lib.lib().vllm_seq_index(
+            ids.data_ptr(), B, L, ctypes.cast(tid, ctypes.c_void_p), ctypes.cast(ttb, ctypes.c_void_p), len(tools),
+            int(emb_token_id), int(num_embs), int(imp_token_id if imp_token_id is not None else -1),
+            ts.data_ptr() if ts is not None else None, tc.data_ptr() if tc is not None else None, int(tokens_per_tile),
+            p.new_ids.data_ptr(), p.kind.data_ptr(), p.row.data_ptr(), p.emb_pos.data_ptr(), p.emb_count.data_ptr(),
+            p.status.data_ptr(), _stream())
+    _lib.check(rc, "vllm_seq_index")
+    return p
+
+
+def assemble_embeds(plan, embed_tokens, emb_det, emb_pose, image_features=None, base_embeds=None):
+    """inputs_embeds [B, L, C] bf16 in one pass from the plan's sources (token table / caller's inputs_embeds, the two
+    [EMB] tables, the ViT image tokens [rows, C])."""
+    C = embed_tokens.shape[1] if embed_tokens is not None else base_embeds.shape[-1]
+    srcs = [embed_tokens, emb_det, emb_pose, image_features, base_embeds]
+    for t in srcs:
+        if t is not None and (t.dtype != torch.bfloat16 or not t.is_cuda or not t.is_contiguous() or t.shape[-1] != C):
+            raise RuntimeError("assemble_embeds: sources must be contiguous CUDA bf16 tensors with the same hidden size")
+    out = torch.empty((plan.B, plan.L, C), dtype=torch.bfloat16, device=plan.kind.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    with torch.cuda.device(out.device), _Prof("seq_assemble", 0.0, 4.0 * plan.B * plan.L * C):
+        rc = _lib.lib().vllm_assemble_embeds_bf16(plan.kind.data_ptr(), plan.row.data_ptr(), *[ptr(t) for t in srcs],
+                                                  out.data_ptr(), plan.B * plan.L, C, _stream())
+    _lib.check(rc, "vllm_assemble_embeds_bf16")
+    return out
+
+
+def text_query_gather(plan, hidden, num_embs, max_patches):
+    """mv2.py:776-787: ([B, mx, num_embs, C] bf16 zero padded, [B, mx] bool) from the [EMB] rows of `hidden` [B, L, C]."""
+    if hidden.dtype != torch.bfloat16 or not hidden.is_contiguous() or hidden.shape[:2] != (plan.B, plan.L):
+        raise RuntimeError("text_query_gather: hidden must be a contiguous bf16 [B, L, C] tensor")
+    C = hidden.shape[2]
+    tq = torch.empty((plan.B, max_patches, num_embs, C), dtype=torch.bfloat16, device=hidden.device)
+    tm = torch.empty((plan.B, max_patches), dtype=torch.bool, device=hidden.device)
+    with torch.cuda.device(hidden.device):
+        rc = _lib.lib().vllm_text_query_gather_bf16(hidden.data_ptr(), plan.emb_pos.data_ptr(), plan.emb_count.data_ptr(),
+                                                    plan.B, plan.L, C, int(num_embs), int(max_patches), tq.data_ptr(),
+                                                    tm.data_ptr(), _stream())
+    _lib.check(rc, "vllm_text_query_gather_bf16")
+    return tq, tm
+
+
+def gather_rows(src, idx):
+    """dst[i] = src[idx[i]]: src [rows, C] bf16 (unit inner stride), idx int64 [n] (negative = from the end)."""
+    _bf16_2d(src, "src")
+    if idx.dtype != torch.int64 or not idx.is_cuda or not idx.is_contiguous():
+        raise RuntimeError("gather_rows: idx must be a contiguous CUDA int64 tensor")
+    out = torch.empty((idx.numel(), src.shape[1]), dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        rc = _lib.lib().vllm_gather_rows_bf16(src.data_ptr(), src.stride(0), src.shape[0], idx.data_ptr(), idx.numel(),
+                                              src.shape[1], out.data_ptr(), _stream())
+    _lib.check(rc, "vllm_gather_rows_bf16")
+    return out
+
+
+def pixel_shuffle_rows(hidden, skip_tokens, ln_weight=None, ln_bias=None, eps=1e-5):
+    """mv2.py:381-392 + :574-579 in one pass: ViT hidden state [tiles, skip + g*g, C] (bf16) -> [tiles, g*g/4, 4C], the CLS
+    slice and both permute copies folded in; with (ln_weight, ln_bias) also the LayerNorm(4C) that opens `internvl_mlp`."""
+    if hidden.dtype != torch.bfloat16 or not hidden.is_cuda or hidden.dim() != 3 or hidden.stride(2) != 1:
+        raise RuntimeError("pixel_shuffle_rows: hidden must be a CUDA bf16 [tiles, tokens, C] tensor with unit inner stride")
+    tiles, T, C = hidden.shape
+    g = int(round((T - skip_tokens) ** 0.5))
+    if g * g != T - skip_tokens or g % 2:
+        raise RuntimeError("pixel_shuffle_rows: the patch tokens must form an even square grid")
+    out = torch.empty((tiles, g * g // 4, 4 * C), dtype=torch.bfloat16, device=hidden.device)
+    for t in (ln_weight, ln_bias):
+        if t is not None and (t.dtype != torch.bfloat16 or t.numel() != 4 * C or not t.is_contiguous()):
+            raise RuntimeError("pixel_shuffle_rows: LayerNorm weight / bias must be contiguous bf16 [4C]")
+    with torch.cuda.device(hidden.device), _Prof("pixel_shuffle", 0.0, 4.0 * out.numel()):
+        rc = _lib.lib().vllm_pixel_shuffle_rows_bf16(
+            hidden.data_ptr(), hidden.stride(0), hidden.stride(1), int(skip_tokens), tiles, g, g, C,
+            ln_weight.data_ptr() if ln_weight is not None else None, ln_bias.data_ptr() if ln_bias is not None else None,
+            float(eps), out.data_ptr(), _stream())
+    _lib.check(rc, "vllm_pixel_shuffle_rows_bf16")
+    return out
