@@ -315,6 +315,37 @@ int vllm_det_postprocess_f32(const float* logits, const float* pred_boxes, const
 int vllm_mask_postprocess_f32(const float* masks, const int64_t* box_idx, int num_det, int mask_h, int mask_w, int mask_stride,
                               int crop_h, int crop_w, int out_h, int out_w, unsigned char* out, void* stream);
 
+/* ---- backward GEMMs (training-side path of BASELINE cfg 5) ----------------------------------------------------
+ * C[M, N] = sum_k A(m, k) * B(n, k), bf16 in, fp32 accumulate, bf16 or fp32 out, same tcgen05 kernel as vllm_gemm_bf16.
+ * Each operand is either K-major ([M|N rows, K cols], pitch lda / ldb) or MN-major ([K rows, M|N cols]); MN-major tiles
+ * are TMA-loaded as 64 x 64 boxes and fed to tcgen05.mma through MN-major shared-memory descriptors, so the backward
+ * of y = x W^T (the reference's nn.Linear autograd, torch.nn.functional.linear) needs no transposed copies:
+ *   dgrad  dx = dy . W      : A = dy [T, out] K-major,  B = W [out, in]  MN-major,  M = T,   N = in, K = out
+ *   wgrad  dW = dy^T . x    : A = dy [T, out] MN-major, B = x [T, in]    MN-major,  M = out, N = in, K = T     */
+int vllm_gemm_bf16_tn(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc, int M,
+                      int N, int K, int out_f32, void* stream);
+
+/* n_batch independent products in one launch (block-diagonal batching): every operand and C are stacks of their
+ * n_batch matrices along the row axis.  causal: 0 none; 1 skip output tiles strictly above the diagonal (S = Q K^T,
+ * dP = dO V^T); 2 / 3 restrict the K range to where a causal P / dS is non-zero (dV = P^T dO, dK = dS^T Q / dQ = dS K).
+ * M % 256 == 0 (and K % 64 == 0 with MN-major operands) so tiles never straddle two matrices. */
+int vllm_gemm_bf16_batched(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
+                           int n_batch, int M, int N, int K, int causal, int out_f32, void* stream);
+/* Row kernels of the training-side path (csrc/train_ops.cu): RMSNorm backward (dx bf16, dweight fp32 ACCUMULATED --
+ * zero it first), SwiGLU forward / backward on the interleaved (gate, up) columns of the gate|up GEMM, the causal
+ * softmax / softmax-backward of the materialised attention backward (in place on [n_mat*T, T] bf16 stacks), and the
+ * CrossEntropyLoss of modeling_visionllmv2.py:741-757 (fp32 logits, int64 labels, -100 ignored; loss_sum accumulated,
+ * dlogits bf16 = (softmax - onehot) / *n_valid). */
+int vllm_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* weight, const void* dy, long long ldy, void* dx,
+                          long long lddx, float* dweight, long long rows, int cols, float eps, void* stream);
+int vllm_swiglu_fwd_bf16(const void* gate_up, long long ldgu, void* h, long long ldh, long long rows, int inter, void* stream);
+int vllm_swiglu_bwd_bf16(const void* gate_up, long long ldgu, const void* dh, long long lddh, void* dgate_up, long long lddgu,
+                         long long rows, int inter, void* stream);
+int vllm_softmax_causal_bf16(void* s, long long ld, long long n_mat, int T, float scale, void* stream);
+int vllm_attn_ds_bf16(const void* p, void* dp, long long ld, long long n_mat, int T, float scale, void* stream);
+int vllm_ce_loss_f32(const float* logits, long long ld, const int64_t* labels, const int64_t* n_valid, long long rows, int vocab,
+                     float* loss_sum, void* dlogits, long long ldd, void* stream);
+
 /* ---- sequence assembly of VisionLLMv2Model.forward (csrc/seqglue.cu) -----------------
  * vllm_seq_index: ONE pass over input_ids [batch, seq_len] (int64, device) producing
  *   new_ids   the ids with [EMB] .. [EMB+num_embs-1] written after every tool token (modeling_visionllmv2.py:447-486,

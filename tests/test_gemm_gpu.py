@@ -181,3 +181,32 @@ def test_rope_matches_hf_formula():
     ref = (qh * cos[:, None]) + (rot * sin[:, None])          # bf16 ops, like HF apply_rotary_pos_emb
     out = ops().rope_(q.clone(), cos, sin, H, D).view(T, H, D)
     assert torch.equal(out, ref)
+
+
+# ---- backward GEMMs: MN-major operands (dgrad / wgrad without transposed copies) ----
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("T,out_f,in_f", [(512, 256, 384), (2048, 4096, 4096), (300, 1376, 4096), (1000, 520, 200)])
+def test_gemm_tn_dgrad_wgrad_match_torch(T, out_f, in_f, variant):
+    """dx = dy . W and dW = dy^T . x through vllm_gemm_bf16_tn vs fp32 torch on the same bf16 inputs (one bf16 output
+    rounding + 1e-3 max|ref|), both CTA-group variants, ragged M / N / K tails."""
+    from visionllm_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(T + out_f)
+    dy = (torch.randn(T, out_f, device="cuda", generator=g) * 0.5).bfloat16()
+    x = (torch.randn(T, in_f, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(out_f, in_f, device="cuda", generator=g) * 0.05).bfloat16()
+    _lib.lib().vllm_gemm_set_variant(variant)
+    try:
+        dx = ops.gemm_tn(dy, w, b_mn=True)
+        dw = ops.gemm_tn(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32)
+        y = ops.gemm_tn(x, w)                                            # both K-major == ops.linear
+        at = ops.gemm_tn(x.t().contiguous(), w, a_mn=True)               # MN-major A alone
+    finally:
+        _lib.lib().vllm_gemm_set_variant(0)
+    ref_dx = dy.float() @ w.float()
+    ref_dw = dy.float().t() @ x.float()
+    ref_y = x.float() @ w.float().t()
+    for got, ref in ((dx, ref_dx), (y, ref_y), (at, ref_y)):
+        assert got.shape == ref.shape
+        assert ((got.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-3 * ref.abs().max()).all()
+    assert dw.dtype == torch.float32 and (dw - ref_dw).abs().max() <= 1e-3 * ref_dw.abs().max()
+    assert torch.equal(y, ops.linear(x, w))

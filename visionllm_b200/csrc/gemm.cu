@@ -49,7 +49,33 @@ struct GemmArgs {
   int sc_rows;
   void* sc_dst[8];
   uint32_t* sc_flag[8];
+  // MN-major operands (vllm_gemm_bf16_tn: the backward GEMMs -- dgrad reads the nn.Linear weight [N_red, K_out] as
+  // B[j, k] = W[k, j], wgrad reads grad_output / activations [tokens, features] with the token axis as K): the operand
+  // is a row-major [K, MN] matrix; a 64-k x 64-mn TMA box is one 128B-swizzled MN-major UMMA atom row, chunks of 64 mn
+  // are 8 KB apart in the stage (LBO), 8 k-rows 1 KB apart (SBO), a k-step of 16 advances 2 KB.
+  int a_mn, b_mn;
+  // Block-diagonal batching (vllm_gemm_bf16_batched: the attention-backward GEMMs over all (batch, head) matrices of a
+  // layer in one launch): every operand is a stack of `bt_rows`-row matrices along its row axis; the output row block
+  // m0 belongs to matrix m0 / bt_rows and only meets that matrix's B rows / K range.  causal: 1 = skip output tiles
+  // strictly above the diagonal (S = Q K^T, dP = dO V^T), 2 = the K range starts at the tile's first row (dV = P^T dO,
+  // dK = dS^T Q: P, dS are zero below), 3 = the K range ends at the tile's last row (dQ = dS K).
+  int bt_rows, causal;
 };
+
+// per-tile K range / operand offsets of the batched mode (identity when bt_rows == 0)
+struct TilePlan { int skip, kb0, kb1, b_row_off, k_off; };
+__device__ __forceinline__ TilePlan plan_tile(const GemmArgs& g, int m0, int n0, int rows_per_tile, int num_kb) {
+  TilePlan p{0, 0, num_kb, 0, 0};
+  if (g.bt_rows) {
+    const int bh = m0 / g.bt_rows, ml = m0 - bh * g.bt_rows;
+    p.b_row_off = bh * g.N;                             // K-major B: a stack of [N, K] matrices along the rows
+    p.k_off = bh * g.K;                                 // MN-major operands: stacks of [K, M|N] matrices along the K rows
+    if (g.causal == 1 && n0 >= ml + rows_per_tile) p.skip = 1;
+    if (g.causal == 2) p.kb0 = ml / BK;
+    if (g.causal == 3) { const int e = (ml + rows_per_tile + BK - 1) / BK; p.kb1 = e < num_kb ? e : num_kb; }
+  }
+  return p;
+}
 
 template <int CG> struct Cfg {
   static constexpr int B_ROWS = BN / CG;               // B rows held by one CTA
@@ -121,12 +147,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0; uint32_t phase = 0;
       for (int t = cluster_id; t < n_tiles; t += n_clusters) {
         int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
-        const int row_a = (tm * CG + (int)rank) * BM;
-        const int row_b = tn * BN + (int)rank * C_::B_ROWS;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const TilePlan tp = plan_tile(g, tm * CG * BM, tn * BN, CG * BM, num_kb);
+        if (tp.skip) continue;
+        const int bt_m0 = g.bt_rows ? (tm * CG * BM) / g.bt_rows * g.bt_rows : 0;
+        // K-major A: global stacked row; MN-major A: column inside its matrix (the stack runs along the K rows)
+        const int row_a = (tm * CG + (int)rank) * BM - (g.a_mn ? bt_m0 : 0);
+        const int row_b = tn * BN + (int)rank * C_::B_ROWS + (g.b_mn ? 0 : tp.b_row_off);
+        const int ka_off = g.a_mn ? tp.k_off : 0, kb_off = g.b_mn ? tp.k_off : 0;
+        for (int kb = tp.kb0; kb < tp.kb1; ++kb) {
           tc::mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C_::STAGE_BYTES, sb = sa + A_BYTES;
-          int ka = kb * BK, ra = row_a;
+          int ka = kb * BK + ka_off, ra = row_a;
           if (g.a_seg_kb) {
             const int seg = kb / g.a_seg_kb;
             ka = (kb - seg * g.a_seg_kb) * BK;
@@ -134,12 +165,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if constexpr (CG == 1) {
             tc::mbar_arrive_expect_tx(full_bar(stage), C_::STAGE_BYTES);
-            tc::tma_load_2d(sa, &tmap_a, full_bar(stage), ka, ra);
-            tc::tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, row_b);
+            if (g.a_mn) {
+              for (int h = 0; h < BM / 64; ++h) tc::tma_load_2d(sa + h * 8192, &tmap_a, full_bar(stage), ra + 64 * h, ka);
+            } else {
+              tc::tma_load_2d(sa, &tmap_a, full_bar(stage), ka, ra);
+            }
+            if (g.b_mn) {
+              for (int h = 0; h < C_::B_ROWS / 64; ++h)
+                tc::tma_load_2d(sb + h * 8192, &tmap_b, full_bar(stage), row_b + 64 * h, kb * BK + kb_off);
+            } else {
+              tc::tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, row_b);
+            }
           } else {
             if (leader) tc::mbar_arrive_expect_tx(full_bar(stage), 2 * C_::STAGE_BYTES);
-            tc::tma_load_2d_cg2(sa, &tmap_a, full_bar(stage), ka, ra);
-            tc::tma_load_2d_cg2(sb, &tmap_b, full_bar(stage), kb * BK, row_b);
+            if (g.a_mn) {
+              for (int h = 0; h < BM / 64; ++h) tc::tma_load_2d_cg2(sa + h * 8192, &tmap_a, full_bar(stage), ra + 64 * h, ka);
+            } else {
+              tc::tma_load_2d_cg2(sa, &tmap_a, full_bar(stage), ka, ra);
+            }
+            if (g.b_mn) {
+              for (int h = 0; h < C_::B_ROWS / 64; ++h)
+                tc::tma_load_2d_cg2(sb + h * 8192, &tmap_b, full_bar(stage), row_b + 64 * h, kb * BK + kb_off);
+            } else {
+              tc::tma_load_2d_cg2(sb, &tmap_b, full_bar(stage), kb * BK, row_b);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -149,23 +198,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
     if (leader) {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(BM * CG, BN);
+      const uint32_t idesc = tc::umma_idesc_bf16_f32(BM * CG, BN) | (g.a_mn ? (1u << 15) : 0u) | (g.b_mn ? (1u << 16) : 0u);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (int t = cluster_id; t < n_tiles; t += n_clusters) {
+        int tm_, tn_; tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm_, tn_);
+        const TilePlan tp = plan_tile(g, tm_ * CG * BM, tn_ * BN, CG * BM, num_kb);
+        if (tp.skip) continue;
         tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = tp.kb0; kb < tp.kb1; ++kb) {
           tc::mbar_wait(full_bar(stage), phase);
           tc::tc_fence_after();
           if (tc::elect_one()) {
             const uint32_t sa = smem_base + stage * C_::STAGE_BYTES, sb = sa + A_BYTES;
-            const uint64_t adesc = tc::umma_desc_kmajor_sw128(sa), bdesc = tc::umma_desc_kmajor_sw128(sb);
+            // K-major: a k-step of 16 bf16 advances the start address by 32 B inside the 128 B swizzle row;
+            // MN-major: by 16 k-rows x 128 B = 2 KB (descriptor address units are 16 B)
+            const uint64_t adesc = g.a_mn ? tc::umma_desc_mnmajor_sw128(sa) : tc::umma_desc_kmajor_sw128(sa);
+            const uint64_t bdesc = g.b_mn ? tc::umma_desc_mnmajor_sw128(sb) : tc::umma_desc_kmajor_sw128(sb);
+            const uint64_t astep = g.a_mn ? 128 : 2, bstep = g.b_mn ? 128 : 2;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              tc::umma_f16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              tc::umma_f16<CG>(d_tmem, adesc + astep * k, bdesc + bstep * k, idesc, (kb != tp.kb0) || (k != 0));
             tc::umma_commit<CG>(empty_bar(stage));
-            if (kb == num_kb - 1) tc::umma_commit<CG>(tfull_bar(acc));
+            if (kb == tp.kb1 - 1) tc::umma_commit<CG>(tfull_bar(acc));
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -184,6 +240,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const bool swiglu = g.act == ACT_SWIGLU;
     for (int t = cluster_id; t < n_tiles; t += n_clusters) {
       int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
+      if (plan_tile(g, tm * CG * BM, tn * BN, CG * BM, num_kb).skip) continue;
       const int n0 = tn * BN;
       const int row = (tm * CG + (int)rank) * BM + quarter * 32 + lane;
       // stage bias / column scale for this tile
@@ -437,10 +494,14 @@ int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cuda
                 int a_cols = -1) {
   using C_ = Cfg<CG>;
   CUtensorMap ta, tb;
-  int rc = vllm_make_tmap_bf16(&ta, A, (uint64_t)(a_rows < 0 ? g.M : a_rows), (uint64_t)(a_cols < 0 ? g.K : a_cols),
-                               (uint64_t)lda, BM);
+  const uint64_t nb = g.bt_rows ? (uint64_t)(g.M / g.bt_rows) : 1;     // matrices in the stack (batched mode)
+  const uint64_t m_local = g.bt_rows ? (uint64_t)g.bt_rows : (uint64_t)g.M;
+  int rc = g.a_mn ? vllm_make_tmap_bf16(&ta, A, nb * (uint64_t)g.K, m_local, (uint64_t)lda, 64)       // [K, M] rows, 64 x 64 boxes
+                  : vllm_make_tmap_bf16(&ta, A, (uint64_t)(a_rows < 0 ? g.M : a_rows),
+                                        (uint64_t)(a_cols < 0 ? g.K : a_cols), (uint64_t)lda, BM);
   if (rc) return rc;
-  rc = vllm_make_tmap_bf16(&tb, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, C_::B_ROWS);
+  rc = g.b_mn ? vllm_make_tmap_bf16(&tb, B, nb * (uint64_t)g.K, (uint64_t)g.N, (uint64_t)ldb, 64)
+              : vllm_make_tmap_bf16(&tb, B, nb * (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, C_::B_ROWS);
   if (rc) return rc;
   g.tiles_m = (g.M + BM * CG - 1) / (BM * CG);
   g.tiles_n = (g.N + BN - 1) / BN;
@@ -496,6 +557,51 @@ int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int 
   g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc;
   g.bias = (const __nv_bfloat16*)bias; g.colscale = (const __nv_bfloat16*)colscale;
   g.residual = (const __nv_bfloat16*)residual; g.ldr = ldr; g.act = act; g.out_f32 = out_f32;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cg = g_gemm_variant ? g_gemm_variant : (K <= 512 ? 1 : 2);
+  if (cg == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);
+  return launch_gemm<1>(A, lda, B, ldb, g, st);
+}
+
+int vllm_gemm_bf16_tn(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc, int M,
+                      int N, int K, int out_f32, void* stream) {
+  // C[M, N] = sum_k A(m, k) * B(n, k) with either operand stored K-major ([rows = M|N, cols = K], like vllm_gemm_bf16) or
+  // MN-major ([rows = K, cols = M|N], pitch lda / ldb): the backward GEMMs of a Linear y = x W^T without transposed copies --
+  //   dgrad  dx[T, in]  = dy[T, out] (K-major A, K = out) x W[out, in] as MN-major B
+  //   wgrad  dW[out, in] = dy[T, out] as MN-major A (K = T) x x[T, in] as MN-major B.
+  if (M < 0 || N <= 0 || K <= 0) return VLLM_EINVAL;
+  if (M == 0) return VLLM_OK;
+  if (!A || !B || !C) return VLLM_EINVAL;
+  if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N) return VLLM_EINVAL;
+  if (!vllm_aligned(A, 16) || !vllm_aligned(B, 16) || (lda % 8) || (ldb % 8)) return VLLM_EALIGN;
+  if (!vllm_aligned(C, 16) || ((size_t)ldc * (out_f32 ? 4 : 2)) % 16) return VLLM_EALIGN;
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.out_f32 = out_f32;
+  g.a_mn = a_mn_major ? 1 : 0; g.b_mn = b_mn_major ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cg = g_gemm_variant ? g_gemm_variant : (K <= 512 ? 1 : 2);
+  if (cg == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);
+  return launch_gemm<1>(A, lda, B, ldb, g, st);
+}
+
+int vllm_gemm_bf16_batched(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
+                           int n_batch, int M, int N, int K, int causal, int out_f32, void* stream) {
+  // n_batch independent products C_b[M, N] = A_b . B_b^T in ONE launch: every operand / the output is a stack of its
+  // n_batch matrices along the row axis (K-major A: [n_batch*M, K]; MN-major A: [n_batch*K, M]; same for B; C: [n_batch*M, N]).
+  // causal (square attention matrices, M == the sequence length): see GemmArgs.  The attention-backward GEMMs of a layer.
+  if (n_batch < 0 || M <= 0 || N <= 0 || K <= 0 || causal < 0 || causal > 3) return VLLM_EINVAL;
+  if (n_batch == 0) return VLLM_OK;
+  if (!A || !B || !C) return VLLM_EINVAL;
+  if (M % 256 || ((a_mn_major || b_mn_major) && K % BK)) return VLLM_EUNSUPPORTED;     // tiles must not straddle matrices
+  if ((long long)n_batch * M > 2147483647LL || (long long)n_batch * K > 2147483647LL || (long long)n_batch * N > 2147483647LL)
+    return VLLM_EUNSUPPORTED;
+  if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N) return VLLM_EINVAL;
+  if (!vllm_aligned(A, 16) || !vllm_aligned(B, 16) || (lda % 8) || (ldb % 8)) return VLLM_EALIGN;
+  if (!vllm_aligned(C, 16) || ((size_t)ldc * (out_f32 ? 4 : 2)) % 16) return VLLM_EALIGN;
+  GemmArgs g{};
+  g.M = n_batch * M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.out_f32 = out_f32;
+  g.a_mn = a_mn_major ? 1 : 0; g.b_mn = b_mn_major ? 1 : 0;
+  g.bt_rows = M; g.causal = causal;
   cudaStream_t st = (cudaStream_t)stream;
   const int cg = g_gemm_variant ? g_gemm_variant : (K <= 512 ? 1 : 2);
   if (cg == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);

@@ -189,7 +189,19 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B    [61,64)
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
+// MN-major operand tile: 128B-swizzled atoms of 64 MN elements x 8 k-rows (1 KB); LBO = distance between 64-element
+// MN chunks (one 64 x 64 TMA box = 8 KB), SBO = distance between 8-row k groups (1 KB).  Same recipe as the V operand
+// of attention_tc2.cu (validated on hardware there).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;                  // LBO = 8 KB
+  d |= (uint64_t)(1024 >> 4) << 32;                  // SBO = 1 KB
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major (bit 15 / 16: A / B MN-major).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
   return (1u << 4)                 // D format F32   [4,6)
          | (1u << 7)               // A format BF16  [7,10)

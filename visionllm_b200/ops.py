@@ -92,6 +92,28 @@ def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dty
     return out.reshape(*lead, n_out)
 
 
+def gemm_tn(a, b, a_mn=False, b_mn=False, out_dtype=torch.bfloat16):
+    """C[M, N] = sum_k A(m, k) B(n, k) on the tcgen05 GEMM with K-major or MN-major operands (the backward GEMMs):
+    a is [M, K] (a_mn=False) or [K, M] (a_mn=True), b is [N, K] or [K, N]; 2-D bf16, unit inner stride.
+      dgrad: gemm_tn(dy, W, b_mn=True)            -> dx [T, in]
+      wgrad: gemm_tn(dy, x, a_mn=True, b_mn=True) -> dW [out, in]"""
+    _bf16_2d(a, "a"); _bf16_2d(b, "b")
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else b.shape
+    if K != Kb:
+        raise RuntimeError(f"gemm_tn: reduction sizes differ ({K} vs {Kb})")
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise RuntimeError("gemm_tn: out_dtype must be bf16 or fp32")
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    with torch.cuda.device(a.device), _Prof("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * N,
+                                            f"{M}x{N}x{K}"):
+        rc = _lib.lib().vllm_gemm_bf16_tn(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
+                                          out.data_ptr(), out.stride(0), M, N, K, 1 if out_dtype == torch.float32 else 0,
+                                          _stream())
+    _lib.check(rc, "vllm_gemm_bf16_tn")
+    return out
+
+
 def conv2d_s1_rows(x, weight_rows, bias, kernel, padding, act=None):
     """Stride-1 KxK convolution of a channels-last map x [B, H, W, C] (bf16) with `weight_rows` [Cout, K*K*C] in
     (dy, dx, c) order -> [B, Ho, Wo, Cout] (a strided view of the kernel's padded-grid output).  One zero-pad copy of x,
