@@ -809,6 +809,86 @@ class InternImageHWorkload(PairForwardWorkload):
                 "parallelism": f"dp{self.world} (batch shard, no forward collective)"}
 
 
+class LlmTrainWorkload(PairForwardWorkload):
+    """BASELINE cfg 5's "fwd+bwd step" on the training-side path (visionllm_b200/train.py): Vicuna-7B random-init bf16,
+    SEQS x 2048 mixed visual/text tokens per GPU per step (the first 1536 positions visual: no language loss), loss = CE on
+    the text positions (modeling_visionllmv2.py:741-757), forward + backward of every decoder op on this repo's kernels
+    (tcgen05 GEMMs incl. MN-major dgrad / wgrad and the batched attention backward; row backward kernels; fused CE).  No
+    optimizer step (stated).  N GPUs: data-parallel replicas with ONE bf16 gradient all-reduce (NCCL) per step inside the
+    timed region -- the tensor-parallel exchange of tp.py is forward-only."""
+    metric = "llm_train_fwd_bwd_tokens_per_sec_2048tok"
+    unit = "tokens/s"
+    dtype = "bf16 (fp32 accumulate, fp32 logits / loss)"
+    SEQS, T = 4, 2048
+
+    def setup(self):
+        import torch
+        import torch.distributed as dist
+        from transformers import LlamaConfig
+        from visionllm_b200.llama import B200LlamaForCausalLM
+        from visionllm_b200.train import B200LlamaForCausalLMTrain
+        self.torch = torch
+        cfg = LlamaConfig(**self.llm)
+        with torch.device("meta"):
+            lm = B200LlamaForCausalLM(cfg)
+        lm = lm.to_empty(device=self.device).to(torch.bfloat16)
+        g = torch.Generator(device=self.device).manual_seed(0)
+        with torch.no_grad():
+            for name, p in lm.named_parameters():
+                if "norm" in name:
+                    p.fill_(1.0)
+                else:
+                    p.copy_(torch.randn(p.shape, device=self.device, generator=g, dtype=torch.float32) * 0.02)
+        self.lm = lm
+        self.model = B200LlamaForCausalLMTrain(lm)
+        gi = torch.Generator(device=self.device).manual_seed(1234 + self.rank)
+        self.ids = torch.randint(0, 32000, (self.SEQS, self.T), device=self.device, generator=gi)
+        self.labels = self.ids.clone()
+        self.labels[:, :1536] = -100
+        self.h_ids = self.ids.cpu().pin_memory()
+        self.h_labels = self.labels.cpu().pin_memory()
+        self.d_ids, self.d_labels = torch.empty_like(self.ids), torch.empty_like(self.labels)
+        self.h_out = torch.empty((1,), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = self.ids.numel() * 16
+        self.d2h_bytes = 4
+        self.dist = dist if self.world > 1 else None
+        self.params = [p for n, p in lm.named_parameters() if n != "model.embed_tokens.weight"]
+
+    def _step(self, ids, labels):
+        torch = self.torch
+        for p in self.params:
+            p.grad = None
+        with torch.no_grad():
+            emb = torch.nn.functional.embedding(ids, self.lm.model.embed_tokens.weight)
+        loss, _, _ = self.model(emb.requires_grad_(True), labels)
+        loss.backward()
+        if self.dist is not None:                                  # the exchange step of data-parallel training
+            flat = torch.cat([p.grad.reshape(-1) for p in self.params])
+            self.dist.all_reduce(flat)
+        return loss.detach()
+
+    def step_device(self):
+        self.out = self._step(self.ids, self.labels)
+
+    def step_e2e(self):
+        self.d_ids.copy_(self.h_ids, non_blocking=True)
+        self.d_labels.copy_(self.h_labels, non_blocking=True)
+        self.h_out.copy_(self._step(self.d_ids, self.d_labels).reshape(1), non_blocking=True)
+
+    def units_per_step(self):
+        return self.SEQS * self.T
+
+    def config(self):
+        return {"workload": f"BASELINE cfg 5 fwd+bwd (training-side path): Vicuna-7B, {self.SEQS} x 2048-token sequences per GPU "
+                            "per step, CE loss on the 512 text positions, forward + backward on this repo's kernels, no optimizer",
+                "global_batch": self.SEQS * self.world, "seq_len": self.T,
+                "l2_policy": "inputs_exceed_l2 (weights 13.5 GB + saved activations ~40 GB)",
+                "parallelism": f"dp{self.world} (one bf16 gradient all-reduce per step)" if self.world > 1 else "dp1"}
+
+    def extra(self):
+        return {"kernel_breakdown": self.breakdown}
+
+
 class Cfg1Workload:
     """BASELINE cfg 1 ("single 224x224 image + 16-token prompt, ViT-B + 1-layer LLM stub, CPU reference fwd"): ViT-B-size
     InternViT -> mlp2x_gelu -> 1-layer Llama -> [EMB] gather -> whole Grounding-DINO stage (Swin backbone, 6 + 6 layers,
@@ -1025,7 +1105,8 @@ def tp_extra(rank, world, device, steps=10, warmup=3):
 WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "msda_encoder_bf16": MsdaEncoderBf16Workload,
              "msda_encoder_pairs": MsdaEncoderPairsWorkload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
              "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload,
-             "llm_tp": LlmTpWorkload, "internimage_h": InternImageHWorkload, "cfg1_forward": Cfg1Workload}
+             "llm_tp": LlmTpWorkload, "internimage_h": InternImageHWorkload, "cfg1_forward": Cfg1Workload,
+             "llm_train": LlmTrainWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
 
@@ -1205,9 +1286,42 @@ def _cpu_cfg1(steps, warmup):
             "reference_modules_cpu_ms_in_build_container_8_threads": ref_ms}
 
 
+def _cpu_llm_train(steps, warmup):
+    """Reference CPU path of the fwd+bwd step, bounded sample: ONE Vicuna-7B layer on one 2048-token sequence, torch fp32
+    autograd on all host cores (oracle/vit_llm_oracle.llama_layer, sum-of-outputs loss); tokens/s extrapolated over 32 layers."""
+    import torch
+    from oracle import vit_llm_oracle as VO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    H, F_, T = 4096, 11008, 2048
+    r = lambda *s: (torch.randn(*s, generator=g) * 0.02).requires_grad_(True)  # noqa: E731
+    lsd = {"l.input_layernorm.weight": torch.ones(H, requires_grad=True), "l.post_attention_layernorm.weight": torch.ones(H, requires_grad=True),
+           "l.self_attn.q_proj.weight": r(H, H), "l.self_attn.k_proj.weight": r(H, H),
+           "l.self_attn.v_proj.weight": r(H, H), "l.self_attn.o_proj.weight": r(H, H),
+           "l.mlp.gate_proj.weight": r(F_, H), "l.mlp.up_proj.weight": r(F_, H), "l.mlp.down_proj.weight": r(H, F_)}
+    x = torch.randn(1, T, H, generator=g).requires_grad_(True)
+
+    def once():
+        for t in list(lsd.values()) + [x]:
+            t.grad = None
+        VO.llama_layer(x, lsd, "l.", 32, 1e-5).sum().backward()
+
+    for _ in range(warmup):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    tl = (time.perf_counter() - t0) / steps
+    return {"value": T / (32 * tl), "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"1 Vicuna-7B layer fwd+bwd x one 2048-token sequence ({tl * 1e3:.0f} ms), fp32 torch CPU autograd; "
+                      "sequence = 32 x layer (extrapolated)",
+            "ms_per_step": 4 * 32 * tl * 1e3, "sample_ms_per_step": tl * 1e3, "extrapolated": True}
+
+
 _CPU = {"msda_encoder": _cpu_msda_encoder, "msda_encoder_bf16": _cpu_msda_encoder, "msda_encoder_pairs": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
         "gdino_stage": _cpu_msda_encoder,
-        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp, "internimage_h": _cpu_internimage_h, "cfg1_forward": _cpu_cfg1}
+        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp, "internimage_h": _cpu_internimage_h, "cfg1_forward": _cpu_cfg1, "llm_train": _cpu_llm_train}
 
 
 def cpu_baseline(name):

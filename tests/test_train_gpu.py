@@ -156,3 +156,19 @@ def test_decoder_fwd_bwd_matches_hf_autograd():
         worst.append((a / (2 * b + 3e-3), n, a, b))
         assert a <= 2 * b + 3e-3, (n, a, b)
     print("worst grad ratio:", max(worst)[:4])
+
+
+def test_b200_rmsnorm_module_forward_backward():
+    from visionllm_b200.norm import B200RMSNorm
+    m = B200RMSNorm(1024, eps=1e-5).to("cuda", torch.bfloat16)
+    with torch.no_grad():
+        m.weight.copy_(1 + 0.1 * torch.randn(1024))
+    x = torch.randn(3, 50, 1024, device="cuda").bfloat16().requires_grad_(True)
+    y = m(x)
+    y.backward(torch.ones_like(y) * 0.1)
+    xf, wf = x.detach().float().requires_grad_(True), m.weight.detach().float().requires_grad_(True)
+    ref = wf * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5))
+    ref.backward(torch.ones_like(ref) * 0.1)
+    assert rel(y, ref) < 5e-3 and rel(x.grad, xf.grad) < 5e-3 and rel(m.weight.grad, wf.grad) < 5e-3
+    with torch.no_grad():
+        assert torch.equal(m(x.detach()), y.detach())            # the no-grad path is the same kernel

@@ -12,12 +12,37 @@ Integer index work (token positions, scatter/gather indices) is vectorised but p
 indices as the reference's python loops; it is checked index-for-index in tests/test_modeling_cpu.py.
 """
 import re
+from dataclasses import dataclass
 from types import SimpleNamespace
+from typing import Any, Optional, Tuple
 
 import torch
 import torch.nn as nn
+from transformers.utils import ModelOutput
 
 from . import ops
+
+
+@dataclass
+class VisionLLMv2ModelOutput(ModelOutput):
+    """Field for field the reference's output class (modeling_visionllmv2.py:57-79): the CausalLMOutputWithPast part
+    plus the atom-tool outputs.  Extra read-only conveniences of this drop-in come after the reference's fields."""
+    loss: Optional[torch.FloatTensor] = None
+    logits: Optional[torch.FloatTensor] = None
+    past_key_values: Optional[Tuple[Tuple[torch.FloatTensor]]] = None
+    hidden_states: Optional[Tuple[torch.FloatTensor]] = None
+    attentions: Optional[Tuple[torch.FloatTensor]] = None
+    loss_gdino: Optional[torch.FloatTensor] = None
+    gdino_outputs: Any = None
+    loss_unipose: Optional[torch.FloatTensor] = None
+    unipose_outputs: Any = None
+    loss_sd: Optional[torch.FloatTensor] = None
+    sd_outputs: Any = None
+    loss_ip2p: Optional[torch.FloatTensor] = None
+    ip2p_outputs: Any = None
+    last_hidden_state: Optional[torch.FloatTensor] = None      # == hidden_states[-1]
+    input_ids: Optional[torch.LongTensor] = None               # the ids with the [EMB] slots rewritten (mv2.py:447-468)
+    vit_outputs: Any = None
 
 
 class BridgeLinear(nn.Linear):
@@ -350,6 +375,8 @@ class B200VisionLLMv2Model(nn.Module):
                 pixel_mask = pixel_values[:, 0, :, :] != 0                                  # mv2.py:773
                 gdino_outputs = self.gdino(pixel_values, pixel_mask=pixel_mask, text_query=tq,
                                            text_query_masks=tm, img_metas=img_metas, labels=None)
-        return SimpleNamespace(loss=None, logits=out.logits, hidden_states=out.hidden_states,
-                               last_hidden_state=hidden, vit_outputs=vit_out, gdino_outputs=gdino_outputs,
-                               input_ids=input_ids)
+        if not return_dict:                                                                  # mv2.py:873-875
+            return (out.logits,) + (None, out.hidden_states, None)
+        return VisionLLMv2ModelOutput(loss=None, logits=out.logits, past_key_values=None, hidden_states=out.hidden_states,
+                                      attentions=None, gdino_outputs=gdino_outputs, last_hidden_state=hidden,
+                                      vit_outputs=vit_out, input_ids=input_ids)
