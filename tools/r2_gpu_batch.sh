@@ -1,0 +1,11 @@
+#!/bin/bash
+# One gpurun call worth of round-2 evidence (1 GPU).  Everything lands under gpurun_out/ (scratch); summaries are copied to
+# profiles/ afterwards.   usage: bash tools/r2_gpu_batch.sh [tag]
+tag=${1:-a}
+mkdir -p gpurun_out
+echo "== gpu tests"; timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 | tee gpurun_out/r2_gputests_$tag.log | tail -25
+echo "== msda window sweep"; timeout 300 python tools/msda_win_sweep.py --out gpurun_out/r2_msda_window_sweep.json 2>&1 | tail -20
+echo "== msda vs reference kernel"; timeout 200 python tools/msda_ref_bench.py --out gpurun_out/r2_msda_vs_reference_kernel.json > /dev/null 2>gpurun_out/msda_ref.err; tail -3 gpurun_out/msda_ref.err
+echo "== bench cfg1"; timeout 300 python bench.py --workload cfg1_forward --steps 20 --warmup 5 > gpurun_out/r2_bench_cfg1_$tag.json 2>gpurun_out/cfg1.err; tail -c 600 gpurun_out/r2_bench_cfg1_$tag.json; tail -3 gpurun_out/cfg1.err
+echo "== bench default"; timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_pair_forward_$tag.json 2>gpurun_out/pair.err; tail -c 1500 gpurun_out/r2_bench_pair_forward_$tag.json; tail -3 gpurun_out/pair.err
+echo "== experimental FHFMA variants"; VLLM_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_msda_gpu.py tests/test_internimage_gpu.py -q -k fhfma 2>&1 | tail -5 | tee gpurun_out/r2_fhfma_$tag.log

@@ -54,9 +54,18 @@ det_topk_kernel(const float* __restrict__ logits, const float* __restrict__ pred
     __syncthreads();
     const unsigned prefix = s_prefix;
     const unsigned mask_hi = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    for (long long i = tid; i < n; i += TOPK_THREADS) {
-      const unsigned key = key_of(i);
-      if ((key & mask_hi) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    for (long long base = 0; base < n; base += TOPK_THREADS) {       // warp-uniform trip count (ballot / match below)
+      const long long i = base + tid;
+      unsigned key = 0u;
+      bool part = false;
+      if (i < n) { key = key_of(i); part = (key & mask_hi) == prefix; }
+      // probabilities share a handful of exponent bytes: aggregate equal digits inside the warp before the shared atomic
+      const unsigned act = __ballot_sync(0xffffffffu, part);
+      if (part) {
+        const unsigned digit = (key >> shift) & 255u;
+        const unsigned peers = __match_any_sync(act, digit);
+        if ((peers & ((1u << (tid & 31)) - 1u)) == 0u) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+      }
     }
     __syncthreads();
     if (tid == 0) {
