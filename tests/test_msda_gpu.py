@@ -384,3 +384,38 @@ def test_pairs_mode_fhfma_variant_within_bf16_weight_error(out_dtype):
                                              torch.float32)                      # sum |w_i| |v_i| per output
     slack = 2.0 ** -8 * bound + (2.0 ** -8 * ref.abs() if out_dtype == torch.bfloat16 else 0) + 1e-6
     assert ((got.float() - ref).abs() <= slack).all()
+
+
+# ---- the reference's OWN CUDA kernel, rebuilt for sm_100 (baseline/build_msda_ref.py), as a GPU-side oracle ----
+def _reference_ext():
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "baseline", "_ref", "msda", "MultiScaleDeformableAttention.so")
+    if not os.path.exists(path):
+        pytest.skip("baseline/_ref/msda not built (python baseline/build_msda_ref.py in the build container)")
+    spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttention", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[3] in (32, 16)][:6], ids=lambda c: f"L{len(c[0])}D{c[3]}P{c[5]}")
+def test_forward_matches_the_reference_cuda_kernel(case):
+    """ms_deform_attn_forward of the reference extension (unipose/ops/src/cuda/ms_deform_im2col_cuda.cuh, nvcc default
+    -fmad=true) vs ours on the same device tensors: fp32 within reassociation noise, fp64 to 1e-12; the backward too."""
+    ref = _reference_ext()
+    ext = _ext()
+    value, shapes, lsi, loc, attw = make_case(*case, seed=21)
+    v, sh, ls, lo, w = _dev(value, shapes, lsi, loc, attw)
+    theirs = ref.ms_deform_attn_forward(v, sh, ls, lo, w, 64)
+    for flags in (0, 1):
+        mine = ext.ms_deform_attn_forward(v, sh, ls, lo, w, 64, flags=flags)
+        assert (mine - theirs).abs().max().item() <= 1e-5 * max(1.0, theirs.abs().max().item())
+    v64, lo64, w64 = v.double(), lo.double(), w.double()
+    t64 = ref.ms_deform_attn_forward(v64, sh, ls, lo64, w64, 64)
+    assert (ext.ms_deform_attn_forward(v64, sh, ls, lo64, w64, 64) - t64).abs().max().item() <= 1e-12
+    go = torch.randn_like(t64)
+    gv_r, gl_r, gw_r = ref.ms_deform_attn_backward(v64, sh, ls, lo64, w64, go, 64)
+    gv, gl, gw = ext.ms_deform_attn_backward(v64, sh, ls, lo64, w64, go, 64)
+    for a, b in ((gv, gv_r), (gl, gl_r), (gw, gw_r)):
+        assert (a - b).abs().max().item() <= 1e-9 * max(1.0, b.abs().max().item())
