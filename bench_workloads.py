@@ -400,7 +400,11 @@ class PairForwardWorkload:
                             "internvl_mlp + Vicuna-7B, T=1536 (1280 image + 256 text), fp32 logits all positions",
                 "pairs_per_gpu_per_step": self.PAIRS, "seq_len": self.T, "tiles_per_image": 5,
                 "l2_policy": "inputs_exceed_l2 (weights 25 GB, activations > 126 MB L2)",
-                "parallelism": f"dp{self.world} (batch shard, no forward collective)"}
+                "parallelism": f"dp{self.world} (batch shard, no forward collective)",
+                # stated, not hidden: bf16 modules are held to the reference's OWN bf16 error, not to
+                # the north-star's literal 1e-3 (one bf16 rounding is 2^-9); integer indices are exact
+                "parity_rule": "bf16 modules: rel_l2(ours, ref_fp32) <= 1.5 x rel_l2(ref_bf16, ref_fp32) + 1e-3; "
+                               "indices / integer outputs exact (tests/, DESIGN.md section 4)"}
 
     def extra(self):
         return {"kernel_breakdown": self.breakdown}

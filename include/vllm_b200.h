@@ -363,7 +363,8 @@ int vllm_ce_loss_f32(const float* logits, long long ld, const int64_t* labels, c
  * [batch, max_patches, num_embs, hidden] zero padded + masks [batch, max_patches] (uint8).  vllm_gather_rows_bf16:
  * dst[i] = src[idx[i]] (negative idx counts from src_rows).  vllm_pixel_shuffle_rows_bf16: :381-392 + the [:, 1:] CLS
  * slice + optionally the LayerNorm(4C) opening the internvl_mlp bridge in one pass: x = ViT hidden state [tiles,
- * skip_tokens + grid_w*grid_h, C] (pitches ld_tile / ld_token), y = [tiles * grid_w/2 * grid_h/2, 4C]. */
+ * skip_tokens + grid_w*grid_h, C] (pitches ld_tile / ld_token), y = [tiles * grid_w/2 * grid_h/2, 4C]; chunk_order 0 = the
+ * reference's pixel_shuffle, 1 = HF SwinPatchMerging's concatenation order (the GDINO backbone's patch merging + its LayerNorm). */
 int vllm_seq_index(const int64_t* input_ids, int batch, int seq_len, const int64_t* tool_ids, const int* tool_tables,
                    int num_tools, int64_t emb_token_id, int num_embs, int64_t imp_token_id, const int* tile_start,
                    const int* tile_count, int tokens_per_tile, int64_t* new_ids, unsigned char* kind, int* row, int* emb_pos,
@@ -378,7 +379,7 @@ int vllm_gather_rows_bf16(const void* src, long long src_ld, long long src_rows,
                           void* dst, void* stream);
 int vllm_pixel_shuffle_rows_bf16(const void* x, long long ld_tile, long long ld_token, int skip_tokens, int tiles, int grid_w,
                                  int grid_h, int channels, const void* ln_weight, const void* ln_bias, float eps, void* y,
-                                 void* stream);
+                                 int chunk_order, void* stream);
 
 #ifdef __cplusplus
 }

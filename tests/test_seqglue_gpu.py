@@ -171,3 +171,20 @@ def test_gather_rows():
     assert torch.equal(ops.gather_rows(src, idx), src[idx])
     view = torch.randn(50, 256, device="cuda").bfloat16()[:, :128]           # row pitch != cols
     assert torch.equal(ops.gather_rows(view, idx), view[idx])
+
+
+def test_swin_patch_merging_order_and_layernorm():
+    """order=1: HF SwinPatchMerging's cat([x(0::2,0::2), x(1::2,0::2), x(0::2,1::2), x(1::2,1::2)]) + LayerNorm(4C), on a
+    non-square grid."""
+    from visionllm_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    B, H, W, Cc = 2, 12, 20, 96
+    x = torch.randn(B, H * W, Cc, device="cuda", generator=gen).bfloat16()
+    x4 = x.view(B, H, W, Cc)
+    ref = torch.cat([x4[:, 0::2, 0::2], x4[:, 1::2, 0::2], x4[:, 0::2, 1::2], x4[:, 1::2, 1::2]], -1).reshape(B, -1, 4 * Cc)
+    assert torch.equal(ops.pixel_shuffle_rows(x, 0, grid=(H, W), order=1), ref)
+    w = (1 + 0.1 * torch.randn(4 * Cc, device="cuda", generator=gen)).bfloat16()
+    b = (0.1 * torch.randn(4 * Cc, device="cuda", generator=gen)).bfloat16()
+    got = ops.pixel_shuffle_rows(x, 0, w, b, 1e-5, grid=(H, W), order=1)
+    want = torch.nn.functional.layer_norm(ref.float(), (4 * Cc,), w.float(), b.float(), 1e-5)
+    assert ((got.float() - want).abs() <= 2.0 ** -8 * want.abs() + 1e-3).all()

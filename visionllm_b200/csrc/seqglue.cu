@@ -204,7 +204,7 @@ template <int VPT, bool LN>
 __global__ void __launch_bounds__(256)
 pixel_shuffle_ln_kernel(const __nv_bfloat16* __restrict__ x, long long ld_tile, long long ld_token, int skip, int gw, int gh,
                         int C, const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias, float eps,
-                        __nv_bfloat16* __restrict__ y) {
+                        __nv_bfloat16* __restrict__ y, int order) {
   __shared__ float sh[8];
   const int ow = gw / 2, oh = gh / 2;
   const long long r = blockIdx.x;                        // (tile, a, b)
@@ -219,8 +219,11 @@ pixel_shuffle_ln_kernel(const __nv_bfloat16* __restrict__ x, long long ld_tile, 
     const int v = threadIdx.x + i * 256;
     reg[i] = make_uint4(0u, 0u, 0u, 0u);
     if (v < nvec) {
-      const int chunk = v / cvec, cv = v - chunk * cvec;           // chunk: (dy, dx) = (chunk >> 1, chunk & 1)
-      const long long tok = (long long)(2 * a + (chunk >> 1)) * gh + (2 * b + (chunk & 1));
+      const int chunk = v / cvec, cv = v - chunk * cvec;
+      // order 0 (pixel shuffle, mv2.py:381-392): chunk = (dy, dx) = (chunk >> 1, chunk & 1);
+      // order 1 (Swin patch merging, HF SwinPatchMerging: cat[x(0::2,0::2), x(1::2,0::2), x(0::2,1::2), x(1::2,1::2)]): (chunk & 1, chunk >> 1)
+      const int dy = order ? (chunk & 1) : (chunk >> 1), dx = order ? (chunk >> 1) : (chunk & 1);
+      const long long tok = (long long)(2 * a + dy) * gh + (2 * b + dx);
       reg[i] = __ldg(reinterpret_cast<const uint4*>(xt + tok * ld_token) + cv);
       if (LN) { float f[8]; unpack8f(reg[i], f);
 #pragma unroll
@@ -342,8 +345,9 @@ int vllm_gather_rows_bf16(const void* src, long long src_ld, long long src_rows,
 
 int vllm_pixel_shuffle_rows_bf16(const void* x, long long ld_tile, long long ld_token, int skip_tokens, int tiles, int grid_w,
                                  int grid_h, int channels, const void* ln_weight, const void* ln_bias, float eps, void* y,
-                                 void* stream) {
+                                 int chunk_order, void* stream) {
   if (tiles < 0 || grid_w <= 0 || grid_h <= 0 || (grid_w & 1) || (grid_h & 1) || channels <= 0 || channels % 8) return VLLM_EINVAL;
+  if (chunk_order != 0 && chunk_order != 1) return VLLM_EINVAL;
   if (tiles == 0) return VLLM_OK;
   if (!x || !y || ((ln_weight == nullptr) != (ln_bias == nullptr))) return VLLM_EINVAL;
   if (ld_token % 8 || ld_tile % 8 || !vllm_aligned(x, 16) || !vllm_aligned(y, 16)) return VLLM_EALIGN;
@@ -356,11 +360,11 @@ int vllm_pixel_shuffle_rows_bf16(const void* x, long long ld_tile, long long ld_
     if (ln)
       pixel_shuffle_ln_kernel<VPT, true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
           (const __nv_bfloat16*)x, ld_tile, ld_token, skip_tokens, grid_w, grid_h, channels, (const __nv_bfloat16*)ln_weight,
-          (const __nv_bfloat16*)ln_bias, eps, (__nv_bfloat16*)y);
+          (const __nv_bfloat16*)ln_bias, eps, (__nv_bfloat16*)y, chunk_order);
     else
       pixel_shuffle_ln_kernel<VPT, false><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
           (const __nv_bfloat16*)x, ld_tile, ld_token, skip_tokens, grid_w, grid_h, channels, nullptr, nullptr, eps,
-          (__nv_bfloat16*)y);
+          (__nv_bfloat16*)y, chunk_order);
     VLLM_CHECK_LAUNCH();
     return VLLM_OK;
   };

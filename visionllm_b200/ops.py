@@ -452,23 +452,27 @@ def gather_rows(src, idx):
     return out
 
 
-def pixel_shuffle_rows(hidden, skip_tokens, ln_weight=None, ln_bias=None, eps=1e-5):
-    """mv2.py:381-392 + :574-579 in one pass: ViT hidden state [tiles, skip + g*g, C] (bf16) -> [tiles, g*g/4, 4C], the CLS
-    slice and both permute copies folded in; with (ln_weight, ln_bias) also the LayerNorm(4C) that opens `internvl_mlp`."""
+def pixel_shuffle_rows(hidden, skip_tokens, ln_weight=None, ln_bias=None, eps=1e-5, grid=None, order=0):
+    """mv2.py:381-392 + :574-579 in one pass: ViT hidden state [tiles, skip + gw*gh, C] (bf16) -> [tiles, gw*gh/4, 4C], the
+    CLS slice and both permute copies folded in; with (ln_weight, ln_bias) also the LayerNorm(4C) that opens `internvl_mlp`.
+    grid=(rows, cols) for non-square token grids; order=1 gives HF SwinPatchMerging's concatenation order."""
     if hidden.dtype != torch.bfloat16 or not hidden.is_cuda or hidden.dim() != 3 or hidden.stride(2) != 1:
         raise RuntimeError("pixel_shuffle_rows: hidden must be a CUDA bf16 [tiles, tokens, C] tensor with unit inner stride")
     tiles, T, C = hidden.shape
-    g = int(round((T - skip_tokens) ** 0.5))
-    if g * g != T - skip_tokens or g % 2:
-        raise RuntimeError("pixel_shuffle_rows: the patch tokens must form an even square grid")
-    out = torch.empty((tiles, g * g // 4, 4 * C), dtype=torch.bfloat16, device=hidden.device)
+    if grid is None:
+        g = int(round((T - skip_tokens) ** 0.5))
+        grid = (g, g)
+    gw, gh = int(grid[0]), int(grid[1])
+    if gw * gh != T - skip_tokens or gw % 2 or gh % 2:
+        raise RuntimeError("pixel_shuffle_rows: the patch tokens must form an even grid")
+    out = torch.empty((tiles, gw * gh // 4, 4 * C), dtype=torch.bfloat16, device=hidden.device)
     for t in (ln_weight, ln_bias):
         if t is not None and (t.dtype != torch.bfloat16 or t.numel() != 4 * C or not t.is_contiguous()):
             raise RuntimeError("pixel_shuffle_rows: LayerNorm weight / bias must be contiguous bf16 [4C]")
     with torch.cuda.device(hidden.device), _Prof("pixel_shuffle", 0.0, 4.0 * out.numel()):
         rc = _lib.lib().vllm_pixel_shuffle_rows_bf16(
-            hidden.data_ptr(), hidden.stride(0), hidden.stride(1), int(skip_tokens), tiles, g, g, C,
+            hidden.data_ptr(), hidden.stride(0), hidden.stride(1), int(skip_tokens), tiles, gw, gh, C,
             ln_weight.data_ptr() if ln_weight is not None else None, ln_bias.data_ptr() if ln_bias is not None else None,
-            float(eps), out.data_ptr(), _stream())
+            float(eps), out.data_ptr(), int(order), _stream())
     _lib.check(rc, "vllm_pixel_shuffle_rows_bf16")
     return out

@@ -142,6 +142,11 @@ class B200SwinBackbone(nn.Module):
     @torch.no_grad()
     def _merge(self, ds, x, H, W):
         B, N, C = x.shape
+        if (x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and H % 2 == 0 and W % 2 == 0
+                and ds.norm.weight.dtype == torch.bfloat16 and C % 8 == 0 and 4 * C <= 16384):
+            # the 2x2 gather (HF SwinPatchMerging's cat order) and the LayerNorm(4C) in ONE pass (csrc/seqglue.cu)
+            y = ops.pixel_shuffle_rows(x, 0, ds.norm.weight, ds.norm.bias, ds.norm.eps, grid=(H, W), order=1)
+            return ops.linear(y, ds.reduction.weight)
         x = x.view(B, H, W, C)
         if H % 2 or W % 2:
             x = nn.functional.pad(x, (0, 0, 0, W % 2, 0, H % 2))

@@ -260,12 +260,13 @@ class B200LlamaForCausalLMTrain(nn.Module):
             act = SwiGLUFn.apply(gu.view(B * T, -1)).view(B, T, -1)
             x = x + LinearFn.apply(act, layer.mlp.down_proj.weight)
         hidden = RMSNormFn.apply(x, model.norm.weight, self.eps)
-        logits = LinearFn.apply(hidden, self.lm.lm_head.weight, True)                      # fp32, like `logits.float()` (mv2.py:738)
+        # fp32 logits like `logits.float()` (mv2.py:738), as a 2-D [B*T, V] view of a pitch-padded buffer so that the loss
+        # kernel and the lm_head backward GEMMs read logits / dlogits in place
+        logits2 = LinearFn.apply(hidden.view(B * T, H), self.lm.lm_head.weight, True)
         loss = None
         if labels is not None:                                                             # mv2.py:741-757: shift, flatten, CE
             # "shift so that tokens < n predict n": instead of slicing the 1.5 GB logits, shift the labels and ignore the
             # last position of every row -- the same set of (logit row, label) pairs, the same mean
-            V = logits.shape[-1]
             shift_labels = torch.cat([labels[:, 1:], torch.full_like(labels[:, :1], -100)], 1).reshape(-1).contiguous()
-            loss = CrossEntropyFn.apply(logits.view(B * T, V), shift_labels)
-        return loss, logits, hidden
+            loss = CrossEntropyFn.apply(logits2, shift_labels)
+        return loss, logits2.view(B, T, -1), hidden
