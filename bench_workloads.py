@@ -893,6 +893,75 @@ class LlmTrainWorkload(PairForwardWorkload):
         return {"kernel_breakdown": self.breakdown}
 
 
+class LlmTpTrainWorkload(LlmTrainWorkload):
+    """BASELINE cfg 5 as written: Vicuna-7B tensor-parallel over the GPUs of the box, fwd+bwd (visionllm_b200/tp_train.py:
+    Megatron split, two NCCL all-reduces per layer forward + two backward over NVLink, every compute op a kernel of this
+    repo), 8 x 2048-token sequences per step for the WHOLE job at any world size (strong scaling)."""
+    metric = "llm_tp_train_fwd_bwd_tokens_per_sec_2048tok"
+    SEQS = 8
+
+    def setup(self):
+        import torch
+        import torch.distributed as dist
+        from transformers import LlamaConfig
+        from visionllm_b200 import tp_train
+        self.torch = torch
+        cfg = LlamaConfig(**self.llm)
+        g = torch.Generator(device=self.device).manual_seed(0)           # the same full weights on every rank, then sharded
+        H, I, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+        r = lambda *sh: (torch.randn(*sh, device=self.device, generator=g, dtype=torch.float32) * 0.02).to(torch.bfloat16)  # noqa: E731
+        sd = {"model.norm.weight": torch.ones(H, device=self.device, dtype=torch.bfloat16), "lm_head.weight": r(V, H)}
+        self.embed = r(V, H)
+        for i in range(cfg.num_hidden_layers):
+            p = f"model.layers.{i}."
+            sd.update({p + "self_attn.q_proj.weight": r(H, H), p + "self_attn.k_proj.weight": r(H, H),
+                       p + "self_attn.v_proj.weight": r(H, H), p + "self_attn.o_proj.weight": r(H, H),
+                       p + "mlp.gate_proj.weight": r(I, H), p + "mlp.up_proj.weight": r(I, H), p + "mlp.down_proj.weight": r(H, I),
+                       p + "input_layernorm.weight": torch.ones(H, device=self.device, dtype=torch.bfloat16),
+                       p + "post_attention_layernorm.weight": torch.ones(H, device=self.device, dtype=torch.bfloat16)})
+            if self.world > 1:                                           # keep only this rank's shard of the layer alive
+                pass
+        shards = tp_train.shard_for_training(sd, cfg, self.rank if self.world > 1 else 0, self.world)
+        del sd
+        torch.cuda.empty_cache()
+        self.model = tp_train.TPLlamaTrain(cfg, shards, group=None)
+        self.params = list(shards.parameters())
+        gi = torch.Generator(device=self.device).manual_seed(1234)       # the same batch on every rank (TP)
+        self.ids = torch.randint(0, 32000, (self.SEQS, self.T), device=self.device, generator=gi)
+        self.labels = self.ids.clone()
+        self.labels[:, :1536] = -100
+        self.h_ids, self.h_labels = self.ids.cpu().pin_memory(), self.labels.cpu().pin_memory()
+        self.d_ids, self.d_labels = torch.empty_like(self.ids), torch.empty_like(self.labels)
+        self.h_out = torch.empty((1,), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = self.ids.numel() * 16
+        self.d2h_bytes = 4
+        self.dist = dist if self.world > 1 else None
+
+    def _step(self, ids, labels):
+        torch = self.torch
+        for p in self.params:
+            p.grad = None
+        with torch.no_grad():
+            emb = torch.nn.functional.embedding(ids, self.embed)
+        loss, _, _ = self.model(emb.requires_grad_(True), labels)
+        loss.backward()
+        return loss.detach()
+
+    def units_per_step(self):
+        return self.SEQS * self.T / self.world        # bench.py multiplies by world: the job's tokens per step
+
+    def config(self):
+        return {"workload": "BASELINE cfg 5: Vicuna-7B tensor-parallel fwd+bwd, 8 x 2048-token sequences per step for the whole "
+                            "job, CE loss on the 512 text positions of each, no optimizer",
+                "global_batch": self.SEQS, "seq_len": self.T,
+                "l2_policy": "inputs_exceed_l2",
+                "parallelism": f"tp{self.world}: column / row parallel attention + MLP, 2 NCCL all-reduces per layer forward and "
+                               "2 backward (north_star: 'a single NCCL allreduce over NVLink per layer' per block)"}
+
+    def extra(self):
+        return {"kernel_breakdown": self.breakdown, "scaling": "strong"}
+
+
 class Cfg1Workload:
     """BASELINE cfg 1 ("single 224x224 image + 16-token prompt, ViT-B + 1-layer LLM stub, CPU reference fwd"): ViT-B-size
     InternViT -> mlp2x_gelu -> 1-layer Llama -> [EMB] gather -> whole Grounding-DINO stage (Swin backbone, 6 + 6 layers,
@@ -1103,6 +1172,67 @@ def tp_extra(rank, world, device, steps=10, warmup=3):
                 "frac_of_sustained_bf16_peak": flops / world / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]})
     del wl
     torch.cuda.empty_cache()
+    try:
+        res["train"] = tp_train_extra(rank, world, device)
+    except Exception as e:                                  # evidence, never a dependency of the line
+        res["train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+    return res
+
+
+def tp_train_extra(rank, world, device, steps=5, warmup=2):
+    """cfg 5 fwd+bwd under the same launch: (1) parity of the tensor-parallel loss / input gradient against the unsharded
+    training path on a 3-layer model, (2) the llm_tp_train workload (Vicuna-7B, 8 x 2048 tokens per step for the job)."""
+    import torch
+    import torch.distributed as dist
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from visionllm_b200 import tp_train
+    from visionllm_b200.llama import B200LlamaForCausalLM
+    from visionllm_b200.train import B200LlamaForCausalLMTrain
+    cfg = LlamaConfig(hidden_size=1024, intermediate_size=2816, num_hidden_layers=3, num_attention_heads=8,
+                      num_key_value_heads=8, vocab_size=1024, rms_norm_eps=1e-5, max_position_embeddings=1024)
+    torch.manual_seed(0)
+    sd = {k: v.to(torch.bfloat16) for k, v in LlamaForCausalLM(cfg).state_dict().items()}
+    B, T = 2, 512
+    gen = torch.Generator().manual_seed(1)
+    emb = (torch.randn(B, T, 1024, generator=gen) * 0.5).bfloat16().to(device)
+    labels = torch.randint(0, 1024, (B, T), generator=gen).to(device)
+    labels[:, :200] = -100
+    single = B200LlamaForCausalLM(cfg)
+    single.load_state_dict({k: v.float() for k, v in sd.items()})
+    single = single.to(device, torch.bfloat16)
+    e1 = emb.clone().requires_grad_(True)
+    l1, _, _ = B200LlamaForCausalLMTrain(single)(e1, labels)
+    l1.backward()
+    shards = tp_train.shard_for_training({k: v.to(device) for k, v in sd.items()}, cfg, rank, world)
+    e2 = emb.clone().requires_grad_(True)
+    l2, _, _ = tp_train.TPLlamaTrain(cfg, shards)(e2, labels)
+    l2.backward()
+    rel = lambda a, b: float(torch.linalg.norm(a.float() - b.float()) / torch.linalg.norm(b.float()))  # noqa: E731
+    t = torch.tensor([abs(float(l2) - float(l1)) / abs(float(l1)), rel(e2.grad, e1.grad)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"parity": {"what": f"{world}-way tensor-parallel fwd+bwd (3-layer Llama 1024/8x128, 2 x 512 tokens) vs the unsharded "
+                              "training path on the same weights: relative loss difference, rel_l2 of d loss / d inputs_embeds; "
+                              "max over ranks",
+                      "loss_rel_diff": float(t[0]), "dinputs_rel_l2": float(t[1]), "ok": bool(t[0] < 5e-3 and t[1] < 3e-2)}}
+    del single, shards
+    torch.cuda.empty_cache()
+    wl = LlmTpTrainWorkload(rank=rank, world=world, device=device)
+    wl.setup()
+    for _ in range(warmup):
+        wl.step_device()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        wl.step_device()
+    e1_.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1_), dist, "cuda") / steps
+    tokens = wl.SEQS * wl.T
+    res.update({"metric": wl.metric, "value": tokens / (ms * 1e-3), "unit": wl.unit, "ms_per_step": ms, "steps": steps,
+                "warmup": warmup, "scaling": "strong", "config": wl.config(), "loss": float(wl.out)})
+    del wl
     return res
 
 
@@ -1110,7 +1240,7 @@ WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "msda_encoder_bf16": MsdaEncod
              "msda_encoder_pairs": MsdaEncoderPairsWorkload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
              "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload,
              "llm_tp": LlmTpWorkload, "internimage_h": InternImageHWorkload, "cfg1_forward": Cfg1Workload,
-             "llm_train": LlmTrainWorkload}
+             "llm_train": LlmTrainWorkload, "llm_tp_train": LlmTpTrainWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
 
@@ -1325,7 +1455,8 @@ def _cpu_llm_train(steps, warmup):
 
 _CPU = {"msda_encoder": _cpu_msda_encoder, "msda_encoder_bf16": _cpu_msda_encoder, "msda_encoder_pairs": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
         "gdino_stage": _cpu_msda_encoder,
-        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp, "internimage_h": _cpu_internimage_h, "cfg1_forward": _cpu_cfg1, "llm_train": _cpu_llm_train}
+        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp, "internimage_h": _cpu_internimage_h, "cfg1_forward": _cpu_cfg1, "llm_train": _cpu_llm_train,
+        "llm_tp_train": _cpu_llm_train}
 
 
 def cpu_baseline(name):
@@ -1348,7 +1479,7 @@ def run_reference_arm(name, n_gpus, steps, warmup):
             "steps": run_steps, "steps_requested": steps, "warmup": run_warm, "ms_per_step": cb["ms_per_step"],
             "extrapolated": cb["extrapolated"], "sample_ms_per_step": cb.get("sample_ms_per_step"), "wall_s": wall,
             "higher_is_better": True,
-            "scaling": "strong" if name == "llm_tp" else "weak", "vs_baseline": None,
+            "scaling": "strong" if name in ("llm_tp", "llm_tp_train") else "weak", "vs_baseline": None,
             "dtype": "f32 (torch CPU; the GPU arm computes in " + wl.dtype + ")",
             "data": "synthetic", "config": {"workload": cb["sample"]}, "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
