@@ -112,6 +112,17 @@ int vllm_msda_set_variant(int variant);
  * window path for bf16 values, variants 1-4 for fp32.  vllm_msda_set_window: tuning knob (process-global) -- level-0
  * patch height / width in pixels and level-0 halo; 0 = default (8 x 16, halo 8 for bf16 rows; 8 x 8, halo 6 for fp32). */
 int vllm_msda_set_window(int patch_h, int patch_w, int halo0);
+/* The deformable-attention MODULE's inner part in one kernel (GroundingDinoMultiscaleDeformableAttention.forward,
+ * modeling_ov_grounding_dino_mask_dn.py:742-776, encoder shape, 4 levels x 4 points, channels 32): qp [batch, num_query,
+ * ld_qp] bf16 = the packed sampling_offsets | attention_weights projection output (M*K*2 offsets then M*K logits per row),
+ * reference_points [batch, num_query, num_levels, 2] fp32.  Does the softmax over the 16 logits, offset / (W, H) in bf16,
+ * reference + offset in fp32 with torch's exact arithmetic, then the window gather of vllm_msda_forward_bf16v; optionally
+ * writes the bf16 attention weights [batch, num_query, M, 16] the module returns.  VLLM_EUNSUPPORTED when the window
+ * path does not apply (the caller keeps the unfused path). */
+int vllm_msda_forward_fused_bf16(const void* value, const int64_t* level_start_index, const void* qp, int ld_qp,
+                                 const float* reference_points, void* out, int out_bf16, void* attn_weights_out, int batch,
+                                 int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                                 const int64_t* host_shapes_hint, void* stream);
 
 /* ---- DCNv3 forward (InternImage core op) ------------------------------------------
  * Replaces `dcnv3_forward` of the reference extension module `DCNv3`

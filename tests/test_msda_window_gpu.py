@@ -153,3 +153,48 @@ def test_full_size_encoder_shape_properties():
     ones = torch.ones_like(value)
     inner = loc.clamp(0.1, 0.9).contiguous()
     assert (ext.ms_deform_attn_forward(ones, shapes, lsi, inner, attw, 64) - 1.0).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("pyr", ["pow2", "npot"])
+def test_fused_module_input_is_bit_identical_to_the_torch_glue(pyr):
+    """GroundingDinoMultiscaleDeformableAttention (encoder self-attention, bf16): softmax over the 16 logits, offset /
+    (W, H) in bf16 and reference + offset in fp32 computed INSIDE the gather kernel must reproduce the five torch
+    elementwise kernels of the unfused path bit for bit -- output and returned attention weights."""
+    from types import SimpleNamespace
+    import visionllm_b200.msda as msda_ext
+    from visionllm_b200.gdino import GroundingDinoMultiscaleDeformableAttention
+    shapes_l = PYRAMIDS[pyr]
+    cfg = SimpleNamespace(d_model=256, num_feature_levels=4, disable_custom_kernels=False)
+    torch.manual_seed(0)
+    m = GroundingDinoMultiscaleDeformableAttention(cfg, num_heads=8, n_points=4)
+    with torch.no_grad():
+        m.attention_weights.weight.normal_(0, 0.05); m.attention_weights.bias.normal_(0, 0.5)
+        m.sampling_offsets.weight.normal_(0, 0.02)
+    m = m.to("cuda", torch.bfloat16).eval()
+    shapes = torch.tensor(shapes_l, dtype=torch.int64, device="cuda")
+    msda_ext.attach_host_shapes(shapes, shapes_l)
+    lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    B = 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, S, 256, device="cuda", generator=g).bfloat16()
+    pos = (torch.randn(B, S, 256, device="cuda", generator=g) * 0.3).bfloat16()
+    refs = []
+    for (H, W) in shapes_l:
+        ys, xs = torch.meshgrid(torch.arange(H, device="cuda", dtype=torch.float32),
+                                torch.arange(W, device="cuda", dtype=torch.float32), indexing="ij")
+        refs.append(torch.stack(((xs + 0.5) / W, (ys + 0.5) / H), -1).reshape(-1, 2))
+    ref = torch.cat(refs, 0)[None, :, None, :].repeat(B, 1, 4, 1) * torch.tensor([[0.9, 0.8]], device="cuda").view(1, 1, 1, 2)
+    mask = torch.ones(B, S, dtype=torch.bool, device="cuda")
+    mask[1, -7:] = False
+    kw = dict(hidden_states=x, attention_mask=mask, encoder_hidden_states=x, position_embeddings=pos,
+              reference_points=ref.contiguous(), spatial_shapes=shapes, level_start_index=lsi)
+    a_out, a_w = m(**kw)
+    msda_ext.FUSED_MODULE_INPUT = False
+    try:
+        b_out, b_w = m(**kw)
+    finally:
+        msda_ext.FUSED_MODULE_INPUT = True
+    assert a_w.dtype == torch.bfloat16 and a_w.shape == b_w.shape == (B, S, 8, 4, 4)
+    assert torch.equal(a_w, b_w)
+    assert torch.equal(a_out, b_out), (a_out.float() - b_out.float()).abs().max().item()

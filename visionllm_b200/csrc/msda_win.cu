@@ -69,12 +69,27 @@ constexpr int WIN_META_ROW = 32 + 2;    // int2 per corner row (32 samples + pad
 
 }  // namespace
 
+// Fused module input (QP = true; the GDINO deformable-attention MODULE rather than the bare operator, gd.py:706-784): the
+// kernel takes the packed `sampling_offsets | attention_weights` projection output qp [N, Lq, ld] (bf16: M*K*2 offsets, then
+// M*K logits) and the 2-d reference points [N, Lq, L, 2] (fp32) and does in phase 1 what the reference does in five
+// elementwise torch kernels -- softmax over the K = 16 logits of a (query, head) (ATen's softmax_warp_forward: fp32 exp /
+// butterfly sum / divide, result rounded to bf16), offset / (W_l, H_l) in bf16 (ATen div with the int64 normaliser cast to
+// bf16), reference point + offset in fp32 -- bit for bit, then the same index arithmetic.  The attention weights the module
+// returns are written as a side output.
+struct MsdaQp {
+  const __nv_bfloat16* qp;       // [N, Lq, ld]
+  const float* ref;              // [N, Lq, L, 2]
+  __nv_bfloat16* attw_out;       // [N, Lq, M, K] or null
+  int ld, n_off;
+};
+
 // NW warps per CTA.  KC > 0: compile-time K = L*P (PC = P).
-template <typename ValT, typename OutT, int NW, int KC, int PC>
+template <typename ValT, typename OutT, int NW, int KC, int PC, bool QP = false>
 __global__ void __launch_bounds__(NW * 32)
 msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __restrict__ value,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc, const float* __restrict__ attw,
-                    OutT* __restrict__ out, int S, int M, int Lq, int P_rt, const __grid_constant__ MsdaWin wp) {
+                    OutT* __restrict__ out, int S, int M, int Lq, int P_rt, const __grid_constant__ MsdaWin wp,
+                    const MsdaQp fq) {
   constexpr int D = 32;
   constexpr bool HALF = sizeof(ValT) == 2;
   constexpr int VB = (int)sizeof(ValT);
@@ -163,10 +178,42 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
 #pragma unroll
       for (int c = 0; c < 4; ++c) meta[c] = make_int2(wp.zero_off, 0);   // weight 0 x the zero row: contributes exactly 0,
                                                                          // and a NaN the reference never touches cannot leak
-      if (q >= 0) {
+      float2 xy = make_float2(0.f, 0.f);
+      if constexpr (QP) {
+        // every lane takes part in the softmax shuffles (idle lanes carry logit 0); K == 16: two pairs per warp
+        float lg = 0.f;
+        uint32_t o2 = 0u;
+        float2 rp = make_float2(0.f, 0.f);
+        if (q >= 0) {
+          const __nv_bfloat16* row = fq.qp + ((size_t)b * Lq + q) * fq.ld;
+          o2 = *reinterpret_cast<const uint32_t*>(row + (m * K + s1) * 2);
+          lg = __bfloat162float(row[fq.n_off + m * K + s1]);
+          rp = *reinterpret_cast<const float2*>(fq.ref + (((size_t)b * Lq + q) * L + l1) * 2);
+        }
+        float mx = lg;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = expf(lg - mx);
+        float sum = e;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const __nv_bfloat16 wb = __float2bfloat16_rn(e / sum);
+        aw = __bfloat162float(wb);
+        if (q >= 0) {
+          if (fq.attw_out) fq.attw_out[(((size_t)b * Lq + q) * M + m) * K + s1] = wb;
+          const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&o2);
+          const float Wb = __bfloat162float(__float2bfloat16_rn((float)wp.W[l1]));
+          const float Hb = __bfloat162float(__float2bfloat16_rn((float)wp.H[l1]));
+          const float ox = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(__low2float(ob), Wb)));
+          const float oy = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(__high2float(ob), Hb)));
+          xy = make_float2(__fadd_rn(rp.x, ox), __fadd_rn(rp.y, oy));
+        }
+      } else if (q >= 0) {
         const size_t si = (((size_t)b * Lq + q) * M + m) * K + s1;
-        const float2 xy = ld_stream_f2(loc + 2 * si);
+        xy = ld_stream_f2(loc + 2 * si);
         aw = ld_stream_f1(attw + si);
+      }
+      if (q >= 0) {
         const int H = wp.H[l1], W = wp.W[l1];
         ge = msda_geom<float>(xy.x, xy.y, H, W);
         if (ge.mask & 1) {
@@ -430,12 +477,54 @@ int msda_launch_window(const ValT* value, const int64_t* lsi, const float* loc, 
       if (err != cudaSuccess) return (int)err;
       configured = 112 * 1024;
     }
-    kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, loc, attw, out, S, M, Lq, P, e->wp);
+    kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, loc, attw, out, S, M, Lq, P, e->wp, MsdaQp{});
     VLLM_CHECK_LAUNCH();
     return VLLM_OK;
   };
   if (L == 4 && P == 4) return launch(msda_fwd_win_kernel<ValT, OutT, NW, 16, 4>);
   return launch(msda_fwd_win_kernel<ValT, OutT, NW, 0, 0>);
+}
+
+// fused module input (bf16 value, K == 16 only); returns 1 when the window path does not apply
+template <typename OutT>
+static int launch_window_qp(const __nv_bfloat16* value, const int64_t* lsi, const MsdaQp& fq, OutT* out, int N, int S, int M, int L,
+                            int Lq, int P, const int64_t* host_shapes, cudaStream_t st) {
+  constexpr int NW = 16;
+  if (!host_shapes || Lq != S || L != 4 || P != 4 || N > 65535) return 1;
+  const WinCacheEntry* e = window_for<__nv_bfloat16>(value, host_shapes, N, S, M, L);
+  if (!e) return 1;
+  dim3 grid((unsigned)(e->wp.RX * e->wp.RY * M), (unsigned)N);
+  auto kern = msda_fwd_win_kernel<__nv_bfloat16, OutT, NW, 16, 4, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (err != cudaSuccess) return (int)err;
+    configured = true;
+  }
+  kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, nullptr, nullptr, out, S, M, Lq, P, e->wp, fq);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+extern "C" int vllm_msda_forward_fused_bf16(const void* value, const int64_t* level_start_index, const void* qp, int ld_qp,
+                                            const float* reference_points, void* out, int out_bf16, void* attn_weights_out,
+                                            int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                                            int num_query, int num_point, const int64_t* host_shapes_hint, void* stream) {
+  if (batch < 0 || spatial_size <= 0 || num_heads <= 0 || num_query < 0) return VLLM_EINVAL;
+  if ((long long)batch * num_query == 0) return VLLM_OK;
+  if (!value || !level_start_index || !qp || !reference_points || !out) return VLLM_EINVAL;
+  const int K = num_levels * num_point;
+  if (channels != 32 || num_levels != 4 || num_point != 4 || ld_qp < num_heads * K * 3 || (ld_qp & 1)) return VLLM_EUNSUPPORTED;
+  if (!vllm_aligned(value, 16) || !vllm_aligned(qp, 4) || !vllm_aligned(reference_points, 8)) return VLLM_EALIGN;
+  if ((long long)spatial_size * num_heads * channels * 4 > INT_MAX) return VLLM_EUNSUPPORTED;
+  MsdaQp fq{(const __nv_bfloat16*)qp, reference_points, (__nv_bfloat16*)attn_weights_out, ld_qp, num_heads * K * 2};
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* v = (const __nv_bfloat16*)value;
+  const int r = out_bf16 ? launch_window_qp<__nv_bfloat16>(v, level_start_index, fq, (__nv_bfloat16*)out, batch, spatial_size,
+                                                           num_heads, num_levels, num_query, num_point, host_shapes_hint, st)
+                         : launch_window_qp<float>(v, level_start_index, fq, (float*)out, batch, spatial_size, num_heads,
+                                                   num_levels, num_query, num_point, host_shapes_hint, st);
+  return r == 1 ? VLLM_EUNSUPPORTED : r;
 }
 
 template int msda_launch_window<float, float>(const float*, const int64_t*, const float*, const float*, float*, int, int, int,

@@ -90,6 +90,14 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
         w, b = self._packed_query_proj(hidden_states.dtype)
         qp = ops.linear(hidden_states, w, bias=b)                    # offsets | weights in one GEMM
         n_off = M * L * P * 2
+        if (reference_points.shape[-1] == 2 and Lq == S and value.dtype == torch.bfloat16 and P == 4
+                and self.output_proj.weight.dtype == torch.bfloat16):
+            # encoder self-attention: softmax / offset normalisation / reference add run inside the gather kernel
+            fused = msda_ext.ms_deform_attn_forward_fused(value.view(B, S, M, D), spatial_shapes, level_start_index, qp,
+                                                          reference_points, self.output_proj.weight.dtype)
+            if fused is not None:
+                out, attention_weights = fused
+                return ops.linear(out, self.output_proj.weight, bias=self.output_proj.bias), attention_weights
         sampling_offsets = qp[..., :n_off].reshape(B, Lq, M, L, P, 2)
         attention_weights = F.softmax(qp[..., n_off:].reshape(B, Lq, M, L * P), -1).view(B, Lq, M, L, P)
         if reference_points.shape[-1] == 2:

@@ -161,6 +161,40 @@ def ms_deform_attn_forward_bf16(value, spatial_shapes, level_start_index, sampli
     return out
 
 
+FUSED_MODULE_INPUT = True       # gdino.py: encoder-shape modules hand the packed projection output to the kernel
+
+
+def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, qp, reference_points, out_dtype=None,
+                                 want_weights=True):
+    """The inner part of `GroundingDinoMultiscaleDeformableAttention.forward` (gd.py:742-776) in ONE kernel for the encoder
+    shape: value bf16 [N, S, M, 32], qp bf16 [N, Lq, >= 3*M*16] = packed offsets | logits of the (query-side) projection,
+    reference_points fp32 [N, Lq, 4, 2].  Returns (out [N, Lq, M*32], attention_weights bf16 [N, Lq, M, 4, 4] or None), or
+    None when the fused path does not apply (caller keeps the unfused torch ops + ms_deform_attn_forward_bf16) -- both
+    paths give bit-identical results."""
+    if not FUSED_MODULE_INPUT or value.dtype != torch.bfloat16 or qp.dtype != torch.bfloat16 or value.dim() != 4:
+        return None
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    if (D != 32 or L != 4 or qp.dim() != 3 or qp.shape[1] != S or qp.shape[0] != N or qp.stride(2) != 1
+            or qp.stride(0) != qp.shape[1] * qp.stride(1) or qp.shape[2] < M * 16 * 3
+            or reference_points.shape != (N, S, L, 2) or not value.is_contiguous()):
+        return None
+    ref = reference_points.to(torch.float32).contiguous()
+    out_dtype = out_dtype or torch.bfloat16
+    out = torch.empty((N, S, M * D), dtype=out_dtype, device=value.device)
+    attw = torch.empty((N, S, M, L, 4), dtype=torch.bfloat16, device=value.device) if want_weights else None
+    hs = _host_shapes(spatial_shapes)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().vllm_msda_forward_fused_bf16(
+            value.data_ptr(), level_start_index.data_ptr(), qp.data_ptr(), qp.stride(1), ref.data_ptr(), out.data_ptr(),
+            1 if out_dtype == torch.bfloat16 else 0, attw.data_ptr() if attw is not None else None, N, S, M, D, L, S, 4,
+            hs.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if rc == -2:                                                  # VLLM_EUNSUPPORTED: window path not applicable
+        return None
+    _lib.check(rc, "ms_deform_attn_forward_fused")
+    return out, attw
+
+
 # GDINO module policy (gdino.py): use the paired-row layout when the queries are (about) as many as the value pixels.
 PAIRS_FOR_DENSE_QUERIES = False
 
