@@ -134,8 +134,12 @@ def test_fused_det_topk_equals_torch_primitives(Q, K, ld, topk):
     from visionllm_b200 import gdino_heads as H
     g = torch.Generator(device="cuda").manual_seed(Q + K)
     B = 3
-    logits = torch.randn(B, Q, ld, device="cuda", generator=g) * 3 - 2
-    logits[:, :, K:] = float("-inf")                      # the -inf class padding of the contrastive head (gd.py:1415-1428)
+    # distinct probabilities (torch.topk leaves the order of ties unspecified; ties have their own test below): a permuted
+    # grid of logits whose sigmoid values are >= 40 fp32 ulps apart
+    logits = torch.full((B, Q, ld), float("-inf"), device="cuda")   # -inf = the class padding of the contrastive head (gd.py:1415-1428)
+    for b in range(B):
+        perm = torch.randperm(Q * K, device="cuda", generator=g)
+        logits[b, :, :K] = torch.linspace(-8.0, 4.0, Q * K, device="cuda")[perm].view(Q, K)
     boxes = torch.rand(B, Q, 4, device="cuda", generator=g)
     tsz = [(480, 640), (1024, 1024), (333, 500)]
     tv, ti, tb, tl, bx = _ref_det(logits, boxes, tsz, K, topk)

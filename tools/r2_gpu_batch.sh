@@ -3,7 +3,7 @@
 # profiles/ afterwards.   usage: bash tools/r2_gpu_batch.sh [tag]
 tag=${1:-a}
 mkdir -p gpurun_out
-echo "== gpu tests"; timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 | tee gpurun_out/r2_gputests_$tag.log | tail -25
+echo "== gpu tests"; timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -80 | tee gpurun_out/r2_gputests_$tag.log | tail -60
 echo "== msda window sweep"; timeout 300 python tools/msda_win_sweep.py --out gpurun_out/r2_msda_window_sweep.json 2>&1 | tail -20
 echo "== msda vs reference kernel"; timeout 200 python tools/msda_ref_bench.py --out gpurun_out/r2_msda_vs_reference_kernel.json > /dev/null 2>gpurun_out/msda_ref.err; tail -3 gpurun_out/msda_ref.err
 echo "== bench cfg1"; timeout 300 python bench.py --workload cfg1_forward --steps 20 --warmup 5 > gpurun_out/r2_bench_cfg1_$tag.json 2>gpurun_out/cfg1.err; tail -c 600 gpurun_out/r2_bench_cfg1_$tag.json; tail -3 gpurun_out/cfg1.err
