@@ -513,15 +513,28 @@ class GdinoHeadWorkload:
             self.msda_value_bytes = 2
             return r
 
+        orig_fused = msda_mod.ms_deform_attn_forward_fused
+
+        def timed_fused(*a, **k):                             # encoder modules: the fused module-input kernel
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig_fused(*a, **k); e1.record()
+            if r is not None:
+                msda_ms.append((e0, e1, a[0].shape, (a[0].shape[0], a[0].shape[1])))
+                self.msda_value_bytes = 2
+                self.msda_fused = True
+            return r
+
         import visionllm_b200.gdino as gd_mod
         gd_mod.msda_ext.ms_deform_attn_forward = timed_msda
         gd_mod.msda_ext.ms_deform_attn_forward_bf16 = timed_msda16
+        gd_mod.msda_ext.ms_deform_attn_forward_fused = timed_fused
         try:
             self.step_device()
             torch.cuda.synchronize()
         finally:
             gd_mod.msda_ext.ms_deform_attn_forward = orig
             gd_mod.msda_ext.ms_deform_attn_forward_bf16 = orig16
+            gd_mod.msda_ext.ms_deform_attn_forward_fused = orig_fused
         prof, ops.PROFILE = ops.PROFILE, None
         agg = {}
         for name, fl, by, e0, e1, *_tag in prof:
@@ -534,12 +547,14 @@ class GdinoHeadWorkload:
         self.breakdown["msda_encoder"] = {"launches": len(enc_ms), "ms": sum(enc_ms)}
         self.breakdown["msda_decoder"] = {"launches": len(dec_ms), "ms": sum(dec_ms)}
         self.msda_enc_ms = sum(enc_ms) / max(1, len(enc_ms))
-        return self.msda_enc_ms
+        return self.msda_enc_ms if enc_ms else float("nan")
 
     def roofline(self, kern_ms, peaks):
         S = self.src.shape[1]
         vb = getattr(self, "msda_value_bytes", 4)            # bf16 value + bf16 out when the module takes the fast mode
-        alg = (S * 256 * vb + (S * 8 * 16 * 2 + S * 8 * 16) * 4 + S * 256 * vb) * self.N
+        # value + (sampling_loc + attn_weight fp32 | fused: the bf16 offsets|logits projection row + reference points) + out
+        side = (S * 8 * 16 * 3 * 2 + S * 4 * 2 * 4) if getattr(self, "msda_fused", False) else (S * 8 * 16 * 2 + S * 8 * 16) * 4
+        alg = (S * 256 * vb + side + S * 256 * vb) * self.N
         ach = alg / (kern_ms * 1e-3) / 1e9
         return {"kernel": "msda_fwd_warp_kernel (encoder launches inside the GDINO step)", "bound": "hbm",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",

@@ -112,6 +112,9 @@ int vllm_msda_set_variant(int variant);
  * window path for bf16 values, variants 1-4 for fp32.  vllm_msda_set_window: tuning knob (process-global) -- level-0
  * patch height / width in pixels and level-0 halo; 0 = default (8 x 16, halo 8 for bf16 rows; 8 x 8, halo 6 for fp32). */
 int vllm_msda_set_window(int patch_h, int patch_w, int halo0);
+/* Window fill of the encoder kernel: 0 (default) = cooperative 16-byte cp.async by the CTA's 512 threads, 1 = one TMA box
+ * (cp.async.bulk.tensor.5d) per level.  Same results; the TMA form is request-rate bound on 64-byte rows. */
+int vllm_msda_set_window_fill(int tma);
 /* The deformable-attention MODULE's inner part in one kernel (GroundingDinoMultiscaleDeformableAttention.forward,
  * modeling_ov_grounding_dino_mask_dn.py:742-776, encoder shape, 4 levels x 4 points, channels 32): qp [batch, num_query,
  * ld_qp] bf16 = the packed sampling_offsets | attention_weights projection output (M*K*2 offsets then M*K logits per row),

@@ -15,7 +15,7 @@ SEEDS = dict(vit=7101, bridge=7102, llm=7103, emb=7104, gdino=7105, data=7106)
 
 def swin_config():
     from transformers import SwinConfig
-    return SwinConfig(image_size=224, embed_dim=48, depths=[2, 2, 2, 2], num_heads=[3, 6, 12, 24], window_size=7,
+    return SwinConfig(image_size=224, embed_dim=96, depths=[2, 2, 2, 2], num_heads=[3, 6, 12, 24], window_size=7,
                       out_features=["stage1", "stage2", "stage3", "stage4"])
 
 

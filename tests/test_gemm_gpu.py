@@ -199,7 +199,9 @@ def test_gemm_tn_dgrad_wgrad_match_torch(T, out_f, in_f, variant):
         dx = ops.gemm_tn(dy, w, b_mn=True)
         dw = ops.gemm_tn(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32)
         y = ops.gemm_tn(x, w)                                            # both K-major == ops.linear
-        at = ops.gemm_tn(x.t().contiguous(), w, a_mn=True)               # MN-major A alone
+        xt = torch.zeros((in_f, (T + 7) // 8 * 8), dtype=torch.bfloat16, device="cuda")   # [K, M] with a 16-byte row pitch
+        xt[:, :T] = x.t()
+        at = ops.gemm_tn(xt[:, :T], w, a_mn=True)                       # MN-major A alone
     finally:
         _lib.lib().vllm_gemm_set_variant(0)
     ref_dx = dy.float() @ w.float()

@@ -36,13 +36,14 @@ def enc_case(shapes_l, N, M, sigma, seed, outlier_frac=0.02, P=4, valid_ratio=No
     return value, shapes, lsi, loc, attw
 
 
-def run(value, shapes, lsi, loc, attw, variant=0, window=(0, 0, 0), out_dtype=None):
+def run(value, shapes, lsi, loc, attw, variant=0, window=(0, 0, 0), out_dtype=None, tma_fill=False):
     """value fp32 -> ms_deform_attn_forward; value bf16 -> ms_deform_attn_forward_bf16(out_dtype)."""
     import visionllm_b200.msda as ext
     from visionllm_b200 import _lib
     L_ = _lib.lib()
     L_.vllm_msda_set_variant(variant)
     L_.vllm_msda_set_window(*window)
+    L_.vllm_msda_set_window_fill(1 if tma_fill else 0)
     try:
         if value.dtype == torch.float32:
             return ext.ms_deform_attn_forward(value, shapes, lsi, loc, attw, 64)
@@ -50,6 +51,7 @@ def run(value, shapes, lsi, loc, attw, variant=0, window=(0, 0, 0), out_dtype=No
     finally:
         L_.vllm_msda_set_variant(0)
         L_.vllm_msda_set_window(0, 0, 0)
+        L_.vllm_msda_set_window_fill(0)
 
 
 def oracle(value, shapes, lsi, loc, attw):
@@ -76,6 +78,8 @@ def test_window_kernel_vs_oracle_and_bit_identical_to_global_path(pyr, mode):
     win = run(value, shapes, lsi, loc, attw, out_dtype=od)
     glob = run(value, shapes, lsi, loc, attw, variant=32 if mode != "f32" else 4, out_dtype=od)
     assert torch.equal(win, glob), (win.float() - glob.float()).abs().max().item()
+    # the two window-fill mechanisms (cooperative cp.async, default; one TMA box per level) give the same bits
+    assert torch.equal(run(value, shapes, lsi, loc, attw, out_dtype=od, tma_fill=True), win)
     ref = oracle(value, shapes, lsi, loc, attw)
     scale = ref.abs().max().item()
     if win.dtype == torch.float32:

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "vllm_msda_sample_indices_f32": (ci, [vp, vp, vp, cll, ci, ci, vp]),
     "vllm_msda_set_variant": (ci, [ci]),
     "vllm_msda_set_window": (ci, [ci, ci, ci]),
+    "vllm_msda_set_window_fill": (ci, [ci]),
     "vllm_msda_forward_fused_bf16": (ci, [vp, vp, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]),
     "vllm_seq_index": (ci, [vp, ci, ci, vp, vp, ci, cll, ci, cll, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]),
     "vllm_assemble_embeds_bf16": (ci, [vp] * 8 + [cll, ci, vp]),

@@ -33,6 +33,7 @@ struct MsdaWin {
   int q_start[MSDA_WIN_LEVELS];          // first query (== first pixel) of the level
   int BW[MSDA_WIN_LEVELS], BH[MSDA_WIN_LEVELS], halo[MSDA_WIN_LEVELS];
   int win_off[MSDA_WIN_LEVELS];          // byte offset of the level's window in dynamic shared memory
+  int fill_tma;                          // 1: windows filled by TMA boxes; 0: by cooperative cp.async (default, see header)
   int zero_off;                          // a 128-byte all-zero row behind the windows: target of out-of-range samples
   int tx_bytes;                          // sum of the box bytes (what the mbarrier waits for)
 };
@@ -57,6 +58,14 @@ __device__ __forceinline__ int region_bound(int k, int P, int Wl, int W0) {
   const unsigned num = 2u * (unsigned)(k * P) * (unsigned)Wl + (unsigned)W0 - 1u;   // n + d - 1 with n = 2kP*Wl - W0, d = 2*W0
   const unsigned b = num / (2u * (unsigned)W0);
   return b > (unsigned)Wl ? Wl : (int)b;
+}
+
+// 16-byte asynchronous copy global -> shared, zero-filled when `bytes` == 0 (the operator's zero padding)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -133,13 +142,15 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
     if (lane < L) s_cum[lane + 1] = cum;
     if (lane == 0) {
       s_cum[0] = 0;
-      const uint32_t bar0 = tc::smem_u32(&s_bar);
-      tc::mbar_init(bar0, 1);
-      tc::mbar_fence_init();
-      tc::mbar_arrive_expect_tx(bar0, (uint32_t)wp.tx_bytes);
+      if (wp.fill_tma) {
+        const uint32_t bar0 = tc::smem_u32(&s_bar);
+        tc::mbar_init(bar0, 1);
+        tc::mbar_fence_init();
+        tc::mbar_arrive_expect_tx(bar0, (uint32_t)wp.tx_bytes);
+      }
     }
     __syncwarp();
-    if (lane < L)                                          // one TMA box per level (the init above is ordered by __syncwarp)
+    if (wp.fill_tma && lane < L)                           // one TMA box per level (the init above is ordered by __syncwarp)
       tma_load_5d(tc::smem_u32(win + wp.win_off[lane]), &maps.m[lane], tc::smem_u32(&s_bar), 0, m, x0 - 1 - wp.halo[lane],
                   y0 - 1 - wp.halo[lane], b);
   }
@@ -148,6 +159,27 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
   __syncthreads();
   const int nq = s_cum[L];
   const uint32_t bar = tc::smem_u32(&s_bar);
+  if (!wp.fill_tma) {
+    // Cooperative window fill: 16-byte cp.async per (pixel, chunk), zero-filled outside the map.  Measured: a TMA box whose
+    // innermost run is one 64-byte (pixel, head) row is request-rate bound (~5 B / clock / SM), the same bytes through
+    // 512 threads of cp.async arrive an order of magnitude faster; the copies fly while phase 1 of the first pass runs.
+    constexpr int CPR = ROWB / 16;
+    const uint32_t wbase = tc::smem_u32(win);
+    for (int l = 0; l < L; ++l) {
+      const int BWl = wp.BW[l], Wl = wp.W[l], Hl = wp.H[l], oxl = s_ox[l], oyl = s_oy[l];
+      const int chunks = BWl * wp.BH[l] * CPR;
+      const char* lvl = reinterpret_cast<const char*>(value + ((size_t)b * S + wp.q_start[l]) * MD + m * D);
+      for (int c = threadIdx.x; c < chunks; c += NW * 32) {
+        const int px = c / CPR, cc = c - px * CPR;
+        const int wy = px / BWl, wx = px - wy * BWl;
+        const int y = oyl + wy, x = oxl + wx;
+        const bool ok = y >= 0 && y < Hl && x >= 0 && x < Wl;
+        const char* src = ok ? lvl + ((size_t)y * Wl + x) * MD * VB + cc * 16 : lvl;
+        cp_async16(wbase + wp.win_off[l] + px * ROWB + cc * 16, src, ok ? 16 : 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   bool landed = false;
 
   // phase-2 roles
@@ -159,37 +191,59 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
   const int g1 = lane / K, s1 = lane - g1 * K;
   const int l1 = s1 / P;
 
+  // per-lane inputs of one pass (this lane's sample of this lane's (query, head) pair), fetched one pass AHEAD so that the
+  // global-memory latency of sampling_loc / attn_weight (or of the packed projection row) hides behind the gather
+  struct Inp { int q; float a, b, c, d; uint32_t o2; };
+  auto fetch = [&](int t0) -> Inp {
+    Inp in; in.q = -1; in.a = in.b = in.c = in.d = 0.f; in.o2 = 0u;
+    const int t = t0 + g1;
+    if (g1 < G && t < nq) {
+      int lq = 0;
+      while (lq + 1 < L && t >= s_cum[lq + 1]) ++lq;
+      const int r = t - s_cum[lq];
+      const int ry = r / s_nx[lq], rx = r - ry * s_nx[lq];
+      in.q = wp.q_start[lq] + (s_by0[lq] + ry) * wp.W[lq] + s_bx0[lq] + rx;
+      if constexpr (QP) {
+        const __nv_bfloat16* row = fq.qp + ((size_t)b * Lq + in.q) * fq.ld;
+        in.o2 = *reinterpret_cast<const uint32_t*>(row + (m * K + s1) * 2);
+        in.c = __bfloat162float(row[fq.n_off + m * K + s1]);                       // logit
+        const float2 rp = *reinterpret_cast<const float2*>(fq.ref + (((size_t)b * Lq + in.q) * L + l1) * 2);
+        in.a = rp.x; in.b = rp.y;
+      } else {
+        const size_t si = (((size_t)b * Lq + in.q) * M + m) * K + s1;
+        const float2 xy = ld_stream_f2(loc + 2 * si);
+        in.a = xy.x; in.b = xy.y;
+        in.c = ld_stream_f1(attw + si);
+      }
+    }
+    return in;
+  };
+  Inp nxt = fetch(warp * G);
+  if (wp.fill_tma) {
+    tc::mbar_wait(bar, 0);
+  } else {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                       // every thread's copies have landed and are visible to all
+  }
+  landed = true;
+
   for (int t0 = warp * G; t0 < nq; t0 += NW * G) {
     // ---- phase 1: one lane per sample ---------------------------------------------------------
-    int q = -1;
+    const Inp in = nxt;
+    nxt = fetch(t0 + NW * G);                              // next pass's loads are in flight during this pass
+    const int q = in.q;
     MsdaGeom<float> ge; ge.mask = 0; ge.h_low = 0; ge.w_low = 0; ge.lh = 0.f; ge.lw = 0.f;
     float aw = 0.f;
     bool in_win = true;
     {
-      const int t = t0 + g1;
-      if (g1 < G && t < nq) {
-        int lq = 0;
-        while (lq + 1 < L && t >= s_cum[lq + 1]) ++lq;
-        const int r = t - s_cum[lq];
-        const int ry = r / s_nx[lq], rx = r - ry * s_nx[lq];
-        q = wp.q_start[lq] + (s_by0[lq] + ry) * wp.W[lq] + s_bx0[lq] + rx;
-      }
       int2 meta[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) meta[c] = make_int2(wp.zero_off, 0);   // weight 0 x the zero row: contributes exactly 0,
                                                                          // and a NaN the reference never touches cannot leak
-      float2 xy = make_float2(0.f, 0.f);
+      float2 xy = make_float2(in.a, in.b);
       if constexpr (QP) {
         // every lane takes part in the softmax shuffles (idle lanes carry logit 0); K == 16: two pairs per warp
-        float lg = 0.f;
-        uint32_t o2 = 0u;
-        float2 rp = make_float2(0.f, 0.f);
-        if (q >= 0) {
-          const __nv_bfloat16* row = fq.qp + ((size_t)b * Lq + q) * fq.ld;
-          o2 = *reinterpret_cast<const uint32_t*>(row + (m * K + s1) * 2);
-          lg = __bfloat162float(row[fq.n_off + m * K + s1]);
-          rp = *reinterpret_cast<const float2*>(fq.ref + (((size_t)b * Lq + q) * L + l1) * 2);
-        }
+        const float lg = in.c;
         float mx = lg;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -201,17 +255,15 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
         aw = __bfloat162float(wb);
         if (q >= 0) {
           if (fq.attw_out) fq.attw_out[(((size_t)b * Lq + q) * M + m) * K + s1] = wb;
-          const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&o2);
+          const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&in.o2);
           const float Wb = __bfloat162float(__float2bfloat16_rn((float)wp.W[l1]));
           const float Hb = __bfloat162float(__float2bfloat16_rn((float)wp.H[l1]));
           const float ox = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(__low2float(ob), Wb)));
           const float oy = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(__high2float(ob), Hb)));
-          xy = make_float2(__fadd_rn(rp.x, ox), __fadd_rn(rp.y, oy));
+          xy = make_float2(__fadd_rn(in.a, ox), __fadd_rn(in.b, oy));
         }
-      } else if (q >= 0) {
-        const size_t si = (((size_t)b * Lq + q) * M + m) * K + s1;
-        xy = ld_stream_f2(loc + 2 * si);
-        aw = ld_stream_f1(attw + si);
+      } else {
+        aw = in.c;
       }
       if (q >= 0) {
         const int H = wp.H[l1], W = wp.W[l1];
@@ -234,7 +286,6 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
     }
     const unsigned outside = __ballot_sync(0xffffffffu, !in_win);
     __syncwarp();
-    if (!landed) { tc::mbar_wait(bar, 0); landed = true; }
     // ---- phase 2 --------------------------------------------------------------------------------
     for (int g = 0; g < G; ++g) {
       const int qg = __shfl_sync(0xffffffffu, q, g * K);
@@ -365,19 +416,22 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
     }
     __syncwarp();
   }
-  if (!landed) tc::mbar_wait(bar, 0);                      // never leave with a TMA in flight into this CTA's smem
+  if (!landed && wp.fill_tma) tc::mbar_wait(bar, 0);       // never leave with a TMA in flight into this CTA's smem
 }
 
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
 static int g_win_ph = 0, g_win_pw = 0, g_win_halo = 0;      // 0: defaults; bench / tuning knob (vllm_msda_set_window)
+static int g_win_fill_tma = 0;                              // vllm_msda_set_window_fill: 0 cp.async (default), 1 TMA boxes
 
 extern "C" int vllm_msda_set_window(int patch_h, int patch_w, int halo0) {
   if (patch_h < 0 || patch_w < 0 || halo0 < 0) return VLLM_EINVAL;
   g_win_ph = patch_h; g_win_pw = patch_w; g_win_halo = halo0;
   return VLLM_OK;
 }
+
+extern "C" int vllm_msda_set_window_fill(int tma) { g_win_fill_tma = tma ? 1 : 0; return VLLM_OK; }
 
 struct WinCacheEntry {
   const void* value; int N, S, M, L, vb; int64_t shapes[2 * MSDA_WIN_LEVELS]; int ph, pw, halo;
@@ -477,7 +531,9 @@ int msda_launch_window(const ValT* value, const int64_t* lsi, const float* loc, 
       if (err != cudaSuccess) return (int)err;
       configured = 112 * 1024;
     }
-    kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, loc, attw, out, S, M, Lq, P, e->wp, MsdaQp{});
+    MsdaWin wp = e->wp;
+    wp.fill_tma = g_win_fill_tma;
+    kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, loc, attw, out, S, M, Lq, P, wp, MsdaQp{});
     VLLM_CHECK_LAUNCH();
     return VLLM_OK;
   };
@@ -501,7 +557,9 @@ static int launch_window_qp(const __nv_bfloat16* value, const int64_t* lsi, cons
     if (err != cudaSuccess) return (int)err;
     configured = true;
   }
-  kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, nullptr, nullptr, out, S, M, Lq, P, e->wp, fq);
+  MsdaWin wp = e->wp;
+  wp.fill_tma = g_win_fill_tma;
+  kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, nullptr, nullptr, out, S, M, Lq, P, wp, fq);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
 }
