@@ -24,3 +24,31 @@ def inputs():
     return dict(src=r(bs, S, d), pos=r(bs, S, d), ref2=ref2, shapes=shapes, lsi=lsi, pad=pad, tgt=r(nq, bs, d),
                 qpos=r(nq, bs, d), ref4=ref4, memory=r(S, bs, d), memory_text=r(bs, ntok, d), text_mask=text_mask,
                 attn_mask=attn_mask)
+
+
+# ---- two-stage keypoint decoder (modeling_unipose.py:2869-3130) -------------------------------------------------------
+DEC = dict(d_model=256, d_ffn=512, n_heads=8, num_layers=4, num_box_decoder_layers=2, num_body_points=19, nq=60, bs=2,
+           ntok=6)
+
+
+def decoder_inputs():
+    g = torch.Generator().manual_seed(23)
+    r = lambda *s: (torch.randn(*s, generator=g) * 0.5).to(torch.bfloat16).float()  # noqa: E731
+    S = sum(h * w for h, w in SHAPES)
+    c = DEC
+    bs, nq, d, nbp, ntok = c["bs"], c["nq"], c["d_model"], c["num_body_points"], c["ntok"]
+    shapes = torch.tensor(SHAPES, dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    pad = torch.zeros(bs, S, dtype=torch.bool)
+    pad[1, 160:192] = True
+    ref_unsig = torch.cat((torch.randn(nq, bs, 2, generator=g), torch.randn(nq, bs, 2, generator=g) * 0.5 - 1.5), -1)
+    valid_ratios = (0.75 + 0.25 * torch.rand(bs, len(SHAPES), 2, generator=g))
+    text_mask = torch.zeros(bs, ntok, dtype=torch.bool)          # True = padding (layer cross-attention)
+    text_mask[1, 4:] = True
+    kpt_vis = torch.zeros(bs, nbp, dtype=torch.long)             # kpt_query_masks: 1 = a real keypoint class
+    kpt_vis[0, :17] = 1
+    kpt_vis[1, :12] = 1
+    return dict(tgt=r(nq, bs, d), memory=r(S, bs, d), pad=pad, shapes=shapes, lsi=lsi,
+                ref_unsig=ref_unsig.to(torch.bfloat16).float(), valid_ratios=valid_ratios.to(torch.bfloat16).float(),
+                memory_text=r(bs, ntok, d), text_mask=text_mask, encoded_text=r(bs, ntok, d) * 2.0,
+                kpt_embed=r(bs, nbp, d), kpt_vis=kpt_vis)

@@ -51,7 +51,7 @@ def run(value, shapes, lsi, loc, attw, variant=0, window=(0, 0, 0), out_dtype=No
     finally:
         L_.vllm_msda_set_variant(0)
         L_.vllm_msda_set_window(0, 0, 0)
-        L_.vllm_msda_set_window_fill(0)
+        L_.vllm_msda_set_window_fill(-1)
 
 
 def oracle(value, shapes, lsi, loc, attw):

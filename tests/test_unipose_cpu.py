@@ -43,3 +43,77 @@ def test_unipose_layers_logic_matches_reference(golden_dir, torch_kernels):  # n
     for got, ref in ((e[:, ::sub], torch.from_numpy(g["enc_f32"])), (d, torch.from_numpy(g["dec_f32"]))):
         assert got.shape == ref.shape
         assert (got.float() - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
+# ---- two-stage keypoint decoder (modeling_unipose.py:2869-3130) -------------------------------------------------------
+def build_decoder():
+    """The B200 decoder built exactly like tests/golden/gen_golden_unipose_decoder.py builds the reference's."""
+    import types
+
+    import torch.nn as nn
+
+    import visionllm_b200.unipose as U
+    from gen_golden_unipose_decoder import build
+    ns = types.SimpleNamespace(DeformableTransformerDecoderLayer=U.DeformableTransformerDecoderLayer,
+                               TransformerDecoder=U.TransformerDecoder, MLP=U.MLP, ContrastiveAssign=U.ContrastiveAssign,
+                               _LN=U._LN)
+    assert nn is not None
+    return build(ns)
+
+
+def decoder_mask(kpt_vis, n_heads, num_body_points):
+    from visionllm_b200.unipose import prepare_for_mask
+    kpt_mask = torch.cat((torch.ones_like(kpt_vis)[..., 0].unsqueeze(-1), kpt_vis), dim=-1)
+    return prepare_for_mask(kpt_mask, n_heads, num_body_points)
+
+
+def run_decoder(dec, x, mask2, c=lambda t: t):
+    text_dict = {"encoded_text": c(x["encoded_text"]), "text_token_mask": ~x["text_mask"]}
+    return dec(tgt=c(x["tgt"]).clone(), memory=c(x["memory"]), tgt_mask=None, tgt_mask2=mask2,
+               memory_key_padding_mask=x["pad"], pos=None, refpoints_unsigmoid=c(x["ref_unsig"]),
+               level_start_index=x["lsi"], spatial_shapes=x["shapes"], valid_ratios=c(x["valid_ratios"]),
+               memory_text=c(x["memory_text"]), text_attention_mask=x["text_mask"], text_dict=text_dict,
+               kpt_embed=c(x["kpt_embed"]))
+
+
+def test_unipose_decoder_mask_matches_reference_prepare_for_mask(golden_dir):
+    from unipose_inputs import DEC, decoder_inputs
+    g = np.load(os.path.join(golden_dir, "mod_unipose_decoder.npz"))
+    x = decoder_inputs()
+    m = decoder_mask(x["kpt_vis"], DEC["n_heads"], DEC["num_body_points"])
+    shp = tuple(int(v) for v in g["mask2_shape"])
+    ref = torch.from_numpy(np.unpackbits(g["mask2_bits"], axis=-1)[..., :shp[-1]].astype(bool)).view(shp)
+    assert m.dtype == torch.bool and m.shape == (shp[0] * DEC["n_heads"], shp[1], shp[2])
+    assert torch.equal(m.view(shp[0], DEC["n_heads"], shp[1], shp[2]), ref[:, None].expand(-1, DEC["n_heads"], -1, -1))
+
+
+def test_unipose_decoder_logic_matches_reference(golden_dir, torch_kernels):  # noqa: F811
+    """Whole decoder loop in fp32 (kernel stand-ins): parameter keys, the top-50 box selection (indices exact), the
+    (1 + num_body_points) query expansion, box / keypoint refinement order, every layer's outputs and reference points."""
+    from unipose_inputs import DEC, decoder_inputs
+    g = np.load(os.path.join(golden_dir, "mod_unipose_decoder.npz"))
+    dec, keys = build_decoder()
+    assert json.loads(str(g["keys"])) == [list(k) for k in keys], "decoder keys differ"
+    x = decoder_inputs()
+    mask2 = decoder_mask(x["kpt_vis"], DEC["n_heads"], DEC["num_body_points"])
+    hs, refs = run_decoder(dec, x, mask2)
+    assert torch.equal(dec.topk_proposals.cpu(), torch.from_numpy(g["topk_f32"])), "top-50 proposal indices differ"
+    assert len(hs) == DEC["num_layers"] and len(refs) == DEC["num_layers"] + 1
+    rows = stored_rows(g)
+    nb = DEC["num_box_decoder_layers"]
+    for i, h in enumerate(hs):
+        ref = torch.from_numpy(g[f"hs{i}_f32"])
+        h = h if i < nb else h[:, rows]
+        assert h.shape == ref.shape
+        assert (h.float() - ref).abs().max().item() <= 3e-4 * max(1.0, ref.abs().max().item()), i
+    for i, r in enumerate(refs):
+        ref = torch.from_numpy(g[f"ref{i}_f32"])
+        r = r if i - 1 < nb else r[:, rows]
+        assert r.shape == ref.shape and (r.float() - ref).abs().max().item() <= 1e-4, i
+
+
+def stored_rows(g):
+    """Expanded-query rows the golden stores (every group_step-th (box + keypoints) group)."""
+    from unipose_inputs import DEC
+    group, step = DEC["num_body_points"] + 1, int(g["group_step"])
+    return torch.cat([torch.arange(gi * group, (gi + 1) * group) for gi in range(0, 50, step)])

@@ -57,20 +57,20 @@ def main():
         finally:
             L_.vllm_msda_set_variant(0)
             L_.vllm_msda_set_window(0, 0, 0)
-            L_.vllm_msda_set_window_fill(0)
-        rows.append({"case": name + (" (TMA fill)" if tma else ""), "variant": variant, "window_ph_pw_halo": list(window), "ms": ms,
+            L_.vllm_msda_set_window_fill(-1)
+        rows.append({"case": name, "fill_tma_level_mask": tma, "variant": variant, "window_ph_pw_halo": list(window), "ms": ms,
                      "GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peaks["hbm_gbs"]})
         print(rows[-1], flush=True)
 
     rec("fp32 global warp-gather (r1 kernel, new reduce-scatter)", 4, (0, 0, 0), f32, alg32)
     rec("fp32 global warp-gather, 8x16 patches", 1, (0, 0, 0), f32, alg32)
-    rec("fp32 window", 0, (0, 0, 0), f32, alg32, tma=1)
-    for w in ((0, 0, 0), (8, 8, 5), (8, 8, 8), (4, 8, 6), (8, 16, 4)):
-        rec("fp32 window", 0, w, f32, alg32)
+    for w in ((0, 0, 0), (8, 8, 5), (8, 8, 8), (8, 16, 8)):
+        for mask in (15, 0, 1, 14):
+            rec("fp32 window", 0, w, f32, alg32, tma=mask)
     rec("bf16 global warp-gather (r1 kernel)", 32, (0, 0, 0), b16, alg16)
-    rec("bf16 window", 0, (0, 0, 0), b16, alg16, tma=1)
-    for w in ((0, 0, 0), (8, 16, 6), (8, 16, 10), (8, 8, 8), (16, 16, 8), (4, 16, 8), (8, 32, 6)):
-        rec("bf16 window", 0, w, b16, alg16)
+    for w in ((0, 0, 0), (8, 16, 6), (8, 16, 10), (16, 16, 8), (8, 32, 8), (16, 32, 8)):
+        for mask in (15, 0, 1, 14):
+            rec("bf16 window", 0, w, b16, alg16, tma=mask)
     res = {"device": torch.cuda.get_device_name(0), "hbm_peak_gbs": peaks["hbm_gbs"], "shape": "N=8 S=Lq=21760 M=8 D=32 L=4 P=4",
            "alg_bytes_fp32": alg32, "alg_bytes_bf16": alg16, "rows": rows}
     if args.out:

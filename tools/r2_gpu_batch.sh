@@ -11,3 +11,4 @@ echo "== bench default"; timeout 600 python bench.py --steps 10 --warmup 3 > gpu
 echo "== experimental FHFMA variants"; VLLM_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_msda_gpu.py tests/test_internimage_gpu.py -q -k fhfma 2>&1 | tail -5 | tee gpurun_out/r2_fhfma_$tag.log
 echo "== bench gdino_stage"; timeout 400 python bench.py --workload gdino_stage --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_gdino_stage_$tag.json 2>gpurun_out/gd.err; tail -c 1200 gpurun_out/r2_bench_gdino_stage_$tag.json; tail -3 gpurun_out/gd.err
 echo "== bench llm_train"; timeout 600 python bench.py --workload llm_train --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_llm_train_$tag.json 2>gpurun_out/train.err; tail -c 1200 gpurun_out/r2_bench_llm_train_$tag.json; tail -5 gpurun_out/train.err
+echo "== ncu targets (set full)"; timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/r2_targets python tools/ncu_targets.py > gpurun_out/ncu_targets.log 2>&1; tail -3 gpurun_out/ncu_targets.log

@@ -33,7 +33,9 @@ struct MsdaWin {
   int q_start[MSDA_WIN_LEVELS];          // first query (== first pixel) of the level
   int BW[MSDA_WIN_LEVELS], BH[MSDA_WIN_LEVELS], halo[MSDA_WIN_LEVELS];
   int win_off[MSDA_WIN_LEVELS];          // byte offset of the level's window in dynamic shared memory
-  int fill_tma;                          // 1: windows filled by TMA boxes; 0: by cooperative cp.async (default, see header)
+  int fill_tma;                          // bit l: level l's window arrives as a TMA box; else cooperative cp.async (see kernel)
+  int px_cum[MSDA_WIN_LEVELS + 1];       // exclusive prefix sum of the window pixel counts BW * BH
+  float inv_bw[MSDA_WIN_LEVELS];         // 1 / BW
   int zero_off;                          // a 128-byte all-zero row behind the windows: target of out-of-range samples
   int tx_bytes;                          // sum of the box bytes (what the mbarrier waits for)
 };
@@ -93,6 +95,13 @@ struct MsdaQp {
 };
 
 // NW warps per CTA.  KC > 0: compile-time K = L*P (PC = P).
+//
+// The kernel is ISSUE bound (r2 ncu: ~430 warp instructions per (query, head) against 64 data wavefronts), so the hot
+// path is written for instruction count: everything that depends only on the lane's role (its sample's level: map and
+// window geometry) lives in registers, the region's query list is a shared-memory table built once per CTA, global
+// indices are 32-bit (host-checked), the bf16 rows are unpacked with one shift / one mask per element pair, and the
+// per-corner metadata of a sample is one 8-byte shared load whose address carries the lane's sample parity.
+
 template <typename ValT, typename OutT, int NW, int KC, int PC, bool QP = false>
 __global__ void __launch_bounds__(NW * 32)
 msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __restrict__ value,
@@ -109,6 +118,7 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
   __shared__ int s_bx0[MSDA_WIN_LEVELS], s_by0[MSDA_WIN_LEVELS], s_nx[MSDA_WIN_LEVELS], s_cum[MSDA_WIN_LEVELS + 1];
   __shared__ int s_ox[MSDA_WIN_LEVELS], s_oy[MSDA_WIN_LEVELS], s_start[MSDA_WIN_LEVELS];
 
+  int* s_q = reinterpret_cast<int*>(win + wp.zero_off + 128);   // region-local index -> query (== pixel) index
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = wp.L;
   const int m = blockIdx.x % M;
@@ -150,7 +160,7 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
       }
     }
     __syncwarp();
-    if (wp.fill_tma && lane < L)                           // one TMA box per level (the init above is ordered by __syncwarp)
+    if (lane < L && ((wp.fill_tma >> lane) & 1))           // one TMA box per level (the init above is ordered by __syncwarp)
       tma_load_5d(tc::smem_u32(win + wp.win_off[lane]), &maps.m[lane], tc::smem_u32(&s_bar), 0, m, x0 - 1 - wp.halo[lane],
                   y0 - 1 - wp.halo[lane], b);
   }
@@ -159,27 +169,41 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
   __syncthreads();
   const int nq = s_cum[L];
   const uint32_t bar = tc::smem_u32(&s_bar);
-  if (!wp.fill_tma) {
-    // Cooperative window fill: 16-byte cp.async per (pixel, chunk), zero-filled outside the map.  Measured: a TMA box whose
-    // innermost run is one 64-byte (pixel, head) row is request-rate bound (~5 B / clock / SM), the same bytes through
-    // 512 threads of cp.async arrive an order of magnitude faster; the copies fly while phase 1 of the first pass runs.
+  for (int t = threadIdx.x; t < nq; t += NW * 32) {        // the region's query list
+    int lq = 0;
+    while (lq + 1 < L && t >= s_cum[lq + 1]) ++lq;
+    const int r = t - s_cum[lq];
+    const int ry = r / s_nx[lq], rx = r - ry * s_nx[lq];
+    s_q[t] = wp.q_start[lq] + (s_by0[lq] + ry) * wp.W[lq] + s_bx0[lq] + rx;
+  }
+  // Window fill.  fill_tma bit l set: level l arrives as one TMA box (issued above); the other levels are copied
+  // cooperatively, one (pixel, head) row = ROWB / 16 cp.async of 16 bytes per thread and step, zero-filled outside the map
+  // (the operator's zero padding).  A TMA box whose innermost run is one 64-byte row is request-rate bound, the
+  // cooperative copy costs issue slots: the mix is a tuning knob (vllm_msda_set_window_fill), both fly while phase 1 of
+  // the first pass runs.
+  {
     constexpr int CPR = ROWB / 16;
     const uint32_t wbase = tc::smem_u32(win);
-    for (int l = 0; l < L; ++l) {
-      const int BWl = wp.BW[l], Wl = wp.W[l], Hl = wp.H[l], oxl = s_ox[l], oyl = s_oy[l];
-      const int chunks = BWl * wp.BH[l] * CPR;
-      const char* lvl = reinterpret_cast<const char*>(value + ((size_t)b * S + wp.q_start[l]) * MD + m * D);
-      for (int c = threadIdx.x; c < chunks; c += NW * 32) {
-        const int px = c / CPR, cc = c - px * CPR;
-        const int wy = px / BWl, wx = px - wy * BWl;
-        const int y = oyl + wy, x = oxl + wx;
-        const bool ok = y >= 0 && y < Hl && x >= 0 && x < Wl;
-        const char* src = ok ? lvl + ((size_t)y * Wl + x) * MD * VB + cc * 16 : lvl;
-        cp_async16(wbase + wp.win_off[l] + px * ROWB + cc * 16, src, ok ? 16 : 0);
-      }
+    const int total = wp.px_cum[L];
+    for (int p = threadIdx.x; p < total; p += NW * 32) {
+      int l = 0;
+      while (l + 1 < L && p >= wp.px_cum[l + 1]) ++l;
+      if ((wp.fill_tma >> l) & 1) continue;
+      const int r = p - wp.px_cum[l];
+      const int BWl = wp.BW[l];
+      const int wy = (int)(((float)r + 0.5f) * wp.inv_bw[l]);       // r / BWl: exact for r < 2^16 (|error| << 0.5 / BWl)
+      const int wx = r - wy * BWl;
+      const int y = s_oy[l] + wy, x = s_ox[l] + wx;
+      const bool ok = (unsigned)y < (unsigned)wp.H[l] && (unsigned)x < (unsigned)wp.W[l];
+      const char* src = reinterpret_cast<const char*>(value + ((size_t)b * S + wp.q_start[l]) * MD + m * D);
+      if (ok) src += ((size_t)y * wp.W[l] + x) * MD * VB;
+      const uint32_t dst = wbase + wp.win_off[l] + r * ROWB;
+#pragma unroll
+      for (int cc = 0; cc < CPR; ++cc) cp_async16(dst + cc * 16, src + cc * 16, ok ? 16 : 0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  __syncthreads();                                         // s_q complete
   bool landed = false;
 
   // phase-2 roles
@@ -187,44 +211,57 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
   const int sp = lane >> 4;
   const uint32_t wl = tc::smem_u32(win) + cq * 16;                             // this lane's 16-byte chunk of a window row
   const char* vbl = reinterpret_cast<const char*>(value + (size_t)b * S * MD + m * D) + cq * 16;   // global fallback
-  // phase-1 roles
+  const uint32_t meta_w = tc::smem_u32(&s_meta[warp][0][lane]);                // phase-1 store slot (corner rows 272 B apart)
+  constexpr int META_ROWB = WIN_META_ROW * 8;
+  // phase-1 roles: lane <-> sample s1 of pair g1; the sample's level l1 never changes, so its geometry sits in registers
   const int g1 = lane / K, s1 = lane - g1 * K;
   const int l1 = s1 / P;
+  const int H1 = wp.H[l1], W1 = wp.W[l1];
+  const int oy1 = s_oy[l1], ox1 = s_ox[l1];
+  const int bh1 = wp.BH[l1] - 1, bw1 = wp.BW[l1] - 1;
+  const int rowp1 = wp.BW[l1] * ROWB;
+  const int woff1 = wp.win_off[l1];
+  // batch / head / sample folded into the input bases: per-pass offsets are 32-bit (host-checked sizes)
+  const float* loc_l = QP ? nullptr : loc + (((size_t)b * Lq * M + m) * K + s1) * 2;
+  const float* attw_l = QP ? nullptr : attw + ((size_t)b * Lq * M + m) * K + s1;
+  const __nv_bfloat16* qp_off = QP ? fq.qp + (size_t)b * Lq * fq.ld + (m * K + s1) * 2 : nullptr;
+  const __nv_bfloat16* qp_lg = QP ? fq.qp + (size_t)b * Lq * fq.ld + fq.n_off + m * K + s1 : nullptr;
+  const float* ref_l = QP ? fq.ref + ((size_t)b * Lq * L + l1) * 2 : nullptr;
+  OutT* out_l = out + ((size_t)b * Lq * M + m) * D + (HALF ? cq * 8 + sp * 4 + (corner >> 1) * 2 + (corner & 1)
+                                                          : cq * 4 + (corner >> 1) * 2 + (corner & 1));
+  float Wb = 0.f, Hb = 0.f;
+  if constexpr (QP) {
+    Wb = __bfloat162float(__float2bfloat16_rn((float)W1));
+    Hb = __bfloat162float(__float2bfloat16_rn((float)H1));
+  }
 
   // per-lane inputs of one pass (this lane's sample of this lane's (query, head) pair), fetched one pass AHEAD so that the
   // global-memory latency of sampling_loc / attn_weight (or of the packed projection row) hides behind the gather
-  struct Inp { int q; float a, b, c, d; uint32_t o2; };
+  struct Inp { int q; float a, b, c; uint32_t o2; };
   auto fetch = [&](int t0) -> Inp {
-    Inp in; in.q = -1; in.a = in.b = in.c = in.d = 0.f; in.o2 = 0u;
+    Inp in; in.q = -1; in.a = in.b = in.c = 0.f; in.o2 = 0u;
     const int t = t0 + g1;
     if (g1 < G && t < nq) {
-      int lq = 0;
-      while (lq + 1 < L && t >= s_cum[lq + 1]) ++lq;
-      const int r = t - s_cum[lq];
-      const int ry = r / s_nx[lq], rx = r - ry * s_nx[lq];
-      in.q = wp.q_start[lq] + (s_by0[lq] + ry) * wp.W[lq] + s_bx0[lq] + rx;
+      in.q = s_q[t];
       if constexpr (QP) {
-        const __nv_bfloat16* row = fq.qp + ((size_t)b * Lq + in.q) * fq.ld;
-        in.o2 = *reinterpret_cast<const uint32_t*>(row + (m * K + s1) * 2);
-        in.c = __bfloat162float(row[fq.n_off + m * K + s1]);                       // logit
-        const float2 rp = *reinterpret_cast<const float2*>(fq.ref + (((size_t)b * Lq + in.q) * L + l1) * 2);
+        const unsigned ro = (unsigned)in.q * (unsigned)fq.ld;
+        in.o2 = *reinterpret_cast<const uint32_t*>(qp_off + ro);
+        in.c = __bfloat162float(qp_lg[ro]);                                           // logit
+        const float2 rp = *reinterpret_cast<const float2*>(ref_l + (unsigned)in.q * (unsigned)(L * 2));
         in.a = rp.x; in.b = rp.y;
       } else {
-        const size_t si = (((size_t)b * Lq + in.q) * M + m) * K + s1;
-        const float2 xy = ld_stream_f2(loc + 2 * si);
+        const unsigned si = (unsigned)in.q * (unsigned)(M * K);
+        const float2 xy = ld_stream_f2(loc_l + 2 * si);
         in.a = xy.x; in.b = xy.y;
-        in.c = ld_stream_f1(attw + si);
+        in.c = ld_stream_f1(attw_l + si);
       }
     }
     return in;
   };
   Inp nxt = fetch(warp * G);
-  if (wp.fill_tma) {
-    tc::mbar_wait(bar, 0);
-  } else {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                                       // every thread's copies have landed and are visible to all
-  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();                                         // every thread's copies have landed and are visible to all
+  if (wp.fill_tma) tc::mbar_wait(bar, 0);
   landed = true;
 
   for (int t0 = warp * G; t0 < nq; t0 += NW * G) {
@@ -256,8 +293,6 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
         if (q >= 0) {
           if (fq.attw_out) fq.attw_out[(((size_t)b * Lq + q) * M + m) * K + s1] = wb;
           const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&in.o2);
-          const float Wb = __bfloat162float(__float2bfloat16_rn((float)wp.W[l1]));
-          const float Hb = __bfloat162float(__float2bfloat16_rn((float)wp.H[l1]));
           const float ox = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(__low2float(ob), Wb)));
           const float oy = __bfloat162float(__float2bfloat16_rn(__fdiv_rn(__high2float(ob), Hb)));
           xy = make_float2(__fadd_rn(in.a, ox), __fadd_rn(in.b, oy));
@@ -266,23 +301,22 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
         aw = in.c;
       }
       if (q >= 0) {
-        const int H = wp.H[l1], W = wp.W[l1];
-        ge = msda_geom<float>(xy.x, xy.y, H, W);
+        ge = msda_geom<float>(xy.x, xy.y, H1, W1);
         if (ge.mask & 1) {
-          const int wy = ge.h_low - s_oy[l1], wx = ge.w_low - s_ox[l1];
-          in_win = (wy >= 0) && (wx >= 0) && (wy + 1 < wp.BH[l1]) && (wx + 1 < wp.BW[l1]);
+          const int wy = ge.h_low - oy1, wx = ge.w_low - ox1;
+          in_win = ((unsigned)wy < (unsigned)bh1) && ((unsigned)wx < (unsigned)bw1);
           const float hh = 1.f - ge.lh, hw = 1.f - ge.lw;
-          const int rowp = wp.BW[l1] * ROWB;
-          const int base = wp.win_off[l1] + (wy * wp.BW[l1] + wx) * ROWB;
+          const int base = woff1 + wy * rowp1 + wx * ROWB;
           // corners outside the MAP but inside the window read TMA zero fill: no predicate needed
           meta[0] = make_int2(base, __float_as_int((hh * hw) * aw));
           meta[1] = make_int2(base + ROWB, __float_as_int((hh * ge.lw) * aw));
-          meta[2] = make_int2(base + rowp, __float_as_int((ge.lh * hw) * aw));
-          meta[3] = make_int2(base + rowp + ROWB, __float_as_int((ge.lh * ge.lw) * aw));
+          meta[2] = make_int2(base + rowp1, __float_as_int((ge.lh * hw) * aw));
+          meta[3] = make_int2(base + rowp1 + ROWB, __float_as_int((ge.lh * ge.lw) * aw));
         }
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) s_meta[warp][c][lane] = meta[c];
+      for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(meta_w + c * META_ROWB), "r"(meta[c].x), "r"(meta[c].y) : "memory");
     }
     const unsigned outside = __ballot_sync(0xffffffffu, !in_win);
     __syncwarp();
@@ -300,13 +334,12 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
 #pragma unroll
           for (int c = 0; c < 4; ++c) meta[c] = make_int2(-1, 0);
           if (ge.mask & 1) {
-            const int W = wp.W[l1];
             const float hh = 1.f - ge.lh, hw = 1.f - ge.lw;
-            const int base = (s_start[l1] + ge.h_low * W + ge.w_low) * MD * VB;
+            const int base = (s_start[l1] + ge.h_low * W1 + ge.w_low) * MD * VB;
             if (ge.mask & 2) meta[0] = make_int2(base, __float_as_int((hh * hw) * aw));
             if (ge.mask & 4) meta[1] = make_int2(base + MD * VB, __float_as_int((hh * ge.lw) * aw));
-            if (ge.mask & 8) meta[2] = make_int2(base + W * MD * VB, __float_as_int((ge.lh * hw) * aw));
-            if (ge.mask & 16) meta[3] = make_int2(base + (W * MD + MD) * VB, __float_as_int((ge.lh * ge.lw) * aw));
+            if (ge.mask & 8) meta[2] = make_int2(base + W1 * MD * VB, __float_as_int((ge.lh * hw) * aw));
+            if (ge.mask & 16) meta[3] = make_int2(base + (W1 * MD + MD) * VB, __float_as_int((ge.lh * ge.lw) * aw));
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c) s_meta[warp][c][lane] = meta[c];
@@ -314,28 +347,26 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
         __syncwarp();
       }
       const int2* mp = &s_meta[warp][corner][g * K];
-      OutT* op = out + (((size_t)b * Lq + qg) * M + m) * D;
+      const int2* mph = mp + sp;                           // bf16 rows: the lane's sample parity rides in the address
+      const int4* mp4 = reinterpret_cast<const int4*>(mp);
+      OutT* op = out_l + (size_t)((unsigned)qg * (unsigned)MD);
       if constexpr (HALF) {
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        auto fma8 = [&](const uint4& raw, float w) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        auto fma8 = [&](const uint4& raw, float w) {       // bf16 -> fp32 is a shift (low half) / a mask (high half)
+          const uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(h[i]);
-            acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
-            acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+            acc[2 * i] = fmaf(w, __uint_as_float(words[i] << 16), acc[2 * i]);
+            acc[2 * i + 1] = fmaf(w, __uint_as_float(words[i] & 0xffff0000u), acc[2 * i + 1]);
           }
         };
         if (!dirty && (K % 2 == 0)) {
-          const int4* mp4 = reinterpret_cast<const int4*>(mp);
 #pragma unroll (KC > 0 ? KC / 2 : 4)
           for (int s = 0; s < K / 2; ++s) {
-            const int4 me = mp4[s];                        // samples 2s (x, y) and 2s + 1 (z, w) of this corner
-            const int off = sp ? me.z : me.x;
-            const float w = __int_as_float(sp ? me.w : me.y);
-            fma8(lds128(wl + off), w);
+            const int2 me = mph[2 * s];                    // sample 2s + sp of this corner: one 8-byte broadcast load
+            fma8(lds128(wl + me.x), __int_as_float(me.y));
           }
         } else if (!dirty) {
           for (int s = sp; s < K; s += 2) {
@@ -366,9 +397,8 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
         const float send = cb0 ? k2[0] : k2[1];
         const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
         const float res = (cb0 ? k2[1] : k2[0]) + recv;
-        const int ch = cq * 8 + sp * 4 + cb1 * 2 + cb0;
-        if constexpr (sizeof(OutT) == 4) op[ch] = res;
-        else op[ch] = __float2bfloat16(res);
+        if constexpr (sizeof(OutT) == 4) *op = res;
+        else *op = __float2bfloat16(res);
       } else {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         auto fma4 = [&](const uint4& v, float w) {
@@ -376,10 +406,9 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
           acc.z = fmaf(w, __uint_as_float(v.z), acc.z); acc.w = fmaf(w, __uint_as_float(v.w), acc.w);
         };
         if (!dirty && (K % 2 == 0)) {
-          const int4* mp4 = reinterpret_cast<const int4*>(mp);
 #pragma unroll (KC > 0 ? KC / 2 : 4)
           for (int s = 0; s < K / 2; ++s) {
-            const int4 me = mp4[s];
+            const int4 me = mp4[s];                        // samples 2s (x, y) and 2s + 1 (z, w) of this corner
             const uint4 v0 = lds128(wl + me.x), v1 = lds128(wl + me.z);
             fma4(v0, __int_as_float(me.y));
             fma4(v1, __int_as_float(me.w));
@@ -409,9 +438,8 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
         const float send = cb0 ? k2[0] : k2[1];
         const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
         const float res = (cb0 ? k2[1] : k2[0]) + recv;
-        const int ch = cq * 4 + cb1 * 2 + cb0;
-        if constexpr (sizeof(OutT) == 4) op[ch] = res;
-        else op[ch] = __float2bfloat16(res);
+        if constexpr (sizeof(OutT) == 4) *op = res;
+        else *op = __float2bfloat16(res);
       }
     }
     __syncwarp();
@@ -423,7 +451,7 @@ msda_fwd_win_kernel(const __grid_constant__ MsdaWinMaps maps, const ValT* __rest
 // Host side
 // ---------------------------------------------------------------------------
 static int g_win_ph = 0, g_win_pw = 0, g_win_halo = 0;      // 0: defaults; bench / tuning knob (vllm_msda_set_window)
-static int g_win_fill_tma = 0;                              // vllm_msda_set_window_fill: 0 cp.async (default), 1 TMA boxes
+static int g_win_fill_tma = -1;   // vllm_msda_set_window_fill: bit l = level l by TMA box; 0 = all cp.async; 1 = (legacy) all TMA; < 0 default
 
 extern "C" int vllm_msda_set_window(int patch_h, int patch_w, int halo0) {
   if (patch_h < 0 || patch_w < 0 || halo0 < 0) return VLLM_EINVAL;
@@ -431,7 +459,22 @@ extern "C" int vllm_msda_set_window(int patch_h, int patch_w, int halo0) {
   return VLLM_OK;
 }
 
-extern "C" int vllm_msda_set_window_fill(int tma) { g_win_fill_tma = tma ? 1 : 0; return VLLM_OK; }
+extern "C" int vllm_msda_set_window_fill(int tma) {
+  g_win_fill_tma = tma == 1 ? (1 << MSDA_WIN_LEVELS) - 1 : tma;     // 1 keeps its r2 meaning: every level by TMA
+  return VLLM_OK;
+}
+
+constexpr int WIN_FILL_DEFAULT_BF16 = (1 << MSDA_WIN_LEVELS) - 1;   // measured (profiles/r2_msda_window_sweep.json)
+constexpr int WIN_FILL_DEFAULT_F32 = (1 << MSDA_WIN_LEVELS) - 1;
+
+static void set_fill(MsdaWin& wp, int vb) {
+  int mask = g_win_fill_tma >= 0 ? g_win_fill_tma : (vb == 2 ? WIN_FILL_DEFAULT_BF16 : WIN_FILL_DEFAULT_F32);
+  mask &= (1 << wp.L) - 1;
+  wp.fill_tma = mask;
+  wp.tx_bytes = 0;
+  for (int l = 0; l < wp.L; ++l)
+    if ((mask >> l) & 1) wp.tx_bytes += wp.BW[l] * wp.BH[l] * 32 * vb;
+}
 
 struct WinCacheEntry {
   const void* value; int N, S, M, L, vb; int64_t shapes[2 * MSDA_WIN_LEVELS]; int ph, pw, halo;
@@ -471,15 +514,20 @@ static bool build_window(WinCacheEntry& e, const ValT* value, const int64_t* hs,
     wp.halo[l] = halo;
     wp.BW[l] = (int)((wp.PW * (long long)wp.W[l] + wp.W[0] - 1) / wp.W[0]) + 2 + 2 * halo;
     wp.BH[l] = (int)((wp.PH * (long long)wp.H[l] + wp.H[0] - 1) / wp.H[0]) + 2 + 2 * halo;
-    if (wp.BW[l] > 256 || wp.BH[l] > 256) return false;
+    if (wp.BW[l] > 256 || wp.BH[l] > 256 || wp.BW[l] * wp.BH[l] > 65535) return false;
     wp.win_off[l] = off;
     const int bytes = wp.BW[l] * wp.BH[l] * ROWB;
-    wp.tx_bytes += bytes;
+    wp.px_cum[l + 1] = wp.px_cum[l] + wp.BW[l] * wp.BH[l];
+    wp.inv_bw[l] = 1.0f / (float)wp.BW[l];
     off += (bytes + 127) & ~127;
   }
   wp.zero_off = off;
   off += 128;
-  if (off > 110 * 1024) return false;
+  long long nq_max = 0;                                      // upper bound of a region's query count (the s_q table behind the zero row)
+  for (int l = 0; l < L; ++l)
+    nq_max += ((wp.PW * (long long)wp.W[l] + wp.W[0] - 1) / wp.W[0] + 1) * ((wp.PH * (long long)wp.H[l] + wp.H[0] - 1) / wp.H[0] + 1);
+  off += (int)((nq_max * 4 + 127) & ~127ll);
+  if (nq_max > 8192 || off > 190 * 1024) return false;     // > 110 KB: one CTA of 32 warps per SM instead of two of 16
   e.smem = off;
   PFN_cuTensorMapEncodeTiled_v12000 enc = vllm_tma_encoder();
   if (!enc) return false;
@@ -524,21 +572,24 @@ int msda_launch_window(const ValT* value, const int64_t* lsi, const float* loc, 
   const WinCacheEntry* e = window_for<ValT>(value, host_shapes, N, S, M, L);
   if (!e) return 1;
   dim3 grid((unsigned)(e->wp.RX * e->wp.RY * M), (unsigned)N);
-  auto launch = [&](auto kern) -> int {
+  const bool big = e->smem > 110 * 1024;                   // one 32-warp CTA per SM (tuning knob territory)
+  auto launch = [&](auto kern, int nw) -> int {
     static int configured = -1;
     if (configured < e->smem) {
-      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      const int want = big ? e->smem : 112 * 1024;
+      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
       if (err != cudaSuccess) return (int)err;
-      configured = 112 * 1024;
+      configured = want;
     }
     MsdaWin wp = e->wp;
-    wp.fill_tma = g_win_fill_tma;
-    kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, loc, attw, out, S, M, Lq, P, wp, MsdaQp{});
+    set_fill(wp, (int)sizeof(ValT));
+    kern<<<grid, nw * 32, e->smem, st>>>(e->maps, value, lsi, loc, attw, out, S, M, Lq, P, wp, MsdaQp{});
     VLLM_CHECK_LAUNCH();
     return VLLM_OK;
   };
-  if (L == 4 && P == 4) return launch(msda_fwd_win_kernel<ValT, OutT, NW, 16, 4>);
-  return launch(msda_fwd_win_kernel<ValT, OutT, NW, 0, 0>);
+  if (L == 4 && P == 4) return big ? launch(msda_fwd_win_kernel<ValT, OutT, 32, 16, 4>, 32) : launch(msda_fwd_win_kernel<ValT, OutT, NW, 16, 4>, NW);
+  if (big) return 1;
+  return launch(msda_fwd_win_kernel<ValT, OutT, NW, 0, 0>, NW);
 }
 
 // fused module input (bf16 value, K == 16 only); returns 1 when the window path does not apply
@@ -548,7 +599,7 @@ static int launch_window_qp(const __nv_bfloat16* value, const int64_t* lsi, cons
   constexpr int NW = 16;
   if (!host_shapes || Lq != S || L != 4 || P != 4 || N > 65535) return 1;
   const WinCacheEntry* e = window_for<__nv_bfloat16>(value, host_shapes, N, S, M, L);
-  if (!e) return 1;
+  if (!e || e->smem > 110 * 1024) return 1;
   dim3 grid((unsigned)(e->wp.RX * e->wp.RY * M), (unsigned)N);
   auto kern = msda_fwd_win_kernel<__nv_bfloat16, OutT, NW, 16, 4, true>;
   static bool configured = false;
@@ -558,7 +609,7 @@ static int launch_window_qp(const __nv_bfloat16* value, const int64_t* lsi, cons
     configured = true;
   }
   MsdaWin wp = e->wp;
-  wp.fill_tma = g_win_fill_tma;
+  set_fill(wp, 2);
   kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, nullptr, nullptr, out, S, M, Lq, P, wp, fq);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
@@ -575,6 +626,7 @@ extern "C" int vllm_msda_forward_fused_bf16(const void* value, const int64_t* le
   if (channels != 32 || num_levels != 4 || num_point != 4 || ld_qp < num_heads * K * 3 || (ld_qp & 1)) return VLLM_EUNSUPPORTED;
   if (!vllm_aligned(value, 16) || !vllm_aligned(qp, 4) || !vllm_aligned(reference_points, 8)) return VLLM_EALIGN;
   if ((long long)spatial_size * num_heads * channels * 4 > INT_MAX) return VLLM_EUNSUPPORTED;
+  if ((long long)num_query * ld_qp > UINT_MAX) return VLLM_EUNSUPPORTED;     // 32-bit row offsets inside one image
   MsdaQp fq{(const __nv_bfloat16*)qp, reference_points, (__nv_bfloat16*)attn_weights_out, ld_qp, num_heads * K * 2};
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* v = (const __nv_bfloat16*)value;
