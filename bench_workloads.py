@@ -717,6 +717,7 @@ class LlmTpWorkload(PairForwardWorkload):
     unit = "tokens/s"
     dtype = "bf16"
     SEQS, T = 8, 2048
+    MICRO = 2              # micro-batches on their own streams / exchange buffers (tp.forward_pipelined); 1 = plain forward
 
     def setup(self):
         import torch
@@ -731,6 +732,10 @@ class LlmTpWorkload(PairForwardWorkload):
         else:
             self.comm = tp.PeerComm.virtual(1, M, cfg.hidden_size, self.device)[0]
         self.model = tp.TPLlamaForCausalLM.random_init(cfg, self.comm, self.device, seed=0)
+        self.micro = None
+        if self.MICRO > 1 and self.world > 1:
+            mk = (lambda: tp.PeerComm.from_process_group(M // self.MICRO, cfg.hidden_size, self.device))
+            self.micro = [mk() for _ in range(self.MICRO)]
         g = torch.Generator(device=self.device).manual_seed(1234)           # the same batch on every rank (TP)
         self.ids = torch.randint(0, 32000, (self.SEQS, self.T), device=self.device, generator=g)
         self.emb = torch.nn.functional.embedding(self.ids, self.model.shards["embed"])
@@ -742,11 +747,17 @@ class LlmTpWorkload(PairForwardWorkload):
         self.dist = dist if self.world > 1 else None
 
     def step_device(self):
-        self.out = self.model(inputs_embeds=self.emb)
+        if self.micro:
+            self.out = self.model.forward_pipelined(self.micro, inputs_embeds=self.emb)
+        else:
+            self.out = self.model(inputs_embeds=self.emb)
 
     def step_e2e(self):
         self.d_ids.copy_(self.h_ids, non_blocking=True)
-        out = self.model(input_ids=self.d_ids)
+        if self.micro:
+            out = self.model.forward_pipelined(self.micro, input_ids=self.d_ids)
+        else:
+            out = self.model(input_ids=self.d_ids)
         self.h_out.copy_(out.last_hidden_state[:, -1, :], non_blocking=True)
 
     def units_per_step(self):
@@ -758,10 +769,16 @@ class LlmTpWorkload(PairForwardWorkload):
                 "global_batch": self.SEQS, "seq_len": self.T,
                 "l2_policy": "inputs_exceed_l2 (weights 13.5 GB / TP shard + replicated MLP, activations > 126 MB L2)",
                 "parallelism": f"tp{self.world} (heads) x sp{self.world} (token rows); 1 reduce-scatter + 1 all-gather "
-                               "per layer inside the GEMM epilogue / norm kernel"}
+                               "per layer inside the GEMM epilogue / norm kernel",
+                "micro_batches": self.MICRO if self.micro else 1}
 
     def extra(self):
         return {"kernel_breakdown": self.breakdown, "scaling": "strong"}
+
+
+class LlmTpPlainWorkload(LlmTpWorkload):
+    """llm_tp without micro-batch pipelining (the r1 schedule), for the comparison."""
+    MICRO = 1
 
 
 class InternImageHWorkload(PairForwardWorkload):
@@ -1096,11 +1113,12 @@ def msda_extra(device, reps=20):
            "peak_source": peaks["source"], "unit": "GB/s"}
     ms = _event_ms(torch, lambda: ext.ms_deform_attn_forward(value, shapes, lsi, loc, attw, 64, host_shapes=hs), reps,
                    flush=flush)
-    out["fp32"] = row(ms, alg32, "msda_fwd_win_kernel<float, float, 16, 16, 4>",
-                      ncu_dram_bytes("r2_msda_win_ncu.json", "msda_fwd_win_kernel<float, float"))
+    out["fp32"] = row(ms, alg32, "msda_fwd_warp_kernel<8, 16, 16, 16, 4, float, float> (global-memory patch kernel: the default for "
+                                 "fp32 rows; the TMA-staged window kernel is variant 33)",
+                      ncu_dram_bytes("r2_msda_win_ncu.json", "msda_fwd_warp_kernel<"))
     v16 = value.bfloat16()
     ms = _event_ms(torch, lambda: ext.ms_deform_attn_forward_bf16(v16, shapes, lsi, loc, attw), reps, flush=flush)
-    out["bf16_value"] = row(ms, alg16, "msda_fwd_win_kernel<__nv_bfloat16, __nv_bfloat16, 16, 16, 4>",
+    out["bf16_value"] = row(ms, alg16, "msda_fwd_win_kernel<__nv_bfloat16, __nv_bfloat16, 32, 16, 4> (TMA-staged windows, 16 x 32 patch)",
                             ncu_dram_bytes("r2_msda_win_ncu.json", "msda_fwd_win_kernel<__nv_bfloat16, __nv_bfloat16"))
     try:
         import importlib.util
@@ -1187,6 +1205,23 @@ def tp_extra(rank, world, device, steps=10, warmup=3):
                 "frac_of_sustained_bf16_peak": flops / world / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]})
     del wl
     torch.cuda.empty_cache()
+    try:                                                    # the r1 schedule (no micro-batch pipelining) beside it
+        wp = LlmTpPlainWorkload(rank=rank, world=world, device=device)
+        wp.setup()
+        for _ in range(warmup):
+            wp.step_device()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            wp.step_device()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        res["plain_schedule_ms_per_step"] = max_over_ranks(e0.elapsed_time(e1), dist, "cuda") / steps
+        del wp
+    except Exception as e:
+        res["plain_schedule_ms_per_step"] = f"{type(e).__name__}: {e}"[:200]
+    torch.cuda.empty_cache()
     try:
         res["train"] = tp_train_extra(rank, world, device)
     except Exception as e:                                  # evidence, never a dependency of the line
@@ -1254,7 +1289,7 @@ def tp_train_extra(rank, world, device, steps=5, warmup=2):
 WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "msda_encoder_bf16": MsdaEncoderBf16Workload,
              "msda_encoder_pairs": MsdaEncoderPairsWorkload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
              "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload,
-             "llm_tp": LlmTpWorkload, "internimage_h": InternImageHWorkload, "cfg1_forward": Cfg1Workload,
+             "llm_tp": LlmTpWorkload, "llm_tp_plain": LlmTpPlainWorkload, "internimage_h": InternImageHWorkload, "cfg1_forward": Cfg1Workload,
              "llm_train": LlmTrainWorkload, "llm_tp_train": LlmTpTrainWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
@@ -1470,7 +1505,7 @@ def _cpu_llm_train(steps, warmup):
 
 _CPU = {"msda_encoder": _cpu_msda_encoder, "msda_encoder_bf16": _cpu_msda_encoder, "msda_encoder_pairs": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
         "gdino_stage": _cpu_msda_encoder,
-        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp, "internimage_h": _cpu_internimage_h, "cfg1_forward": _cpu_cfg1, "llm_train": _cpu_llm_train,
+        "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp, "llm_tp_plain": _cpu_llm_tp, "internimage_h": _cpu_internimage_h, "cfg1_forward": _cpu_cfg1, "llm_train": _cpu_llm_train,
         "llm_tp_train": _cpu_llm_train}
 
 
@@ -1494,7 +1529,7 @@ def run_reference_arm(name, n_gpus, steps, warmup):
             "steps": run_steps, "steps_requested": steps, "warmup": run_warm, "ms_per_step": cb["ms_per_step"],
             "extrapolated": cb["extrapolated"], "sample_ms_per_step": cb.get("sample_ms_per_step"), "wall_s": wall,
             "higher_is_better": True,
-            "scaling": "strong" if name in ("llm_tp", "llm_tp_train") else "weak", "vs_baseline": None,
+            "scaling": "strong" if name in ("llm_tp", "llm_tp_plain", "llm_tp_train") else "weak", "vs_baseline": None,
             "dtype": "f32 (torch CPU; the GPU arm computes in " + wl.dtype + ")",
             "data": "synthetic", "config": {"workload": cb["sample"]}, "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -175,6 +175,12 @@ int vllm_dcnv3_backward_f32(const float* input, const float* offset, const float
 int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                    const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
                    void* stream);
+/* Same GEMM with a row mask: rows m with row_keep[m] == 0 are stored as exact zeros whatever the epilogue computed --
+ * `value = value_proj(x).masked_fill(~attention_mask[..., None], 0)` of the deformable-attention module
+ * (modeling_ov_grounding_dino_mask_dn.py:729-732) without the extra read + write of `value`.  Not with SwiGLU. */
+int vllm_gemm_bf16_rowmask(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                           const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
+                           const unsigned char* row_keep, void* stream);
 /* Tuning knob (process-global): 0 = auto (default), 1 = cta_group::1 tiles 128x256, 2 = CTA-pair tiles 256x256. */
 /* Stride-1 KxK convolution over a zero-padded channels-last map as ONE implicit GEMM (no im2col buffer): the 3x3
  * `output_convs` of the Grounding-DINO mask-feature FPN (modeling_ov_grounding_dino_mask_dn.py:2136-2146, :2476).

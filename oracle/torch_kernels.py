@@ -16,7 +16,7 @@ _ACT = {None: lambda z: z, "none": lambda z: z, "relu": torch.relu, "gelu": F.ge
         "quick_gelu": lambda z: z * torch.sigmoid(1.702 * z)}
 
 
-def linear(x, w, bias=None, act=None, colscale=None, residual=None, out_dtype=None, out=None):
+def linear(x, w, bias=None, act=None, colscale=None, residual=None, out_dtype=None, out=None, row_keep=None):
     y = F.linear(x.float(), w.float(), None if bias is None else bias.float())
     if act == "swiglu":                                   # gate / up rows interleaved in `w` (llama.py packed operand)
         y = F.silu(y[..., 0::2]) * y[..., 1::2]
@@ -26,6 +26,8 @@ def linear(x, w, bias=None, act=None, colscale=None, residual=None, out_dtype=No
         y = y * colscale.float()
     if residual is not None:
         y = y + residual.float().reshape(y.shape)
+    if row_keep is not None:                               # rows with False are stored as exact zeros (ops.linear)
+        y = y.masked_fill(~row_keep.bool().reshape(y.shape[:-1])[..., None], 0.0)
     if out is not None:
         out.copy_(y)
         return out

@@ -100,7 +100,7 @@ def test_attention_head_dim_256_and_key_mask():
     s = s.masked_fill(~km[:, None, None, :], float("-inf"))
     ref = (torch.softmax(s, -1) @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
     check(out, ref)
-    # head_dim 128 with a key mask takes the warp-MMA kernel (the TMEM kernel has no mask operand)
+    # head_dim 128 with a key mask: tcgen05 kernel with the mask operand (r2)
     q2, k2, v2 = q[..., :128].contiguous(), k[..., :128].contiguous(), v[..., :128].contiguous()
     out2 = ops.attention(q2, k2, v2, key_mask=km)
     s2 = (q2.float().permute(0, 2, 1, 3) @ k2.float().permute(0, 2, 3, 1)) * 128 ** -0.5
@@ -144,3 +144,37 @@ def test_attention_split_kv_few_queries_many_keys(D, H):
             s_ = s_.masked_fill(~mask[:, None, None, :], float("-inf"))
         ref = (torch.softmax(s_, -1) @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
         check(out, ref)
+
+
+@pytest.mark.parametrize("D", [128, 256])
+@pytest.mark.parametrize("Tq,Tk", [(300, 80), (80, 4352), (257, 640), (1500, 96)])
+def test_attention_tcgen05_key_mask_and_split_kv(D, Tq, Tk):
+    """r2: head_dim 256 and key-masked head_dim 128 calls run on the tcgen05 kernel (attention_tc2.cu<D, KM>): the
+    GDINO bi-attention's two shapes (many vision queries x 80 text keys; 80 text queries x thousands of vision keys,
+    split along the key axis) with arbitrary key masks -- 16-byte mask loads (Tk % 16 == 0), fully masked 64-key tiles,
+    a batch entry whose mask leaves a single key.  Checked against fp32 torch and against the warp-MMA kernel."""
+    from visionllm_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(D + Tq + Tk)
+    B, H = 3, 4
+    q = torch.randn(B, Tq, H, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Tk, H, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Tk, H, D, device="cuda", generator=g).bfloat16()
+    km = torch.rand(B, Tk, device="cuda", generator=g) > 0.3
+    km[0, :] = True
+    if Tk >= 256:
+        km[1, 64:192] = False                              # two whole key tiles masked out
+    km[2, :] = False
+    km[2, Tk // 2] = True                                  # one key left
+    for mask in (km, None):
+        out = ops.attention(q, k, v, key_mask=mask)
+        s_ = (q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 3, 1)) * D ** -0.5
+        if mask is not None:
+            s_ = s_.masked_fill(~mask[:, None, None, :], float("-inf"))
+        ref = (torch.softmax(s_, -1) @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
+        check(out, ref)
+        _lib.lib().vllm_attention_set_variant(1)
+        try:
+            warp = ops.attention(q, k, v, key_mask=mask)
+        finally:
+            _lib.lib().vllm_attention_set_variant(0)
+        check(out, warp.float())

@@ -22,13 +22,15 @@ def torch_kernels(monkeypatch):
     import visionllm_b200.ops as ops
     from oracle import msda_oracle as O
 
-    def linear(x, w, bias=None, act=None, colscale=None, residual=None, out_dtype=None, out=None):
+    def linear(x, w, bias=None, act=None, colscale=None, residual=None, out_dtype=None, out=None, row_keep=None):
         y = F.linear(x.float(), w.float(), None if bias is None else bias.float())
         y = {"relu": torch.relu, "gelu": F.gelu, "silu": F.silu, None: lambda z: z}[act](y)
         if colscale is not None:
             y = y * colscale.float()
         if residual is not None:
             y = y + residual.float().reshape(y.shape)
+        if row_keep is not None:
+            y = y.masked_fill(~row_keep.bool().reshape(y.shape[:-1])[..., None], 0.0)
         if out is not None:
             out.copy_(y)
             return out

@@ -41,6 +41,8 @@ def run(value, shapes, lsi, loc, attw, variant=0, window=(0, 0, 0), out_dtype=No
     import visionllm_b200.msda as ext
     from visionllm_b200 import _lib
     L_ = _lib.lib()
+    if value.dtype == torch.float32 and variant == 0:
+        variant = 33                                   # fp32 rows: the window kernel is opt-in (the default is the patch kernel)
     L_.vllm_msda_set_variant(variant)
     L_.vllm_msda_set_window(*window)
     L_.vllm_msda_set_window_fill(1 if tma_fill else 0)
@@ -145,8 +147,9 @@ def test_full_size_encoder_shape_properties():
     value, shapes, lsi, loc, attw = B.msda_encoder_inputs(torch, 2, torch.device("cuda"), 77)
     hs = shapes.cpu()
     import visionllm_b200.msda as ext
-    win = ext.ms_deform_attn_forward(value, shapes, lsi, loc, attw, 64, host_shapes=hs)
+    win = run(value, shapes, lsi, loc, attw)
     assert torch.equal(win, run(value, shapes, lsi, loc, attw, variant=4))
+    assert torch.equal(win, ext.ms_deform_attn_forward(value, shapes, lsi, loc, attw, 64, host_shapes=hs))   # default path
     strict = ext.ms_deform_attn_forward(value, shapes, lsi, loc, attw, 64, flags=ext.STRICT)
     assert (win - strict).abs().max().item() <= 1e-5 * strict.abs().max().item()
     v16 = value.bfloat16()

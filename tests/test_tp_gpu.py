@@ -152,6 +152,42 @@ def test_tp_world1_matches_unsharded():
     assert rel_l2(out.logits_local.view(B, T, -1), one.logits) < 5e-3
 
 
+@pytest.mark.parametrize("world", [1, 2])
+def test_tp_micro_batched_forward_equals_the_plain_forward(world):
+    """r2: the batch cut into two micro-batches with their own exchange buffers (TPLlamaForCausalLM.micro_generators /
+    forward_pipelined: two CUDA streams, the halves' exchange steps hide behind each other's GEMMs) must give the plain
+    forward's states and logits -- every op is row-wise or per sequence.  W = 1 runs the real two-stream schedule, W = 2
+    the virtual ranks in lock step; twice in a row (epochs, buffer reuse)."""
+    from visionllm_b200 import tp
+    cfg, hf, sd, emb, am = _hf_and_inputs(False)
+    B, T, H = emb.shape
+    assert B % 2 == 0
+    comms = tp.PeerComm.virtual(world, B * T, H)
+    ranks = [tp.TPLlamaForCausalLM.from_full_state_dict(cfg, c, sd, device="cuda") for c in comms]
+    plain = tp.run_lockstep(ranks, emb.cuda())
+    torch.cuda.synchronize()
+    micro = [tp.PeerComm.virtual(world, B * T // 2, H) for _ in range(2)]          # micro[i][rank]
+    per_rank = [[micro[i][r] for i in range(2)] for r in range(world)]
+    Rm = B * T // 2 // world
+    for rep in range(2):
+        if world == 1:
+            out = ranks[0].forward_pipelined(per_rank[0], inputs_embeds=emb.cuda())
+            torch.cuda.synchronize()
+            res = [ranks[0].results]
+            assert torch.equal(out.last_hidden_state, plain[0].last_hidden_state)
+        else:
+            res = tp.run_lockstep_micro(ranks, per_rank, emb.cuda())
+            torch.cuda.synchronize()
+        full_logits = torch.cat([p.logits_local for p in plain], 0).view(B, T, -1)
+        for r in range(world):
+            for i in range(2):
+                got = res[r][i]
+                assert torch.equal(got.last_hidden_state, plain[0].last_hidden_state[i * (B // 2):(i + 1) * (B // 2)])
+                assert got.row_range == (r * Rm, (r + 1) * Rm)
+                want = full_logits[i * (B // 2):(i + 1) * (B // 2)].reshape(B * T // 2, -1)[r * Rm:(r + 1) * Rm]
+                assert torch.equal(got.logits_local, want)
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["VLLM_ROOT"])
@@ -179,6 +215,11 @@ for rep in range(3):
     e1 = rel(out.last_hidden_state, one.hidden_states[-1])
     e2 = rel(out.logits_local, one.logits.reshape(B * T, -1)[lo:hi])
     assert e1 < 1e-2 and e2 < 1e-2, (rank, rep, e1, e2)
+mc = [tp.PeerComm.from_process_group(B * T // 2, H, torch.device("cuda", rank)) for _ in range(2)]
+for rep in range(3):
+    outp = m.forward_pipelined(mc, inputs_embeds=emb)
+    torch.cuda.synchronize()
+    assert torch.equal(outp.last_hidden_state, out.last_hidden_state), (rank, rep, "pipelined states differ")
 dist.barrier()
 print(f"rank {rank} ok {e1:.2e} {e2:.2e}", flush=True)
 dist.destroy_process_group()

@@ -5,6 +5,7 @@
     4. MSDA window kernel, fp32 value / fp32 out, cfg-2b encoder shape (N=8, S=Lq=21760)
     5. MSDA window kernel, bf16 value / bf16 out, same shape
     6. MSDA global warp-gather kernel (variant 4), fp32 -- the r1 kernel, for comparison
+    7. MSDA global patch kernel (variant 0 = the fp32 default)
 
   ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r2_targets \
       python tools/ncu_targets.py
@@ -17,7 +18,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 LABELS = [("gemm", "41000x12800x3200"), ("gemm", "41000x3200x12800"), ("gemm", "41000x9600x3200"),
-          ("msda", "window fp32"), ("msda", "window bf16"), ("msda", "global warp-gather fp32 (variant 4)")]
+          ("msda", "window fp32 (variant 33)"), ("msda", "window bf16 (default)"), ("msda", "global warp-gather fp32 (variant 4)"),
+          ("msda", "global patch kernel fp32 (default)")]
 
 
 def run():
@@ -44,11 +46,14 @@ def run():
         ops.linear(x32, w1, bias=b1, act="gelu")
         ops.linear(x128, w2, bias=b2, colscale=ls, residual=x32)
         ops.linear(x32, wq)
+        L_.vllm_msda_set_variant(33)                           # fp32 rows: the window kernel is opt-in
         ext.ms_deform_attn_forward(value, shapes, lsi, loc, attw, 64, host_shapes=hs)
+        L_.vllm_msda_set_variant(0)
         ext.ms_deform_attn_forward_bf16(v16, shapes, lsi, loc, attw)
         L_.vllm_msda_set_variant(4)
         ext.ms_deform_attn_forward(value, shapes, lsi, loc, attw, 64, host_shapes=hs)
         L_.vllm_msda_set_variant(0)
+        ext.ms_deform_attn_forward(value, shapes, lsi, loc, attw, 64, host_shapes=hs)
 
     for _ in range(2):
         targets()

@@ -367,6 +367,42 @@ int vllm_attention_tc2_d128(const void* q, const void* k, const void* v, void* o
                             int kv_heads, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
                             long long v_ts, long long o_bs, long long o_ts, const int* seqlens, int causal, float scale,
                             cudaStream_t st);
+int vllm_attention_tc2(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk, int heads,
+                       int kv_heads, int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts,
+                       long long v_bs, long long v_ts, long long o_bs, long long o_ts, const int* seqlens,
+                       const unsigned char* key_mask, int causal, float scale, int n_splits, float* ws, cudaStream_t st);
+
+// tcgen05 path for head_dim 256 and for key-masked head_dim 128 calls (r2): picks a split-KV count like launch<> below
+// when the query tiles alone cannot fill the SMs, then merges the partials with the same combine kernel.
+template <int D>
+static int launch_tc2_split(const AttnArgs& a, int batch, float scale, cudaStream_t st, void* workspace,
+                            long long workspace_bytes) {
+  const int q_tiles = (a.Tq + 127) / 128;
+  const long long ctas = (long long)q_tiles * a.heads * batch;
+  const int n_tiles = (a.Tk + 63) / 64;
+  long long best = 1;
+  if (workspace && !a.causal && ctas < 2LL * vllm_num_sms() && n_tiles >= 16) {
+    const long long slots = (long long)vllm_num_sms() * (D == 128 ? 2 : 1);
+    long long best_cost = (ctas + slots - 1) / slots * (n_tiles + 4);
+    const long long max_s = n_tiles / 4 < 64 ? n_tiles / 4 : 64;
+    for (long long sp = 2; sp <= max_s; ++sp) {
+      if ((long long)batch * a.heads * sp * a.Tq * (D + 2) * 4 > workspace_bytes) break;
+      const long long waves = (ctas * sp + slots - 1) / slots;
+      const long long cost = waves * ((n_tiles + sp - 1) / sp + 4);       // +4 tiles: Q load, prologue, partial write-out
+      if (cost < best_cost) { best_cost = cost; best = sp; }
+    }
+  }
+  const int rc = vllm_attention_tc2(a.q, a.k, a.v, a.o, batch, a.Tq, a.Tk, a.heads, a.kv_heads, D, a.q_bs, a.q_ts, a.k_bs,
+                                    a.k_ts, a.v_bs, a.v_ts, a.o_bs, a.o_ts, a.seqlens, a.key_mask, a.causal, scale, (int)best,
+                                    best > 1 ? (float*)workspace : nullptr, st);
+  if (rc != VLLM_OK || best == 1) return rc;
+  const long long n_rows = (long long)batch * a.heads * a.Tq;
+  splitkv_combine_kernel<D><<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>((const float*)workspace, a.o, a.o_bs, a.o_ts, a.Tq,
+                                                                         a.heads, (int)best, n_rows);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
 // head_dim 128 without masks: 0 = tcgen05 "tc2" schedule (default: 1 Q tile/CTA, 2 CTAs/SM, double-buffered S),
 // 2 = tcgen05 ping-pong schedule (attention_tc.cu); 1 = always the warp-MMA kernel.
 static int g_attn_variant = 0;
@@ -400,6 +436,11 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
     const int rc = vllm_attention_tc2_d128(q, k, v, o, batch, Tq, Tk, heads, kv_heads, q_batch_pitch, q_token_pitch,
                                            k_batch_pitch, k_token_pitch, v_batch_pitch, v_token_pitch, o_batch_pitch,
                                            o_token_pitch, seqlens, causal, scale, st);
+    if (rc != VLLM_EUNSUPPORTED) return rc;
+  }
+  if ((head_dim == 256 || (head_dim == 128 && key_mask)) && g_attn_variant == 0 && !attn_mask && !attn_bias) {
+    const int rc = head_dim == 256 ? launch_tc2_split<256>(a, batch, scale, st, workspace, workspace_bytes)
+                                   : launch_tc2_split<128>(a, batch, scale, st, workspace, workspace_bytes);
     if (rc != VLLM_EUNSUPPORTED) return rc;
   }
   if (head_dim == 128 && g_attn_variant == 2 && !key_mask && !attn_mask && !attn_bias) {

@@ -1,4 +1,4 @@
-// Fused attention on tcgen05/TMEM, head_dim 128 -- second schedule ("tc2").
+// Fused attention on tcgen05/TMEM, head_dim 128 or 256 -- second schedule ("tc2").
 //
 // Same operator and building blocks as attention_tc.cu; different occupancy plan.  Instead of one CTA carrying
 // two ping-pong Q tiles, each CTA carries ONE 128-row Q tile with K/V tiles of 64 keys, a DOUBLE-BUFFERED score
@@ -6,16 +6,26 @@
 //   TMEM: S[0] (64 cols) | S[1] (64 cols) | O (128 cols); P[b] (bf16) aliases the first 32 columns of S[b].
 //   The MMA warp issues S(j+2) right after PV(j), i.e. scores run two tiles ahead of the softmax, so the softmax
 //   warpgroup never waits for its own MMAs; the other resident CTA fills the tensor pipe in the meantime.
+// head_dim 256 (r2: the GDINO bi-attention, 4 heads x 256 -- modeling_ov_grounding_dino_mask_dn.py:893-1006): the same
+// schedule with Q = 4 x 16 KB column chunks, K/V tiles of 64 keys x 512 B, O = 256 TMEM columns (S[0] | S[1] | O in a
+// 512-column allocation), 193 KB smem => one CTA per SM.  KM = true adds an arbitrary key mask [batch, Tk] (1 = attend:
+// the text / vision padding masks of the bi-attention); n_splits > 1 lets several CTAs share one query tile along the key
+// axis (80 text queries over 21760 pixels) and write unnormalised partials in attention.cu's split-KV workspace layout.
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int D = 128, BQ = 128, BKV = 64, STG = 2;
-constexpr int Q_BYTES = BQ * D * 2, Q_HALF = Q_BYTES / 2;       // two 64-column halves of 128 rows
-constexpr int KV_BYTES = BKV * D * 2, KV_HALF = KV_BYTES / 2;   // two 64-column halves of 64 rows
+constexpr int BQ = 128, BKV = 64, STG = 2;
 constexpr int THREADS = 256;
-constexpr int SMEM = Q_BYTES + 2 * STG * KV_BYTES + 1024 + 256;
+template <int D> struct Cfg {
+  static constexpr int NCH = D / 64;                         // 64-column (128-byte, one swizzle atom wide) chunks
+  static constexpr int Q_BYTES = BQ * D * 2, Q_CHUNK = BQ * 128;
+  static constexpr int KV_BYTES = BKV * D * 2, KV_CHUNK = BKV * 128;
+  static constexpr int SMEM = Q_BYTES + 2 * STG * KV_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = D == 128 ? 256 : 512;     // S[0] | S[1] | O (power of two)
+  static constexpr int CTAS = D == 128 ? 2 : 1;
+};
 
 struct Args {
   __nv_bfloat16* o;
@@ -23,6 +33,10 @@ struct Args {
   const int* seqlens;
   int Tq, Tk, heads, kv_heads, causal;
   float scale_log2;
+  const unsigned char* key_mask;   // [batch, Tk], 1 = attend (KM instantiations only)
+  int km_vec;                      // mask rows can be read as 16-byte vectors
+  int n_splits;                    // CTAs per query tile along the key axis
+  float* ws;                       // [batch*heads*n_splits*Tq][D + 2] fp32: unnormalised O, m (log2 domain), l
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
@@ -104,9 +118,12 @@ __device__ __forceinline__ void exp_half(const uint32_t (&r)[32], uint32_t taddr
   tmem_st_32x16(taddr, pk);
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
+template <int D, bool KM>
+__global__ void __launch_bounds__(THREADS, Cfg<D>::CTAS)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const Args a) {
+  constexpr int NCH = Cfg<D>::NCH, Q_BYTES = Cfg<D>::Q_BYTES, Q_CHUNK = Cfg<D>::Q_CHUNK;
+  constexpr int KV_BYTES = Cfg<D>::KV_BYTES, KV_CHUNK = Cfg<D>::KV_CHUNK, TMEM_COLS = Cfg<D>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -123,13 +140,17 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, head = blockIdx.y, b = blockIdx.z;
+  const int split = blockIdx.x % a.n_splits;
+  const int q0 = (blockIdx.x / a.n_splits) * BQ, head = blockIdx.y, b = blockIdx.z;
   const int kvh = head / (a.heads / a.kv_heads);
   const int len = a.seqlens ? min(a.seqlens[b], a.Tk) : a.Tk;
   const int coff = a.Tk - a.Tq;
   int k_end = len;
   if (a.causal) k_end = min(k_end, q0 + BQ + coff);
-  const int n = k_end > 0 ? (k_end + BKV - 1) / BKV : 0;
+  const int n_all = k_end > 0 ? (k_end + BKV - 1) / BKV : 0;
+  const int per_split = (n_all + a.n_splits - 1) / a.n_splits;
+  const int t0 = split * per_split;                        // this CTA's key tiles: [t0, t0 + n)
+  const int n = max(0, min(n_all - t0, per_split));
 
   if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tm_q); tc::tma_prefetch_desc(&tm_k); tc::tma_prefetch_desc(&tm_v); }
   if (warp == 1 && lane == 0) {
@@ -141,7 +162,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tc::mbar_init(o_full, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 2) tc::tmem_alloc<1>(tmem_slot, 256);
+  if (warp == 2) tc::tmem_alloc<1>(tmem_slot, TMEM_COLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -152,16 +173,16 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     // ===================== TMA producer =====================
     if (tc::elect_one() && n > 0) {
       tc::mbar_arrive_expect_tx(q_full, Q_BYTES);
-      for (int h = 0; h < 2; ++h) tma_load_3d(sQ + h * Q_HALF, &tm_q, q_full, head * D + h * 64, q0, b);
+      for (int h = 0; h < NCH; ++h) tma_load_3d(sQ + h * Q_CHUNK, &tm_q, q_full, head * D + h * 64, q0, b);
       for (int j = 0; j < n; ++j) {
         const int s = j % STG;
         const uint32_t ph = ((j / STG) & 1) ^ 1;
         tc::mbar_wait(k_empty(s), ph);
         tc::mbar_arrive_expect_tx(k_full(s), KV_BYTES);
-        for (int h = 0; h < 2; ++h) tma_load_3d(sK + s * KV_BYTES + h * KV_HALF, &tm_k, k_full(s), kvh * D + h * 64, j * BKV, b);
+        for (int h = 0; h < NCH; ++h) tma_load_3d(sK + s * KV_BYTES + h * KV_CHUNK, &tm_k, k_full(s), kvh * D + h * 64, (t0 + j) * BKV, b);
         tc::mbar_wait(v_empty(s), ph);
         tc::mbar_arrive_expect_tx(v_full(s), KV_BYTES);
-        for (int h = 0; h < 2; ++h) tma_load_3d(sV + s * KV_BYTES + h * KV_HALF, &tm_v, v_full(s), kvh * D + h * 64, j * BKV, b);
+        for (int h = 0; h < NCH; ++h) tma_load_3d(sV + s * KV_BYTES + h * KV_CHUNK, &tm_v, v_full(s), kvh * D + h * 64, (t0 + j) * BKV, b);
       }
     }
     __syncwarp();
@@ -174,8 +195,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t ka = sK + s * KV_BYTES;
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
-        tc::umma_f16<1>(tmem + s * 64, desc_sw128(sQ + (kk >> 2) * Q_HALF + (kk & 3) * 32, 16, 1024),
-                        desc_sw128(ka + (kk >> 2) * KV_HALF + (kk & 3) * 32, 16, 1024), idesc_s, kk != 0);
+        tc::umma_f16<1>(tmem + s * 64, desc_sw128(sQ + (kk >> 2) * Q_CHUNK + (kk & 3) * 32, 16, 1024),
+                        desc_sw128(ka + (kk >> 2) * KV_CHUNK + (kk & 3) * 32, 16, 1024), idesc_s, kk != 0);
       tc::umma_commit<1>(s_full(s));
       tc::umma_commit<1>(k_empty(s));
     };
@@ -184,7 +205,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t va = sV + s * KV_BYTES;
 #pragma unroll
       for (int kk = 0; kk < BKV / 16; ++kk)
-        umma_ts(tO, tmem + s * 64 + kk * 8, desc_sw128(va + kk * 2048, KV_HALF, 1024), idesc_pv, (j | kk) != 0);
+        umma_ts(tO, tmem + s * 64 + kk * 8, desc_sw128(va + kk * 2048, KV_CHUNK, 1024), idesc_pv, (j | kk) != 0);
       tc::umma_commit<1>(o_full);
       tc::umma_commit<1>(v_empty(s));
     };
@@ -228,7 +249,30 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc::tmem_ld_32x32(tS, ra);
       tc::tmem_ld_32x32(tS + 32, rb);
       tc::tmem_ld_wait();
-      const int n0 = j * BKV;
+      const int n0 = (t0 + j) * BKV;
+      if constexpr (KM) {
+        // arbitrary key mask: the 64 mask bytes of this tile are the same for every row (broadcast loads)
+        const unsigned char* km = a.key_mask + (size_t)b * a.Tk + n0;
+        if (a.km_vec && n0 + BKV <= a.Tk) {
+          const uint4* kp = reinterpret_cast<const uint4*>(km);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const uint4 w = __ldg(kp + h);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool keep = (ww[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+              if (!keep) { if (h < 2) ra[h * 16 + i] = 0xff800000u; else rb[(h - 2) * 16 + i] = 0xff800000u; }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            if (n0 + k < a.Tk && !__ldg(km + k)) ra[k] = 0xff800000u;
+            if (n0 + 32 + k < a.Tk && !__ldg(km + 32 + k)) rb[k] = 0xff800000u;
+          }
+        }
+      }
       const bool need_mask = (n0 + BKV > len) || (a.causal && (n0 + BKV - 1 > q0 + coff));
       if (need_mask) {
         const int lim = (a.causal ? min(len, row + coff + 1) : len) - n0;
@@ -279,6 +323,24 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc::mbar_wait(o_full, (n - 1) & 1);
       tc::tc_fence_after();
     }
+    if (a.n_splits > 1) {
+      // partial of this key range: unnormalised O, the running max actually used (log2 domain) and the sum
+      float* wp = a.ws + ((((size_t)b * a.heads + head) * a.n_splits + split) * a.Tq + row) * (D + 2);
+#pragma unroll 1
+      for (int c = 0; c < D; c += 32) {
+        uint32_t o[32];
+        if (n > 0) { tc::tmem_ld_32x32(tO + lane_addr + c, o); tc::tmem_ld_wait(); }
+        else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] = 0u;
+        }
+        if (row < a.Tq) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) *reinterpret_cast<uint2*>(wp + c + k) = make_uint2(o[k], o[k + 1]);
+        }
+      }
+      if (row < a.Tq) { wp[D] = n > 0 ? m : -INFINITY; wp[D + 1] = l; }
+    } else {
     const float inv = l > 0.f ? 1.f / l : 0.f;
     __nv_bfloat16* op = a.o + b * a.o_bs + (long long)row * a.o_ts + head * D;
 #pragma unroll
@@ -303,11 +365,12 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
       }
     }
+    }
   }
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc<1>(tmem, 256);
+  if (warp == 2) tc::tmem_dealloc<1>(tmem, TMEM_COLS);
 }
 
 int make_tmap(CUtensorMap* m, const void* base, uint64_t cols, uint64_t tokens, uint64_t batch, uint64_t token_pitch,
@@ -327,25 +390,48 @@ int make_tmap(CUtensorMap* m, const void* base, uint64_t cols, uint64_t tokens, 
 
 }  // namespace
 
-int vllm_attention_tc2_d128(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk, int heads,
-                            int kv_heads, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
-                            long long v_ts, long long o_bs, long long o_ts, const int* seqlens, int causal, float scale,
-                            cudaStream_t st) {
+template <int D, bool KM>
+static int launch_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Args& a, int batch,
+                      cudaStream_t st) {
+  auto kern = attn_fwd_tc2_kernel<D, KM>;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    set = true;
+  }
+  dim3 grid((unsigned)(((a.Tq + BQ - 1) / BQ) * a.n_splits), a.heads, batch);
+  kern<<<grid, THREADS, Cfg<D>::SMEM, st>>>(tq, tk, tv, a);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
+// head_dim 128 / 256; key_mask optional ([batch, Tk] bytes, 1 = attend); n_splits > 1: partials go to `ws`
+// ([batch*heads*n_splits*Tq][head_dim + 2] fp32) and the caller merges them (attention.cu splitkv_combine_kernel).
+int vllm_attention_tc2(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk, int heads,
+                       int kv_heads, int head_dim, long long q_bs, long long q_ts, long long k_bs, long long k_ts,
+                       long long v_bs, long long v_ts, long long o_bs, long long o_ts, const int* seqlens,
+                       const unsigned char* key_mask, int causal, float scale, int n_splits, float* ws, cudaStream_t st) {
+  if (head_dim != 128 && head_dim != 256) return VLLM_EUNSUPPORTED;
+  if (n_splits < 1 || (n_splits > 1 && (!ws || causal))) return VLLM_EINVAL;
+  const uint64_t D = (uint64_t)head_dim;
   CUtensorMap tq, tk, tv;
   if (make_tmap(&tq, q, (uint64_t)heads * D, Tq, batch, q_ts, q_bs, BQ)) return VLLM_EUNSUPPORTED;
   if (make_tmap(&tk, k, (uint64_t)kv_heads * D, Tk, batch, k_ts, k_bs, BKV)) return VLLM_EUNSUPPORTED;
   if (make_tmap(&tv, v, (uint64_t)kv_heads * D, Tk, batch, v_ts, v_bs, BKV)) return VLLM_EUNSUPPORTED;
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return (int)e;
-    set = true;
-  }
   Args a;
   a.o = (__nv_bfloat16*)o; a.o_bs = o_bs; a.o_ts = o_ts; a.seqlens = seqlens; a.Tq = Tq; a.Tk = Tk;
   a.heads = heads; a.kv_heads = kv_heads; a.causal = causal; a.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((Tq + BQ - 1) / BQ, heads, batch);
-  attn_fwd_tc2_kernel<<<grid, THREADS, SMEM, st>>>(tq, tk, tv, a);
-  VLLM_CHECK_LAUNCH();
-  return VLLM_OK;
+  a.key_mask = key_mask; a.km_vec = (key_mask && Tk % 16 == 0 && vllm_aligned(key_mask, 16)) ? 1 : 0;
+  a.n_splits = n_splits; a.ws = ws;
+  if (head_dim == 128) return key_mask ? launch_tc2<128, true>(tq, tk, tv, a, batch, st) : launch_tc2<128, false>(tq, tk, tv, a, batch, st);
+  return key_mask ? launch_tc2<256, true>(tq, tk, tv, a, batch, st) : launch_tc2<256, false>(tq, tk, tv, a, batch, st);
+}
+
+int vllm_attention_tc2_d128(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk, int heads,
+                            int kv_heads, long long q_bs, long long q_ts, long long k_bs, long long k_ts, long long v_bs,
+                            long long v_ts, long long o_bs, long long o_ts, const int* seqlens, int causal, float scale,
+                            cudaStream_t st) {
+  return vllm_attention_tc2(q, k, v, o, batch, Tq, Tk, heads, kv_heads, 128, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts,
+                            seqlens, nullptr, causal, scale, 1, nullptr, st);
 }

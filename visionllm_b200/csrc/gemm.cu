@@ -37,6 +37,7 @@ struct GemmArgs {
   void* C; int ldc;
   const __nv_bfloat16* bias; const __nv_bfloat16* colscale; const __nv_bfloat16* residual; int ldr;
   int act; int out_f32;
+  const unsigned char* row_keep;   // optional [M]: rows with 0 are written as exact zeros (value.masked_fill of the MSDA module)
   int tiles_m, tiles_n;  // tiles_m counts 128*CG-row blocks
   int group_m;           // row-blocks per rasterisation group (see pick_group_m)
   // Implicit convolution over a zero-padded channels-last image (vllm_conv_rows_bf16): the K axis is a_segs segments
@@ -255,6 +256,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       const bool row_ok = row < g.M;
+      const bool zero_row = g.row_keep && row_ok && !g.row_keep[row];
       // the 32-column step of the general path: direct row-per-thread stores (fp32 output, SwiGLU, ragged N)
       auto direct32 = [&](int c) {
         const int col0 = n0 + c;
@@ -330,6 +332,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             } else {
               for (int j = 0; j < 32; ++j) if (col0 + j < g.N) v[j] += __bfloat162float(rp[j]);
             }
+          }
+          if (zero_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           if (g.out_f32) {
             float* cp = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col0;
@@ -412,6 +418,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 v[8 * q + 2 * j] += f.x; v[8 * q + 2 * j + 1] += f.y;
               }
             }
+          }
+          if (zero_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -538,9 +548,26 @@ extern "C" {
 int vllm_gemm_set_variant(int v) { g_gemm_variant = (v == 1 || v == 2) ? v : 0; return VLLM_OK; }
 int vllm_gemm_set_group_m(int gm) { g_group_m_override = gm; return VLLM_OK; }
 
+static int gemm_bf16_common(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                            const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
+                            const unsigned char* row_keep, void* stream);
+
 int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                    const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
                    void* stream) {
+  return gemm_bf16_common(A, lda, B, ldb, C, ldc, M, N, K, bias, colscale, residual, ldr, act, out_f32, nullptr, stream);
+}
+
+int vllm_gemm_bf16_rowmask(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                           const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
+                           const unsigned char* row_keep, void* stream) {
+  if (!row_keep || act == ACT_SWIGLU) return VLLM_EINVAL;
+  return gemm_bf16_common(A, lda, B, ldb, C, ldc, M, N, K, bias, colscale, residual, ldr, act, out_f32, row_keep, stream);
+}
+
+static int gemm_bf16_common(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                            const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
+                            const unsigned char* row_keep, void* stream) {
   if (M < 0 || N <= 0 || K <= 0 || lda < K || ldb < K) return VLLM_EINVAL;
   if (M == 0) return VLLM_OK;
   if (!A || !B || !C) return VLLM_EINVAL;
@@ -557,6 +584,7 @@ int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int 
   g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc;
   g.bias = (const __nv_bfloat16*)bias; g.colscale = (const __nv_bfloat16*)colscale;
   g.residual = (const __nv_bfloat16*)residual; g.ldr = ldr; g.act = act; g.out_f32 = out_f32;
+  g.row_keep = row_keep;
   cudaStream_t st = (cudaStream_t)stream;
   const int cg = g_gemm_variant ? g_gemm_variant : (K <= 512 ? 1 : 2);
   if (cg == 2) return launch_gemm<2>(A, lda, B, ldb, g, st);

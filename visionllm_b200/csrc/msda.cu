@@ -715,7 +715,10 @@ int vllm_msda_forward_f32(const float* value, const int64_t* spatial_shapes, con
   const int K = num_levels * num_point;
   if (!strict && channels == 32 && K <= 32 && vllm_aligned(value, 16) && vllm_aligned(out, 16) &&
       vllm_aligned(sampling_loc, 8)) {
-    if (g_msda_variant == 0 || g_msda_variant == 33) {   // encoder shape: TMA-staged windows (msda_win.cu)
+    // encoder shape, fp32 rows: the TMA-staged window kernel (msda_win.cu) is opt-in (variant 33) -- 128-byte rows leave
+    // room for an 8 x 8 patch only and it measures 0.62 ms against 0.59 ms for the global-memory patch kernel below
+    // (profiles/r2_msda_window_sweep.json); bf16 rows (vllm_msda_forward_bf16v) take the window kernel by default
+    if (g_msda_variant == 33) {
       const int r = msda_launch_window<float, float>(value, level_start_index, sampling_loc, attn_weight, out, batch,
                                                      spatial_size, num_heads, num_levels, num_query, num_point,
                                                      host_shapes_hint, st);

@@ -498,9 +498,11 @@ static bool build_window(WinCacheEntry& e, const ValT* value, const int64_t* hs,
     tot += H * W;
   }
   if (tot != S) return false;
-  // level-0 patch: 8 x 16 pixels for bf16 rows (64 B), 8 x 8 for fp32 rows (128 B) -- about 80-100 KB of windows, 2 CTAs / SM
-  wp.PH = g_win_ph > 0 ? g_win_ph : 8;
-  wp.PW = g_win_pw > 0 ? g_win_pw : (VB == 2 ? 16 : 8);
+  // level-0 patch: 16 x 32 pixels for bf16 rows (64 B): 159 KB of windows, one 32-warp CTA per SM (measured best,
+  // profiles/r2_msda_window_sweep.json: the halo is amortised over 4x the queries of an 8 x 16 patch); 8 x 8 for fp32 rows
+  // (128 B): 95 KB, two 16-warp CTAs per SM
+  wp.PH = g_win_ph > 0 ? g_win_ph : (VB == 2 ? 16 : 8);
+  wp.PW = g_win_pw > 0 ? g_win_pw : (VB == 2 ? 32 : 8);
   const int halo0 = g_win_halo > 0 ? g_win_halo : (VB == 2 ? 8 : 6);
   wp.RX = (wp.W[0] + wp.PW - 1) / wp.PW;
   wp.RY = (wp.H[0] + wp.PH - 1) / wp.PH;
@@ -596,23 +598,27 @@ int msda_launch_window(const ValT* value, const int64_t* lsi, const float* loc, 
 template <typename OutT>
 static int launch_window_qp(const __nv_bfloat16* value, const int64_t* lsi, const MsdaQp& fq, OutT* out, int N, int S, int M, int L,
                             int Lq, int P, const int64_t* host_shapes, cudaStream_t st) {
-  constexpr int NW = 16;
   if (!host_shapes || Lq != S || L != 4 || P != 4 || N > 65535) return 1;
   const WinCacheEntry* e = window_for<__nv_bfloat16>(value, host_shapes, N, S, M, L);
-  if (!e || e->smem > 110 * 1024) return 1;
+  if (!e) return 1;
   dim3 grid((unsigned)(e->wp.RX * e->wp.RY * M), (unsigned)N);
-  auto kern = msda_fwd_win_kernel<__nv_bfloat16, OutT, NW, 16, 4, true>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    if (err != cudaSuccess) return (int)err;
-    configured = true;
-  }
-  MsdaWin wp = e->wp;
-  set_fill(wp, 2);
-  kern<<<grid, NW * 32, e->smem, st>>>(e->maps, value, lsi, nullptr, nullptr, out, S, M, Lq, P, wp, fq);
-  VLLM_CHECK_LAUNCH();
-  return VLLM_OK;
+  const bool big = e->smem > 110 * 1024;
+  auto launch = [&](auto kern, int nw) -> int {
+    static int configured = -1;
+    if (configured < e->smem) {
+      const int want = big ? e->smem : 112 * 1024;
+      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      if (err != cudaSuccess) return (int)err;
+      configured = want;
+    }
+    MsdaWin wp = e->wp;
+    set_fill(wp, 2);
+    kern<<<grid, nw * 32, e->smem, st>>>(e->maps, value, lsi, nullptr, nullptr, out, S, M, Lq, P, wp, fq);
+    VLLM_CHECK_LAUNCH();
+    return VLLM_OK;
+  };
+  return big ? launch(msda_fwd_win_kernel<__nv_bfloat16, OutT, 32, 16, 4, true>, 32)
+             : launch(msda_fwd_win_kernel<__nv_bfloat16, OutT, 16, 16, 4, true>, 16);
 }
 
 extern "C" int vllm_msda_forward_fused_bf16(const void* value, const int64_t* level_start_index, const void* qp, int ld_qp,

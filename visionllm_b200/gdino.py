@@ -44,6 +44,10 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
         self._packed = None
         self._reset_parameters()
 
+    # the reference module always returns the attention weights (gd.py:784); an owner that never reads them (the B200 GDINO
+    # stage) clears this so the fused gather kernel skips the [B, Lq, M, L, P] side output
+    need_weights = True
+
     def _reset_parameters(self):
         # same init as the reference (:688-706)
         nn.init.constant_(self.sampling_offsets.weight.data, 0.0)
@@ -84,9 +88,9 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
             raise ValueError("Make sure to align the spatial shapes with the sequence length of the encoder "
                              "hidden states")
         M, L, P, D = self.n_heads, self.n_levels, self.n_points, self.d_model // self.n_heads
-        value = ops.linear(encoder_hidden_states, self.value_proj.weight, bias=self.value_proj.bias)
-        if attention_mask is not None:
-            value = value.masked_fill(~attention_mask[..., None], float(0))
+        # padded pixels are zeroed in `value` before the op (gd.py:730-732): a row mask of the projection's epilogue
+        value = ops.linear(encoder_hidden_states, self.value_proj.weight, bias=self.value_proj.bias,
+                           row_keep=attention_mask)
         w, b = self._packed_query_proj(hidden_states.dtype)
         qp = ops.linear(hidden_states, w, bias=b)                    # offsets | weights in one GEMM
         n_off = M * L * P * 2
@@ -94,7 +98,8 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
                 and self.output_proj.weight.dtype == torch.bfloat16):
             # encoder self-attention: softmax / offset normalisation / reference add run inside the gather kernel
             fused = msda_ext.ms_deform_attn_forward_fused(value.view(B, S, M, D), spatial_shapes, level_start_index, qp,
-                                                          reference_points, self.output_proj.weight.dtype)
+                                                          reference_points, self.output_proj.weight.dtype,
+                                                          want_weights=self.need_weights or output_attentions)
             if fused is not None:
                 out, attention_weights = fused
                 return ops.linear(out, self.output_proj.weight, bias=self.output_proj.bias), attention_weights

@@ -138,6 +138,8 @@ class _Encoder(nn.Module):
     def __init__(self, config):
         super().__init__()
         self.layers = nn.ModuleList([GroundingDinoEncoderLayer(config) for _ in range(config.encoder_layers)])
+        for layer in self.layers:                              # this stage discards the encoder's attention maps (forward_test)
+            layer.deformable_layer.self_attn.need_weights = False
 
     @staticmethod
     def get_reference_points(spatial_shapes, valid_ratios, device):

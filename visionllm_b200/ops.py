@@ -47,11 +47,14 @@ def _bf16_2d(t, name):
     return t
 
 
-def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dtype=torch.bfloat16, out=None):
+def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dtype=torch.bfloat16, out=None,
+           row_keep=None):
     """y = epi(x @ weight.T): x [..., K] bf16, weight [N, K] bf16 (nn.Linear layout).
 
     epi = (+bias) -> act -> (*colscale) -> (+residual); act='swiglu' expects gate/up rows
     interleaved in `weight` and returns N/2 columns.  One tcgen05 kernel launch.
+    row_keep: optional bool/uint8 [...] (one per row): rows with False are stored as exact zeros
+    (`masked_fill(~row_keep[..., None], 0)` folded into the epilogue).
     """
     lead = x.shape[:-1]
     K = x.shape[-1]
@@ -80,14 +83,22 @@ def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dty
     for v, nm in ((bias, "bias"), (colscale, "colscale")):
         if v is not None and (v.dtype != torch.bfloat16 or v.numel() != N or not v.is_contiguous()):
             raise RuntimeError(f"linear: {nm} must be contiguous bf16 [N]")
+    rk = None
+    if row_keep is not None:
+        if row_keep.numel() != M or not row_keep.is_cuda or a == 4:
+            raise RuntimeError("linear: row_keep must be a CUDA mask with one entry per row (not with swiglu)")
+        rk = row_keep.reshape(-1).to(torch.uint8).contiguous()
     with torch.cuda.device(x.device), _Prof("gemm", 2.0 * M * N * K,
                                             2.0 * (M * K + N * K) + out.element_size() * M * n_out, f"{M}x{N}x{K}"):
-        rc = _lib.lib().vllm_gemm_bf16(
-            x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(), out.stride(0),
-            M, N, K, bias.data_ptr() if bias is not None else None,
-            colscale.data_ptr() if colscale is not None else None,
-            res2.data_ptr() if res2 is not None else None, res2.stride(0) if res2 is not None else 0,
-            a, 1 if out_dtype == torch.float32 else 0, _stream())
+        args = (x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(), out.stride(0),
+                M, N, K, bias.data_ptr() if bias is not None else None,
+                colscale.data_ptr() if colscale is not None else None,
+                res2.data_ptr() if res2 is not None else None, res2.stride(0) if res2 is not None else 0,
+                a, 1 if out_dtype == torch.float32 else 0)
+        if rk is None:
+            rc = _lib.lib().vllm_gemm_bf16(*args, _stream())
+        else:
+            rc = _lib.lib().vllm_gemm_bf16_rowmask(*args, rk.data_ptr(), _stream())
     _lib.check(rc, "vllm_gemm_bf16")
     return out.reshape(*lead, n_out)
 

@@ -358,10 +358,11 @@ class TPLlamaForCausalLM(nn.Module):
         return m
 
     # ---- forward --------------------------------------------------------------------------------------------
-    def phases(self, inputs_embeds, attention_mask=None, position_ids=None, compute_logits=True):
+    def phases(self, inputs_embeds, attention_mask=None, position_ids=None, compute_logits=True, comm=None, slot=None):
         """Generator: yields after every step that publishes data to peers, so `run_lockstep` can interleave the
-        virtual ranks of one device.  The result is left in `self.result`."""
-        c, S = self.comm, self.shards
+        virtual ranks of one device.  The result is left in `self.result` (or `self.results[slot]` for a micro-batch
+        of `forward_pipelined`, which passes that micro-batch's own `comm`)."""
+        c, S = comm or self.comm, self.shards
         B, T, H = inputs_embeds.shape
         M = B * T
         if M != c.M or H != c.H:
@@ -406,8 +407,65 @@ class TPLlamaForCausalLM(nn.Module):
             logits = buf[:, :V]
         # `hidden_states[-1]` / `logits` are what the composite forward reads (modeling_visionllmv2.py:733-751); the full
         # [B, T, V] logits are never materialised here -- each rank keeps the rows it owns.
-        self.result = SimpleNamespace(last_hidden_state=last, hidden_states=(last,), logits=None, logits_local=logits,
-                                      row_range=(r * R, (r + 1) * R), past_key_values=None, attentions=None)
+        res = SimpleNamespace(last_hidden_state=last, hidden_states=(last,), logits=None, logits_local=logits,
+                              row_range=(r * R, (r + 1) * R), past_key_values=None, attentions=None)
+        if slot is None:
+            self.result = res
+        else:
+            self.results[slot] = res
+
+    # ---- micro-batch pipelining (r2): hide the layer's all-gather / reduce-scatter behind the other half's GEMMs ----------
+    def micro_generators(self, micro_comms, inputs_embeds, attention_mask=None, position_ids=None, compute_logits=True):
+        """One `phases` generator per micro-batch: the batch is cut into len(micro_comms) equal groups of sequences, each
+        with its OWN exchange buffers / counters (`micro_comms[i]` is a PeerComm for B/n * T token rows), so the groups'
+        protocols are independent and their kernels may overlap freely."""
+        n = len(micro_comms)
+        B = inputs_embeds.shape[0]
+        if B % n:
+            raise RuntimeError(f"batch {B} does not split into {n} micro-batches")
+        b = B // n
+        self.results = [None] * n
+        cut = lambda t, i: None if t is None else t[i * b:(i + 1) * b]   # noqa: E731
+        return [self.phases(cut(inputs_embeds, i), cut(attention_mask, i), cut(position_ids, i), compute_logits,
+                            comm=micro_comms[i], slot=i) for i in range(n)]
+
+    @torch.no_grad()
+    def forward_pipelined(self, micro_comms, inputs_embeds=None, input_ids=None, attention_mask=None, position_ids=None,
+                          compute_logits=True):
+        """The same forward with the batch cut into micro-batches that run on their own CUDA streams: while one
+        micro-batch waits for its peers' o_proj partials or pushes its normalised rows over NVLink (both bound by the
+        link, not by the SMs), the other one's GEMMs own the tensor cores.  Results: `last_hidden_state` of the whole
+        batch; `logits_local` / `row_range` become per-micro-batch lists (a rank owns R / n rows of every micro-batch)."""
+        if inputs_embeds is None:
+            inputs_embeds = torch.nn.functional.embedding(input_ids, self.shards["embed"])
+        dev = inputs_embeds.device
+        n = len(micro_comms)
+        if getattr(self, "_streams", None) is None or len(self._streams) != n:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        main = torch.cuda.current_stream(dev)
+        gens = self.micro_generators(micro_comms, inputs_embeds, attention_mask, position_ids, compute_logits)
+        for st in self._streams:
+            st.wait_stream(main)
+        live = True
+        while live:                                        # round-robin issue: the streams' kernels interleave on the device
+            live = False
+            for g, st in zip(gens, self._streams):
+                with torch.cuda.stream(st):
+                    try:
+                        next(g)
+                        live = True
+                    except StopIteration:
+                        pass
+        for st, res in zip(self._streams, self.results):
+            main.wait_stream(st)
+            res.last_hidden_state.record_stream(main)
+            if res.logits_local is not None:
+                res.logits_local.record_stream(main)
+        last = torch.cat([r.last_hidden_state for r in self.results], 0)
+        self.result = SimpleNamespace(last_hidden_state=last, hidden_states=(last,), logits=None,
+                                      logits_local=[r.logits_local for r in self.results],
+                                      row_range=[r.row_range for r in self.results], past_key_values=None, attentions=None)
+        return self.result
 
     # ---- the parts of the HF interface the composite model touches (modeling_visionllmv2.py:420,571,724-751) -------
     @property
@@ -428,6 +486,23 @@ class TPLlamaForCausalLM(nn.Module):
         for _ in self.phases(inputs_embeds, attention_mask, position_ids, compute_logits):
             pass
         return self.result
+
+
+@torch.no_grad()
+def run_lockstep_micro(ranks, micro_comms_per_rank, inputs_embeds, **kw):
+    """`run_lockstep` for the micro-batched forward: every (virtual rank, micro-batch) generator advances phase by phase
+    on the current stream.  Returns per-rank lists of per-micro-batch results."""
+    gens = [g for m, mc in zip(ranks, micro_comms_per_rank) for g in m.micro_generators(mc, inputs_embeds, **kw)]
+    live = True
+    while live:
+        live = False
+        for g in gens:
+            try:
+                next(g)
+                live = True
+            except StopIteration:
+                pass
+    return [m.results for m in ranks]
 
 
 @torch.no_grad()

@@ -196,8 +196,12 @@ class ContrastiveAssign(nn.Module):
     @torch.no_grad()
     def forward(self, x, text_dict):
         y, mask = text_dict["encoded_text"], text_dict["text_token_mask"]
-        res = torch.stack([ops.linear(x[b].contiguous(), y[b].to(x.dtype).contiguous()) for b in range(x.shape[0])])
-        res = res.masked_fill(~mask[:, None, :], float("-inf"))
+        B, Q, _ = x.shape
+        T = y.shape[1]
+        buf = torch.empty((B, Q, (T + 7) // 8 * 8), dtype=x.dtype, device=x.device)     # 16-byte output row pitch
+        for b in range(B):
+            ops.linear(x[b].contiguous(), y[b].to(x.dtype).contiguous(), out=buf[b, :, :T])
+        res = buf[..., :T].masked_fill(~mask[:, None, :], float("-inf"))
         return res.float()                                     # `new_res` is a default-dtype (fp32) buffer (:988-990)
 
 
