@@ -536,12 +536,19 @@ class GdinoHeadWorkload:
             gd_mod.msda_ext.ms_deform_attn_forward_bf16 = orig16
             gd_mod.msda_ext.ms_deform_attn_forward_fused = orig_fused
         prof, ops.PROFILE = ops.PROFILE, None
-        agg = {}
-        for name, fl, by, e0, e1, *_tag in prof:
+        agg, shapes = {}, {}
+        for name, fl, by, e0, e1, *tag in prof:
+            ms = e0.elapsed_time(e1)
             a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
-            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl; a[3] += by
+            a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
+            if name == "gemm" and tag and tag[0]:
+                sh = shapes.setdefault(tag[0], [0, 0.0, fl, by])
+                sh[0] += 1; sh[1] += ms
         self.breakdown = {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / v[1] / 1e9 if v[1] else 0.0,
                               "gbps": v[3] / v[1] / 1e6 if v[1] else 0.0} for k, v in agg.items()}
+        self.gemm_shapes = {k: {"launches": v[0], "ms_total": v[1], "tflops": v[2] / (v[1] / v[0]) / 1e9,
+                                "gbps": v[3] / (v[1] / v[0]) / 1e6}
+                            for k, v in list(sorted(shapes.items(), key=lambda kv: -kv[1][1]))[:10]}
         enc_ms = [a.elapsed_time(b) for a, b, vs, ls in msda_ms if ls[1] == vs[1]]
         dec_ms = [a.elapsed_time(b) for a, b, vs, ls in msda_ms if ls[1] != vs[1]]
         self.breakdown["msda_encoder"] = {"launches": len(enc_ms), "ms": sum(enc_ms)}
@@ -556,7 +563,10 @@ class GdinoHeadWorkload:
         side = (S * 8 * 16 * 3 * 2 + S * 4 * 2 * 4) if getattr(self, "msda_fused", False) else (S * 8 * 16 * 2 + S * 8 * 16) * 4
         alg = (S * 256 * vb + side + S * 256 * vb) * self.N
         ach = alg / (kern_ms * 1e-3) / 1e9
-        return {"kernel": "msda_fwd_warp_kernel (encoder launches inside the GDINO step)", "bound": "hbm",
+        kern = ("msda_fwd_win_kernel<bf16, bf16, 32, 16, 4, QP> (fused module input: softmax / offset normalisation / reference "
+                "add inside the TMA-staged window gather; encoder launches inside the GDINO step)"
+                if getattr(self, "msda_fused", False) else "msda_fwd_win/warp_kernel (encoder launches inside the GDINO step)")
+        return {"kernel": kern, "bound": "hbm (nominal; issue-bound gather, DESIGN 6.2)",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": alg}
@@ -568,7 +578,7 @@ class GdinoHeadWorkload:
                 "parallelism": f"dp{self.world}"}
 
     def extra(self):
-        return {"kernel_breakdown": self.breakdown}
+        return {"kernel_breakdown": self.breakdown, "top_gemm_shapes": getattr(self, "gemm_shapes", None)}
 
 
 def build_gdino_stage(torch, device, hidden, backbone="b200"):

@@ -181,6 +181,10 @@ int vllm_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int 
 int vllm_gemm_bf16_rowmask(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                            const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,
                            const unsigned char* row_keep, void* stream);
+/* SM budgets of the persistent GEMM grid (process-global; 0 = every SM): `all_gemms` caps every launch, `scatter_gemm` the
+ * scatter GEMM alone.  A GEMM CTA owns its SM, so the link-bound exchange kernels of another stream (tensor-parallel
+ * micro-batches, visionllm_b200/tp.py) overlap a GEMM only on SMs its grid leaves free. */
+int vllm_gemm_set_sm_limit(int all_gemms, int scatter_gemm);
 /* Tuning knob (process-global): 0 = auto (default), 1 = cta_group::1 tiles 128x256, 2 = CTA-pair tiles 256x256. */
 /* Stride-1 KxK convolution over a zero-padded channels-last map as ONE implicit GEMM (no im2col buffer): the 3x3
  * `output_convs` of the Grounding-DINO mask-feature FPN (modeling_ov_grounding_dino_mask_dn.py:2136-2146, :2476).
@@ -212,6 +216,13 @@ int vllm_layernorm_bf16(const void* x, long long ldx, const void* weight, const 
  * branch, ops_dcnv3/modules/dcnv3.py:252-267). */
 int vllm_layernorm_gelu_bf16(const void* x, long long ldx, const void* weight, const void* bias, void* y,
                              long long ldy, long long rows, int cols, float eps, void* stream);
+/* LayerNorm with a row gather in the same pass: output row (b, j) = LN(x[b, index[j]]) for j < rows_out, b < batch;
+ * index[j] >= rows_in marks a padding slot and yields an all-zero row.  The window partition of a Swin block (HF
+ * SwinLayer: layernorm_before -> pad -> roll -> window_partition) as one kernel: `index` is the window-major list of
+ * raster positions (visionllm_b200/swin.py), x [batch * rows_in, cols], y [batch * rows_out, cols]. */
+int vllm_layernorm_gather_bf16(const void* x, long long ldx, const int64_t* index, long long rows_in, long long rows_out,
+                               long long batch, const void* weight, const void* bias, void* y, long long ldy, int cols,
+                               float eps, void* stream);
 /* y = residual + LayerNorm(x): the post-norm residual of InternImage-H (`x + res_post_norm(dcn(norm(x)))`,
  * grounding_dino/modeling_ov_grounding_dino_mask_dn.py:4866-4868) in one pass. */
 int vllm_layernorm_residual_bf16(const void* x, long long ldx, const void* weight, const void* bias,
@@ -244,6 +255,13 @@ long long vllm_groupnorm_workspace_bytes(int batch, int groups);
 int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, int batch, long long hw,
                              int channels, int groups, float eps, int relu, void* workspace, long long workspace_bytes,
                              void* stream);
+/* FPN top-down step of the Grounding-DINO mask-feature head (modeling_ov_grounding_dino_mask_dn.py:2486-2492):
+ * out = lateral + F.interpolate(top, size=(out_h, out_w), mode="bilinear", align_corners=False) over channels-last bf16
+ * maps top [batch, in_h, in_w, channels], lateral / out [batch, out_h, out_w, channels] in one pass (ATen's
+ * upsample_bilinear2d arithmetic; the interpolated value is rounded to bf16 before the bf16 add, like the torch ops).
+ * channels % 8 == 0. */
+int vllm_upsample_add_nhwc_bf16(const void* top, const void* lateral, void* out, int batch, int in_h, int in_w, int out_h,
+                                int out_w, int channels, void* stream);
 /* In-place rotate-half RoPE on x[tokens, heads, head_dim] rows with pitch ld; cos/sin
  * [tokens, head_dim] bf16 gathered per position (HF Llama apply_rotary_pos_emb;
  * internlm2/modeling_internlm2.py:218-232). */

@@ -102,6 +102,17 @@ def conv2d_s1_rows(x, w_rows, bias, kernel, padding, act=None):
     return _ACT[act](y.permute(0, 2, 3, 1))
 
 
+def layernorm_gather(x, index, weight, bias, eps):
+    h = F.layer_norm(x.float(), (x.shape[-1],), weight.float(), bias.float(), eps)
+    h = torch.cat((h, h.new_zeros(h.shape[0], 1, h.shape[2])), 1)
+    return h.index_select(1, index.clamp(max=x.shape[1]))
+
+
+def upsample_add_nhwc(top, lateral):
+    up = F.interpolate(top.float().permute(0, 3, 1, 2), size=lateral.shape[1:3], mode="bilinear", align_corners=False)
+    return lateral.float() + up.permute(0, 2, 3, 1)
+
+
 def msda_forward(value, shapes, lsi, loc, w, step=64, **kw):
     from . import msda_oracle as O
     return O.forward_grid_sample(value.float(), shapes, loc.float(), w.float())
@@ -113,7 +124,8 @@ def patched():
     import visionllm_b200.msda as msda
     import visionllm_b200.ops as ops
     table = {"linear": linear, "rmsnorm": rmsnorm, "layernorm": layernorm, "rope_": rope_, "attention": attention,
-             "groupnorm_nhwc": groupnorm_nhwc, "conv2d_s1_rows": conv2d_s1_rows}
+             "groupnorm_nhwc": groupnorm_nhwc, "conv2d_s1_rows": conv2d_s1_rows, "upsample_add_nhwc": upsample_add_nhwc,
+             "layernorm_gather": layernorm_gather}
     saved = {k: getattr(ops, k) for k in table}
     saved_msda = (msda.ms_deform_attn_forward, msda.ms_deform_attn_forward_bf16)
     try:

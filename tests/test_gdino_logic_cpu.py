@@ -53,6 +53,13 @@ def torch_kernels(monkeypatch):
     monkeypatch.setattr(ops, "linear", linear)
     monkeypatch.setattr(ops, "layernorm", lambda x, w, b, eps, out=None: F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), eps))
     monkeypatch.setattr(ops, "attention", attention)
+
+    def layernorm_gather(x, index, w, b, eps):            # LN + zero pad + row gather (Swin window partition)
+        h = F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), eps)
+        h = torch.cat((h, h.new_zeros(h.shape[0], 1, h.shape[2])), 1)
+        return h.index_select(1, index.clamp(max=x.shape[1]))
+
+    monkeypatch.setattr(ops, "layernorm_gather", layernorm_gather)
     monkeypatch.setattr(msda, "ms_deform_attn_forward",
                         lambda value, shapes, lsi, loc, w, step, **kw: O.forward_grid_sample(value, shapes, loc, w))
 

@@ -59,8 +59,13 @@ def gn_kernel(monkeypatch, torch_kernels):  # noqa: F811
         y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None if bias is None else bias.float(), padding=padding)
         return y.permute(0, 2, 3, 1)
 
+    def upsample_add_nhwc(top, lateral):
+        up = F.interpolate(top.float().permute(0, 3, 1, 2), size=lateral.shape[1:3], mode="bilinear", align_corners=False)
+        return lateral.float() + up.permute(0, 2, 3, 1)
+
     monkeypatch.setattr(ops, "groupnorm_nhwc", groupnorm_nhwc)
     monkeypatch.setattr(ops, "conv2d_s1_rows", conv2d_s1_rows)
+    monkeypatch.setattr(ops, "upsample_add_nhwc", upsample_add_nhwc)
 
 
 @pytest.mark.parametrize("ragged,b200_backbone", [(False, False), (True, False), (True, True)])

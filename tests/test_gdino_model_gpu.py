@@ -137,6 +137,28 @@ def test_groupnorm_kernel(shape, relu):
     assert torch.equal(y, y2)                                                    # deterministic statistics
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 32, 32, 256), (1, 13, 17, 25, 34, 64), (2, 8, 8, 8, 8, 48), (1, 5, 7, 20, 9, 8)])
+def test_upsample_add_kernel_matches_the_torch_ops(shape):
+    """vllm_upsample_add_nhwc_bf16 (FPN top-down step) vs the reference's ops: bf16 F.interpolate(bilinear,
+    align_corners=False) + bf16 add.  ATen's kernel may contract the tap sums differently, so the interpolated value can
+    differ by a bf16 ulp: checked against the fp32 interpolation with one bf16 rounding of each step."""
+    from visionllm_b200 import ops
+    B, Hi, Wi, Ho, Wo, C = shape
+    g = torch.Generator(device="cuda").manual_seed(Hi * Wo)
+    top = torch.randn(B, Hi, Wi, C, device="cuda", generator=g).bfloat16()
+    lat = torch.randn(B, Ho, Wo, C, device="cuda", generator=g).bfloat16()
+    out = ops.upsample_add_nhwc(top, lat)
+    up16 = torch.nn.functional.interpolate(top.permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=False)
+    ref_ops = lat + up16.permute(0, 2, 3, 1)                                     # the reference's bf16 ops
+    up32 = torch.nn.functional.interpolate(top.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear",
+                                           align_corners=False).permute(0, 2, 3, 1)
+    ref32 = lat.float() + up32
+    assert out.shape == lat.shape and out.dtype == torch.bfloat16
+    tol = 2.0 ** -7 * ref32.abs() + 2.0 ** -7 * up32.abs() + 1e-6
+    assert ((out.float() - ref32).abs() <= tol).all()
+    assert (out != ref_ops).float().mean().item() < 0.02                         # bit-equal to the torch ops but for rare ulps
+
+
 def test_groupnorm_rejects_bad_arguments():
     from visionllm_b200 import ops
     x = torch.zeros(1, 8, 48, device="cuda", dtype=torch.bfloat16)

@@ -63,3 +63,22 @@ def test_attention_additive_bias(T, H, D, nB):
     assert rel(out, ref) < 6e-3
     with pytest.raises(RuntimeError):
         ops.attention(q, k, v, attn_bias=bias[:, :, :, :-1].contiguous())
+
+
+def test_layernorm_gather_kernel_equals_layernorm_then_gather():
+    """ops.layernorm_gather (LN + zero pad + row gather of the Swin window partition in one pass) must be bit-identical to
+    ops.layernorm followed by cat(zero row) + index_select -- rows are independent, the arithmetic is the same kernel's."""
+    from visionllm_b200 import ops
+    from visionllm_b200.swin import _window_rows
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for (H, W, ws, shift, C) in ((10, 13, 7, 3, 96), (16, 16, 4, 0, 192), (9, 9, 7, 3, 48)):
+        B = 3
+        x = torch.randn(B, H * W, C, device="cuda", generator=g).bfloat16()
+        w = (1 + 0.1 * torch.randn(C, device="cuda", generator=g)).bfloat16()
+        b = (0.1 * torch.randn(C, device="cuda", generator=g)).bfloat16()
+        fwd, inv, Hp, Wp = _window_rows(H, W, ws, shift, x.device)
+        got = ops.layernorm_gather(x, fwd, w, b, 1e-5)
+        h = ops.layernorm(x, w, b, 1e-5)
+        h = torch.cat((h, h.new_zeros(B, 1, C)), 1)
+        assert torch.equal(got, h.index_select(1, fwd))
+        assert torch.equal(got.index_select(1, inv), ops.layernorm(x, w, b, 1e-5))      # the inverse map drops the pads

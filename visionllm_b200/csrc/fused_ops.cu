@@ -56,13 +56,24 @@ template <int MODE, int VPT, int TPR>
 __global__ void __launch_bounds__(NT)
 norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __restrict__ w,
                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* y, long long ldy, long long rows,
-                 int cols, float eps, int act, const __nv_bfloat16* __restrict__ res, long long ldr) {
+                 int cols, float eps, int act, const __nv_bfloat16* __restrict__ res, long long ldr,
+                 const int64_t* __restrict__ gidx = nullptr, long long g_in = 0, long long g_out = 0) {
   __shared__ float sh[NT / 32];
   constexpr int RPC = NT / TPR;
   const int tr = threadIdx.x % TPR;
   const long long row = (long long)blockIdx.x * RPC + threadIdx.x / TPR;
-  const bool row_ok = row < rows;
-  const __nv_bfloat16* xr = x + (row_ok ? row : 0) * ldx;
+  bool row_ok = row < rows;
+  // row gather (Swin window partition): output row (batch, j) normalises input row (batch, gidx[j]); gidx[j] >= g_in marks
+  // a padded window slot -> an all-zero output row
+  long long src = row;
+  bool zero_row = false;
+  if (gidx && row_ok) {
+    const long long bb = row / g_out;
+    const long long si = gidx[row - bb * g_out];
+    zero_row = si >= g_in;
+    src = bb * g_in + (zero_row ? 0 : si);
+  }
+  const __nv_bfloat16* xr = x + (row_ok ? src : 0) * ldx;
   __nv_bfloat16* yr = y + (row_ok ? row : 0) * ldy;
   const int nvec = cols / 8;
   uint4 reg[VPT];
@@ -122,14 +133,15 @@ norm_rows_kernel(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __r
           o[j] = wv[j] * n;
         }
       }
-      *(reinterpret_cast<uint4*>(yr) + v) = pack8(o);
+      *(reinterpret_cast<uint4*>(yr) + v) = zero_row ? make_uint4(0u, 0u, 0u, 0u) : pack8(o);
     }
   }
 }
 
 template <int MODE>
 int launch_norm(const void* x, long long ldx, const void* w, const void* b, void* y, long long ldy, long long rows,
-                int cols, float eps, cudaStream_t st, int act = 0, const void* res = nullptr, long long ldr = 0) {
+                int cols, float eps, cudaStream_t st, int act = 0, const void* res = nullptr, long long ldr = 0,
+                const int64_t* gidx = nullptr, long long g_in = 0, long long g_out = 0) {
   const int nvec = cols / 8;
   auto go = [&](auto vpt, auto tpr) -> int {
     constexpr int VPT = decltype(vpt)::value, TPR = decltype(tpr)::value;
@@ -137,7 +149,7 @@ int launch_norm(const void* x, long long ldx, const void* w, const void* b, void
     if (blocks > 2147483647LL) return VLLM_EUNSUPPORTED;
     norm_rows_kernel<MODE, VPT, TPR><<<(unsigned)blocks, NT, 0, st>>>(
         (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, rows,
-        cols, eps, act, (const __nv_bfloat16*)res, ldr);
+        cols, eps, act, (const __nv_bfloat16*)res, ldr, gidx, g_in, g_out);
     VLLM_CHECK_LAUNCH();
     return VLLM_OK;
   };
@@ -257,6 +269,19 @@ int vllm_layernorm_gelu_bf16(const void* x, long long ldx, const void* weight, c
   if (rc) return rc;
   if (!weight || !bias || !vllm_aligned(weight, 16) || !vllm_aligned(bias, 16)) return VLLM_EINVAL;
   return launch_norm<1>(x, ldx, weight, bias, y, ldy, rows, cols, eps, (cudaStream_t)stream, 1);
+}
+
+int vllm_layernorm_gather_bf16(const void* x, long long ldx, const int64_t* index, long long rows_in, long long rows_out,
+                               long long batch, const void* weight, const void* bias, void* y, long long ldy, int cols,
+                               float eps, void* stream) {
+  if (rows_in <= 0 || rows_out < 0 || batch < 0) return VLLM_EINVAL;
+  if (!index) return VLLM_EINVAL;
+  int rc = check_rows(x, ldx, y, ldy, batch * rows_out, cols);
+  if (rc == 1000) return VLLM_OK;
+  if (rc) return rc;
+  if (!weight || !bias || !vllm_aligned(weight, 16) || !vllm_aligned(bias, 16)) return VLLM_EINVAL;
+  return launch_norm<1>(x, ldx, weight, bias, y, ldy, batch * rows_out, cols, eps, (cudaStream_t)stream, 0, nullptr, 0, index,
+                        rows_in, rows_out);
 }
 
 int vllm_layernorm_residual_bf16(const void* x, long long ldx, const void* weight, const void* bias,

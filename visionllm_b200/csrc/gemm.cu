@@ -493,6 +493,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // r1_gemm_raster_experiment.md): DRAM traffic and ncu durations move by < 3 % between group sizes 1..8 at the
 // ViT shapes and get worse below 8 for the wide LLM gate|up GEMM, so 8 stays; the knob remains for sweeps.
 int g_group_m_override = 0;
+// SM budgets (0 = every SM): a persistent GEMM CTA owns its SM (168 registers x 384 threads = the whole register file), so a
+// link-bound kernel of another stream -- the peer pushes of the tensor-parallel exchange -- can only overlap a GEMM on SMs
+// the GEMM's grid leaves free.  g_sm_limit caps every launch, g_scatter_sm_limit the scatter GEMM (vllm_gemm_bf16_scatter),
+// whose epilogue stores ride NVLink while the other micro-batch's GEMM runs beside it (visionllm_b200/tp.py).
+int g_sm_limit = 0, g_scatter_sm_limit = 0;
 int pick_group_m(int, int, long long) { return g_group_m_override > 0 ? g_group_m_override : 8; }
 
 // 0: auto (cta_group::2 CTA pairs, 256x256 tiles; cta_group::1 when K <= 512, where the cross-CTA hand-offs of
@@ -517,6 +522,8 @@ int launch_gemm(const void* A, int lda, const void* B, int ldb, GemmArgs g, cuda
   g.tiles_n = (g.N + BN - 1) / BN;
   const int n_tiles = g.tiles_m * g.tiles_n;
   int sms = vllm_num_sms();
+  const int limit = g.sc_rows ? (g_scatter_sm_limit > 0 ? g_scatter_sm_limit : g_sm_limit) : g_sm_limit;
+  if (limit > 0 && limit < sms) sms = limit < CG ? CG : limit;
   int clusters = sms / CG;
   if (clusters > n_tiles) clusters = n_tiles;
   g.group_m = pick_group_m(sms / CG, g.tiles_n, (long long)g.N * g.K * 2);
@@ -547,6 +554,11 @@ extern "C" {
 
 int vllm_gemm_set_variant(int v) { g_gemm_variant = (v == 1 || v == 2) ? v : 0; return VLLM_OK; }
 int vllm_gemm_set_group_m(int gm) { g_group_m_override = gm; return VLLM_OK; }
+int vllm_gemm_set_sm_limit(int all_gemms, int scatter_gemm) {
+  if (all_gemms < 0 || scatter_gemm < 0) return VLLM_EINVAL;
+  g_sm_limit = all_gemms; g_scatter_sm_limit = scatter_gemm;
+  return VLLM_OK;
+}
 
 static int gemm_bf16_common(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                             const void* bias, const void* colscale, const void* residual, int ldr, int act, int out_f32,

@@ -300,8 +300,7 @@ class B200GroundingDinoModel(nn.Module):
         top = enc_vision[:, :H0 * W0].reshape(B, H0, W0, -1)                              # level-0 slab, channels-last
         for idx in range(self.num_fpn_levels):
             cur, Hc, Wc = self.lateral_convs[idx].rows(feats[idx])
-            up = F.interpolate(top.permute(0, 3, 1, 2).float(), size=(Hc, Wc), mode="bilinear", align_corners=False)
-            y = cur.view(B, Hc, Wc, -1) + up.permute(0, 2, 3, 1).to(cur.dtype)
+            y = ops.upsample_add_nhwc(top.contiguous(), cur.view(B, Hc, Wc, -1).contiguous())   # lateral + bilinear(top), one pass
             top, Hc, Wc = self.output_convs[idx].rows(y)
             top = top.view(B, Hc, Wc, -1)
         mf, Hm, Wm = conv_rows(top, self.mask_features)

@@ -205,6 +205,22 @@ def layernorm(x, weight, bias, eps, out=None, gelu=False, residual=None):
     return out
 
 
+def layernorm_gather(x, index, weight, bias, eps):
+    """out[b, j] = LN(x[b, index[j]]) (zeros where index[j] >= x.shape[1]): nn.LayerNorm + zero pad + row gather in one
+    pass -- the window partition of a Swin block.  x [B, N, C] contiguous bf16, index int64 [Nout] -> [B, Nout, C]."""
+    if x.dim() != 3 or x.dtype != torch.bfloat16 or not x.is_cuda or not x.is_contiguous():
+        raise RuntimeError("layernorm_gather: x must be a contiguous CUDA bf16 [B, N, C] tensor")
+    if index.dtype != torch.int64 or index.dim() != 1 or not index.is_cuda or not index.is_contiguous():
+        raise RuntimeError("layernorm_gather: index must be a contiguous CUDA int64 vector")
+    B, N, C = x.shape
+    out = torch.empty((B, index.numel(), C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device), _Prof("layernorm", 0.0, 2.0 * C * (x.shape[0] * N + out.shape[0] * out.shape[1])):
+        rc = _lib.lib().vllm_layernorm_gather_bf16(x.data_ptr(), C, index.data_ptr(), N, index.numel(), B, weight.data_ptr(),
+                                                   bias.data_ptr(), out.data_ptr(), C, C, float(eps), _stream())
+    _lib.check(rc, "vllm_layernorm_gather_bf16")
+    return out
+
+
 def dcnv3_prep(packed, group, taps, with_scale):
     """packed [..., >= G*K*3 (+G)] fp32 rows (one GEMM output) -> (offset [..., G*K*2], mask [..., G*K] = softmax over
     the K taps of each group, scale [..., G] = sigmoid(logit) or None), contiguous fp32.  One launch."""
@@ -284,6 +300,24 @@ def groupnorm_nhwc(x, weight, bias, groups, eps, relu=False):
         rc = _lib.lib().vllm_groupnorm_nhwc_bf16(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(), n, hw, c,
                                                  groups, float(eps), int(bool(relu)), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "vllm_groupnorm_nhwc_bf16")
+    return out
+
+
+def upsample_add_nhwc(top, lateral):
+    """lateral + F.interpolate(top, size=lateral's (H, W), mode='bilinear', align_corners=False) for channels-last bf16
+    maps top [B, Hi, Wi, C], lateral [B, Ho, Wo, C] (the FPN top-down step, gd.py:2486-2492) in one pass."""
+    for t, nm in ((top, "top"), (lateral, "lateral")):
+        if t.dim() != 4 or t.dtype != torch.bfloat16 or not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError(f"upsample_add_nhwc: {nm} must be a contiguous CUDA bf16 [B, H, W, C] tensor")
+    B, Hi, Wi, C = top.shape
+    if lateral.shape[0] != B or lateral.shape[3] != C:
+        raise RuntimeError("upsample_add_nhwc: batch / channel mismatch")
+    Ho, Wo = lateral.shape[1], lateral.shape[2]
+    out = torch.empty_like(lateral)
+    with torch.cuda.device(top.device), _Prof("upsample_add", 0.0, 2.0 * (top.numel() + 2 * lateral.numel())):
+        rc = _lib.lib().vllm_upsample_add_nhwc_bf16(top.data_ptr(), lateral.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C,
+                                                    _stream())
+    _lib.check(rc, "vllm_upsample_add_nhwc_bf16")
     return out
 
 

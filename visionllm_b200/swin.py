@@ -122,10 +122,8 @@ class B200SwinBackbone(nn.Module):
         fwd, inv, Hp, Wp, mask = self._rows(H, W, ws, int(shift), x.device)
         w_qkv, b_qkv, bias = self._layer_pack(layer, mask, (H, W))
         ln = layer.layernorm_before
-        h = ops.layernorm(x, ln.weight, ln.bias, ln.eps)
-        if Hp != H or Wp != W:
-            h = torch.cat((h, h.new_zeros(B, 1, C)), 1)                   # the zero row padded slots point at
-        win = h.index_select(1, fwd)                                       # [B, nW*T, C], window-major
+        # layernorm_before + zero pad + roll + window partition in ONE pass: fwd[j] = raster row of window slot j (N = pad)
+        win = ops.layernorm_gather(x.contiguous(), fwd, ln.weight, ln.bias, ln.eps)     # [B, nW*T, C], window-major
         T = ws * ws
         nW = (Hp // ws) * (Wp // ws)
         qkv = ops.linear(win, w_qkv, bias=b_qkv).view(B * nW, T, 3, nH, D)

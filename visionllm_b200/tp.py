@@ -38,6 +38,7 @@ Forward only.  No CPU path: the collectives ARE the CUDA kernels; tests that run
 double for the comm object (tests/test_tp_cpu.py).
 """
 import ctypes
+import os
 from types import SimpleNamespace
 
 import torch
@@ -318,6 +319,8 @@ class TPLlamaForCausalLM(nn.Module):
             theta = rp.get("rope_theta", 10000.0) if isinstance(rp, dict) else 10000.0
         self.theta = theta
         self.shards = None
+        # forward_pipelined: SMs of the compute GEMMs / of the scatter GEMM (0 = all); measured on 8 x B200
+        self.compute_sms, self.scatter_sms = 120, 28
         if shards is not None:
             self.load_shards(shards, device, dtype)
 
@@ -446,16 +449,26 @@ class TPLlamaForCausalLM(nn.Module):
         gens = self.micro_generators(micro_comms, inputs_embeds, attention_mask, position_ids, compute_logits)
         for st in self._streams:
             st.wait_stream(main)
-        live = True
-        while live:                                        # round-robin issue: the streams' kernels interleave on the device
-            live = False
-            for g, st in zip(gens, self._streams):
-                with torch.cuda.stream(st):
-                    try:
-                        next(g)
-                        live = True
-                    except StopIteration:
-                        pass
+        # a GEMM CTA owns its SM (register file), so the other micro-batch's link-bound steps overlap a GEMM only on SMs
+        # its grid leaves free: compute GEMMs get `compute_sms`, the scatter GEMM (NVLink-bound epilogue) `scatter_sms`
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        comp = int(os.environ.get("VLLM_TP_COMPUTE_SMS", self.compute_sms))
+        scat = int(os.environ.get("VLLM_TP_SCATTER_SMS", self.scatter_sms))
+        if micro_comms[0].world > 1 and 0 < comp < n_sms:
+            _lib.check(_lib.lib().vllm_gemm_set_sm_limit(comp, scat), "vllm_gemm_set_sm_limit")
+        try:
+            live = True
+            while live:                                    # round-robin issue: the streams' kernels interleave on the device
+                live = False
+                for g, st in zip(gens, self._streams):
+                    with torch.cuda.stream(st):
+                        try:
+                            next(g)
+                            live = True
+                        except StopIteration:
+                            pass
+        finally:
+            _lib.lib().vllm_gemm_set_sm_limit(0, 0)
         for st, res in zip(self._streams, self.results):
             main.wait_stream(st)
             res.last_hidden_state.record_stream(main)
