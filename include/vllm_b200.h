@@ -378,6 +378,20 @@ int vllm_gemm_bf16_batched(const void* A, int lda, int a_mn_major, const void* B
  * dlogits bf16 = (softmax - onehot) / *n_valid). */
 int vllm_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* weight, const void* dy, long long ldy, void* dx,
                           long long lddx, float* dweight, long long rows, int cols, float eps, void* stream);
+/* Layout change of the attention backward (visionllm_b200/train.py): src [batch, tokens, parts, heads, head_dim] bf16 (parts = 3:
+ * the packed q | k | v projection rows; 1: dO) -> dst [parts, batch, heads, tokens, head_dim] (every (batch, head) matrix stacked
+ * along rows for vllm_gemm_bf16_batched) when to_stacked != 0, the inverse (stacked gradients -> packed d(qkv)) otherwise.
+ * One pass of 16-byte vectors; contiguous tensors. */
+int vllm_head_stack_bf16(const void* src, void* dst, int batch, int tokens, int parts, int heads, int head_dim,
+                         int to_stacked, void* stream);
+/* The same backward with the dweight reduction done through a workspace instead of atomics: every CTA writes its partial
+ * column sums to one row of partials [n_partials >= vllm_rmsnorm_bwd_partials(rows), cols] (fp32, 16-byte aligned) and a
+ * second kernel sums the rows in order -- deterministic (the atomic form puts ~1200 atomics on each of the 4096 column
+ * addresses at 8192 x 4096 rows).  dweight is overwritten (no zero-init needed). */
+int vllm_rmsnorm_bwd_partials(long long rows);
+int vllm_rmsnorm_bwd_ws_bf16(const void* x, long long ldx, const void* weight, const void* dy, long long ldy, void* dx,
+                             long long lddx, float* dweight, float* partials, int n_partials, long long rows, int cols,
+                             float eps, void* stream);
 int vllm_swiglu_fwd_bf16(const void* gate_up, long long ldgu, void* h, long long ldh, long long rows, int inter, void* stream);
 int vllm_swiglu_bwd_bf16(const void* gate_up, long long ldgu, const void* dh, long long lddh, void* dgate_up, long long lddgu,
                          long long rows, int inter, void* stream);

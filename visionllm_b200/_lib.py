@@ -52,6 +52,9 @@ _SIGNATURES = {
     "vllm_gemm_bf16_tn": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, ci, vp]),
     "vllm_gemm_bf16_batched": (ci, [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
     "vllm_rmsnorm_bwd_bf16": (ci, [vp, cll, vp, vp, cll, vp, cll, vp, cll, ci, cf, vp]),
+    "vllm_head_stack_bf16": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+    "vllm_rmsnorm_bwd_partials": (ci, [cll]),
+    "vllm_rmsnorm_bwd_ws_bf16": (ci, [vp, cll, vp, vp, cll, vp, cll, vp, vp, ci, cll, ci, cf, vp]),
     "vllm_swiglu_fwd_bf16": (ci, [vp, cll, vp, cll, cll, ci, vp]),
     "vllm_swiglu_bwd_bf16": (ci, [vp, cll, vp, cll, vp, cll, cll, ci, vp]),
     "vllm_softmax_causal_bf16": (ci, [vp, cll, cll, ci, cf, vp]),

@@ -58,7 +58,8 @@ template <int VPT>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
                    const __nv_bfloat16* __restrict__ dy, long long ldy, __nv_bfloat16* __restrict__ dx, long long lddx,
-                   float* __restrict__ dw, long long rows, int cols, float eps, int rows_per_cta) {
+                   float* __restrict__ dw, long long rows, int cols, float eps, int rows_per_cta,
+                   float* __restrict__ partials = nullptr) {
   __shared__ float sh[8];
   const int nvec = cols / 8;
   float dwacc[VPT][8];
@@ -115,9 +116,36 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __n
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * 256;
-    if (v < nvec)
+    if (v < nvec) {
+      if (partials) {                                      // one coalesced row of partials per CTA, summed by the second kernel
+        float* pr = partials + (size_t)blockIdx.x * cols + v * 8;
+        *reinterpret_cast<float4*>(pr) = make_float4(dwacc[i][0], dwacc[i][1], dwacc[i][2], dwacc[i][3]);
+        *reinterpret_cast<float4*>(pr + 4) = make_float4(dwacc[i][4], dwacc[i][5], dwacc[i][6], dwacc[i][7]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dw + v * 8 + j, dwacc[i][j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(dw + v * 8 + j, dwacc[i][j]);
+      }
+    }
+  }
+}
+
+// dw[c] = sum over the n per-CTA partial rows in a fixed order (deterministic, unlike the atomic form): a CTA owns 32 columns,
+// its 8 warps take every 8th row (128-byte coalesced reads), shared-memory tree at the end
+__global__ void __launch_bounds__(256)
+colsum_partials_kernel(const float* __restrict__ partials, float* __restrict__ dw, int n, int cols) {
+  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float a = 0.f;
+  if (c < cols)
+    for (int r = grp; r < n; r += 8) a += partials[(size_t)r * cols + c];
+  sh[grp][lane] = a;
+  __syncthreads();
+  if (grp == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += sh[g][lane];
+    dw[c] = t;
   }
 }
 
@@ -204,10 +232,13 @@ softmax_causal_kernel(__nv_bfloat16* __restrict__ s, long long lds, int T, float
 #pragma unroll
     for (int j = 0; j < 8; ++j) { v[k][j] = __expf(v[k][j] - mx); sum += v[k][j]; }     // exp(-inf) = 0 above the diagonal
   const float inv = 1.f / block_sum<256>(sum, sh);
+  // zeros are only needed inside the 256-aligned diagonal block: the causal batched GEMMs (gemm.cu, causal 2 / 3) never read
+  // a 64-column k-block that lies wholly above a tile's diagonal block, and tiles are at most 256 rows
+  const int wvec = min(nvec, ((i >> 8) + 1) * 32);
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
     const int vi = threadIdx.x + k * 256;
-    if (vi < nvec) {
+    if (vi < wvec) {
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = v[k][j] * inv;
@@ -244,15 +275,36 @@ attn_ds_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ 
     }
   }
   dot = block_sum<256>(dot, sh);
+  const int wvec = min(nvec, ((i >> 8) + 1) * 32);            // see softmax_causal_kernel
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
     const int vi = threadIdx.x + k * 256;
-    if (vi < nvec) {
+    if (vi < wvec) {
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = scale * pv[k][j] * (dv[k][j] - dot);
       *(reinterpret_cast<uint4*>(dr) + vi) = pack8(o);
     }
+  }
+}
+
+// [B, T, 3, H, D] (the packed q | k | v projection rows) <-> [3, B, H, T, D] (every (batch, head) matrix of q, k, v stacked
+// along rows for the block-diagonal batched GEMMs of the attention backward), 16-byte vectors; `to_stacked` = 0 goes back
+// (the packed gradient).  NP = 3 for qkv, 1 for a plain [B, T, H, D] tensor (dO).
+__global__ void __launch_bounds__(256)
+head_stack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int T, int NP, int H, int DV,
+                  int to_stacked, long long n_vec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the STACKED tensor [NP, B, H, T, DV] (coalesced on the stacked side, 256-byte runs on the packed side)
+    const int d = (int)(i % DV);
+    long long r = i / DV;
+    const int t = (int)(r % T); r /= T;
+    const int h = (int)(r % H); r /= H;
+    const int b = (int)(r % B);
+    const int part = (int)(r / B);
+    const long long packed = ((((long long)b * T + t) * NP + part) * H + h) * DV + d;
+    if (to_stacked) dst[i] = src[packed];
+    else dst[packed] = src[i];
   }
 }
 
@@ -316,6 +368,61 @@ int vllm_rmsnorm_bwd_bf16(const void* x, long long ldx, const void* weight, cons
   if (nvec <= 512) return go(std::integral_constant<int, 2>{});
   if (nvec <= 1024) return go(std::integral_constant<int, 4>{});
   return VLLM_EUNSUPPORTED;
+}
+
+static int rmsnorm_bwd_ctas(long long rows) {
+  const int rows_per_cta = (int)((rows + (long long)vllm_num_sms() * 8 - 1) / ((long long)vllm_num_sms() * 8));
+  return rows_per_cta > 0 ? (int)((rows + rows_per_cta - 1) / rows_per_cta) : 0;
+}
+
+/* rows of the `partials` workspace vllm_rmsnorm_bwd_ws_bf16 needs for `rows` activation rows */
+int vllm_rmsnorm_bwd_partials(long long rows) { return rows > 0 ? rmsnorm_bwd_ctas(rows) : 0; }
+
+int vllm_rmsnorm_bwd_ws_bf16(const void* x, long long ldx, const void* weight, const void* dy, long long ldy, void* dx,
+                             long long lddx, float* dweight, float* partials, int n_partials, long long rows, int cols,
+                             float eps, void* stream) {
+  if (rows < 0 || cols <= 0 || cols % 8) return VLLM_EINVAL;
+  if (rows == 0) return VLLM_OK;
+  if (!x || !weight || !dy || !dx || !dweight || !partials) return VLLM_EINVAL;
+  if (ldx % 8 || ldy % 8 || lddx % 8 || !vllm_aligned(x, 16) || !vllm_aligned(dy, 16) || !vllm_aligned(dx, 16) ||
+      !vllm_aligned(partials, 16))
+    return VLLM_EALIGN;
+  const int nvec = cols / 8;
+  const int rows_per_cta = (int)((rows + (long long)vllm_num_sms() * 8 - 1) / ((long long)vllm_num_sms() * 8));
+  const int blocks = rmsnorm_bwd_ctas(rows);
+  if (n_partials < blocks) return VLLM_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto vpt) -> int {
+    constexpr int VPT = decltype(vpt)::value;
+    rmsnorm_bwd_kernel<VPT><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)weight,
+                                                             (const __nv_bfloat16*)dy, ldy, (__nv_bfloat16*)dx, lddx, dweight,
+                                                             rows, cols, eps, rows_per_cta, partials);
+    VLLM_CHECK_LAUNCH();
+    colsum_partials_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, st>>>(partials, dweight, blocks, cols);
+    VLLM_CHECK_LAUNCH();
+    return VLLM_OK;
+  };
+  if (nvec <= 256) return go(std::integral_constant<int, 1>{});
+  if (nvec <= 512) return go(std::integral_constant<int, 2>{});
+  if (nvec <= 1024) return go(std::integral_constant<int, 4>{});
+  return VLLM_EUNSUPPORTED;
+}
+
+int vllm_head_stack_bf16(const void* src, void* dst, int batch, int tokens, int parts, int heads, int head_dim,
+                         int to_stacked, void* stream) {
+  if (batch < 0 || tokens < 0 || parts <= 0 || heads <= 0 || head_dim <= 0) return VLLM_EINVAL;
+  const long long n_vec = (long long)batch * tokens * parts * heads * (head_dim / 8);
+  if (n_vec == 0) return VLLM_OK;
+  if (!src || !dst) return VLLM_EINVAL;
+  if (head_dim % 8) return VLLM_EUNSUPPORTED;
+  if (!vllm_aligned(src, 16) || !vllm_aligned(dst, 16)) return VLLM_EALIGN;
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = (long long)vllm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  head_stack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, batch, tokens, parts,
+                                                                       heads, head_dim / 8, to_stacked ? 1 : 0, n_vec);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
 }
 
 int vllm_swiglu_fwd_bf16(const void* gate_up, long long ldgu, void* h, long long ldh, long long rows, int inter, void* stream) {

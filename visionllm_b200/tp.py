@@ -319,8 +319,10 @@ class TPLlamaForCausalLM(nn.Module):
             theta = rp.get("rope_theta", 10000.0) if isinstance(rp, dict) else 10000.0
         self.theta = theta
         self.shards = None
-        # forward_pipelined: SMs of the compute GEMMs / of the scatter GEMM (0 = all); measured on 8 x B200
-        self.compute_sms, self.scatter_sms = 120, 28
+        # forward_pipelined: optional SM budgets of the compute GEMMs / of the scatter GEMM (0 = all SMs, the default).
+        # Measured on 8 x B200: every budget tried LOSES against plain two-stream overlap (45.7 ms) -- the
+        # scatter GEMM's peer stores need many SMs to fill the links (28 SMs: 57.6 ms, 16 SMs: 71.0 ms)
+        self.compute_sms, self.scatter_sms = 0, 0
         if shards is not None:
             self.load_shards(shards, device, dtype)
 

@@ -54,8 +54,12 @@ def kernel_fns():
     from . import train as T
     return {"linear": lambda x, w: T.LinearFn.apply(x, w), "linear_f32": lambda x, w: T.LinearFn.apply(x, w, True),
             "rmsnorm": lambda x, w, eps: T.RMSNormFn.apply(x, w, eps),
-            "rope": lambda qkv2, cos, sin, heads, D: T.RopeFn.apply(qkv2, cos, sin, heads, D),
+            "rope": lambda qkv2, cos, sin, heads, D, neg_sin=None: T.RopeFn.apply(qkv2, cos, sin, heads, D, neg_sin),
+            # projection + rotation as one node (in-place rotation of the fresh GEMM output / of the incoming gradient)
+            "qkv_rope": lambda x2, w, cos, sin, neg_sin, heads, D: T.QKVRopeFn.apply(x2, w, cos, sin, neg_sin, heads, D),
             "attention": lambda q, k, v, scale: T.CausalAttentionFn.apply(q, k, v, scale),
+            # packed [B, T, 3, H, D] projection output in, packed gradient out: no per-tensor copies (train.py)
+            "attention_packed": lambda qkv5, scale: T.CausalAttentionPackedFn.apply(qkv5, scale),
             "swiglu": lambda gu2: T.SwiGLUFn.apply(gu2), "ce": lambda logits2, labels: T.CrossEntropyFn.apply(logits2, labels)}
 
 
@@ -117,14 +121,20 @@ class TPLlamaTrain(nn.Module):
         nql, D = self.nq_local, self.D
         pos = torch.arange(T, device=inputs_embeds.device)[None].expand(B, T)
         cos, sin = self.rope_tables(pos, D, self.theta, inputs_embeds.dtype)
+        packed = "attention_packed" in f                     # the kernel op set; torch-native test sets take q, k, v
+        neg_sin = (-sin).contiguous() if packed else None
         tp_in = (lambda t: CopyToTP.apply(t, grp)) if W > 1 else (lambda t: t)
         tp_out = (lambda t: ReduceFromTP.apply(t, grp)) if W > 1 else (lambda t: t)
         x = inputs_embeds
         for ly in self.shards["layers"]:
             h = tp_in(f["rmsnorm"](x, ly["ln1"], self.eps))
-            qkv = f["linear"](h, ly["wqkv"])                                             # [B, T, 3 * nql * D]
-            qkv = f["rope"](qkv.reshape(B * T, 3 * nql * D), cos, sin, 2 * nql, D).view(B, T, 3, nql, D)
-            ctx = f["attention"](qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], D ** -0.5)
+            if packed:
+                qkv = f["qkv_rope"](h.reshape(B * T, H), ly["wqkv"], cos, sin, neg_sin, 2 * nql, D).view(B, T, 3, nql, D)
+                ctx = f["attention_packed"](qkv, D ** -0.5)
+            else:
+                qkv = f["linear"](h, ly["wqkv"])                                         # [B, T, 3 * nql * D]
+                qkv = f["rope"](qkv.reshape(B * T, 3 * nql * D), cos, sin, 2 * nql, D).view(B, T, 3, nql, D)
+                ctx = f["attention"](qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], D ** -0.5)
             x = x + tp_out(f["linear"](ctx.reshape(B, T, nql * D), ly["wo"]))            # ONE all-reduce (attention block)
             h = tp_in(f["rmsnorm"](x, ly["ln2"], self.eps))
             gu = f["linear"](h, ly["wgu"])

@@ -41,11 +41,15 @@ def _check(rc, what):
 def rmsnorm_bwd(x2, weight, dy2, eps):
     rows, cols = x2.shape
     dx = torch.empty_like(x2)
-    dw = torch.zeros(cols, dtype=torch.float32, device=x2.device)
+    dw = torch.empty(cols, dtype=torch.float32, device=x2.device)
+    L = _lib.lib()
+    n_part = L.vllm_rmsnorm_bwd_partials(rows)
+    part = torch.empty((n_part, cols), dtype=torch.float32, device=x2.device)     # per-CTA dweight partials, summed in order
     with torch.cuda.device(x2.device):
-        rc = _lib.lib().vllm_rmsnorm_bwd_bf16(x2.data_ptr(), x2.stride(0), weight.data_ptr(), dy2.data_ptr(), dy2.stride(0),
-                                              dx.data_ptr(), dx.stride(0), dw.data_ptr(), rows, cols, float(eps), _stream())
-    _check(rc, "vllm_rmsnorm_bwd_bf16")
+        rc = L.vllm_rmsnorm_bwd_ws_bf16(x2.data_ptr(), x2.stride(0), weight.data_ptr(), dy2.data_ptr(), dy2.stride(0),
+                                        dx.data_ptr(), dx.stride(0), dw.data_ptr(), part.data_ptr(), n_part, rows, cols,
+                                        float(eps), _stream())
+    _check(rc, "vllm_rmsnorm_bwd_ws_bf16")
     return dx, dw
 
 
@@ -68,9 +72,20 @@ def swiglu_bwd(gu, dh):
     return dgu
 
 
-def gemm_batched(a, b, n_batch, M, N, K, a_mn=False, b_mn=False, causal=0, out_dtype=torch.bfloat16):
+def head_stack(t, B, T, parts, H, D, to_stacked):
+    """[B, T, parts, H, D] -> [parts, B, H, T, D] (to_stacked) or back, one 16-byte-vector pass (vllm_head_stack_bf16)."""
+    src = t if t.is_contiguous() else t.contiguous()
+    out = torch.empty((parts, B, H, T, D) if to_stacked else (B, T, parts, H, D), dtype=src.dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        rc = _lib.lib().vllm_head_stack_bf16(src.data_ptr(), out.data_ptr(), B, T, parts, H, D, 1 if to_stacked else 0, _stream())
+    _check(rc, "vllm_head_stack_bf16")
+    return out
+
+
+def gemm_batched(a, b, n_batch, M, N, K, a_mn=False, b_mn=False, causal=0, out_dtype=torch.bfloat16, out=None):
     """n_batch block-diagonal products C_b = A_b . B_b^T in one tcgen05 launch (operands / output stacked along rows)."""
-    out = torch.empty((n_batch * M, N), dtype=out_dtype, device=a.device)
+    if out is None:
+        out = torch.empty((n_batch * M, N), dtype=out_dtype, device=a.device)
     with torch.cuda.device(a.device), ops._Prof("gemm", 2.0 * n_batch * M * N * K * (0.5 if causal else 1.0), 0.0,
                                                f"b{n_batch}x{M}x{N}x{K}"):
         rc = _lib.lib().vllm_gemm_bf16_batched(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
@@ -80,37 +95,49 @@ def gemm_batched(a, b, n_batch, M, N, K, a_mn=False, b_mn=False, causal=0, out_d
     return out
 
 
-def attention_backward(q, k, v, do, scale):
-    """Backward of causal softmax(q k^T * scale) v for q, k, v, do [B, T, H, D] bf16 (MHA: the same head count).
-    Returns (dq, dk, dv) in the same layout."""
-    B, T, H, D = q.shape
-    if T % 256 or D % 64:
+def attention_backward_packed(qkv5, do, scale):
+    """Backward of causal softmax(q k^T * scale) v for the PACKED projection output qkv5 [B, T, 3, H, D] (bf16, q | k | v
+    along dim 2, MHA) and do [B, T, H*D].  Returns d(qkv5) in the same packed layout.  The (batch, head) matrices are
+    stacked along rows for the block-diagonal batched GEMMs by ONE permuting copy of qkv5 (and one of do); the three
+    gradient GEMMs write slices of one stacked buffer that ONE permuting copy turns back into the packed layout -- no
+    per-tensor .contiguous() / stack / unstack passes, no zero-filled slice gradients for autograd to add up."""
+    B, T, three, H, D = qkv5.shape
+    if three != 3 or T % 256 or D % 64:
         raise RuntimeError("attention_backward: sequence length must be a multiple of 256 and head_dim of 64")
     BH = B * H
-    stack = lambda t: t.permute(0, 2, 1, 3).reshape(BH * T, D).contiguous()       # noqa: E731  [B,T,H,D] -> [(b,h), T, D]
-    qs, ks, vs, dos = stack(q), stack(k), stack(v), stack(do)
+    stk = head_stack(qkv5, B, T, 3, H, D, True).view(3, BH * T, D)                # [3, (b, h), T, D]
+    qs, ks, vs = stk[0], stk[1], stk[2]
+    dos = head_stack(do, B, T, 1, H, D, True).view(BH * T, D)
     L_ = _lib.lib()
     p = gemm_batched(qs, ks, BH, T, T, D, causal=1)                              # S = Q K^T, tiles above the diagonal skipped
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(qkv5.device):
         _check(L_.vllm_softmax_causal_bf16(p.data_ptr(), p.stride(0), BH, T, float(scale), _stream()), "vllm_softmax_causal_bf16")
     dp = gemm_batched(dos, vs, BH, T, T, D, causal=1)                            # dP = dO V^T
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(qkv5.device):
         _check(L_.vllm_attn_ds_bf16(p.data_ptr(), dp.data_ptr(), p.stride(0), BH, T, float(scale), _stream()), "vllm_attn_ds_bf16")
     ds = dp
-    dv = gemm_batched(p, dos, BH, T, D, T, a_mn=True, b_mn=True, causal=2)        # dV = P^T dO
-    dk = gemm_batched(ds, qs, BH, T, D, T, a_mn=True, b_mn=True, causal=2)        # dK = dS^T Q
-    dq = gemm_batched(ds, ks, BH, T, D, T, b_mn=True, causal=3)                   # dQ = dS K
-    unstack = lambda t: t.view(B, H, T, D).permute(0, 2, 1, 3).contiguous()       # noqa: E731
-    return unstack(dq), unstack(dk), unstack(dv)
+    dstk = torch.empty((3, BH * T, D), dtype=qkv5.dtype, device=qkv5.device)
+    gemm_batched(p, dos, BH, T, D, T, a_mn=True, b_mn=True, causal=2, out=dstk[2])   # dV = P^T dO
+    gemm_batched(ds, qs, BH, T, D, T, a_mn=True, b_mn=True, causal=2, out=dstk[1])   # dK = dS^T Q
+    gemm_batched(ds, ks, BH, T, D, T, b_mn=True, causal=3, out=dstk[0])              # dQ = dS K
+    return head_stack(dstk, B, T, 3, H, D, False).view(B, T, 3, H, D)                # packed gradient
+
+
+def attention_backward(q, k, v, do, scale):
+    """Backward for separate q, k, v, do [B, T, H, D] tensors (MHA).  Returns (dq, dk, dv) in the same layout."""
+    d = attention_backward_packed(torch.stack((q, k, v), 2), do.reshape(q.shape[0], q.shape[1], -1), scale)
+    return d[:, :, 0], d[:, :, 1], d[:, :, 2]
 
 
 # ---- autograd Functions --------------------------------------------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, out_f32=False):
+    def forward(ctx, x, weight, out_f32=False, residual=None):
         ctx.save_for_backward(x, weight)
+        ctx.has_res = residual is not None
         if not out_f32:
-            return ops.linear(x, weight)
+            return ops.linear(x, weight, residual=residual)      # y = x W^T (+ residual in the GEMM epilogue)
+        assert residual is None
         # fp32 rows need a 16-byte pitch (V = 32026 is not a multiple of 4): pad the pitch, return the [.., :V] view
         N = weight.shape[0]
         rows = x.numel() // x.shape[-1]
@@ -128,8 +155,12 @@ class LinearFn(torch.autograd.Function):
             dy2 = padded[:, :dy.shape[-1]]
         x2 = x.reshape(-1, x.shape[-1])
         dx = ops.gemm_tn(dy2, w, b_mn=True).view(x.shape) if ctx.needs_input_grad[0] else None
-        dw = ops.gemm_tn(dy2, x2, a_mn=True, b_mn=True, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
-        return dx, (dw.to(w.dtype) if dw is not None else None), None
+        # wgrad: fp32 accumulation in TMEM, ONE rounding to the parameter dtype in the epilogue (== fp32 result .to(bf16))
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm_tn(dy2, x2, a_mn=True, b_mn=True, out_dtype=torch.bfloat16 if w.dtype == torch.bfloat16 else torch.float32)
+            dw = dw if dw.dtype == w.dtype else dw.to(w.dtype)
+        return dx, dw, None, (dy if ctx.has_res else None)
 
 
 class RMSNormFn(torch.autograd.Function):
@@ -147,22 +178,50 @@ class RMSNormFn(torch.autograd.Function):
 
 
 class RopeFn(torch.autograd.Function):
-    """Rotate-half RoPE on the first `heads` heads of the packed [tokens, width] rows (q and k of the packed qkv)."""
+    """Rotate-half RoPE on the first `heads` heads of the packed [tokens, width] rows (q and k of the packed qkv).  Stand-alone
+    (out-of-place) form; the decoder uses QKVRopeFn, which rotates in place inside the projection's autograd node."""
 
     @staticmethod
-    def forward(ctx, qkv2, cos, sin, heads, head_dim):
-        ctx.save_for_backward(cos, sin)
-        ctx.heads, ctx.head_dim = heads, head_dim
+    def forward(ctx, qkv2, cos, sin, heads, head_dim, neg_sin=None):
+        ctx.save_for_backward(cos, sin if neg_sin is None else neg_sin)
+        ctx.heads, ctx.head_dim, ctx.have_neg = heads, head_dim, neg_sin is not None
         out = qkv2.clone()
         ops.rope_(out, cos, sin, heads, head_dim)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        cos, sin = ctx.saved_tensors
+        cos, s_ = ctx.saved_tensors
+        nsin = s_ if ctx.have_neg else (-s_).contiguous()
         g = dy.clone()
-        ops.rope_(g, cos, (-sin).contiguous(), ctx.heads, ctx.head_dim)          # R(theta)^T = R(-theta)
-        return g, None, None, None, None
+        ops.rope_(g, cos, nsin, ctx.heads, ctx.head_dim)                          # R(theta)^T = R(-theta)
+        return g, None, None, None, None, None
+
+
+class QKVRopeFn(torch.autograd.Function):
+    """Packed q|k|v projection + rotate-half RoPE on the q and k heads as one autograd node: the rotation runs in place on
+    the fresh GEMM output (forward) and on the incoming packed gradient (backward: R(theta)^T = R(-theta), then the
+    dgrad / wgrad GEMMs) -- no clone of the [tokens, 3H] tensor either way."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, cos, sin, neg_sin, heads, head_dim):
+        qkv = ops.linear(x2, weight)
+        ops.rope_(qkv, cos, sin, heads, head_dim)
+        ctx.save_for_backward(x2, weight, cos, neg_sin)
+        ctx.heads, ctx.head_dim = heads, head_dim
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, cos, neg_sin = ctx.saved_tensors
+        g = dy if (dy.dim() == 2 and dy.stride(1) == 1 and dy.stride(0) % 8 == 0) else dy.reshape(dy.shape[0], -1).contiguous()
+        ops.rope_(g, cos, neg_sin, ctx.heads, ctx.head_dim)                       # in place: this edge owns the gradient
+        dx = ops.gemm_tn(g, w, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm_tn(g, x2, a_mn=True, b_mn=True, out_dtype=torch.bfloat16 if w.dtype == torch.bfloat16 else torch.float32)
+            dw = dw if dw.dtype == w.dtype else dw.to(w.dtype)
+        return dx, dw, None, None, None, None, None
 
 
 class CausalAttentionFn(torch.autograd.Function):
@@ -176,9 +235,24 @@ class CausalAttentionFn(torch.autograd.Function):
     def backward(ctx, dctx):
         q, k, v = ctx.saved_tensors
         B, T, H, D = q.shape
-        dq, dk, dv = attention_backward(q.contiguous(), k.contiguous(), v.contiguous(), dctx.reshape(B, T, H, D).contiguous(),
-                                        ctx.scale)
+        dq, dk, dv = attention_backward(q, k, v, dctx.reshape(B, T, H, D), ctx.scale)
         return dq, dk, dv, None
+
+
+class CausalAttentionPackedFn(torch.autograd.Function):
+    """Causal attention on the packed projection output qkv5 [B, T, 3, H, D]: the forward reads q / k / v as strided views
+    (no copies), the backward returns the packed gradient (attention_backward_packed)."""
+
+    @staticmethod
+    def forward(ctx, qkv5, scale):
+        ctx.save_for_backward(qkv5)
+        ctx.scale = scale
+        return ops.attention(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], causal=True, scale=scale)
+
+    @staticmethod
+    def backward(ctx, dctx):
+        (qkv5,) = ctx.saved_tensors
+        return attention_backward_packed(qkv5, dctx, ctx.scale), None
 
 
 class SwiGLUFn(torch.autograd.Function):
@@ -247,18 +321,18 @@ class B200LlamaForCausalLMTrain(nn.Module):
         model = self.lm.model
         pos = torch.arange(T, device=inputs_embeds.device)[None].expand(B, T)
         cos, sin = rope_tables(pos, D, self.theta, inputs_embeds.dtype)
+        neg_sin = (-sin).contiguous()
         x = inputs_embeds
         for layer in model.layers:
             wqkv, wgu = self._packed(layer)
             h = RMSNormFn.apply(x, layer.input_layernorm.weight, self.eps)
-            qkv = LinearFn.apply(h, wqkv)
-            qkv = RopeFn.apply(qkv.view(B * T, 3 * H), cos, sin, 2 * nq, D).view(B, T, 3, nq, D)
-            ctx = CausalAttentionFn.apply(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], D ** -0.5)
-            x = x + LinearFn.apply(ctx, layer.self_attn.o_proj.weight)
+            qkv = QKVRopeFn.apply(h.view(B * T, H), wqkv, cos, sin, neg_sin, 2 * nq, D).view(B, T, 3, nq, D)
+            ctx = CausalAttentionPackedFn.apply(qkv, D ** -0.5)
+            x = LinearFn.apply(ctx, layer.self_attn.o_proj.weight, False, x)               # + residual in the GEMM epilogue
             h = RMSNormFn.apply(x, layer.post_attention_layernorm.weight, self.eps)
             gu = LinearFn.apply(h, wgu)
             act = SwiGLUFn.apply(gu.view(B * T, -1)).view(B, T, -1)
-            x = x + LinearFn.apply(act, layer.mlp.down_proj.weight)
+            x = LinearFn.apply(act, layer.mlp.down_proj.weight, False, x)
         hidden = RMSNormFn.apply(x, model.norm.weight, self.eps)
         # fp32 logits like `logits.float()` (mv2.py:738), as a 2-D [B*T, V] view of a pitch-padded buffer so that the loss
         # kernel and the lm_head backward GEMMs read logits / dlogits in place
