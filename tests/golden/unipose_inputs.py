@@ -52,3 +52,41 @@ def decoder_inputs():
                 ref_unsig=ref_unsig.to(torch.bfloat16).float(), valid_ratios=valid_ratios.to(torch.bfloat16).float(),
                 memory_text=r(bs, ntok, d), text_mask=text_mask, encoded_text=r(bs, ntok, d) * 2.0,
                 kpt_embed=r(bs, nbp, d), kpt_vis=kpt_vis)
+
+
+# ---- the whole transformer: fused encoder + two-stage selection + keypoint decoder (modeling_unipose.py:2206-2700) ----------
+TR = dict(d_model=256, nhead=8, num_queries=60, num_encoder_layers=2, num_decoder_layers=4, dim_feedforward=512,
+          num_feature_levels=4, num_box_decoder_layers=2, num_body_points=19, bs=2, ntok=6)
+
+
+def transformer_kwargs():
+    c = TR
+    return dict(d_model=c["d_model"], nhead=c["nhead"], num_queries=c["num_queries"], num_encoder_layers=c["num_encoder_layers"],
+                num_decoder_layers=c["num_decoder_layers"], dim_feedforward=c["dim_feedforward"], dropout=0.0,
+                return_intermediate_dec=True, query_dim=4, deformable_encoder=True, deformable_decoder=True,
+                num_feature_levels=c["num_feature_levels"], enc_n_points=4, dec_n_points=4, learnable_tgt_init=True,
+                two_stage_type="standard", embed_init_tgt=True, use_text_enhancer=True, use_fusion_layer=True,
+                use_text_cross_attention=True, text_dropout=0.0, fusion_dropout=0.0, fusion_droppath=0.0, decoder_sa_type="sa")
+
+
+def transformer_inputs():
+    g = torch.Generator().manual_seed(31)
+    r = lambda *s: (torch.randn(*s, generator=g) * 0.5).to(torch.bfloat16).float()  # noqa: E731
+    c = TR
+    bs, d, nbp, ntok = c["bs"], c["d_model"], c["num_body_points"], c["ntok"]
+    srcs = [r(bs, d, h, w) for h, w in SHAPES]
+    poss = [r(bs, d, h, w) for h, w in SHAPES]
+    masks = []
+    for h, w in SHAPES:                                          # batch entry 1 is padded on the right / bottom
+        m = torch.zeros(bs, h, w, dtype=torch.bool)
+        m[1, :, int(w * 0.75):] = True
+        m[1, int(h * 0.8):, :] = True
+        masks.append(m)
+    obj_mask = torch.zeros(bs, ntok, dtype=torch.long)           # obj_query_masks: 1 = a real class token
+    obj_mask[0, :5] = 1
+    obj_mask[1, :3] = 1
+    kpt_vis = torch.zeros(bs, nbp, dtype=torch.long)
+    kpt_vis[0, :17] = 1
+    kpt_vis[1, :12] = 1
+    return dict(srcs=srcs, poss=poss, masks=masks, obj_mask=obj_mask, encoded_text=r(bs, ntok, d) * 2.0, kpt_embed=r(bs, nbp, d),
+                kpt_vis=kpt_vis)

@@ -117,3 +117,56 @@ def stored_rows(g):
     from unipose_inputs import DEC
     group, step = DEC["num_body_points"] + 1, int(g["group_step"])
     return torch.cat([torch.arange(gi * group, (gi + 1) * group) for gi in range(0, 50, step)])
+
+
+# ---- the whole transformer (modeling_unipose.py:2206-2700) ----------------------------------------------------------------
+def build_transformer():
+    import types
+
+    import visionllm_b200.unipose as U
+    from gen_golden_unipose_transformer import build
+    ns = types.SimpleNamespace(DeformableTransformer=U.DeformableTransformer, MLP=U.MLP, ContrastiveAssign=U.ContrastiveAssign)
+    return build(ns)
+
+
+def run_transformer(tr, x, mask2, c=lambda t: t):
+    from visionllm_b200.unipose import generate_masks_with_text_query_masks
+    sa, pid = generate_masks_with_text_query_masks(x["obj_mask"])
+    text_dict = {"encoded_text": c(x["encoded_text"]), "text_token_mask": x["obj_mask"].bool(), "position_ids": pid,
+                 "text_self_attention_masks": sa}
+    return tr([c(s) for s in x["srcs"]], x["masks"], None, [c(p) for p in x["poss"]], None, None, mask2, text_dict, None, None,
+              c(x["kpt_embed"]))
+
+
+def test_text_query_masks_match_reference(golden_dir):
+    from unipose_inputs import transformer_inputs
+    from visionllm_b200.unipose import generate_masks_with_text_query_masks
+    g = np.load(os.path.join(golden_dir, "mod_unipose_transformer.npz"))
+    sa, pid = generate_masks_with_text_query_masks(transformer_inputs()["obj_mask"])
+    assert torch.equal(sa, torch.from_numpy(g["text_sa"])) and torch.equal(pid, torch.from_numpy(g["text_pid"]))
+
+
+def test_unipose_transformer_logic_matches_reference(golden_dir, torch_kernels):  # noqa: F811
+    """Encoder (fusion + text enhancer + deformable layers), two-stage selection (top-k indices exact), decoder: fp32 logic
+    against the reference's own DeformableTransformer."""
+    from unipose_inputs import TR, transformer_inputs
+    g = np.load(os.path.join(golden_dir, "mod_unipose_transformer.npz"))
+    tr, keys = build_transformer()
+    assert json.loads(str(g["keys"])) == [list(k) for k in keys], "transformer keys differ"
+    x = transformer_inputs()
+    mask2 = decoder_mask(x["kpt_vis"], TR["nhead"], TR["num_body_points"])
+    hs, refs, hs_enc, ref_enc, init_box = run_transformer(tr, x, mask2)
+    assert torch.equal(tr.topk_proposals.cpu(), torch.from_numpy(g["topk_enc"])), "two-stage proposal indices differ"
+    assert torch.equal(tr.decoder.topk_proposals.cpu(), torch.from_numpy(g["topk_dec"])), "top-50 box indices differ"
+    rows, nb = stored_rows(g), TR["num_box_decoder_layers"]
+    for i, h in enumerate(hs):
+        ref = torch.from_numpy(g[f"hs{i}_f32"])
+        h = h if i < nb else h[:, rows]
+        assert h.shape == ref.shape and (h.float() - ref).abs().max().item() <= 5e-4 * max(1.0, ref.abs().max().item()), i
+    for i, r in enumerate(refs):
+        ref = torch.from_numpy(g[f"ref{i}_f32"])
+        r = r if i - 1 < nb else r[:, rows]
+        assert r.shape == ref.shape and (r.float() - ref).abs().max().item() <= 2e-4, i
+    for got, name in ((hs_enc, "hs_enc"), (ref_enc, "ref_enc"), (init_box, "init_box")):
+        ref = torch.from_numpy(g[f"{name}_f32"])
+        assert got.shape == ref.shape and (got.float() - ref).abs().max().item() <= 5e-4 * max(1.0, ref.abs().max().item()), name

@@ -73,3 +73,36 @@ def test_unipose_keypoint_decoder_matches_reference(golden_dir):
         r = r if i - 1 < nb else r[:, rows]
         assert r.shape == r32.shape
         assert (r.float() - r32).abs().max().item() <= 1.5 * (r16 - r32).abs().max().item() + 4e-3, i
+
+
+def test_unipose_transformer_matches_reference(golden_dir):
+    """The whole UniPose transformer (text-fused deformable encoder -> two-stage query selection -> keypoint decoder,
+    modeling_unipose.py:2206-2700) on our kernels in bf16 vs the reference's fp32 run; both top-k selections are pinned to
+    the fp32 run's (as for the golden's bf16 run), module rule against the reference's own bf16 error."""
+    from unipose_inputs import TR, transformer_inputs
+    from test_unipose_cpu import build_transformer, decoder_mask, run_transformer, stored_rows
+    g = np.load(os.path.join(golden_dir, "mod_unipose_transformer.npz"))
+    tr, keys = build_transformer()
+    assert json.loads(str(g["keys"])) == [list(k) for k in keys]
+    tr = tr.to("cuda", torch.bfloat16)
+    x = transformer_inputs()
+    x = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in x.items()}
+    mask2 = decoder_mask(x["kpt_vis"], TR["nhead"], TR["num_body_points"])
+    cast = lambda t: t.bfloat16() if t.is_floating_point() else t  # noqa: E731
+    tr.forced_topk = torch.from_numpy(g["topk_enc"]).cuda()
+    tr.decoder.forced_topk = torch.from_numpy(g["topk_dec"]).cuda()
+    hs, refs, hs_enc, ref_enc, init_box = run_transformer(tr, x, mask2, c=cast)
+    rows, nb = stored_rows(g).cuda(), TR["num_box_decoder_layers"]
+    for i, h in enumerate(hs):
+        ref32, ref16 = torch.from_numpy(g[f"hs{i}_f32"]).cuda(), torch.from_numpy(g[f"hs{i}_refbf16"]).cuda()
+        h = h if i < nb else h[:, rows]
+        assert h.shape == ref32.shape and h.dtype == torch.bfloat16
+        budget = 1.5 * rel_l2(ref16, ref32) + 1e-3
+        assert rel_l2(h, ref32) <= budget, (i, rel_l2(h, ref32), budget)
+    for i, r in enumerate(refs):
+        r32, r16 = torch.from_numpy(g[f"ref{i}_f32"]).cuda(), torch.from_numpy(g[f"ref{i}_refbf16"]).cuda()
+        r = r if i - 1 < nb else r[:, rows]
+        assert r.shape == r32.shape
+        assert (r.float() - r32).abs().max().item() <= 1.5 * (r16 - r32).abs().max().item() + 4e-3, i
+    e32, e16 = torch.from_numpy(g["hs_enc_f32"]).cuda(), torch.from_numpy(g["hs_enc_refbf16"]).cuda()
+    assert rel_l2(hs_enc, e32) <= 1.5 * rel_l2(e16, e32) + 1e-3

@@ -267,7 +267,7 @@ class TransformerDecoder(nn.Module):
             query_sine_embed = gen_sineembed_for_position(rp_in[:, :, 0, :]).to(tgt.dtype)
             query_pos = self.ref_point_head(query_sine_embed)
             output = layer(tgt=output, tgt_query_pos=query_pos, tgt_query_sine_embed=query_sine_embed,
-                           tgt_key_padding_mask=tgt_key_padding_mask, tgt_reference_points=rp_in.to(tgt.dtype),
+                           tgt_key_padding_mask=tgt_key_padding_mask, tgt_reference_points=rp_in,
                            memory_text=memory_text, text_attention_mask=text_attention_mask, memory=memory,
                            memory_key_padding_mask=memory_key_padding_mask, memory_level_start_index=level_start_index,
                            memory_spatial_shapes=spatial_shapes, memory_pos=pos, self_attn_mask=tgt_mask,
@@ -334,3 +334,298 @@ def prepare_for_mask(kpt_mask, nheads, num_body_points, num_group=50):
         s0 = idx * length
         m[:, s0:s0 + length, s0:s0 + length] = ~equal
     return m[:, None].repeat(1, nheads, 1, 1).flatten(0, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The UniPose transformer: text-fused deformable encoder, two-stage query selection, keypoint decoder
+# (modeling_unipose.py:1943-2204 fusion / text layers, 2206-2700 DeformableTransformer, 2701-2868 TransformerEncoder)
+# ---------------------------------------------------------------------------------------------------------------------
+from . import gdino_heads as _H   # noqa: E402
+from . import msda as _msda   # noqa: E402
+from .gdino import get_sine_pos_embed   # noqa: E402
+
+
+class BiMultiHeadAttention(nn.Module):
+    """modeling_unipose.py:1943-2082 (parameter names v_proj / l_proj / values_v_proj / values_l_proj / out_v_proj /
+    out_l_proj).  Both directions share S = (v_proj(v) * scale) l_proj(l)^T: softmax over the text keys updates the image
+    tokens, softmax over the image keys of S^T the text tokens; the reference's global `S - S.max()` and +-50000 clamps do not
+    change either softmax.  Masks: True = padding.  Two tcgen05 attention calls (head_dim = embed_dim / heads, 256 for the
+    released config) on packed projection GEMMs."""
+
+    def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, cfg=None):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim
+        self.v_dim, self.l_dim, self.scale, self.dropout = v_dim, l_dim, self.head_dim ** (-0.5), dropout
+        self.v_proj, self.l_proj = nn.Linear(v_dim, embed_dim), nn.Linear(l_dim, embed_dim)
+        self.values_v_proj, self.values_l_proj = nn.Linear(v_dim, embed_dim), nn.Linear(l_dim, embed_dim)
+        self.out_v_proj, self.out_l_proj = nn.Linear(embed_dim, v_dim), nn.Linear(embed_dim, l_dim)
+        self.stable_softmax_2d = self.clamp_min_for_underflow = self.clamp_max_for_overflow = True
+
+    @torch.no_grad()
+    def forward(self, v, l, attention_mask_v=None, attention_mask_l=None, v_epilogue=None, l_epilogue=None):   # noqa: E741
+        E, H, D = self.embed_dim, self.num_heads, self.head_dim
+        wv = torch.cat([self.v_proj.weight, self.values_v_proj.weight], 0)
+        bv = torch.cat([self.v_proj.bias, self.values_v_proj.bias], 0)
+        wl = torch.cat([self.l_proj.weight, self.values_l_proj.weight], 0)
+        bl = torch.cat([self.l_proj.bias, self.values_l_proj.bias], 0)
+        pv = ops.linear(v, wv, bias=bv)                           # [B, S, 2E]: query side | values
+        pl = ops.linear(l, wl, bias=bl)                           # [B, T, 2E]: key side | values
+        vq, vval = pv[..., :E].unflatten(-1, (H, D)), pv[..., E:].unflatten(-1, (H, D))
+        lk, lval = pl[..., :E].unflatten(-1, (H, D)), pl[..., E:].unflatten(-1, (H, D))
+        km_l = None if attention_mask_l is None else ~attention_mask_l
+        km_v = None if attention_mask_v is None else ~attention_mask_v
+        v_ctx = ops.attention(vq, lk, lval, scale=self.scale, key_mask=km_l)      # image queries over text keys
+        l_ctx = ops.attention(lk, vq, vval, scale=self.scale, key_mask=km_v)      # text queries over image keys
+        dv = ops.linear(v_ctx, self.out_v_proj.weight, bias=self.out_v_proj.bias, **(v_epilogue or {}))
+        dl = ops.linear(l_ctx, self.out_l_proj.weight, bias=self.out_l_proj.bias, **(l_epilogue or {}))
+        return dv, dl
+
+
+class BiAttentionBlock(nn.Module):
+    """modeling_unipose.py:2169-2203: pre-LayerNorm, bi-attention, LayerScale (gam_v / gam_l) + residual ON THE NORMALISED
+    features; LayerScale and residual ride in the output projections' GEMM epilogues."""
+
+    def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, drop_path=.0, init_values=1e-4, cfg=None):
+        super().__init__()
+        self.layer_norm_v, self.layer_norm_l = _LN(v_dim), _LN(l_dim)
+        self.attn = BiMultiHeadAttention(v_dim=v_dim, l_dim=l_dim, embed_dim=embed_dim, num_heads=num_heads, dropout=dropout)
+        self.drop_path = nn.Identity()
+        self.gam_v = nn.Parameter(init_values * torch.ones((v_dim)), requires_grad=True)
+        self.gam_l = nn.Parameter(init_values * torch.ones((l_dim)), requires_grad=True)
+
+    @torch.no_grad()
+    def forward(self, v, l, attention_mask_v=None, attention_mask_l=None):   # noqa: E741
+        v, l = self.layer_norm_v(v), self.layer_norm_l(l)   # noqa: E741
+        return self.attn(v, l, attention_mask_v=attention_mask_v, attention_mask_l=attention_mask_l,
+                         v_epilogue=dict(colscale=self.gam_v, residual=v), l_epilogue=dict(colscale=self.gam_l, residual=l))
+
+
+class TransformerEncoderLayer(nn.Module):
+    """modeling_unipose.py:2122-2166, the text enhancer: post-norm MHA + FFN on sequence-first [n_text, bs, d] tensors.
+    `src_mask` [bs, nq, nk] bool (True = blocked) is expanded like the reference does -- `repeat(nhead, 1, 1)`, batch-minor,
+    while nn.MultiheadAttention indexes batch-major: (batch b, head h) gets the mask of batch (b * nhead + h) % bs; identical
+    for bs == 1, reproduced exactly for bs > 1.  `src_key_padding_mask` is ignored like in the reference (:2157)."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False):
+        super().__init__()
+        assert not normalize_before
+        self.self_attn = _MHA(d_model, nhead, dropout=dropout)
+        self.linear1, self.linear2 = nn.Linear(d_model, dim_feedforward), nn.Linear(dim_feedforward, d_model)
+        self.norm1, self.norm2 = _LN(d_model), _LN(d_model)
+        self.act = _activation(activation)
+        self.normalize_before, self.nhead = normalize_before, nhead
+
+    @torch.no_grad()
+    def forward(self, src, src_mask=None, src_key_padding_mask=None, pos=None):
+        x = src.transpose(0, 1).contiguous()                                  # [bs, n, d]
+        full = None
+        if src_mask is not None:
+            am = src_mask
+            if am.dim() == 3 and am.shape[0] == x.shape[0]:
+                am = am.repeat(self.nhead, 1, 1)
+            elif am.dim() == 2:
+                am = am[None].expand(x.shape[0] * self.nhead, -1, -1)
+            full = ~am
+        qk = x if pos is None else x + pos.transpose(0, 1).to(x.dtype)
+        x = self.norm1(self.self_attn.run(qk, qk, x, attn_mask=full, residual=x))
+        h = ops.linear(x, self.linear1.weight, bias=self.linear1.bias, act=self.act)
+        x = self.norm2(ops.linear(h, self.linear2.weight, bias=self.linear2.bias, residual=x))
+        return x.transpose(0, 1)
+
+
+class TransformerEncoder(nn.Module):
+    """modeling_unipose.py:2701-2866: per layer -- fusion (BiAttentionBlock), text enhancer, deformable layer."""
+
+    def __init__(self, encoder_layer, num_layers, d_model=256, num_queries=300, enc_layer_share=False, text_enhance_layer=None,
+                 feature_fusion_layer=None, use_checkpoint=False, use_transformer_ckpt=False):
+        super().__init__()
+        self.layers, self.text_layers, self.fusion_layers = [], [], []
+        if num_layers > 0:
+            self.layers = _get_clones(encoder_layer, num_layers, layer_share=enc_layer_share)
+            if text_enhance_layer is not None:
+                self.text_layers = _get_clones(text_enhance_layer, num_layers, layer_share=enc_layer_share)
+            if feature_fusion_layer is not None:
+                self.fusion_layers = _get_clones(feature_fusion_layer, num_layers, layer_share=enc_layer_share)
+        self.query_scale, self.num_queries, self.num_layers, self.d_model = None, num_queries, num_layers, d_model
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        refs = []
+        for lvl, (H_, W_) in enumerate(_msda.host_shape_list(spatial_shapes)):
+            ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_, device=device),
+                                          torch.linspace(0.5, W_ - 0.5, W_, device=device), indexing="ij")
+            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
+            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
+            refs.append(torch.stack((ref_x, ref_y), -1))
+        reference_points = torch.cat(refs, 1)
+        return reference_points[:, :, None] * valid_ratios[:, None]
+
+    @torch.no_grad()
+    def forward(self, src, pos, spatial_shapes, level_start_index, valid_ratios, key_padding_mask, memory_text=None,
+                text_attention_mask=None, pos_text=None, text_self_attention_masks=None, position_ids=None):
+        output = src
+        reference_points = None
+        if self.num_layers > 0:
+            reference_points = self.get_reference_points(spatial_shapes, valid_ratios.float(), device=src.device)
+        if self.text_layers:
+            bs, n_text, _ = memory_text.shape
+            if pos_text is None and position_ids is None:
+                pt = torch.arange(n_text, device=memory_text.device).float()[None, :, None].repeat(bs, 1, 1)
+                pos_text = get_sine_pos_embed(pt, num_pos_feats=256, exchange_xy=False)
+            if position_ids is not None:
+                pos_text = get_sine_pos_embed(position_ids[..., None], num_pos_feats=256, exchange_xy=False)
+        for layer_id, layer in enumerate(self.layers):
+            if self.fusion_layers:
+                output, memory_text = self.fusion_layers[layer_id](v=output, l=memory_text, attention_mask_v=key_padding_mask,
+                                                                   attention_mask_l=text_attention_mask)
+            if self.text_layers:
+                memory_text = self.text_layers[layer_id](
+                    src=memory_text.transpose(0, 1), src_mask=~text_self_attention_masks,
+                    src_key_padding_mask=text_attention_mask,
+                    pos=(pos_text.transpose(0, 1) if pos_text is not None else None)).transpose(0, 1)
+            output = layer(src=output, pos=pos, reference_points=reference_points, spatial_shapes=spatial_shapes,
+                           level_start_index=level_start_index, key_padding_mask=key_padding_mask)
+        return output, memory_text
+
+
+class DeformableTransformer(nn.Module):
+    """modeling_unipose.py:2206-2700 for the configuration the UniPose builder produces (:4241-4330): deformable encoder
+    and decoder, text enhancer + fusion layers, text cross-attention in the decoder, two-stage 'standard' query selection,
+    learnable (`embed_init_tgt`) decoder queries.  Same constructor keywords and parameter names (`encoder.*`, `decoder.*`,
+    `level_embed`, `tgt_embed`, `enc_output`, `enc_output_norm`; `enc_out_bbox_embed` / `enc_out_class_embed` and the
+    decoder's heads are bound by the owner model, :233-257).  Unsupported switches raise."""
+
+    def __init__(self, d_model=256, nhead=8, num_queries=300, num_encoder_layers=6, num_unicoder_layers=0, num_decoder_layers=6,
+                 dim_feedforward=2048, dropout=0.0, activation="relu", normalize_before=False, return_intermediate_dec=False,
+                 query_dim=4, num_patterns=0, modulate_hw_attn=False, deformable_encoder=False, deformable_decoder=False,
+                 num_feature_levels=1, enc_n_points=4, dec_n_points=4, use_deformable_box_attn=False, box_attn_type='roi_align',
+                 learnable_tgt_init=False, decoder_query_perturber=None, add_channel_attention=False, add_pos_value=False,
+                 random_refpoints_xy=False, two_stage_type='standard', two_stage_pat_embed=0, two_stage_add_query_num=0,
+                 two_stage_learn_wh=False, two_stage_keep_all_tokens=False, dec_layer_number=None, rm_enc_query_scale=True,
+                 rm_dec_query_scale=True, rm_self_attn_layers=None, key_aware_type=None, layer_share_type=None, rm_detach=None,
+                 decoder_sa_type='ca', module_seq=['sa', 'ca', 'ffn'], embed_init_tgt=False, use_detached_boxes_dec_out=False,
+                 use_text_enhancer=False, use_fusion_layer=False, use_checkpoint=False, use_transformer_ckpt=False,
+                 use_text_cross_attention=False, text_dropout=0.1, fusion_dropout=0.1, fusion_droppath=0.0,
+                 binary_query_selection=False, ffn_extra_layernorm=False, num_box_decoder_layers=2, num_body_points=68):
+        super().__init__()
+        unsupported = dict(binary_query_selection=binary_query_selection, use_deformable_box_attn=use_deformable_box_attn,
+                           add_channel_attention=add_channel_attention, two_stage_pat_embed=two_stage_pat_embed,
+                           two_stage_add_query_num=two_stage_add_query_num, two_stage_learn_wh=two_stage_learn_wh,
+                           two_stage_keep_all_tokens=two_stage_keep_all_tokens, rm_self_attn_layers=rm_self_attn_layers,
+                           layer_share_type=layer_share_type, rm_detach=rm_detach, num_patterns=num_patterns,
+                           normalize_before=normalize_before, ffn_extra_layernorm=ffn_extra_layernorm)
+        bad = {k: v for k, v in unsupported.items() if v}
+        if bad or not (deformable_encoder and deformable_decoder) or two_stage_type != 'standard' or query_dim != 4:
+            raise NotImplementedError(f"DeformableTransformer: configuration outside the UniPose builder's ({bad})")
+        assert learnable_tgt_init, "why not learnable_tgt_init"
+        assert decoder_sa_type in ('sa', 'ca_label', 'ca_content')
+        self.num_feature_levels, self.num_encoder_layers, self.num_decoder_layers = num_feature_levels, num_encoder_layers, num_decoder_layers
+        self.num_queries, self.d_model, self.nhead, self.dec_layers = num_queries, d_model, nhead, num_decoder_layers
+        self.two_stage_type, self.embed_init_tgt, self.decoder_sa_type = two_stage_type, embed_init_tgt, decoder_sa_type
+        self.use_detached_boxes_dec_out = use_detached_boxes_dec_out
+        encoder_layer = DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels,
+                                                          nhead, enc_n_points)
+        text_layer = (TransformerEncoderLayer(d_model=d_model, nhead=nhead // 2, dim_feedforward=dim_feedforward // 2,
+                                              dropout=text_dropout) if use_text_enhancer else None)
+        fusion_layer = (BiAttentionBlock(v_dim=d_model, l_dim=d_model, embed_dim=dim_feedforward // 2, num_heads=nhead // 2,
+                                         dropout=fusion_dropout, drop_path=fusion_droppath) if use_fusion_layer else None)
+        self.encoder = TransformerEncoder(encoder_layer, num_encoder_layers, d_model=d_model, num_queries=num_queries,
+                                          text_enhance_layer=text_layer, feature_fusion_layer=fusion_layer)
+        decoder_layer = DeformableTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels, nhead,
+                                                          dec_n_points, use_text_cross_attention=use_text_cross_attention)
+        self.decoder = TransformerDecoder(decoder_layer, num_decoder_layers, _LN(d_model), return_intermediate=return_intermediate_dec,
+                                          d_model=d_model, query_dim=query_dim, modulate_hw_attn=modulate_hw_attn,
+                                          num_feature_levels=num_feature_levels, deformable_decoder=deformable_decoder,
+                                          rm_dec_query_scale=rm_dec_query_scale,
+                                          use_detached_boxes_dec_out=use_detached_boxes_dec_out,
+                                          num_box_decoder_layers=num_box_decoder_layers, num_body_points=num_body_points)
+        self.level_embed = (nn.Parameter(torch.zeros(num_feature_levels, d_model))
+                            if (num_feature_levels > 1 and num_encoder_layers > 0) else None)
+        self.tgt_embed = nn.Embedding(num_queries, d_model) if embed_init_tgt else None
+        self.enc_output, self.enc_output_norm = nn.Linear(d_model, d_model), _LN(d_model)
+        self.two_stage_wh_embedding = None
+        self.enc_out_class_embed = self.enc_out_bbox_embed = None
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        _, H, W = mask.shape
+        valid_H, valid_W = torch.sum(~mask[:, :, 0], 1), torch.sum(~mask[:, 0, :], 1)
+        return torch.stack([valid_W.float() / W, valid_H.float() / H], -1)
+
+    @torch.no_grad()
+    def forward(self, srcs, masks, refpoint_embed, pos_embeds, tgt, attn_mask=None, attn_mask2=None, text_dict=None,
+                dn_meta=None, targets=None, kpt_embed=None):
+        """srcs / pos_embeds: per-level [bs, c, h, w] maps, masks [bs, h, w] (True = padding); refpoint_embed / tgt: the
+        denoising queries (training only: must be None).  Returns (hs, references, hs_enc, ref_enc, init_box_proposal)."""
+        if refpoint_embed is not None or tgt is not None or self.training:
+            raise NotImplementedError("denoising queries / training are outside the forward hot path")
+        src_l, mask_l, pos_l, shapes = [], [], [], []
+        for lvl, (src, mask, pos_embed) in enumerate(zip(srcs, masks, pos_embeds)):
+            bs, c, h, w = src.shape
+            shapes.append((h, w))
+            src_l.append(src.flatten(2).transpose(1, 2))
+            mask_l.append(mask.flatten(1))
+            pe = pos_embed.flatten(2).transpose(1, 2)
+            if self.num_feature_levels > 1 and self.level_embed is not None:
+                pe = pe + self.level_embed[lvl].view(1, 1, -1)
+            pos_l.append(pe)
+        src_flatten, mask_flatten = torch.cat(src_l, 1).contiguous(), torch.cat(mask_l, 1)
+        lvl_pos = torch.cat(pos_l, 1).contiguous()
+        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=src_flatten.device)
+        _msda.attach_host_shapes(spatial_shapes, shapes)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+
+        memory, memory_text = self.encoder(
+            src_flatten, pos=lvl_pos, level_start_index=level_start_index, spatial_shapes=spatial_shapes,
+            valid_ratios=valid_ratios, key_padding_mask=mask_flatten, memory_text=text_dict['encoded_text'],
+            text_attention_mask=~text_dict['text_token_mask'], position_ids=text_dict['position_ids'],
+            text_self_attention_masks=text_dict['text_self_attention_masks'])
+        text_dict = dict(text_dict)
+        text_dict['encoded_text'] = memory_text
+
+        # two-stage 'standard' query selection (:2557-2606); top-k indices through torch.topk like the reference
+        output_memory, output_proposals = _H.gen_encoder_output_proposals(self.enc_output, self.enc_output_norm, memory,
+                                                                          mask_flatten, spatial_shapes)
+        cls = self.enc_out_class_embed(output_memory, text_dict)
+        topk_logits = cls.max(-1)[0]
+        coord_unselected = self.enc_out_bbox_embed(output_memory).float() + output_proposals
+        topk_proposals = torch.topk(topk_logits, self.num_queries, dim=1)[1]
+        if getattr(self, "forced_topk", None) is not None:
+            topk_proposals = self.forced_topk.to(topk_proposals.device)
+        self.topk_proposals = topk_proposals
+        refpoint_undetach = torch.gather(coord_unselected, 1, topk_proposals.unsqueeze(-1).repeat(1, 1, 4))
+        init_box_proposal = torch.gather(output_proposals, 1, topk_proposals.unsqueeze(-1).repeat(1, 1, 4)).sigmoid()
+        tgt_undetach = torch.gather(output_memory, 1, topk_proposals.unsqueeze(-1).repeat(1, 1, self.d_model))
+        bs = memory.shape[0]
+        if self.embed_init_tgt:
+            tgt_ = self.tgt_embed.weight[:, None, :].repeat(1, bs, 1).transpose(0, 1)
+        else:
+            tgt_ = tgt_undetach
+        refpoint_embed, tgt = refpoint_undetach, tgt_.to(memory.dtype)
+
+        hs, references = self.decoder(
+            tgt=tgt.transpose(0, 1).contiguous(), memory=memory.transpose(0, 1), memory_key_padding_mask=mask_flatten,
+            pos=lvl_pos.transpose(0, 1), refpoints_unsigmoid=refpoint_embed.transpose(0, 1),      # fp32, like the reference
+            level_start_index=level_start_index, spatial_shapes=spatial_shapes, valid_ratios=valid_ratios,
+            tgt_mask=attn_mask, tgt_mask2=attn_mask2, memory_text=text_dict['encoded_text'],
+            text_attention_mask=~text_dict['text_token_mask'], text_dict=text_dict, dn_meta=dn_meta, targets=targets,
+            kpt_embed=kpt_embed)
+        hs_enc = tgt_undetach.unsqueeze(0)
+        ref_enc = refpoint_undetach.sigmoid().unsqueeze(0)
+        return hs, references, hs_enc, ref_enc, init_box_proposal
+
+
+def generate_masks_with_text_query_masks(text_query_masks):
+    """modeling_unipose.py:928-945: text_query_masks [bs, n] (1 = a real class token) -> (self_attention_mask [bs, n, n] bool:
+    identity plus the all-pairs block of the first num_valid tokens; position_ids [bs, n]: 0..num_valid-1, then zeros).
+    Vectorised (the reference loops over the batch with a device sync per sample)."""
+    bs, n = text_query_masks.shape
+    dev = text_query_masks.device
+    nv = text_query_masks.sum(1).to(torch.long)                                   # [bs]
+    ar = torch.arange(n, device=dev)
+    inside = ar[None, :] < nv[:, None]                                           # [bs, n]
+    mask = torch.eye(n, device=dev, dtype=torch.bool)[None].repeat(bs, 1, 1) | (inside[:, :, None] & inside[:, None, :])
+    position_ids = torch.where(inside, ar[None, :].expand(bs, n), torch.zeros((), dtype=torch.long, device=dev))
+    return mask, position_ids
