@@ -90,3 +90,32 @@ def transformer_inputs():
     kpt_vis[1, :12] = 1
     return dict(srcs=srcs, poss=poss, masks=masks, obj_mask=obj_mask, encoded_text=r(bs, ntok, d) * 2.0, kpt_embed=r(bs, nbp, d),
                 kpt_vis=kpt_vis)
+
+
+# ---- the model behind its backbone (modeling_unipose.py:69-655) -------------------------------------------------------------
+MODEL = dict(l_hidden=64, backbone_channels=(32, 48, 64), n_obj=6, n_kpt=19, n_emb=4)
+
+
+def model_inputs():
+    """Backbone outputs of a padded 2-image batch (3 levels; the 4th is derived by input_proj[3]) + LLM [EMB] states."""
+    g = torch.Generator().manual_seed(37)
+    r = lambda *s: (torch.randn(*s, generator=g) * 0.5).to(torch.bfloat16).float()  # noqa: E731
+    bs = TR["bs"]
+    Hs, Ws = 96, 128                                              # padded batch size in pixels (stride 8 -> 12 x 16)
+    sample_mask = torch.zeros(bs, Hs, Ws, dtype=torch.bool)
+    sample_mask[1, :, 96:] = True
+    sample_mask[1, 80:, :] = True
+    feats, poss = [], []
+    for (h, w), c in zip(SHAPES[:3], MODEL["backbone_channels"]):
+        m = torch.nn.functional.interpolate(sample_mask[None].float(), size=(h, w)).to(torch.bool)[0]
+        feats.append((r(bs, c, h, w), m))
+        poss.append(r(bs, TR["d_model"], h, w))
+    obj_mask = torch.zeros(bs, MODEL["n_obj"], dtype=torch.long)
+    obj_mask[0, :5] = 1
+    obj_mask[1, :3] = 1
+    kpt_mask = torch.zeros(bs, MODEL["n_kpt"], dtype=torch.long)
+    kpt_mask[0, :17] = 1
+    kpt_mask[1, :12] = 1
+    tq = dict(obj_querys=r(bs, MODEL["n_obj"], MODEL["n_emb"], MODEL["l_hidden"]) * 2, obj_query_masks=obj_mask,
+              kpt_querys=r(bs, MODEL["n_kpt"], MODEL["n_emb"], MODEL["l_hidden"]) * 2, kpt_query_masks=kpt_mask)
+    return dict(feats=feats, poss=poss, sample_mask=sample_mask, text_query=tq)

@@ -170,3 +170,43 @@ def test_unipose_transformer_logic_matches_reference(golden_dir, torch_kernels):
     for got, name in ((hs_enc, "hs_enc"), (ref_enc, "ref_enc"), (init_box, "init_box")):
         ref = torch.from_numpy(g[f"{name}_f32"])
         assert got.shape == ref.shape and (got.float() - ref).abs().max().item() <= 5e-4 * max(1.0, ref.abs().max().item()), name
+
+
+# ---- the model behind its backbone (modeling_unipose.py:69-655) --------------------------------------------------------------
+def build_unipose_model():
+    from unipose_inputs import MODEL, TR, transformer_kwargs
+    from visionllm_b200.unipose import B200UniPose
+    kw = {k: v for k, v in transformer_kwargs().items() if k not in ("d_model", "nhead", "num_queries", "num_feature_levels")}
+    m = B200UniPose(hidden_dim=TR["d_model"], l_hidden_size=MODEL["l_hidden"], backbone_channels=MODEL["backbone_channels"],
+                    num_feature_levels=TR["num_feature_levels"], num_queries=TR["num_queries"],
+                    num_body_points=TR["num_body_points"], num_box_decoder_layers=TR["num_box_decoder_layers"], nheads=TR["nhead"],
+                    pe_temperatureH=20, pe_temperatureW=20, **kw).eval()
+    m.load_state_dict(seeded_state_dict(m, 71))
+    return m
+
+
+def test_unipose_model_logic_matches_reference_forward(golden_dir, torch_kernels, monkeypatch):  # noqa: F811
+    """B200UniPose vs the reference's own `UniPose.forward` (golden): [EMB] projections, input_proj incl. the derived 4th
+    level + its sine position embedding, text masks, transformer, box / class / keypoint heads.  fp32 stand-in kernels."""
+    import torch.nn.functional as F
+    import visionllm_b200.ops as ops
+    from unipose_inputs import model_inputs
+
+    def groupnorm_nhwc(x, w, b, groups, eps, relu=False):
+        y = F.group_norm(x.float().transpose(1, 2), groups, w.float(), b.float(), eps).transpose(1, 2)
+        return torch.relu(y) if relu else y
+
+    monkeypatch.setattr(ops, "groupnorm_nhwc", groupnorm_nhwc)
+    g = np.load(os.path.join(golden_dir, "mod_unipose_model.npz"))
+    m = build_unipose_model()
+    assert json.loads(str(g["keys"])) == [list(k) for k in key_shapes(m)], "model keys differ"
+    x = model_inputs()
+    out = m(x["feats"], x["poss"], x["text_query"], sample_mask=x["sample_mask"])
+    assert torch.equal(m.transformer.topk_proposals, torch.from_numpy(g["topk_enc"]))
+    assert torch.equal(m.transformer.decoder.topk_proposals, torch.from_numpy(g["topk_dec"]))
+    ref_l = torch.from_numpy(g["logits_f32"])
+    assert out.pred_logits.shape == ref_l.shape and torch.equal(torch.isfinite(out.pred_logits), torch.isfinite(ref_l))
+    fin = torch.isfinite(ref_l)
+    assert (out.pred_logits[fin] - ref_l[fin]).abs().max().item() <= 1e-3 * max(1.0, ref_l[fin].abs().max().item())
+    assert (out.pred_boxes - torch.from_numpy(g["boxes_f32"])).abs().max().item() <= 2e-4
+    assert (out.pred_keypoints - torch.from_numpy(g["keypoints_f32"])).abs().max().item() <= 2e-4

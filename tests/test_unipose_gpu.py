@@ -106,3 +106,29 @@ def test_unipose_transformer_matches_reference(golden_dir):
         assert (r.float() - r32).abs().max().item() <= 1.5 * (r16 - r32).abs().max().item() + 4e-3, i
     e32, e16 = torch.from_numpy(g["hs_enc_f32"]).cuda(), torch.from_numpy(g["hs_enc_refbf16"]).cuda()
     assert rel_l2(hs_enc, e32) <= 1.5 * rel_l2(e16, e32) + 1e-3
+
+
+def test_unipose_model_matches_reference_forward(golden_dir):
+    """B200UniPose on our kernels (bf16) vs the reference's own `UniPose.forward` run (fp32 golden, bf16 golden on the same
+    selections): pred_boxes / pred_keypoints within 1.5x the reference's own bf16 deviation, finite logits likewise, the
+    -inf pattern of the padded class slots exact."""
+    from unipose_inputs import model_inputs
+    from test_unipose_cpu import build_unipose_model
+    g = np.load(os.path.join(golden_dir, "mod_unipose_model.npz"))
+    m = build_unipose_model().to("cuda", torch.bfloat16)
+    x = model_inputs()
+    cast = lambda t: (t.bfloat16() if t.is_floating_point() else t).cuda()  # noqa: E731
+    feats = [(cast(t), mk.cuda()) for t, mk in x["feats"]]
+    poss = [cast(p) for p in x["poss"]]
+    tq = {k: cast(v) for k, v in x["text_query"].items()}
+    m.transformer.forced_topk = torch.from_numpy(g["topk_enc"]).cuda()
+    m.transformer.decoder.forced_topk = torch.from_numpy(g["topk_dec"]).cuda()
+    out = m(feats, poss, tq, sample_mask=x["sample_mask"].cuda())
+    l32, l16 = torch.from_numpy(g["logits_f32"]).cuda(), torch.from_numpy(g["logits_refbf16"]).cuda()
+    fin = torch.isfinite(l32)
+    assert torch.equal(torch.isfinite(out.pred_logits), fin)
+    assert (out.pred_logits[fin] - l32[fin]).abs().max().item() <= 1.5 * (l16[fin] - l32[fin]).abs().max().item() + 5e-2
+    for name, got in (("boxes", out.pred_boxes), ("keypoints", out.pred_keypoints)):
+        r32, r16 = torch.from_numpy(g[f"{name}_f32"]).cuda(), torch.from_numpy(g[f"{name}_refbf16"]).cuda()
+        assert got.dtype == torch.float32 and got.shape == r32.shape
+        assert (got - r32).abs().max().item() <= 1.5 * (r16 - r32).abs().max().item() + 4e-3, name

@@ -13,6 +13,7 @@ from types import SimpleNamespace
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from .gdino import GroundingDinoMultiscaleDeformableAttention, _LN, _MHA
@@ -584,6 +585,7 @@ class DeformableTransformer(nn.Module):
             text_self_attention_masks=text_dict['text_self_attention_masks'])
         text_dict = dict(text_dict)
         text_dict['encoded_text'] = memory_text
+        self.decoder_text = memory_text                      # the reference mutates the caller's text_dict (:2546); kept for the heads
 
         # two-stage 'standard' query selection (:2557-2606); top-k indices through torch.topk like the reference
         output_memory, output_proposals = _H.gen_encoder_output_proposals(self.enc_output, self.enc_output_norm, memory,
@@ -629,3 +631,148 @@ def generate_masks_with_text_query_masks(text_query_masks):
     mask = torch.eye(n, device=dev, dtype=torch.bool)[None].repeat(bs, 1, 1) | (inside[:, :, None] & inside[:, None, :])
     position_ids = torch.where(inside, ar[None, :].expand(bs, n), torch.zeros((), dtype=torch.long, device=dev))
     return mask, position_ids
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The UniPose model behind its backbone (modeling_unipose.py:69-655, inference path)
+# ---------------------------------------------------------------------------------------------------------------------
+from .gdino_model import conv_rows as _conv_rows   # noqa: E402
+
+
+class PositionEmbeddingSineHW(nn.Module):
+    """modeling_unipose.py:1037-1078 (no parameters); takes the padding mask [bs, h, w] (True = padding), returns NCHW fp32."""
+
+    def __init__(self, num_pos_feats=64, temperatureH=10000, temperatureW=10000, normalize=False, scale=None):
+        super().__init__()
+        if scale is not None and normalize is False:
+            raise ValueError("normalize should be True if scale is passed")
+        self.num_pos_feats, self.temperatureH, self.temperatureW, self.normalize = num_pos_feats, temperatureH, temperatureW, normalize
+        self.scale = 2 * math.pi if scale is None else scale
+
+    @torch.no_grad()
+    def forward(self, mask):
+        not_mask = ~mask
+        y_embed, x_embed = not_mask.cumsum(1, dtype=torch.float32), not_mask.cumsum(2, dtype=torch.float32)
+        if self.normalize:
+            eps = 1e-6
+            y_embed = y_embed / (y_embed[:, -1:, :] + eps) * self.scale
+            x_embed = x_embed / (x_embed[:, :, -1:] + eps) * self.scale
+        d = torch.arange(self.num_pos_feats, dtype=torch.float32, device=mask.device)
+        pos_x = x_embed[:, :, :, None] / (self.temperatureW ** (2 * (d // 2) / self.num_pos_feats))
+        pos_y = y_embed[:, :, :, None] / (self.temperatureH ** (2 * (d // 2) / self.num_pos_feats))
+        pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
+        pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
+        return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+def keypoint_xyzxyz_to_xyxyzz(keypoints):
+    """utils/keypoint_ops.py:18-29: (x, y, z) triples -> all (x, y) pairs, then all z."""
+    res = torch.zeros_like(keypoints)
+    n = keypoints.shape[-1] // 3
+    res[..., 0:2 * n:2] = keypoints[..., 0::3]
+    res[..., 1:2 * n:2] = keypoints[..., 1::3]
+    res[..., 2 * n:] = keypoints[..., 2::3]
+    return res
+
+
+class B200UniPose(nn.Module):
+    """`UniPose` (modeling_unipose.py:69-655) behind its image backbone, inference path: [EMB]-state projections
+    (`projection_llava`, `projection_kpt_llava`), `input_proj` (1x1 conv + GroupNorm per backbone level, 3x3 stride-2 conv +
+    GroupNorm for the extra levels), the transformer above, and the box / class / keypoint heads with the reference's
+    parameter names (shared heads repeated like its ModuleLists).  The backbone (`Joiner`: Swin + sine position embedding) is
+    injected: `forward(features=[(map NCHW, mask)], poss=[NCHW], text_query=...)` takes what `self.backbone(samples)` returns.
+    """
+
+    def __init__(self, hidden_dim=256, l_hidden_size=4096, backbone_channels=(192, 384, 768), num_feature_levels=4,
+                 num_queries=900, num_body_points=68, num_box_decoder_layers=2, nheads=8, pe_temperatureH=20, pe_temperatureW=20,
+                 transformer=None, **transformer_kwargs):
+        super().__init__()
+        self.hidden_dim, self.num_feature_levels, self.num_queries, self.nheads = hidden_dim, num_feature_levels, num_queries, nheads
+        self.num_body_points, self.num_box_decoder_layers = num_body_points, num_box_decoder_layers
+        self.transformer = transformer if transformer is not None else DeformableTransformer(
+            d_model=hidden_dim, nhead=nheads, num_queries=num_queries, num_feature_levels=num_feature_levels,
+            num_box_decoder_layers=num_box_decoder_layers, num_body_points=num_body_points, **transformer_kwargs)
+        self.position_embedding = PositionEmbeddingSineHW(hidden_dim // 2, pe_temperatureH, pe_temperatureW, normalize=True)
+        self.projection_llava = MLP(l_hidden_size, hidden_dim, hidden_dim, 3)
+        self.projection_kpt_llava = MLP(l_hidden_size, hidden_dim, hidden_dim, 3)
+        proj, cin = [], None
+        for cin in backbone_channels:
+            proj.append(nn.Sequential(nn.Conv2d(cin, hidden_dim, kernel_size=1), nn.GroupNorm(32, hidden_dim)))
+        for _ in range(num_feature_levels - len(backbone_channels)):
+            proj.append(nn.Sequential(nn.Conv2d(cin, hidden_dim, kernel_size=3, stride=2, padding=1), nn.GroupNorm(32, hidden_dim)))
+            cin = hidden_dim
+        self.input_proj = nn.ModuleList(proj)
+        n_dec = self.transformer.num_decoder_layers
+        bbox, pose, pose_hw, cls = MLP(hidden_dim, hidden_dim, 4, 3), MLP(hidden_dim, hidden_dim, 2, 3), MLP(hidden_dim, hidden_dim, 2, 3), ContrastiveAssign()
+        self.bbox_embed = nn.ModuleList([bbox for _ in range(n_dec)])                      # dec_pred_bbox_embed_share (:166)
+        self.class_embed = nn.ModuleList([cls for _ in range(n_dec)])
+        self.pose_embed = nn.ModuleList([pose for _ in range(n_dec - num_box_decoder_layers + 1)])
+        self.pose_hw_embed = nn.ModuleList([pose_hw for _ in range(n_dec - num_box_decoder_layers)])
+        d = self.transformer.decoder
+        d.bbox_embed, d.class_embed, d.pose_embed, d.pose_hw_embed = self.bbox_embed, self.class_embed, self.pose_embed, self.pose_hw_embed
+        self.transformer.enc_out_bbox_embed = copy.deepcopy(bbox)                          # two_stage_bbox_embed_share = False (:249)
+        self.transformer.enc_out_class_embed = copy.deepcopy(cls)
+
+    @torch.no_grad()
+    def _proj(self, idx, x_nchw):
+        """input_proj[idx] (Conv2d + GroupNorm(32)) on a NCHW map -> NCHW, through the GEMM + GroupNorm kernels."""
+        conv, gn = self.input_proj[idx][0], self.input_proj[idx][1]
+        rows, Ho, Wo = _conv_rows(x_nchw.permute(0, 2, 3, 1).contiguous(), conv)
+        y = ops.groupnorm_nhwc(rows, gn.weight, gn.bias, gn.num_groups, gn.eps)
+        return y.reshape(x_nchw.shape[0], Ho, Wo, -1).permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def forward(self, features, poss, text_query, sample_mask=None):
+        """features: [(map [bs, c_l, h_l, w_l], mask [bs, h_l, w_l])] per backbone level; poss: their position embeddings;
+        text_query: {'obj_querys' [bs, n_obj, n_emb, C], 'obj_query_masks' [bs, n_obj], 'kpt_querys', 'kpt_query_masks'};
+        sample_mask [bs, H, W]: the padded batch's pixel mask (needed when extra feature levels are derived, :434-438)."""
+        if self.training:
+            raise NotImplementedError("training (denoising queries, criterion) is outside the forward hot path")
+        dt = features[0][0].dtype
+        bs = text_query['obj_querys'].shape[0]
+        encoded_text = self.projection_llava(text_query['obj_querys']).mean(-2)
+        kpt_embed = torch.zeros((bs, self.num_body_points, self.hidden_dim), dtype=dt, device=features[0][0].device)
+        kpt_all = self.projection_kpt_llava(text_query['kpt_querys']).mean(-2)
+        n_kpt = text_query['kpt_query_masks'].sum(1)
+        keep = torch.arange(kpt_all.shape[1], device=kpt_all.device)[None, :] < n_kpt[:, None]        # first n_kpt rows per sample
+        nk = min(kpt_all.shape[1], self.num_body_points)
+        kpt_embed[:, :nk] = torch.where(keep[:, :nk, None], kpt_all[:, :nk].to(dt), kpt_embed[:, :nk])
+        kpt_vis = text_query["kpt_query_masks"][:, :self.num_body_points]
+        kpt_mask = torch.cat((torch.ones_like(kpt_vis)[..., 0].unsqueeze(-1), kpt_vis), dim=-1)
+        sa, pid = generate_masks_with_text_query_masks(text_query['obj_query_masks'])
+        text_dict = {'encoded_text': encoded_text, 'text_token_mask': text_query['obj_query_masks'].bool(), 'position_ids': pid,
+                     'text_self_attention_masks': sa}
+        srcs, masks, poss = [], [], list(poss)
+        for lvl, (src, mask) in enumerate(features):
+            srcs.append(self._proj(lvl, src))
+            masks.append(mask)
+        for lvl in range(len(srcs), self.num_feature_levels):
+            src = self._proj(lvl, features[-1][0] if lvl == len(features) else srcs[-1])
+            mask = F.interpolate(sample_mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
+            srcs.append(src)
+            masks.append(mask)
+            poss.append(self.position_embedding(mask).to(src.dtype))
+        attn_mask2 = prepare_for_mask(kpt_mask, self.nheads, self.num_body_points)
+        hs, reference, hs_enc, ref_enc, init_box = self.transformer(srcs, masks, None, poss, None, None, attn_mask2, text_dict,
+                                                                    None, None, kpt_embed)
+        text_dict = dict(text_dict)
+        nbp, nb = self.num_body_points, self.num_box_decoder_layers
+        coords, classes, keypoints = [], [], []
+        kpt_index = torch.tensor([x for x in range(50 * (nbp + 1)) if x % (nbp + 1) != 0], device=hs[0].device)
+        text_dict['encoded_text'] = self.transformer.decoder_text if hasattr(self.transformer, "decoder_text") else text_dict['encoded_text']
+        for lid, (ref_sig, bbox_embed, cls_embed, layer_hs) in enumerate(zip(reference[:-1], self.bbox_embed, self.class_embed, hs)):
+            if lid < nb:
+                coords.append((bbox_embed(layer_hs) + inverse_sigmoid(ref_sig)).sigmoid().to(torch.float32))
+                classes.append(cls_embed(layer_hs, text_dict).to(torch.float32))
+                keypoints.append(layer_hs.new_zeros((bs, self.num_queries, nbp * 3)).to(torch.float32))
+            else:
+                hs_box, ref_box = layer_hs[:, 0::(nbp + 1), :].contiguous(), ref_sig[:, 0::(nbp + 1), :]
+                coords.append((bbox_embed(hs_box) + inverse_sigmoid(ref_box)).sigmoid().to(torch.float32))
+                classes.append(cls_embed(hs_box, text_dict).to(torch.float32))
+                hs_kpt = layer_hs.index_select(1, kpt_index)
+                ref_kpt = ref_sig.index_select(1, kpt_index)
+                xy_unsig = self.pose_embed[lid - nb](hs_kpt) + inverse_sigmoid(ref_kpt[..., :2])
+                xyv = torch.cat((xy_unsig, torch.ones_like(xy_unsig)[:, :, 0].unsqueeze(-1)), dim=-1).sigmoid()
+                keypoints.append(keypoint_xyzxyz_to_xyxyzz(xyv.reshape((bs, 50, nbp, 3)).flatten(2, 3)).to(torch.float32))
+        return SimpleNamespace(loss=None, loss_dict=None, pred_logits=classes[-1], pred_boxes=coords[-1], pred_keypoints=keypoints[-1],
+                               aux=dict(classes=classes, coords=coords, keypoints=keypoints, hs_enc=hs_enc, ref_enc=ref_enc))
