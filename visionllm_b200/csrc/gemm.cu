@@ -83,7 +83,7 @@ template <int CG> struct Cfg {
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = CG == 1 ? 3 : 5;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias, scale*/ +
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * BN * 4 /*bias, scale: double-buffered*/ +
                               EPI_WARPS * EPI_STAGE_BYTES /*per-warp store staging*/;
 };
 
@@ -116,9 +116,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   auto tempty_bar = [&](int a) { return bar_base + 8 * (2 * STAGES + ACC + a); };
   const uint32_t tmem_slot = bar_base + 8 * (2 * STAGES + 2 * ACC);
   uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_gen + STAGES * C_::STAGE_BYTES + 8 * (2 * STAGES + 2 * ACC));
-  float* s_bias = reinterpret_cast<float*>(smem_gen + STAGES * C_::STAGE_BYTES + 256);
-  float* s_scale = s_bias + BN;
-  uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_scale + BN);   // EPI_WARPS x 32 rows x EPI_PITCH bytes
+  float* s_bs = reinterpret_cast<float*>(smem_gen + STAGES * C_::STAGE_BYTES + 256);   // [2][bias BN | scale BN]
+  uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_bs + 4 * BN);   // EPI_WARPS x 32 rows x EPI_PITCH bytes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? tc::cluster_ctarank() : 0;
@@ -239,19 +238,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int et = threadIdx.x - 128;  // 0..255
     int acc = 0; uint32_t acc_phase = 0;
     const bool swiglu = g.act == ACT_SWIGLU;
+    // bias / column scale of a tile live in shared memory (broadcast reads in the epilogue math); the NEXT tile's slice is
+    // fetched into registers at the top of a tile and parked in the other buffer at its end, so the global-load latency
+    // (~1 us, as long as a whole K = 256 main loop) never sits between two tiles (static_assert: one element per thread)
+    static_assert(BN == 256, "one bias / scale element per epilogue thread");
+    int staged_tile = -1, buf = 0;
+    auto fetch_bs = [&](int tn_, float& b_, float& s_) {
+      const int col = tn_ * BN + et;
+      b_ = (g.bias && col < g.N) ? __bfloat162float(g.bias[col]) : 0.f;
+      s_ = (g.colscale && col < g.N) ? __bfloat162float(g.colscale[col]) : 1.f;
+    };
     for (int t = cluster_id; t < n_tiles; t += n_clusters) {
       int tm, tn; tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
       if (plan_tile(g, tm * CG * BM, tn * BN, CG * BM, num_kb).skip) continue;
       const int n0 = tn * BN;
       const int row = (tm * CG + (int)rank) * BM + quarter * 32 + lane;
-      // stage bias / column scale for this tile
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int c = et; c < BN; c += 256) {
-        const int col = n0 + c;
-        s_bias[c] = (g.bias && col < g.N) ? __bfloat162float(g.bias[col]) : 0.f;
-        s_scale[c] = (g.colscale && col < g.N) ? __bfloat162float(g.colscale[col]) : 1.f;
+      if (staged_tile != t) {                              // first tile (or the predicted successor was skipped)
+        float b0, s0; fetch_bs(tn, b0, s0);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        s_bs[buf * 2 * BN + et] = b0; s_bs[buf * 2 * BN + BN + et] = s0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float* s_bias = s_bs + buf * 2 * BN;
+      float* s_scale = s_bias + BN;
+      const int t_next = t + n_clusters;
+      float nb = 0.f, ns = 1.f;
+      if (t_next < n_tiles) { int tm2, tn2; tile_coords(t_next, g.tiles_m, g.tiles_n, g.group_m, tm2, tn2); fetch_bs(tn2, nb, ns); }
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
@@ -479,6 +491,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(g.sc_flag[row_base / g.sc_rows]), "r"(1u) : "memory");
       }
       if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
+      if (t_next < n_tiles) {                              // park the successor's bias / scale (nobody reads that buffer now)
+        s_bs[(buf ^ 1) * 2 * BN + et] = nb; s_bs[(buf ^ 1) * 2 * BN + BN + et] = ns;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        staged_tile = t_next; buf ^= 1;
+      }
     }
   }
 
