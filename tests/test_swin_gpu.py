@@ -48,7 +48,7 @@ def test_swin_backbone_vs_hf_on_gpu(hw, ws, embed, heads, depths):
         assert e <= 1.5 * e_ref + 1e-3, f"stage{i + 1}: ours {e:.5f} vs hf-bf16 {e_ref:.5f}"
 
 
-@pytest.mark.parametrize("T,H,D,nB", [(49, 3, 32, 4), (144, 2, 32, 1), (16, 8, 32, 6), (49, 2, 64, 3)])
+@pytest.mark.parametrize("T,H,D,nB", [(49, 3, 32, 4), (144, 2, 32, 1), (16, 8, 32, 6), (49, 2, 64, 3), (64, 5, 32, 2), (1, 2, 32, 1)])
 def test_attention_additive_bias(T, H, D, nB):
     """attn_bias [nB, H, T, T] fp32, batch b uses slab b % nB (incl. -100 shift-mask entries)."""
     from visionllm_b200 import ops
@@ -61,6 +61,23 @@ def test_attention_additive_bias(T, H, D, nB):
     s = (q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 3, 1)) * D ** -0.5 + bias.repeat(3, 1, 1, 1)
     ref = (torch.softmax(s, -1) @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, T, H * D)
     assert rel(out, ref) < 6e-3
+    if D == 32 and T <= 64:
+        # r2: these calls take the one-warp-per-(window, head) kernel; same arithmetic order as the general kernel
+        from visionllm_b200 import _lib
+        _lib.lib().vllm_attention_set_variant(1)
+        try:
+            general = ops.attention(q, k, v, attn_bias=bias.contiguous())
+        finally:
+            _lib.lib().vllm_attention_set_variant(0)
+        assert torch.equal(out, general)
+        qkv = torch.randn(B, T, 3, H, D, device="cuda", generator=g).bfloat16()          # packed, strided views like swin.py
+        o1 = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], attn_bias=bias.contiguous())
+        _lib.lib().vllm_attention_set_variant(1)
+        try:
+            o2 = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], attn_bias=bias.contiguous())
+        finally:
+            _lib.lib().vllm_attention_set_variant(0)
+        assert torch.equal(o1, o2)
     with pytest.raises(RuntimeError):
         ops.attention(q, k, v, attn_bias=bias[:, :, :, :-1].contiguous())
 

@@ -311,6 +311,178 @@ splitkv_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__
   for (int i = 0; i < D / 32; ++i) op[lane + 32 * i] = __float2bfloat16(acc[i] * inv);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Window attention (Swin: head_dim 32, <= 64 tokens per window, additive fp32 bias slab = relative-position bias +
+// shifted-window mask, HF SwinSelfAttention / modeling_unipose.py:1277-1354): ONE WARP per (window, head), four independent
+// warps per CTA walking a strided item list -- no block-wide barrier anywhere, so 16 resident warps per SM overlap their
+// global-load latencies (the general kernel above spends a whole CTA and three __syncthreads on one 49 x 49 problem:
+// 33 k CTAs per Swin-T stage-1 layer at 1024^2).  Per item the warp stages Q / K / V (<= 64 rows x 64 B each) in its own
+// 12 KB of shared memory with cp.async, then for each 16-row query tile: bias loads issued first, S = Q K^T (16 HMMA),
+// softmax in registers, O = P V (16 HMMA), one 64-byte store per row.  Same arithmetic order as flash_fwd_kernel<32, 64>
+// for a single key tile (scores in the log2 domain, fp32 softmax, bf16 P), so results are bit-identical to it.
+// ---------------------------------------------------------------------------------------------------------------------
+struct WinArgs {
+  const __nv_bfloat16 *q, *k, *v;
+  __nv_bfloat16* o;
+  long long q_bs, k_bs, v_bs, o_bs, q_ts, k_ts, v_ts, o_ts;
+  const float* bias;               // [bias_batches, heads, T, T]
+  int bias_batches, T, heads;
+  long long n_items;               // batch (= windows) x heads
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(128, 4)
+window_attn_kernel(const WinArgs a) {
+  constexpr int D = 32, ROWS = 64, CH = D / 8, TILE = ROWS * D * 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(smem) + warp * 3 * TILE, sK = sQ + TILE, sV = sK + TILE;
+  const int g = lane >> 2, tq = lane & 3;
+  const int T = a.T;
+  for (long long item = (long long)blockIdx.x * 4 + warp; item < a.n_items; item += (long long)gridDim.x * 4) {
+    const long long b = item / a.heads;
+    const int head = (int)(item - b * a.heads);
+    const __nv_bfloat16* qb = a.q + b * a.q_bs + (long long)head * D;
+    const __nv_bfloat16* kb = a.k + b * a.k_bs + (long long)head * D;
+    const __nv_bfloat16* vb = a.v + b * a.v_bs + (long long)head * D;
+    __syncwarp();                                          // the previous item's ldmatrix reads are done
+    for (int i = lane; i < ROWS * CH; i += 32) {
+      const int r = i / CH, c = i % CH;
+      const bool ok = r < T;
+      const long long rr = ok ? r : 0;
+      cp_async16(sQ + sw_off<D>(r, c), qb + rr * a.q_ts + c * 8, ok);
+      cp_async16(sK + sw_off<D>(r, c), kb + rr * a.k_ts + c * 8, ok);
+      cp_async16(sV + sw_off<D>(r, c), vb + rr * a.v_ts + c * 8, ok);
+    }
+    cp_async_commit();
+    const float* ab = a.bias + (((long long)(b % a.bias_batches)) * a.heads + head) * T * T;
+    cp_async_wait<0>();
+    __syncwarp();
+    __nv_bfloat16* ob = a.o + b * a.o_bs + (long long)head * D;
+    const int n_mt = (T + 15) / 16;
+    for (int mt = 0; mt < n_mt; ++mt) {
+      // bias of this thread's score fragment first: the loads fly while the Q / K fragments are fetched and multiplied
+      const int qr0 = mt * 16 + g;
+      float bv[ROWS / 8][4];
+#pragma unroll
+      for (int j = 0; j < ROWS / 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = j * 8 + tq * 2 + (e & 1), qr = qr0 + (e >> 1) * 8;
+          bv[j][e] = (key < T && qr < T) ? __ldg(ab + (long long)qr * T + key) : 0.f;
+        }
+      uint32_t qf[D / 16][4];
+      {
+        const int r = mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const int chunk = kk * 2 + (lane >> 4);
+          ldsm_x4(sQ + sw_off<D>(r, chunk), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+        }
+      }
+      float s[ROWS / 8][4];
+#pragma unroll
+      for (int j = 0; j < ROWS / 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+        for (int j = 0; j < ROWS / 8; j += 2) {
+          const int key = j * 8 + (lane & 7) + 8 * (lane >> 4);
+          const int chunk = kk * 2 + ((lane >> 3) & 1);
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(sK + sw_off<D>(key, chunk), b0, b1, b2, b3);
+          mma_bf16(s[j], qf[kk], b0, b1);
+          mma_bf16(s[j + 1], qf[kk], b2, b3);
+        }
+      }
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < ROWS / 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = j * 8 + tq * 2 + (e & 1), qr = qr0 + (e >> 1) * 8;
+          float v = s[j][e] * a.scale_log2;
+          if (key >= T) v = -INFINITY;
+          else if (qr < T) v = fmaf(bv[j][e], 1.4426950408889634f, v);
+          s[j][e] = v;
+          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
+      }
+      float rs[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        if (mx[r] == -INFINITY) mx[r] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < ROWS / 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p = exp2f(s[j][e] - mx[e >> 1]);
+          s[j][e] = p;
+          rs[e >> 1] += p;
+        }
+      }
+      float o[D / 8][4];
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < ROWS / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int j = 0; j < D / 8; j += 2) {
+          const int key = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+          const int chunk = j + (lane >> 4);
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(sV + sw_off<D>(key, chunk), b0, b1, b2, b3);
+          mma_bf16(o[j], pa, b0, b1);
+          mma_bf16(o[j + 1], pa, b2, b3);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+        const int row = qr0 + r * 8;
+        if (row < T) {
+          const float inv = rs[r] > 0.f ? 1.f / rs[r] : 0.f;
+          __nv_bfloat16* op = ob + (long long)row * a.o_ts;
+#pragma unroll
+          for (int j = 0; j < D / 8; ++j)
+            *reinterpret_cast<__nv_bfloat162*>(op + j * 8 + tq * 2) = __floats2bfloat162_rn(o[j][2 * r] * inv, o[j][2 * r + 1] * inv);
+        }
+      }
+    }
+  }
+}
+
+static int launch_window(const AttnArgs& a, int batch, cudaStream_t st) {
+  constexpr int SMEM = 4 * 3 * 64 * 32 * 2;               // 4 warps x (Q, K, V) x 64 rows x 64 B
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return (int)e;
+    set = true;
+  }
+  WinArgs w;
+  w.q = a.q; w.k = a.k; w.v = a.v; w.o = a.o;
+  w.q_bs = a.q_bs; w.k_bs = a.k_bs; w.v_bs = a.v_bs; w.o_bs = a.o_bs;
+  w.q_ts = a.q_ts; w.k_ts = a.k_ts; w.v_ts = a.v_ts; w.o_ts = a.o_ts;
+  w.bias = a.attn_bias; w.bias_batches = a.bias_batches; w.T = a.Tq; w.heads = a.heads;
+  w.n_items = (long long)batch * a.heads; w.scale_log2 = a.scale_log2;
+  long long ctas = (w.n_items + 3) / 4;
+  const long long cap = (long long)vllm_num_sms() * 4 * 4;  // 4 resident CTAs per SM, a few items per warp
+  if (ctas > cap) ctas = cap;
+  window_attn_kernel<<<(unsigned)ctas, 128, SMEM, st>>>(w);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
+}
+
 template <int D, int BN = 64>
 int launch(AttnArgs a, int batch, cudaStream_t st, void* workspace, long long workspace_bytes) {
   constexpr int SMEM = BM * D * 2 + 4 * BN * D * 2;
@@ -449,6 +621,10 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
                                           o_token_pitch, seqlens, causal, scale, st);
     if (rc != VLLM_EUNSUPPORTED) return rc;   // views a TMA descriptor cannot express use the warp-MMA kernel
   }
+  // Swin windows: head_dim 32, one key tile, additive bias only -> one warp per (window, head) (variant 1 keeps the general kernel)
+  if (head_dim == 32 && g_attn_variant != 1 && attn_bias && !key_mask && !attn_mask && !seqlens && !causal && Tq == Tk && Tq <= 64 &&
+      kv_heads == heads)
+    return launch_window(a, batch, st);
   switch (head_dim) {
     case 128: return launch<128>(a, batch, st, workspace, workspace_bytes);
     case 64: return launch<64>(a, batch, st, workspace, workspace_bytes);
