@@ -257,12 +257,12 @@ class MsdaEncoderPairsWorkload(MsdaEncoderBf16Workload):
         return c
 
 
-def anyres_tiles_1024(torch, n_pairs, device, seed, tile=448, dtype=None):
+def anyres_tiles_1024(torch, n_pairs, device, seed, tile=448, dtype=None, tiles=5):
     """What the reference's data pipeline hands to forward() for a 1024x1024 image under 'anyres'
     (mm_utils.py:39-75: image_size 448, max 6 tiles -> (2,2) grid + thumbnail = 5 tiles): a list of
     [5, 3, 448, 448] tensors, floats already cast to bf16 by dict_to_cuda (util/misc.py:499-515)."""
     g = torch.Generator(device=device).manual_seed(seed)
-    return [torch.randn(5, 3, tile, tile, device=device, generator=g).to(dtype or torch.bfloat16)
+    return [torch.randn(tiles, 3, tile, tile, device=device, generator=g).to(dtype or torch.bfloat16)
             for _ in range(n_pairs)]
 
 
@@ -275,6 +275,8 @@ class PairForwardWorkload:
     dtype = "bf16"
     PAIRS = 8
     IMP, VOCAB = 32002, 32026
+    TILE, TOK_PER_TILE, TILES = 448, 256, 5            # anyres (2, 2) grid + thumbnail; 1024 ViT tokens -> pixel shuffle -> 256
+    BRIDGE, PIXEL_SHUFFLE, VIS_LAYER = "internvl_mlp", True, -1
     vit = dict(hidden_size=3200, num_attention_heads=25, num_hidden_layers=48, intermediate_size=12800,
                image_size=448, patch_size=14)
     llm = dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
@@ -290,12 +292,11 @@ class PairForwardWorkload:
         from visionllm_b200.internvit import B200InternVisionModel, InternVisionConfig
         from visionllm_b200.llama import B200LlamaForCausalLM
         from visionllm_b200.modeling import B200VisionLLMv2Model
-        cfg = SimpleNamespace(use_pixelshuffle=True, vl_bridge_type="internvl_mlp", vis_output_layer=-1, num_embs=4,
-                              imp_token_id=self.IMP, emb_token_id=32010, det_tool_id=32003, seg_tool_id=32005,
+        cfg = SimpleNamespace(use_pixelshuffle=self.PIXEL_SHUFFLE, vl_bridge_type=self.BRIDGE, vis_output_layer=self.VIS_LAYER,
+                              num_embs=4, imp_token_id=self.IMP, emb_token_id=32010, det_tool_id=32003, seg_tool_id=32005,
                               grd_tool_id=32004, pose_tool_id=32006)
         with torch.device("meta"):
-            model = B200VisionLLMv2Model(cfg, B200InternVisionModel(InternVisionConfig(**self.vit)),
-                                         B200LlamaForCausalLM(LlamaConfig(**self.llm)))
+            model = B200VisionLLMv2Model(cfg, self.vision_tower(), B200LlamaForCausalLM(LlamaConfig(**self.llm)))
         model = model.to_empty(device=self.device).to(torch.bfloat16)
         g = torch.Generator(device=self.device).manual_seed(0)      # same weights on every rank
         with torch.no_grad():
@@ -311,18 +312,22 @@ class PairForwardWorkload:
                     p.copy_(torch.randn(p.shape, device=self.device, generator=g, dtype=torch.float32) * 0.02)
         return model.eval()
 
+    def vision_tower(self):
+        from visionllm_b200.internvit import B200InternVisionModel, InternVisionConfig
+        return B200InternVisionModel(InternVisionConfig(**self.vit))
+
     def setup(self):
         import torch
         self.torch = torch
         self.model = self.build()
-        n_img = 5 * 256
+        n_img = self.TILES * self.TOK_PER_TILE
         T = n_img + 256
         g = torch.Generator(device=self.device).manual_seed(1234 + self.rank)
         ids = torch.randint(0, 32000, (self.PAIRS, T), device=self.device, generator=g)
         ids[:, :n_img] = self.IMP
         self.ids = ids
         self.mask = torch.ones_like(ids)
-        self.images = anyres_tiles_1024(torch, self.PAIRS, self.device, 99 + self.rank)
+        self.images = anyres_tiles_1024(torch, self.PAIRS, self.device, 99 + self.rank, tile=self.TILE, tiles=self.TILES)
         self.h_images = [t.cpu().pin_memory() for t in self.images]
         self.h_ids = ids.cpu().pin_memory()
         self.d_images = [torch.empty_like(t) for t in self.images]
@@ -408,6 +413,44 @@ class PairForwardWorkload:
 
     def extra(self):
         return {"kernel_breakdown": self.breakdown}
+
+
+class PairForward1TileWorkload(PairForwardWorkload):
+    """SURVEY 8(d) cfg 3, the single-tile 'pad' variant: one 448^2 view per image (256 image tokens) + 256 text = T = 512."""
+    TILES = 1
+
+    def config(self):
+        c = super().config()
+        c.update(workload="BASELINE cfg 3, single-tile 'pad' variant: InternViT-6B(448, 1 tile) + pixel-shuffle + internvl_mlp + "
+                          "Vicuna-7B, T=512 (256 image + 256 text), fp32 logits all positions", tiles_per_image=1)
+        return c
+
+
+class PairForwardClipWorkload(PairForwardWorkload):
+    """SURVEY 8(d) cfg 3, the RELEASED 7B preset (vl/train/train.py:350-352, constant.py): CLIP-L/14-336 (24 layers, 1024
+    wide, 577 tokens per tile, hidden_states[-2] without CLS) -> mlp2x_gelu bridge -> Vicuna-7B; 5 anyres tiles x 576 + 256
+    text tokens = T = 3136."""
+    TILE, TOK_PER_TILE = 336, 576
+    BRIDGE, PIXEL_SHUFFLE, VIS_LAYER = "mlp2x_gelu", False, -2
+    clip = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16, image_size=336,
+                patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5)
+
+    def vision_tower(self):
+        from transformers import CLIPVisionConfig
+        from visionllm_b200.clip import B200CLIPVisionModel
+        return B200CLIPVisionModel(CLIPVisionConfig(**self.clip))
+
+    def config(self):
+        c = super().config()
+        c.update(workload=f"BASELINE cfg 3, released-7B preset: CLIP-L/14-336 ({self.TILES} tile(s) of a 1024^2 image, "
+                          f"hidden_states[-2]) + mlp2x_gelu + Vicuna-7B, T={self.T} ({self.TILES * 576} image + 256 text), "
+                          "fp32 logits all positions", tiles_per_image=self.TILES)
+        return c
+
+
+class PairForwardClip1TileWorkload(PairForwardClipWorkload):
+    """the released preset's single-tile 'pad' variant: T = 576 + 256 = 832."""
+    TILES = 1
 
 
 class GdinoHeadWorkload:
@@ -1300,7 +1343,9 @@ WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "msda_encoder_bf16": MsdaEncod
              "msda_encoder_pairs": MsdaEncoderPairsWorkload, "pair_forward": PairForwardWorkload, "gdino_head": GdinoHeadWorkload,
              "gdino_stage": GdinoStageWorkload, "pair_forward_gdino": PairForwardGdinoWorkload,
              "llm_tp": LlmTpWorkload, "llm_tp_plain": LlmTpPlainWorkload, "internimage_h": InternImageHWorkload, "cfg1_forward": Cfg1Workload,
-             "llm_train": LlmTrainWorkload, "llm_tp_train": LlmTpTrainWorkload}
+             "llm_train": LlmTrainWorkload, "llm_tp_train": LlmTpTrainWorkload,
+             "pair_forward_1tile": PairForward1TileWorkload, "pair_forward_clip7b": PairForwardClipWorkload,
+             "pair_forward_clip7b_1tile": PairForwardClip1TileWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
 
@@ -1325,11 +1370,57 @@ def _cpu_msda_encoder(steps, warmup):
             "ms_per_step": dt * 1e3, "sample_ms_per_step": dt * 1e3, "extrapolated": False}
 
 
-def _cpu_pair_forward(steps, warmup):
+def _cpu_pair_forward_clip(steps, warmup, tiles=5):
+    """Reference CPU path of one pair of the released-7B preset, bounded sample: ONE CLIP-L layer on one 336^2 tile (577
+    tokens) and ONE Vicuna-7B layer on the T-token sequence, fp32 torch on all host cores (oracle/vit_llm_oracle.py); pair
+    time extrapolated as tiles x 24 x t_clip + 32 x t_llm (hidden_states[-2] still runs all 24 layers in HF)."""
+    import torch
+    from oracle import vit_llm_oracle as VO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    C, I, H, F_ = 1024, 4096, 4096, 11008
+    T = tiles * 576 + 256
+    r = lambda *s: torch.randn(*s, generator=g) * 0.02  # noqa: E731
+    csd = {"l.layer_norm1.weight": torch.ones(C), "l.layer_norm1.bias": torch.zeros(C), "l.layer_norm2.weight": torch.ones(C),
+           "l.layer_norm2.bias": torch.zeros(C), "l.mlp.fc1.weight": r(I, C), "l.mlp.fc1.bias": torch.zeros(I),
+           "l.mlp.fc2.weight": r(C, I), "l.mlp.fc2.bias": torch.zeros(C)}
+    for n in ("q", "k", "v", "out"):
+        csd[f"l.self_attn.{n}_proj.weight"], csd[f"l.self_attn.{n}_proj.bias"] = r(C, C), torch.zeros(C)
+    lsd = {"l.input_layernorm.weight": torch.ones(H), "l.post_attention_layernorm.weight": torch.ones(H),
+           "l.self_attn.q_proj.weight": r(H, H), "l.self_attn.k_proj.weight": r(H, H),
+           "l.self_attn.v_proj.weight": r(H, H), "l.self_attn.o_proj.weight": r(H, H),
+           "l.mlp.gate_proj.weight": r(F_, H), "l.mlp.up_proj.weight": r(F_, H), "l.mlp.down_proj.weight": r(H, F_)}
+    xv, xl = torch.randn(1, 577, C, generator=g), torch.randn(1, T, H, generator=g)
+
+    def once():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            VO.clip_layer(xv, csd, "l.", 16)
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            VO.llama_layer(xl, lsd, "l.", 32, 1e-5)
+        return t1 - t0, time.perf_counter() - t1
+
+    for _ in range(warmup):
+        once()
+    tv = tl = 0.0
+    for _ in range(steps):
+        a, b = once()
+        tv += a; tl += b
+    tv /= steps; tl /= steps
+    pair_s = tiles * 24 * tv + 32 * tl
+    return {"value": 1.0 / pair_s, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"1 CLIP-L/336 layer x 1 tile ({tv * 1e3:.0f} ms) + 1 Vicuna-7B layer x {T} tokens ({tl * 1e3:.0f} ms), "
+                      f"fp32 torch CPU; pair = {tiles * 24} x clip + 32 x llm (extrapolated)",
+            "ms_per_step": pair_s * 1e3, "sample_ms_per_step": (tv + tl) * 1e3, "extrapolated": True}
+
+
+def _cpu_pair_forward(steps, warmup, tiles=5):
     """Reference CPU path of one pair, bounded sample: ONE InternViT-6B layer on one 448^2 tile (1025 tokens) and
-    ONE Vicuna-7B layer on the 1536-token sequence, fp32 torch on all host cores (oracle/vit_llm_oracle.py);
-    pair time extrapolated as 5 tiles x 48 layers x t_vit + 32 layers x t_llm (embeddings, bridge, lm_head
-    left out, so the CPU figure is slightly optimistic)."""
+    ONE Vicuna-7B layer on the T-token sequence (1536 with 5 tiles), fp32 torch on all host cores
+    (oracle/vit_llm_oracle.py); pair time extrapolated as tiles x 48 layers x t_vit + 32 layers x t_llm (embeddings,
+    bridge, lm_head left out, so the CPU figure is slightly optimistic)."""
     import torch
     from oracle import vit_llm_oracle as VO
     cores = os.cpu_count() or 1
@@ -1346,7 +1437,8 @@ def _cpu_pair_forward(steps, warmup):
            "l.self_attn.q_proj.weight": r(H, H), "l.self_attn.k_proj.weight": r(H, H),
            "l.self_attn.v_proj.weight": r(H, H), "l.self_attn.o_proj.weight": r(H, H),
            "l.mlp.gate_proj.weight": r(F_, H), "l.mlp.up_proj.weight": r(F_, H), "l.mlp.down_proj.weight": r(H, F_)}
-    xv, xl = torch.randn(1, 1025, C, generator=g), torch.randn(1, 1536, H, generator=g)
+    T = tiles * 256 + 256
+    xv, xl = torch.randn(1, 1025, C, generator=g), torch.randn(1, T, H, generator=g)
 
     def once():
         t0 = time.perf_counter()
@@ -1364,10 +1456,10 @@ def _cpu_pair_forward(steps, warmup):
         a, b = once()
         tv += a; tl += b
     tv /= steps; tl /= steps
-    pair_s = 5 * 48 * tv + 32 * tl
+    pair_s = tiles * 48 * tv + 32 * tl
     return {"value": 1.0 / pair_s, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": f"1 InternViT-6B layer x 1 tile ({tv * 1e3:.0f} ms) + 1 Vicuna-7B layer x 1536 tokens "
-                      f"({tl * 1e3:.0f} ms), fp32 torch CPU; pair = 240 x vit + 32 x llm (extrapolated)",
+            "sample": f"1 InternViT-6B layer x 1 tile ({tv * 1e3:.0f} ms) + 1 Vicuna-7B layer x {T} tokens "
+                      f"({tl * 1e3:.0f} ms), fp32 torch CPU; pair = {tiles * 48} x vit + 32 x llm (extrapolated)",
             "ms_per_step": pair_s * 1e3, "sample_ms_per_step": (tv + tl) * 1e3, "extrapolated": True}
 
 
@@ -1516,7 +1608,10 @@ def _cpu_llm_train(steps, warmup):
 _CPU = {"msda_encoder": _cpu_msda_encoder, "msda_encoder_bf16": _cpu_msda_encoder, "msda_encoder_pairs": _cpu_msda_encoder, "pair_forward": _cpu_pair_forward, "gdino_head": _cpu_msda_encoder,
         "gdino_stage": _cpu_msda_encoder,
         "pair_forward_gdino": _cpu_pair_forward, "llm_tp": _cpu_llm_tp, "llm_tp_plain": _cpu_llm_tp, "internimage_h": _cpu_internimage_h, "cfg1_forward": _cpu_cfg1, "llm_train": _cpu_llm_train,
-        "llm_tp_train": _cpu_llm_train}
+        "llm_tp_train": _cpu_llm_train,
+        "pair_forward_1tile": lambda steps, warmup: _cpu_pair_forward(steps, warmup, tiles=1),
+        "pair_forward_clip7b": _cpu_pair_forward_clip,
+        "pair_forward_clip7b_1tile": lambda steps, warmup: _cpu_pair_forward_clip(steps, warmup, tiles=1)}
 
 
 def cpu_baseline(name):

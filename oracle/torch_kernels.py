@@ -108,6 +108,10 @@ def layernorm_gather(x, index, weight, bias, eps):
     return h.index_select(1, index.clamp(max=x.shape[1]))
 
 
+def ce_loss(logits, labels):
+    return F.cross_entropy(logits.float(), labels.reshape(-1), ignore_index=-100)
+
+
 def upsample_add_nhwc(top, lateral):
     up = F.interpolate(top.float().permute(0, 3, 1, 2), size=lateral.shape[1:3], mode="bilinear", align_corners=False)
     return lateral.float() + up.permute(0, 2, 3, 1)
@@ -125,7 +129,7 @@ def patched():
     import visionllm_b200.ops as ops
     table = {"linear": linear, "rmsnorm": rmsnorm, "layernorm": layernorm, "rope_": rope_, "attention": attention,
              "groupnorm_nhwc": groupnorm_nhwc, "conv2d_s1_rows": conv2d_s1_rows, "upsample_add_nhwc": upsample_add_nhwc,
-             "layernorm_gather": layernorm_gather}
+             "layernorm_gather": layernorm_gather, "ce_loss": ce_loss}
     saved = {k: getattr(ops, k) for k in table}
     saved_msda = (msda.ms_deform_attn_forward, msda.ms_deform_attn_forward_bf16)
     try:

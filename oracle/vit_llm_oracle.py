@@ -47,6 +47,21 @@ def internvit_layer(x, sd, pre, heads, eps, qk_norm=True):
     return x + h * sd[pre + "ls2"]
 
 
+def clip_layer(x, sd, pre, heads, eps=1e-5):
+    # transformers/models/clip/modeling_clip.py CLIPEncoderLayer (the released-7B preset's tower, constant.py / train.py:350-352):
+    # pre-LN, q/k/v/out projections with bias, softmax(q k^T / sqrt(d)), quick-GELU MLP
+    B, N, C = x.shape
+    h = F.layer_norm(x, (C,), sd[pre + "layer_norm1.weight"], sd[pre + "layer_norm1.bias"], eps)
+    q, k, v = (F.linear(h, sd[pre + f"self_attn.{n}_proj.weight"], sd[pre + f"self_attn.{n}_proj.bias"])
+               .view(B, N, heads, C // heads).transpose(1, 2) for n in "qkv")
+    att = ((q * (C // heads) ** -0.5) @ k.transpose(-2, -1)).softmax(-1)
+    a = (att @ v).transpose(1, 2).reshape(B, N, C)
+    x = x + F.linear(a, sd[pre + "self_attn.out_proj.weight"], sd[pre + "self_attn.out_proj.bias"])
+    h = F.layer_norm(x, (C,), sd[pre + "layer_norm2.weight"], sd[pre + "layer_norm2.bias"], eps)
+    h = F.linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])
+    return x + F.linear(h * torch.sigmoid(1.702 * h), sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+
+
 def internvit_forward(px, sd, layers, heads, patch, eps=1e-6):
     x = internvit_embeddings(px, sd, patch)
     states = [x]

@@ -119,3 +119,21 @@ def model_inputs():
     tq = dict(obj_querys=r(bs, MODEL["n_obj"], MODEL["n_emb"], MODEL["l_hidden"]) * 2, obj_query_masks=obj_mask,
               kpt_querys=r(bs, MODEL["n_kpt"], MODEL["n_emb"], MODEL["l_hidden"]) * 2, kpt_query_masks=kpt_mask)
     return dict(feats=feats, poss=poss, sample_mask=sample_mask, text_query=tq)
+
+
+# ---- the image backbone: Joiner(SwinTransformer, PositionEmbeddingSineHW) (modeling_unipose.py:1212-1226, 1638-1858) --------
+BACKBONE = dict(embed_dim=64, depths=[2, 2, 2, 2], num_heads=[2, 4, 8, 16], window_size=7, out_indices=[1, 2, 3],
+                hidden_dim=256)
+
+
+def backbone_inputs():
+    """A padded 2-image batch as `nested_tensor_from_tensor_list` builds it: image 1 is 80 x 110 inside 100 x 138 (zeros and
+    mask = True outside).  138 is not a multiple of the patch size (pad in PatchEmbed); 25 x 35 tokens pad to 28 x 35 windows."""
+    g = torch.Generator().manual_seed(41)
+    bs, H, W = 2, 100, 138
+    x = torch.randn(bs, 3, H, W, generator=g).to(torch.bfloat16).float()
+    mask = torch.zeros(bs, H, W, dtype=torch.bool)
+    mask[1, 80:, :] = True
+    mask[1, :, 110:] = True
+    x[1] = x[1] * (~mask[1]).float()
+    return x, mask

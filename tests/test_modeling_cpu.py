@@ -260,3 +260,131 @@ def test_gdino_task_gate_follows_reference():
     assert calls == [(1, 3, 64, 64)]                                                            # padded to /32
     with pytest.raises(NotImplementedError):
         m(input_ids=ids, images_aug=aug, img_metas=[{"task": "pose"}])
+
+
+def _tiny_composite_with_head(unipose=None):
+    """_tiny_composite whose LLM stand-in also has an lm_head (fp32 logits), for the loss / pose paths."""
+    from types import SimpleNamespace
+    import torch.nn as nn
+    m = _tiny_composite()
+    C, V = 8, 64
+
+    class FakeLLM(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.config = SimpleNamespace(hidden_size=C, vocab_size=V)
+            self.emb = nn.Embedding(V, C)
+            self.head = nn.Linear(C, V, bias=False)
+            self.dtype = torch.float32
+
+        def get_input_embeddings(self):
+            return self.emb
+
+        def forward(self, attention_mask=None, inputs_embeds=None, output_hidden_states=True):
+            h = torch.tanh(inputs_embeds)
+            return SimpleNamespace(hidden_states=(inputs_embeds, h), logits=self.head(h).float())
+
+    from visionllm_b200.modeling import B200VisionLLMv2Model
+    torch.manual_seed(3)
+    return B200VisionLLMv2Model(m.config, m.vis_encoder, FakeLLM(), unipose=unipose).eval()
+
+
+def test_labels_give_the_reference_loss(monkeypatch):
+    """mv2.py:740-757: [EMB] labels -> IGNORE_INDEX (in place, like the reference), shift, flatten, CrossEntropyLoss()."""
+    import torch.nn.functional as F
+    import visionllm_b200.ops as ops
+    from oracle import torch_kernels as TK
+    monkeypatch.setattr(ops, "ce_loss", TK.ce_loss)
+    m = _tiny_composite_with_head()
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, 30, (2, 16), generator=g)
+    ids[0, 3] = 50; ids[0, 4:8] = 45                                                    # [DET] + 4 [EMB] slots
+    labels = ids.clone()
+    labels[:, :3] = -100                                                                  # prompt positions
+    labels[0, 4:8] = torch.tensor([45, 46, 47, 48])                                       # collator leaves the [EMB] ids in labels
+    labels_in = labels.clone()
+    out = m(input_ids=ids, labels=labels)
+    # the reference's lines, literally
+    ref_labels = labels_in.clone()
+    ref_labels[(ref_labels >= 45) & (ref_labels <= 48)] = -100
+    shift_logits = out.logits[..., :-1, :].contiguous().view(-1, 64)
+    shift_labels = ref_labels[..., 1:].contiguous().view(-1)
+    ref = F.cross_entropy(shift_logits, shift_labels)
+    assert out.loss.dtype == torch.float32 and out.loss.dim() == 0
+    assert abs(out.loss.item() - ref.item()) <= 1e-6 * max(1.0, abs(ref.item()))
+    assert torch.equal(labels, ref_labels)                                                # caller's labels masked in place
+    tup = m(input_ids=ids, labels=labels_in.clone(), return_dict=False)                   # mv2.py:873-875: (loss,) + output
+    assert tup[0].item() == out.loss.item() and tup[1] is not None and len(tup) == 5
+    assert len(m(input_ids=ids, return_dict=False)) == 4
+    import pytest
+    with pytest.raises(NotImplementedError):
+        m(input_ids=ids, targets=[{}])
+    with pytest.raises(ValueError):
+        m(input_ids=ids, labels=labels_in.clone(), logits_rows=torch.tensor([0, 1]))
+
+
+def test_pad_images_aug_mask_matches_reference_nested_tensor():
+    from visionllm_b200.modeling import pad_images_aug
+    g = torch.Generator().manual_seed(1)
+    ragged = [torch.randn(3, 50, 67, generator=g), torch.randn(6, 64, 40, generator=g)]       # a 6-channel entry splits in two
+    t, mask = pad_images_aug(ragged, 32, return_mask=True)
+    assert torch.equal(t, _ref_nested_tensor(ragged, 32)) and mask.shape == (3, 64, 96) and mask.dtype == torch.bool
+    ref_mask = torch.ones(3, 64, 96, dtype=torch.bool)                                         # util/misc.py:310-313
+    ref_mask[0, :50, :67] = False; ref_mask[1, :64, :40] = False; ref_mask[2, :64, :40] = False
+    assert torch.equal(mask, ref_mask)
+    same = torch.randn(2, 3, 64, 96, generator=g)
+    t2, m2 = pad_images_aug(same, 32, return_mask=True)
+    assert torch.equal(t2, same) and not m2.any()
+
+
+def test_pose_branch_routes_emb_states_to_unipose():
+    """mv2.py:795-836: for task 'pose' the per-sample [EMB] patches split into the first len(id2index) object-class patches
+    and the keypoint patches (100 zero-padded slots each), and UniPose gets the /32-padded NestedTensor with its own mask."""
+    import torch.nn as nn
+    from types import SimpleNamespace
+    seen = {}
+
+    class FakeUniPose(nn.Module):
+        def forward_samples(self, tensors, mask, text_query):
+            seen.update(tensors=tensors, mask=mask, tq=text_query)
+            return SimpleNamespace(pred_boxes="boxes")
+
+    m = _tiny_composite_with_head(unipose=FakeUniPose())
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(0, 30, (3, 40), generator=g)
+    # sample 0: 1 object class + 3 keypoint classes; sample 1: 2 + 2; sample 2: object classes only (skipped by the reference)
+    n_patch, n_obj = [4, 4, 2], [1, 2, 2]
+    for b, n in enumerate(n_patch):
+        for j in range(n):
+            p = 2 + 5 * j
+            ids[b, p] = 51                                                                # [POSE] tool token
+            ids[b, p + 1:p + 5] = 45                                                      # its 4 [EMB] slots
+    aug = [torch.randn(3, 40, 50, generator=g), torch.randn(3, 33, 64, generator=g), torch.randn(3, 20, 20, generator=g)]
+    metas = [{"task": "pose", "id2index": {i: i for i in range(n)}} for n in n_obj]
+    out = m(input_ids=ids, images_aug=aug, img_metas=metas)
+    assert out.unipose_outputs.pred_boxes == "boxes" and out.gdino_outputs is None
+    # the reference's loop, literally (mv2.py:801-823), on the same hidden states / rewritten ids
+    hidden, new_ids = out.last_hidden_state, out.input_ids
+    emb_select = (new_ids >= 45) & (new_ids <= 48)
+    num_patches = emb_select.sum(-1) // 4
+    obj = torch.zeros(3, 100, 4, 8); objm = torch.zeros(3, 100, dtype=torch.bool)
+    kpt = torch.zeros(3, 100, 4, 8); kptm = torch.zeros(3, 100, dtype=torch.bool)
+    for b in range(3):
+        num_objcls = len(metas[b]["id2index"])
+        num_kpts = int(num_patches[b]) - num_objcls
+        if num_objcls != 0 and num_kpts != 0:
+            tq_i = hidden[b, emb_select[b], :].reshape(-1, 4, 8)
+            obj[b, :num_objcls] = tq_i[:num_objcls]; objm[b, :num_objcls] = 1
+            kpt[b, :num_kpts] = tq_i[num_objcls:]; kptm[b, :num_kpts] = 1
+    tq = seen["tq"]
+    assert torch.equal(tq["obj_querys"], obj) and torch.equal(tq["obj_query_masks"], objm)
+    assert torch.equal(tq["kpt_querys"], kpt) and torch.equal(tq["kpt_query_masks"], kptm)
+    assert not objm[2].any() and objm[0].sum() == 1 and kptm[0].sum() == 3
+    assert torch.equal(seen["tensors"], _ref_nested_tensor(aug, 32)) and seen["tensors"].shape == (3, 3, 64, 64)
+    assert seen["mask"][0, :40, :50].logical_not().all() and seen["mask"][0, 40:].all() and seen["mask"][0, :, 50:].all()
+    # no [EMB] tokens at all: UniPose is not called
+    seen.clear()
+    plain = torch.randint(0, 30, (1, 12), generator=g)
+    assert m(input_ids=plain, images_aug=aug[:1], img_metas=metas[:1]).unipose_outputs is None and not seen
+    # other tasks never reach it
+    assert m(input_ids=ids, images_aug=aug, img_metas=[{"task": "det"}] * 3).unipose_outputs is None and not seen

@@ -132,3 +132,50 @@ def test_unipose_model_matches_reference_forward(golden_dir):
         r32, r16 = torch.from_numpy(g[f"{name}_f32"]).cuda(), torch.from_numpy(g[f"{name}_refbf16"]).cuda()
         assert got.dtype == torch.float32 and got.shape == r32.shape
         assert (got - r32).abs().max().item() <= 1.5 * (r16 - r32).abs().max().item() + 4e-3, name
+
+
+def test_unipose_backbone_matches_reference(golden_dir):
+    """UniPose's image backbone on our kernels (bf16) vs the reference's own `Joiner(SwinTransformer, PositionEmbeddingSineHW)`
+    (fp32 golden + its bf16 run): every out-index map at rel_l2 <= 1.5 x the reference's own bf16 error + 1e-3, padding masks
+    exact, position embeddings at one bf16 rounding of the fp32 golden."""
+    from unipose_inputs import backbone_inputs
+    from test_unipose_backbone_cpu import build_joiner
+    g = np.load(os.path.join(golden_dir, "mod_unipose_backbone.npz"))
+    j = build_joiner().to("cuda", torch.bfloat16)
+    x, mask = backbone_inputs()
+    feats, poss = j(x.bfloat16().cuda(), mask.cuda())
+    assert len(feats) == 3
+    for i, ((t, m), p) in enumerate(zip(feats, poss)):
+        r32, r16 = torch.from_numpy(g[f"map{i}_f32"]).cuda(), torch.from_numpy(g[f"map{i}_refbf16"]).cuda()
+        assert t.shape == r32.shape and t.dtype == torch.bfloat16
+        assert rel_l2(t, r32) <= 1.5 * rel_l2(r16, r32) + 1e-3, (i, rel_l2(t, r32), rel_l2(r16, r32))
+        assert torch.equal(m.cpu(), torch.from_numpy(g[f"mask{i}"])), i
+        assert p.dtype == torch.bfloat16
+        assert (p.float().cpu() - torch.from_numpy(g[f"pos{i}_f32"])).abs().max().item() <= 2 ** -8, i
+
+
+def test_unipose_model_from_pixels_runs_on_gpu():
+    """`B200UniPose(backbone=...).forward_samples` (the reference's :430 wiring) end to end on the GPU kernels: same result
+    as forward() on the backbone's own maps, finite boxes / keypoints."""
+    from unipose_inputs import MODEL, TR, backbone_inputs, model_inputs, transformer_kwargs
+    from test_unipose_backbone_cpu import build_joiner
+    from weights_util import seeded_state_dict
+    from visionllm_b200.unipose import B200UniPose
+    j = build_joiner()
+    kw = transformer_kwargs()
+    for k in ("d_model", "nhead", "num_queries", "num_feature_levels"):
+        kw.pop(k)
+    m = B200UniPose(hidden_dim=TR["d_model"], l_hidden_size=MODEL["l_hidden"], backbone_channels=tuple(j.num_channels),
+                    num_feature_levels=4, num_queries=TR["num_queries"], num_body_points=TR["num_body_points"],
+                    num_box_decoder_layers=TR["num_box_decoder_layers"], nheads=TR["nhead"], backbone=j, **kw).eval()
+    m.load_state_dict(seeded_state_dict(m, 5))
+    m = m.to("cuda", torch.bfloat16)
+    x, mask = backbone_inputs()
+    cast = lambda t: (t.bfloat16() if t.is_floating_point() else t).cuda()  # noqa: E731
+    tq = {k: cast(v) for k, v in model_inputs()["text_query"].items()}
+    a = m.forward_samples(x.bfloat16().cuda(), mask.cuda(), tq)
+    feats, poss = m.backbone(x.bfloat16().cuda(), mask.cuda())
+    b = m(feats, poss, tq, sample_mask=mask.cuda())
+    assert torch.equal(a.pred_boxes, b.pred_boxes) and torch.equal(a.pred_keypoints, b.pred_keypoints)
+    assert torch.isfinite(a.pred_boxes).all() and torch.isfinite(a.pred_keypoints).all()
+    assert a.pred_boxes.dtype == torch.float32

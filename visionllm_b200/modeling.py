@@ -117,14 +117,16 @@ def emb_overwrite_indices(input_ids, tool_ids, num_embs):
 # logic that the CPU tests pin against the reference's python loops.
 FUSED_SEQUENCE = True
 
+IGNORE_INDEX = -100                                                                         # visionllmv2/constant.py:7
 GDINO_TASKS = ("det", "det_cap", "grd", "seg", "count_text", "count_visual", "interactive", "ic_mask")   # mv2.py:763
 
 
-def pad_images_aug(images_aug, size_divisibility=32):
+def pad_images_aug(images_aug, size_divisibility=32, return_mask=False):
     """`nested_tensor_from_tensor_list(images_aug, size_divisibility=32).tensors` (util/misc.py:288-316, called at
     mv2.py:771): every [3k, H, W] entry is split into 3-channel images, the batch is zero-padded bottom/right to the
-    per-axis maximum rounded UP to a multiple of `size_divisibility`.  (The NestedTensor's own mask is discarded by
-    the caller -- mv2.py:773 re-derives pixel_mask from the red channel -- so only the tensor is built.)"""
+    per-axis maximum rounded UP to a multiple of `size_divisibility`.  (The GDINO caller discards the NestedTensor's own
+    mask -- mv2.py:773 re-derives pixel_mask from the red channel; the UniPose caller, mv2.py:798, keeps it:
+    `return_mask=True` also returns `.mask` [n, H, W] bool, True = padding, util/misc.py:310-313.)"""
     if torch.is_tensor(images_aug):
         if images_aug.ndim != 4:
             raise ValueError("not supported")
@@ -138,12 +140,40 @@ def pad_images_aug(images_aug, size_divisibility=32):
     if size_divisibility > 1:
         h = (h + size_divisibility - 1) // size_divisibility * size_divisibility
         w = (w + size_divisibility - 1) // size_divisibility * size_divisibility
+    mask = None
+    if return_mask:
+        mask = torch.ones((len(imgs), h, w), dtype=torch.bool, device=imgs[0].device)
+        for im, m in zip(imgs, mask):
+            m[: im.shape[1], : im.shape[2]] = False
     if all(tuple(im.shape) == (c, h, w) for im in imgs):
-        return torch.stack(imgs)
-    out = torch.zeros((len(imgs), c, h, w), dtype=imgs[0].dtype, device=imgs[0].device)
-    for im, dst in zip(imgs, out):
-        dst[: im.shape[0], : im.shape[1], : im.shape[2]].copy_(im)
-    return out
+        out = torch.stack(imgs)
+    else:
+        out = torch.zeros((len(imgs), c, h, w), dtype=imgs[0].dtype, device=imgs[0].device)
+        for im, dst in zip(imgs, out):
+            dst[: im.shape[0], : im.shape[1], : im.shape[2]].copy_(im)
+    return (out, mask) if return_mask else out
+
+
+def pose_text_query(text_query, text_query_masks, num_patches, num_objcls, max_obj=100, max_kpt=100):
+    """mv2.py:801-831: split every sample's [EMB] patches into its first `num_objcls[b]` object-class patches and the
+    remaining keypoint patches, zero-padded to 100 slots each.  `text_query` [bs, mx, num_embs, C] / `text_query_masks`
+    [bs, mx] are the per-sample patch lists the GDINO branch also builds (same rows of `hidden_states`); `num_patches`
+    and `num_objcls` are host ints (len(img_metas[b]['id2index'])).  A sample with no object class or no keypoint keeps
+    all-zero queries and masks (the reference's `if num_objcls != 0 and num_kpts != 0`)."""
+    bs, _, n_emb, C = text_query.shape
+    obj = text_query.new_zeros((bs, max_obj, n_emb, C))
+    kpt = text_query.new_zeros((bs, max_kpt, n_emb, C))
+    obj_m = torch.zeros((bs, max_obj), dtype=torch.bool, device=text_query.device)
+    kpt_m = torch.zeros((bs, max_kpt), dtype=torch.bool, device=text_query.device)
+    for b in range(bs):
+        no, nk = int(num_objcls[b]), int(num_patches[b]) - int(num_objcls[b])
+        if no != 0 and nk != 0:
+            if no > max_obj or nk > max_kpt or nk < 0:
+                raise ValueError(f"sample {b}: {no} object-class / {nk} keypoint [EMB] patches do not fit the reference's "
+                                 f"{max_obj} / {max_kpt} slots (mv2.py:806-809)")
+            obj[b, :no], obj_m[b, :no] = text_query[b, :no], True
+            kpt[b, :nk], kpt_m[b, :nk] = text_query[b, no:no + nk], True
+    return dict(obj_querys=obj, obj_query_masks=obj_m, kpt_querys=kpt, kpt_query_masks=kpt_m)
 
 
 def region_encoder_inputs(images, regions, vit_hidden_states, split_sizes, num_splits=None):
@@ -199,7 +229,7 @@ def scatter_region_tokens(input_ids, inputs_embeds, region_features, reg_token_i
 
 
 class B200VisionLLMv2Model(nn.Module):
-    def __init__(self, config, vis_encoder, llm, gdino=None, region_encoder=None):
+    def __init__(self, config, vis_encoder, llm, gdino=None, region_encoder=None, unipose=None):
         super().__init__()
         self.config = config
         self.vis_encoder = vis_encoder
@@ -215,6 +245,9 @@ class B200VisionLLMv2Model(nn.Module):
         self.use_region_encoder = region_encoder is not None
         if region_encoder is not None:
             self.region_encoder = region_encoder
+        self.use_unipose = unipose is not None                         # a B200UniPose built with backbone= (mv2.py:795-836)
+        if unipose is not None:
+            self.unipose = unipose
         self.num_embs = int(getattr(config, "num_embs", 4))
         self.emb_embeddings_det = nn.Embedding(self.num_embs, self.l_hidden_size)
         self.emb_embeddings_pose = nn.Embedding(self.num_embs, self.l_hidden_size)
@@ -319,8 +352,11 @@ class B200VisionLLMv2Model(nn.Module):
                 region_sample_points=None, logits_rows=None, **unused):
         if past_key_values is not None or use_cache:
             raise NotImplementedError("generation with KV cache is outside the forward hot path")
-        if labels is not None or targets is not None:
-            raise NotImplementedError("training losses are outside the forward hot path (SURVEY 8f)")
+        if targets is not None:
+            raise NotImplementedError("detection / pose training losses (matcher, criterion, denoising queries) are outside "
+                                      "the forward hot path (SURVEY 8f)")
+        if labels is not None and logits_rows is not None:
+            raise ValueError("labels need the logits of every position: do not pass logits_rows together with labels")
         embed_w = self.llm.get_input_embeddings().weight
         fused = (FUSED_SEQUENCE and input_ids is not None and input_ids.is_cuda and embed_w.dtype == torch.bfloat16
                  and (inputs_embeds is None or (inputs_embeds.dtype == torch.bfloat16 and inputs_embeds.is_contiguous())))
@@ -358,11 +394,20 @@ class B200VisionLLMv2Model(nn.Module):
         head_kw = {} if logits_rows is None else {"logits_rows": logits_rows}
         out = self.llm(attention_mask=attention_mask, inputs_embeds=inputs_embeds, output_hidden_states=True, **head_kw)
         hidden = out.hidden_states[-1]
-        gdino_outputs = None
+        loss = None
+        if labels is not None:                                                               # mv2.py:740-757
+            # the reference masks the [EMB] slots of the CALLER's labels in place (:743-744); so does this drop-in
+            labels[(labels >= self.emb_token_id) & (labels <= self.emb_token_id + self.num_embs - 1)] = IGNORE_INDEX
+            # "shift so that tokens < n predict n": rather than slicing the fp32 logits (a 1.5 GB copy at cfg 3), shift the
+            # labels and ignore each row's last position -- the same (logit row, label) pairs, the same mean
+            shift = torch.cat((labels[:, 1:], torch.full_like(labels[:, :1], IGNORE_INDEX)), 1).to(out.logits.device)
+            lg = out.logits
+            loss = ops.ce_loss(lg.reshape(-1, lg.shape[-1]), shift.reshape(-1))
+        gdino_outputs, unipose_outputs = None, None
         task = img_metas[0]["task"] if img_metas is not None else None                       # mv2.py:755-758
-        if task == "pose":
-            raise NotImplementedError("task 'pose' routes the [EMB] states to UniPose (mv2.py:795-), which is not "
-                                      "wired into this composite")
+        if task == "pose" and images_aug is not None and not self.use_unipose:
+            raise NotImplementedError("task 'pose' routes the [EMB] states to UniPose (mv2.py:795-836): build the composite "
+                                      "with unipose=B200UniPose(..., backbone=build_backbone(...))")
         # mv2.py:762-763: the region decoder runs only for these tasks (no img_metas -> task None -> no gdino_outputs)
         if self.use_gdino and images_aug is not None and task in GDINO_TASKS:
             if plan is not None and hidden.dtype == torch.bfloat16 and hidden.is_contiguous():
@@ -375,8 +420,22 @@ class B200VisionLLMv2Model(nn.Module):
                 pixel_mask = pixel_values[:, 0, :, :] != 0                                  # mv2.py:773
                 gdino_outputs = self.gdino(pixel_values, pixel_mask=pixel_mask, text_query=tq,
                                            text_query_masks=tm, img_metas=img_metas, labels=None)
+        if self.use_unipose and task == "pose" and images_aug is not None:                   # mv2.py:795-836
+            if plan is not None and hidden.dtype == torch.bfloat16 and hidden.is_contiguous():
+                n_patch = (plan.emb_count // self.num_embs).tolist() if plan.B else []
+                mx = max(n_patch) if n_patch else 0
+                tq, tm = ops.text_query_gather(plan, hidden, self.num_embs, mx) if mx > 0 else (None, None)
+            else:
+                tq, tm = self.gather_text_query(input_ids, hidden)
+                n_patch = tm.sum(-1).tolist() if tm is not None else []
+            if tq is not None:                                                               # "if have [EMB] tokens" (:801)
+                tensors, pad_mask = pad_images_aug(images_aug, 32, return_mask=True)         # :798
+                n_obj = [len(m["id2index"]) for m in img_metas]                              # :812
+                unipose_outputs = self.unipose.forward_samples(tensors, pad_mask,
+                                                               pose_text_query(tq, tm, n_patch, n_obj))
         if not return_dict:                                                                  # mv2.py:873-875
-            return (out.logits,) + (None, out.hidden_states, None)
-        return VisionLLMv2ModelOutput(loss=None, logits=out.logits, past_key_values=None, hidden_states=out.hidden_states,
-                                      attentions=None, gdino_outputs=gdino_outputs, last_hidden_state=hidden,
-                                      vit_outputs=vit_out, input_ids=input_ids)
+            output = (out.logits,) + (None, out.hidden_states, None)
+            return (loss,) + output if loss is not None else output
+        return VisionLLMv2ModelOutput(loss=loss, logits=out.logits, past_key_values=None, hidden_states=out.hidden_states,
+                                      attentions=None, gdino_outputs=gdino_outputs, unipose_outputs=unipose_outputs,
+                                      last_hidden_state=hidden, vit_outputs=vit_out, input_ids=input_ids)

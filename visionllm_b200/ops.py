@@ -484,6 +484,25 @@ def text_query_gather(plan, hidden, num_embs, max_patches):
     return tq, tm
 
 
+def ce_loss(logits, labels):
+    """`CrossEntropyLoss()(logits.view(-1, V), labels.view(-1))` of modeling_visionllmv2.py:750-756, forward only: fp32
+    logits [rows, V] (unit inner stride, any row pitch), int64 labels [rows] (-100 = ignore) -> fp32 scalar, the mean over
+    the non-ignored rows (nan when every row is ignored, like torch).  One pass of `ce_loss_kernel` (csrc/train_ops.cu)."""
+    if logits.dtype != torch.float32 or not logits.is_cuda or logits.dim() != 2 or logits.stride(1) != 1:
+        raise RuntimeError("ce_loss: logits must be a CUDA fp32 [rows, V] matrix with unit inner stride")
+    if labels.dtype != torch.int64 or not labels.is_cuda or labels.numel() != logits.shape[0]:
+        raise RuntimeError("ce_loss: labels must be CUDA int64 [rows]")
+    labels = labels.reshape(-1).contiguous()
+    rows, V = logits.shape
+    loss_sum = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device), _Prof("ce_loss", 0.0, 4.0 * rows * V):
+        rc = _lib.lib().vllm_ce_loss_f32(logits.data_ptr(), logits.stride(0), labels.data_ptr(), None, rows, V,
+                                         loss_sum.data_ptr(), None, 0, _stream())
+    _lib.check(rc, "vllm_ce_loss_f32")
+    n_valid = ((labels >= 0) & (labels < V)).sum()
+    return (loss_sum / n_valid.float()).reshape(())
+
+
 def gather_rows(src, idx):
     """dst[i] = src[idx[i]]: src [rows, C] bf16 (unit inner stride), idx int64 [n] (negative = from the end)."""
     _bf16_2d(src, "src")

@@ -681,12 +681,16 @@ class B200UniPose(nn.Module):
     GroupNorm for the extra levels), the transformer above, and the box / class / keypoint heads with the reference's
     parameter names (shared heads repeated like its ModuleLists).  The backbone (`Joiner`: Swin + sine position embedding) is
     injected: `forward(features=[(map NCHW, mask)], poss=[NCHW], text_query=...)` takes what `self.backbone(samples)` returns.
+    With `backbone=` (a `unipose_backbone.B200Joiner`, state-dict prefix `backbone.0.` like the reference's `self.backbone`)
+    `forward_samples(tensors, mask, text_query)` is the reference's `forward(samples, None, text_query)` on the padded batch.
     """
 
     def __init__(self, hidden_dim=256, l_hidden_size=4096, backbone_channels=(192, 384, 768), num_feature_levels=4,
                  num_queries=900, num_body_points=68, num_box_decoder_layers=2, nheads=8, pe_temperatureH=20, pe_temperatureW=20,
-                 transformer=None, **transformer_kwargs):
+                 transformer=None, backbone=None, **transformer_kwargs):
         super().__init__()
+        if backbone is not None:
+            self.backbone = backbone
         self.hidden_dim, self.num_feature_levels, self.num_queries, self.nheads = hidden_dim, num_feature_levels, num_queries, nheads
         self.num_body_points, self.num_box_decoder_layers = num_body_points, num_box_decoder_layers
         self.transformer = transformer if transformer is not None else DeformableTransformer(
@@ -720,6 +724,16 @@ class B200UniPose(nn.Module):
         rows, Ho, Wo = _conv_rows(x_nchw.permute(0, 2, 3, 1).contiguous(), conv)
         y = ops.groupnorm_nhwc(rows, gn.weight, gn.bias, gn.num_groups, gn.eps)
         return y.reshape(x_nchw.shape[0], Ho, Wo, -1).permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def forward_samples(self, tensors, mask, text_query):
+        """`UniPose.forward(samples, None, text_query)` (:330-655): tensors [bs, 3, H, W] = the zero-padded batch of
+        `nested_tensor_from_tensor_list`, mask [bs, H, W] bool (True = padding)."""
+        if not hasattr(self, "backbone"):
+            raise RuntimeError("B200UniPose was built without a backbone: pass backbone=build_backbone(...) or call forward() "
+                               "with the backbone's maps")
+        features, poss = self.backbone(tensors, mask)                                      # :430
+        return self.forward(features, poss, text_query, sample_mask=mask)
 
     @torch.no_grad()
     def forward(self, features, poss, text_query, sample_mask=None):
