@@ -108,6 +108,10 @@ def layernorm_gather(x, index, weight, bias, eps):
     return h.index_select(1, index.clamp(max=x.shape[1]))
 
 
+def gather_rows(src, idx):
+    return src[idx]
+
+
 def ce_loss(logits, labels):
     return F.cross_entropy(logits.float(), labels.reshape(-1), ignore_index=-100)
 
@@ -129,7 +133,7 @@ def patched():
     import visionllm_b200.ops as ops
     table = {"linear": linear, "rmsnorm": rmsnorm, "layernorm": layernorm, "rope_": rope_, "attention": attention,
              "groupnorm_nhwc": groupnorm_nhwc, "conv2d_s1_rows": conv2d_s1_rows, "upsample_add_nhwc": upsample_add_nhwc,
-             "layernorm_gather": layernorm_gather, "ce_loss": ce_loss}
+             "layernorm_gather": layernorm_gather, "ce_loss": ce_loss, "gather_rows": gather_rows}
     saved = {k: getattr(ops, k) for k in table}
     saved_msda = (msda.ms_deform_attn_forward, msda.ms_deform_attn_forward_bf16)
     try:

@@ -60,6 +60,7 @@ def torch_kernels(monkeypatch):
         return h.index_select(1, index.clamp(max=x.shape[1]))
 
     monkeypatch.setattr(ops, "layernorm_gather", layernorm_gather)
+    monkeypatch.setattr(ops, "gather_rows", lambda src, idx: src[idx])      # Swin window reverse (one row gather)
     monkeypatch.setattr(msda, "ms_deform_attn_forward",
                         lambda value, shapes, lsi, loc, w, step, **kw: O.forward_grid_sample(value, shapes, loc, w))
 

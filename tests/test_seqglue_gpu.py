@@ -171,6 +171,13 @@ def test_gather_rows():
     assert torch.equal(ops.gather_rows(src, idx), src[idx])
     view = torch.randn(50, 256, device="cuda").bfloat16()[:, :128]           # row pitch != cols
     assert torch.equal(ops.gather_rows(view, idx), view[idx])
+    # wide rows (>= 128 vectors) take the CTA-per-row kernel, narrow ones the flat vector-per-thread kernel; both are copies
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for rows, C in ((3000, 96), (777, 8), (40, 1016), (33, 1024), (9, 4096), (100000, 192)):
+        src = torch.randn(rows, C, device="cuda", generator=g).bfloat16()
+        idx = torch.randint(-rows, rows, (rows * 2 + 5,), device="cuda", generator=g)
+        assert torch.equal(ops.gather_rows(src, idx), src[idx]), (rows, C)
+    assert ops.gather_rows(src, idx[:0]).shape == (0, 192)
 
 
 def test_swin_patch_merging_order_and_layernorm():

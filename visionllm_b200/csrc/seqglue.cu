@@ -192,6 +192,21 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long ld, const in
   }
 }
 
+// Narrow rows (the Swin window-reverse gather: C = 96 ... 768): one 16-byte vector per thread, flat over (row, vector), so a
+// warp writes 512 contiguous bytes and reads whole source rows; the CTA-per-row kernel above would keep 12 of 256 threads busy.
+__global__ void __launch_bounds__(256)
+gather_rows_flat_kernel(const __nv_bfloat16* __restrict__ src, long long ld, const int64_t* __restrict__ idx, long long n,
+                        long long src_rows, int nvec, __nv_bfloat16* __restrict__ dst) {
+  const long long total = n * nvec;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+    const long long i = v / nvec;
+    const int c = (int)(v - i * nvec);
+    long long r = idx[i];
+    if (r < 0) r += src_rows;
+    reinterpret_cast<uint4*>(dst)[v] = __ldg(reinterpret_cast<const uint4*>(src + r * ld) + c);
+  }
+}
+
 __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -336,6 +351,17 @@ int vllm_gather_rows_bf16(const void* src, long long src_ld, long long src_rows,
   if (n < 0 || cols <= 0 || cols % 8 || src_ld < cols) return VLLM_EINVAL;
   if (n == 0) return VLLM_OK;
   if (!src || !idx || !dst) return VLLM_EINVAL;
+  if (src_ld % 8 || !vllm_aligned(src, 16) || !vllm_aligned(dst, 16)) return VLLM_EALIGN;
+  const int nvec = cols / 8;
+  if (nvec < 128) {
+    long long blocks = (n * nvec + 255) / 256;
+    const long long cap = (long long)vllm_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    gather_rows_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ld, idx, n, src_rows,
+                                                                               nvec, (__nv_bfloat16*)dst);
+    VLLM_CHECK_LAUNCH();
+    return VLLM_OK;
+  }
   long long blocks = n < (long long)vllm_num_sms() * 16 ? n : (long long)vllm_num_sms() * 16;
   gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ld, idx, n, src_rows, cols,
                                                                          (__nv_bfloat16*)dst);

@@ -57,6 +57,15 @@ def _shift_mask(Hp, Wp, ws, shift, device):
     return m.masked_fill(m != 0, -100.0).masked_fill(m == 0, 0.0)
 
 
+def _window_reverse(cache, ctx2d, inv, B, slots, N):
+    """window_reverse + un-shift + crop as ONE row gather ctx2d[b * slots + inv[n]] -> [B, N, C] (`vllm_gather_rows_bf16`,
+    flat 16-byte-vector kernel for these narrow rows); the batched int64 index is cached per (geometry, batch)."""
+    key = ("flat", inv.data_ptr(), B, slots)
+    if key not in cache:
+        cache[key] = (torch.arange(B, device=inv.device)[:, None] * slots + inv[None, :]).reshape(-1).contiguous()
+    return ops.gather_rows(ctx2d, cache[key]).view(B, N, ctx2d.shape[-1])
+
+
 class B200SwinBackbone(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -128,7 +137,7 @@ class B200SwinBackbone(nn.Module):
         nW = (Hp // ws) * (Wp // ws)
         qkv = ops.linear(win, w_qkv, bias=b_qkv).view(B * nW, T, 3, nH, D)
         ctx = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=1.0 / math.sqrt(D), attn_bias=bias)
-        ctx = ctx.view(B, nW * T, C).index_select(1, inv)                  # back to raster order, pads dropped
+        ctx = _window_reverse(self._idx, ctx.view(B * nW * T, C), inv, B, nW * T, N)   # back to raster order, pads dropped
         dense = layer.attention.output.dense
         x = ops.linear(ctx, dense.weight, bias=dense.bias, residual=x)
         ln2 = layer.layernorm_after

@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .swin import _shift_mask, _window_rows
+from .swin import _shift_mask, _window_reverse, _window_rows
 
 SWIN_PRESETS = {                                                     # build_swin_transformer (:4082-4120)
     "swin_T_224_1k": dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7),
@@ -164,7 +164,7 @@ class B200UniPoseSwin(nn.Module):
         T, nW = ws * ws, (Hp // ws) * (Wp // ws)
         qkv = ops.linear(win, blk.attn.qkv.weight, bias=blk.attn.qkv.bias).view(B * nW, T, 3, nH, D)
         ctx = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=1.0 / math.sqrt(D), attn_bias=bias)
-        ctx = ctx.view(B, nW * T, C).index_select(1, inv)
+        ctx = _window_reverse(self._idx, ctx.view(B * nW * T, C), inv, B, nW * T, N)
         x = ops.linear(ctx, blk.attn.proj.weight, bias=blk.attn.proj.bias, residual=x)
         n2 = blk.norm2
         h = ops.layernorm(x, n2.weight, n2.bias, n2.eps)
