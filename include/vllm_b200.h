@@ -435,6 +435,19 @@ int vllm_pixel_shuffle_rows_bf16(const void* x, long long ld_tile, long long ld_
                                  int grid_h, int channels, const void* ln_weight, const void* ln_bias, float eps, void* y,
                                  int chunk_order, void* stream);
 
+/* ---- sine position embeddings of the Grounding-DINO stage (csrc/posembed.cu) ----
+ * Replaces the elementwise chains of GroundingDinoSinePositionEmbedding.forward (grounding_dino/
+ * modeling_ov_grounding_dino_mask_dn.py:529-564, + the `.to(dtype)` and `+ level_embed` of :2420-2424) and of
+ * get_proposal_pos_embed (:1755-1790) by one launch:
+ *   out[r, f * nd + d] = (d even ? sin : cos)((feat_f[r * feat_stride] * pre_scale) / dim_t[d]),  f < nfeat <= 4, nd % 8 == 0,
+ * fp32 IEEE arithmetic in the reference's order; pre_scale == 0 skips the multiply; dim_t [nd] fp32 is the reference's own
+ * temperature ** (2 * (d // 2) / nd) tensor.  out: fp32 [rows, ldo] or (out_bf16) bf16 rounded like `.to(bfloat16)`, then
+ * optionally + add_row_bf16 [nfeat * nd] as a bf16 tensor add (fp32 sum, rounded again).  rows_per_batch > 0: output row r is
+ * row r % rows_per_batch of slab r / rows_per_batch, slabs out_batch_stride elements apart (one level of a [B, S, C] buffer). */
+int vllm_sine_embed_f32(const float* f0, const float* f1, const float* f2, const float* f3, long long feat_stride, int nfeat,
+                        float pre_scale, const float* dim_t, int nd, long long rows, void* out, long long ldo, int out_bf16,
+                        long long rows_per_batch, long long out_batch_stride, const void* add_row_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,9 @@ def test_round2_entry_points_marshal_and_accept_empty_problems():
     assert L.vllm_seq_index(None, 0, 128, None, None, 0, 32010, 4, 32002, None, None, 0, None, None, None, None, None, None, None) == 0
     assert L.vllm_seq_index(None, 1, 128, None, None, 9, 32010, 4, 32002, None, None, 0, None, None, None, None, None, None, None) < 0
     assert L.vllm_assemble_embeds_bf16(None, None, None, None, None, None, None, None, 0, 4096, None) == 0
+    assert L.vllm_sine_embed_f32(None, None, None, None, 1, 2, 0.0, None, 128, 0, None, 256, 1, 0, 0, None, None) == 0
+    assert L.vllm_sine_embed_f32(None, None, None, None, 1, 5, 0.0, None, 128, 0, None, 1024, 1, 0, 0, None, None) < 0    # > 4 features
+    assert L.vllm_sine_embed_f32(None, None, None, None, 1, 2, 0.0, None, 100, 0, None, 256, 1, 0, 0, None, None) < 0     # nd % 8
     assert L.vllm_assemble_embeds_bf16(None, None, None, None, None, None, None, None, 4, 4097, None) < 0          # hidden % 8
     assert L.vllm_text_query_gather_bf16(None, None, None, 2, 128, 4096, 4, 0, None, None, None) == 0
     assert L.vllm_gather_rows_bf16(None, 4096, 10, None, 0, 4096, None, None) == 0

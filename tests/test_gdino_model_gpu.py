@@ -8,6 +8,7 @@ discrete: the reference's own bf16 run already selects a different set than its 
 after the selection are compared with the selection pinned to the golden's indices (as the generator does for the
 reference's bf16 leg), and the free-running selection is checked for overlap."""
 import json
+import math
 import os
 import sys
 
@@ -200,3 +201,55 @@ def test_implicit_gemm_conv_vs_torch(B, Hh, W, C, Cout, k, p):
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=p).relu().permute(0, 2, 3, 1)
     assert y.shape == ref.shape
     assert ((y.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 2e-3).all(), (y.float() - ref).abs().max().item()
+
+
+def _torch_sine(feats, dim_t, pre):
+    cols = []
+    for f in feats:
+        e = (f * pre if pre else f)[:, None] / dim_t
+        cols.append(torch.stack((e[:, 0::2].sin(), e[:, 1::2].cos()), dim=2).flatten(1))
+    return torch.cat(cols, 1)
+
+
+def test_sine_embed_kernel_matches_the_torch_chain():
+    """csrc/posembed.cu vs the reference's elementwise chains evaluated by torch on the same GPU (gd.py:529-564 neck form with
+    `.to(bf16) + level_embed` into a level slab of a [B, S, C] buffer; gd.py:1755-1790 decoder form with strided columns):
+    same IEEE operations in the same order, so fp32 results agree to the last bit unless the two libdevice builds differ
+    (then <= 2 ulp); bf16 results differ on no more than a rounding tie."""
+    from visionllm_b200 import ops
+    from visionllm_b200.gdino_model import GroundingDinoSinePositionEmbedding
+    g = torch.Generator(device="cuda").manual_seed(11)
+    # decoder form: proposals [B, Q, L, 4] fp32, level-0 slice, feature order (y, x, w, h), 2 pi pre-scale
+    B, Q = 3, 100
+    ref_in = torch.rand(B, Q, 4, 4, device="cuda", generator=g)
+    p = ref_in[:, :, 0, :]
+    d = torch.arange(128, dtype=torch.float32, device="cuda")
+    dim_t = 10000 ** (2 * torch.div(d, 2, rounding_mode="floor") / 128)
+    want = _torch_sine([p[:, :, c].reshape(-1) for c in (1, 0, 2, 3)], dim_t, 2 * math.pi)
+    got = ops.sine_embed([p[:, :, c] for c in (1, 0, 2, 3)], p.stride(1), dim_t, B * Q, pre_scale=2 * math.pi)
+    assert got.shape == (B * Q, 512) and got.dtype == torch.float32
+    assert (got - want).abs().max().item() <= 2.4e-7 and (got == want).float().mean().item() >= 0.999
+    got16 = ops.sine_embed([p[:, :, c] for c in (1, 0, 2, 3)], p.stride(1), dim_t, B * Q, pre_scale=2 * math.pi, out_dtype=torch.bfloat16)
+    w16 = want.bfloat16()
+    assert (got16 == w16).float().mean().item() >= 0.999 and (got16.float() - w16.float()).abs().max().item() <= 2 ** -7
+    # neck form: a padded mask, two levels written into one [B, S, 256] buffer with the level embedding added in bf16
+    pe = GroundingDinoSinePositionEmbedding(128, 20, normalize=True)
+    lvl = (torch.randn(2, 256, device="cuda", generator=g) * 0.5).bfloat16()
+    masks = []
+    for (h, w) in ((24, 40), (12, 20)):
+        m = torch.ones(2, h, w, dtype=torch.bool, device="cuda")
+        m[1, int(h * 0.8):] = False
+        m[1, :, int(w * 0.7):] = False
+        masks.append(m)
+    S = sum(m.shape[1] * m.shape[2] for m in masks)
+    buf = torch.full((2, S, 256), 7.0, dtype=torch.bfloat16, device="cuda")
+    off = 0
+    for i, m in enumerate(masks):
+        y, x = pe.embeds(m)
+        n = m.shape[1] * m.shape[2]
+        ops.sine_embed([y.contiguous(), x.contiguous()], 1, pe.dim_t(m.device), 2 * n, out=buf[:, off:off + n], add_row=lvl[i].contiguous())
+        ref = pe(m).to(torch.bfloat16).flatten(1, 2) + lvl[i].view(1, 1, -1)
+        got = buf[:, off:off + n]
+        assert (got == ref).float().mean().item() >= 0.999, i
+        assert (got.float() - ref.float()).abs().max().item() <= 2 ** -6, i
+        off += n

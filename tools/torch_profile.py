@@ -20,7 +20,7 @@ def main():
     for _ in range(3):
         wl.step_device()
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
         wl.step_device()
         torch.cuda.synchronize()
     rows = []
@@ -35,8 +35,22 @@ def main():
     print(f"total device time {total / 1e3:.2f} ms over {sum(r['calls'] for r in rows)} launches")
     for r in rows[:40]:
         print(f"{r['us'] / 1e3:9.3f} ms {100 * r['us'] / total:5.1f}% x{r['calls']:<5d} {r['kernel']}")
+    # the torch-side glue, by the aten op (and input shapes) that launched it: self device time of CPU-side op events
+    glue = []
+    for e in prof.key_averages(group_by_input_shape=True):
+        t = getattr(e, "self_device_time_total", None)
+        if t is None:
+            t = getattr(e, "self_cuda_time_total", 0)
+        if e.device_type == torch.autograd.DeviceType.CPU and t > 0 and e.key.startswith("aten::"):
+            glue.append({"op": e.key, "shapes": str(e.input_shapes)[:160], "calls": e.count, "us": t})
+    glue.sort(key=lambda r: -r["us"])
+    gl_total = sum(r["us"] for r in glue)
+    print(f"aten ops: {gl_total / 1e3:.2f} ms self device time")
+    for r in glue[:40]:
+        print(f"{r['us'] / 1e3:9.3f} ms x{r['calls']:<4d} {r['op']:<28s} {r['shapes']}")
     if out:
-        json.dump({"workload": name, "total_ms": total / 1e3, "kernels": rows[:80]}, open(out, "w"), indent=1)
+        json.dump({"workload": name, "total_ms": total / 1e3, "kernels": rows[:80], "aten_ms": gl_total / 1e3, "aten_ops": glue[:80]},
+                  open(out, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "vllm_text_query_gather_bf16": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]),
     "vllm_gather_rows_bf16": (ci, [vp, cll, cll, vp, cll, ci, vp, vp]),
     "vllm_pixel_shuffle_rows_bf16": (ci, [vp, cll, cll, ci, ci, ci, ci, ci, vp, vp, cf, vp, ci, vp]),
+    "vllm_sine_embed_f32": (ci, [vp, vp, vp, vp, cll, ci, cf, vp, ci, cll, vp, cll, ci, cll, cll, vp, vp]),
     "vllm_det_postprocess_f32": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
     "vllm_mask_postprocess_f32": (ci, [vp, vp] + [ci] * 8 + [vp, vp]),
     "vllm_dcnv3_forward_f32": (ci, [vp, vp, vp, vp] + [ci] * 15 + [cf, ci, vp]),

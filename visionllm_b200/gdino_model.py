@@ -61,15 +61,28 @@ class GroundingDinoSinePositionEmbedding(nn.Module):
         self.scale = 2 * math.pi if scale is None else scale
 
     @torch.no_grad()
-    def forward(self, pixel_mask):
+    def embeds(self, pixel_mask):
+        """(y_embed, x_embed) fp32 [B, H, W]: the normalised cumulative coordinates (gd.py:545-551)."""
         y_embed = pixel_mask.cumsum(1, dtype=torch.float32)
         x_embed = pixel_mask.cumsum(2, dtype=torch.float32)
         if self.normalize:
             eps = 1e-6
             y_embed = y_embed / (y_embed[:, -1:, :] + eps) * self.scale
             x_embed = x_embed / (x_embed[:, :, -1:] + eps) * self.scale
-        dim_t = torch.arange(self.embedding_dim, dtype=torch.float32, device=pixel_mask.device)
-        dim_t = self.temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / self.embedding_dim)
+        return y_embed, x_embed
+
+    def dim_t(self, device):
+        """temperature ** (2 * (d // 2) / embedding_dim), fp32 [embedding_dim] (gd.py:553-554), cached per device."""
+        cache = self.__dict__.setdefault("_dim_t", {})
+        if str(device) not in cache:
+            d = torch.arange(self.embedding_dim, dtype=torch.float32, device=device)
+            cache[str(device)] = self.temperature ** (2 * torch.div(d, 2, rounding_mode="floor") / self.embedding_dim)
+        return cache[str(device)]
+
+    @torch.no_grad()
+    def forward(self, pixel_mask):
+        y_embed, x_embed = self.embeds(pixel_mask)
+        dim_t = self.dim_t(pixel_mask.device)
         pos_x = x_embed[:, :, :, None] / dim_t
         pos_y = y_embed[:, :, :, None] / dim_t
         pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
@@ -166,11 +179,31 @@ class _Decoder(nn.Module):
         self.bbox_embed = None
         self.d_model = config.d_model
 
+    def _dim_t(self, device):
+        cache = self.__dict__.setdefault("_dim_t_cache", {})
+        if str(device) not in cache:
+            num_pos_feats = self.d_model // 2
+            d = torch.arange(num_pos_feats, dtype=torch.float32, device=device)
+            cache[str(device)] = 10000 ** (2 * torch.div(d, 2, rounding_mode="floor") / num_pos_feats)
+        return cache[str(device)]
+
+    def proposal_pos_embed_rows(self, proposals, out_dtype):
+        """`get_proposal_pos_embed(proposals).to(out_dtype)` for fp32 CUDA proposals [B, Q, 2 | 4] whose last-axis elements are
+        `proposals.stride(1)` apart per query (e.g. `ref_in[:, :, 0, :]`): ONE launch of csrc/posembed.cu instead of ~26."""
+        B, Q, k = proposals.shape
+        if (not proposals.is_cuda or proposals.dtype != torch.float32 or out_dtype not in (torch.float32, torch.bfloat16)
+                or proposals.stride(2) != 1 or proposals.stride(0) != Q * proposals.stride(1) or k not in (2, 4)):
+            return self.get_proposal_pos_embed(proposals).to(out_dtype)
+        order = (1, 0) if k == 2 else (1, 0, 2, 3)
+        feats = [proposals[:, :, c] for c in order]
+        out = ops.sine_embed(feats, proposals.stride(1), self._dim_t(proposals.device), B * Q, pre_scale=2 * math.pi,
+                             out_dtype=out_dtype)
+        return out.view(B, Q, -1)
+
     def get_proposal_pos_embed(self, proposals):
         """gd.py:1755-1790: (y, x[, w, h]) sin/cos features, fp32."""
         num_pos_feats = self.d_model // 2
-        dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=proposals.device)
-        dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+        dim_t = self._dim_t(proposals.device)
 
         def feat(col):
             e = (proposals[:, :, col] * (2 * math.pi))[:, :, None] / dim_t
@@ -282,12 +315,25 @@ class B200GroundingDinoModel(nn.Module):
             sources.append(ops.groupnorm_nhwc(y, seq[1].weight, seq[1].bias, seq[1].num_groups, seq[1].eps))
             masks.append(F.interpolate(pm, size=(Ho, Wo)).to(torch.bool)[0])
             shapes.append((Ho, Wo))
-        for level, m in enumerate(masks):
-            pos = pos_embed(m).to(dtype).flatten(1, 2)                                    # [B, HW, d]
-            poss.append(pos + self.level_embed[level].view(1, 1, -1))
         source_flatten = torch.cat(sources, 1)
         mask_flatten = torch.cat([m.flatten(1) for m in masks], 1)
-        lvl_pos_embed_flatten = torch.cat(poss, 1)
+        if (dtype == torch.bfloat16 and source_flatten.is_cuda and self.level_embed.dtype == torch.bfloat16
+                and isinstance(pos_embed, GroundingDinoSinePositionEmbedding)):
+            # sine position embedding -> bf16 -> + level embedding, one launch per level, written straight into its slab of
+            # the flattened buffer (csrc/posembed.cu: the reference's fp32 arithmetic, element for element)
+            lvl_pos_embed_flatten = torch.empty_like(source_flatten)
+            dim_t, off = pos_embed.dim_t(source_flatten.device), 0
+            for level, m in enumerate(masks):
+                y_embed, x_embed = pos_embed.embeds(m)
+                n = m.shape[1] * m.shape[2]
+                ops.sine_embed([y_embed.contiguous(), x_embed.contiguous()], 1, dim_t, m.shape[0] * n,
+                               out=lvl_pos_embed_flatten[:, off:off + n], add_row=self.level_embed[level].contiguous())
+                off += n
+        else:
+            for level, m in enumerate(masks):
+                pos = pos_embed(m).to(dtype).flatten(1, 2)                                # [B, HW, d]
+                poss.append(pos + self.level_embed[level].view(1, 1, -1))
+            lvl_pos_embed_flatten = torch.cat(poss, 1)
         spatial_shapes, level_start_index = self._shape_tensors(tuple(shapes), source_flatten.device)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1).float()
         return source_flatten, mask_flatten, lvl_pos_embed_flatten, spatial_shapes, level_start_index, valid_ratios
@@ -347,7 +393,7 @@ class B200GroundingDinoModel(nn.Module):
         vr2 = torch.cat([valid_ratios, valid_ratios], -1)[:, None]
         for idx, layer in enumerate(dec.layers):
             ref_in = reference_points[:, :, None] * vr2
-            query_pos = dec.reference_points_head(dec.get_proposal_pos_embed(ref_in[:, :, 0, :]).to(h.dtype))
+            query_pos = dec.reference_points_head(dec.proposal_pos_embed_rows(ref_in[:, :, 0, :], h.dtype))
             (h,) = layer(hidden_states=h, position_embeddings=query_pos, reference_points=ref_in.contiguous(),
                          spatial_shapes=spatial_shapes, level_start_index=lsi, vision_encoder_hidden_states=v,
                          vision_encoder_attention_mask=mask_flatten, text_encoder_hidden_states=t,

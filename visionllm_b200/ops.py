@@ -484,6 +484,34 @@ def text_query_gather(plan, hidden, num_embs, max_patches):
     return tq, tm
 
 
+def sine_embed(feats, stride, dim_t, rows, pre_scale=0.0, out=None, out_dtype=torch.float32, add_row=None):
+    """out[r, f * nd + d] = (sin | cos by parity of d)((feats[f][r * stride] * pre_scale) / dim_t[d]) -- the sine position
+    embeddings of the GDINO stage in one launch (csrc/posembed.cu).  feats: 1..4 fp32 CUDA tensors addressed as
+    base + r * stride (columns of one [rows, k] tensor, or contiguous maps); dim_t fp32 [nd]; out (optional): where to write,
+    fp32 or bf16 with unit inner stride -- a 2-D [rows, nfeat * nd] view, or a 3-D [B, rows / B, nfeat * nd] view (one level's
+    slab of a [B, S, C] buffer); add_row: bf16 [nfeat * nd] added after the bf16 rounding (the level embedding)."""
+    nf, nd = len(feats), dim_t.numel()
+    if not 1 <= nf <= 4 or any(f.dtype != torch.float32 or not f.is_cuda for f in feats):
+        raise RuntimeError("sine_embed: 1..4 CUDA fp32 feature tensors")
+    if dim_t.dtype != torch.float32 or not dim_t.is_contiguous():
+        raise RuntimeError("sine_embed: dim_t must be contiguous fp32")
+    if out is None:
+        out = torch.empty((rows, nf * nd), dtype=out_dtype, device=feats[0].device)
+    if out.dim() not in (2, 3) or out.numel() != rows * nf * nd or out.shape[-1] != nf * nd or out.stride(-1) != 1 or \
+            out.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("sine_embed: out must be [rows, nfeat * nd] or [B, rows / B, nfeat * nd], fp32 / bf16, unit inner stride")
+    if add_row is not None and (add_row.dtype != torch.bfloat16 or add_row.numel() != nf * nd or not add_row.is_contiguous()):
+        raise RuntimeError("sine_embed: add_row must be contiguous bf16 [nfeat * nd]")
+    rpb, obs, ldo = (0, 0, out.stride(0)) if out.dim() == 2 else (out.shape[1], out.stride(0), out.stride(1))
+    ptr = [f.data_ptr() for f in feats] + [None] * (4 - nf)
+    with torch.cuda.device(out.device), _Prof("sine_embed", 0.0, float(out.numel() * out.element_size())):
+        rc = _lib.lib().vllm_sine_embed_f32(ptr[0], ptr[1], ptr[2], ptr[3], int(stride), nf, float(pre_scale), dim_t.data_ptr(), nd,
+                                            int(rows), out.data_ptr(), int(ldo), int(out.dtype == torch.bfloat16), int(rpb),
+                                            int(obs), None if add_row is None else add_row.data_ptr(), _stream())
+    _lib.check(rc, "vllm_sine_embed_f32")
+    return out
+
+
 def ce_loss(logits, labels):
     """`CrossEntropyLoss()(logits.view(-1, V), labels.view(-1))` of modeling_visionllmv2.py:750-756, forward only: fp32
     logits [rows, V] (unit inner stride, any row pitch), int64 labels [rows] (-100 = ignore) -> fp32 scalar, the mean over
