@@ -79,7 +79,9 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
     @torch.no_grad()
     def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
                 position_embeddings=None, reference_points=None, spatial_shapes=None, level_start_index=None,
-                output_attentions=False):
+                output_attentions=False, residual=None):
+        """residual (extension): added in the output projection's epilogue, so the caller's `x + attn` before its LayerNorm
+        costs no extra pass (fp32 accumulator + bias + residual, one rounding instead of the reference's two)."""
         if position_embeddings is not None:
             hidden_states = hidden_states + position_embeddings
         B, Lq, _ = hidden_states.shape
@@ -102,7 +104,7 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
                                                           want_weights=self.need_weights or output_attentions)
             if fused is not None:
                 out, attention_weights = fused
-                return ops.linear(out, self.output_proj.weight, bias=self.output_proj.bias), attention_weights
+                return ops.linear(out, self.output_proj.weight, bias=self.output_proj.bias, residual=residual), attention_weights
         sampling_offsets = qp[..., :n_off].reshape(B, Lq, M, L, P, 2)
         attention_weights = F.softmax(qp[..., n_off:].reshape(B, Lq, M, L * P), -1).view(B, Lq, M, L, P)
         if reference_points.shape[-1] == 2:
@@ -131,7 +133,7 @@ class GroundingDinoMultiscaleDeformableAttention(nn.Module):
                                                   level_start_index, loc.float().contiguous(),
                                                   attention_weights.float().contiguous(), self.im2col_step)
             out = out.to(self.output_proj.weight.dtype)
-        out = ops.linear(out, self.output_proj.weight, bias=self.output_proj.bias)
+        out = ops.linear(out, self.output_proj.weight, bias=self.output_proj.bias, residual=residual)
         return out, attention_weights
 
 
@@ -165,8 +167,8 @@ class GroundingDinoDeformableLayer(nn.Module):
         attn, w = self.self_attn(hidden_states=hidden_states, attention_mask=attention_mask,
                                  encoder_hidden_states=hidden_states, encoder_attention_mask=attention_mask,
                                  position_embeddings=position_embeddings, reference_points=reference_points,
-                                 spatial_shapes=spatial_shapes, level_start_index=level_start_index)
-        x = self.self_attn_layer_norm(hidden_states + attn)
+                                 spatial_shapes=spatial_shapes, level_start_index=level_start_index, residual=hidden_states)
+        x = self.self_attn_layer_norm(attn)                          # attn already holds hidden_states + attention (epilogue)
         h = ops.linear(x, self.fc1.weight, bias=self.fc1.bias, act=self.act)
         x = self.final_layer_norm(ops.linear(h, self.fc2.weight, bias=self.fc2.bias, residual=x))
         return x, w
@@ -231,8 +233,8 @@ class GroundingDinoDecoderLayer(nn.Module):
                                     encoder_hidden_states=vision_encoder_hidden_states,
                                     encoder_attention_mask=vision_encoder_attention_mask, position_embeddings=pos,
                                     reference_points=reference_points, spatial_shapes=spatial_shapes,
-                                    level_start_index=level_start_index)
-        x = self.encoder_attn_layer_norm(x + attn)
+                                    level_start_index=level_start_index, residual=x)
+        x = self.encoder_attn_layer_norm(attn)                       # x + attention, added in the output_proj epilogue
         h = ops.linear(x, self.fc1.weight, bias=self.fc1.bias, act=self.act)
         x = self.final_layer_norm(ops.linear(h, self.fc2.weight, bias=self.fc2.bias, residual=x))
         return (x,)

@@ -60,6 +60,9 @@ class GroundingDinoContrastiveEmbedding(nn.Module):
         return out
 
 
+_GRID_CACHE = {}
+
+
 @torch.no_grad()
 def gen_encoder_output_proposals(enc_output_linear, enc_output_norm, enc_output, padding_mask, spatial_shapes):
     """OVGroundingDinoModel.gen_encoder_output_proposals (gd.py:2228-2276): one (cx, cy, w, h) proposal per pixel,
@@ -72,19 +75,23 @@ def gen_encoder_output_proposals(enc_output_linear, enc_output_norm, enc_output,
         m = padding_mask[:, pos:pos + H * W].view(B, H, W)
         valid_h = (~m[:, :, 0]).sum(1)
         valid_w = (~m[:, 0, :]).sum(1)
-        gy, gx = torch.meshgrid(torch.linspace(0, H - 1, H, dtype=torch.float32, device=dev),
-                                torch.linspace(0, W - 1, W, dtype=torch.float32, device=dev), indexing="ij")
-        grid = torch.stack((gx, gy), -1)[None].expand(B, -1, -1, -1)
+        key = (H, W, level, str(dev))
+        if key not in _GRID_CACHE:                             # the mask-independent part: (grid + 0.5) and the level's w, h
+            gy, gx = torch.meshgrid(torch.linspace(0, H - 1, H, dtype=torch.float32, device=dev),
+                                    torch.linspace(0, W - 1, W, dtype=torch.float32, device=dev), indexing="ij")
+            grid = torch.stack((gx, gy), -1)[None]
+            _GRID_CACHE[key] = (grid + 0.5, torch.ones_like(grid) * 0.05 * (2.0 ** level))
+        g05, wh = _GRID_CACHE[key]
         scale = torch.stack((valid_w, valid_h), 1).view(B, 1, 1, 2)
-        grid = (grid + 0.5) / scale
-        wh = torch.ones_like(grid) * 0.05 * (2.0 ** level)
-        proposals.append(torch.cat((grid, wh), -1).view(B, -1, 4))
+        proposals.append(torch.cat((g05 / scale, wh.expand(B, -1, -1, -1)), -1).view(B, -1, 4))
         pos += H * W
     prop = torch.cat(proposals, 1)
     valid = ((prop > 0.01) & (prop < 0.99)).all(-1, keepdim=True)
     prop = torch.log(prop / (1 - prop))
-    prop = prop.masked_fill(padding_mask.unsqueeze(-1), float("inf")).masked_fill(~valid, float("inf"))
-    q = enc_output.masked_fill(padding_mask.unsqueeze(-1), 0.0).masked_fill(~valid, 0.0)
+    # the reference's two masked_fills per tensor (padding, then ~valid) as one pass over the union of the masks
+    drop = padding_mask.unsqueeze(-1) | ~valid
+    prop = prop.masked_fill(drop, float("inf"))
+    q = enc_output.masked_fill(drop, 0.0)
     q = ops.linear(q, enc_output_linear.weight, bias=enc_output_linear.bias)
     q = ops.layernorm(q, enc_output_norm.weight, enc_output_norm.bias, enc_output_norm.eps)
     return q, prop

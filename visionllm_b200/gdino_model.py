@@ -369,11 +369,16 @@ class B200GroundingDinoModel(nn.Module):
         kpm = ~mask_flatten
         ref2 = _Encoder.get_reference_points(spatial_shapes, valid_ratios, src.device)
         v, t = src, text_query
+        # the text position embedding depends on position_ids only: computed once, not once per layer (gd.py:1131-1150 recomputes
+        # the same tensor in every layer)
+        tpos = (self.encoder.layers[0].get_text_position_embeddings(t, None, position_ids).to(src.dtype)
+                if len(self.encoder.layers) else None)
+        text_pad = ~text_token_mask
         for layer in self.encoder.layers:
             (v, t), _ = layer(vision_features=v, vision_position_embedding=pos, spatial_shapes=spatial_shapes,
                               level_start_index=lsi, key_padding_mask=kpm, reference_points=ref2, text_features=t,
-                              text_attention_mask=~text_token_mask, text_position_embedding=None,
-                              text_self_attention_masks=tsa, text_position_ids=position_ids)
+                              text_attention_mask=text_pad, text_position_embedding=tpos,
+                              text_self_attention_masks=tsa, text_position_ids=None)
         mask_features = self.build_mask_features(feats, v, spatial_shapes)
         # two-stage query selection (gd.py:2503-2545)
         oq, proposals = H.gen_encoder_output_proposals(self.enc_output, self.enc_output_norm, v, kpm, spatial_shapes)
@@ -397,7 +402,7 @@ class B200GroundingDinoModel(nn.Module):
             (h,) = layer(hidden_states=h, position_embeddings=query_pos, reference_points=ref_in.contiguous(),
                          spatial_shapes=spatial_shapes, level_start_index=lsi, vision_encoder_hidden_states=v,
                          vision_encoder_attention_mask=mask_flatten, text_encoder_hidden_states=t,
-                         text_encoder_attention_mask=~text_token_mask)
+                         text_encoder_attention_mask=text_pad)
             if dec.bbox_embed is not None:
                 reference_points = (dec.bbox_embed[idx](h) + inverse_sigmoid(reference_points)).sigmoid()
             inter.append(ops.layernorm(h, dec.layer_norm.weight, dec.layer_norm.bias, dec.layer_norm.eps))
