@@ -697,6 +697,89 @@ class GdinoStageWorkload(GdinoHeadWorkload):
                 "parallelism": f"dp{self.world}"}
 
 
+class UniPoseStageWorkload(GdinoHeadWorkload):
+    """SURVEY 8(f) rank 4 at the reference's real size: UniPose from pixels -- its own Swin-T backbone (`Joiner`, out indices
+    1..3) -> input_proj (+ derived 4th level) -> 6 text-fused deformable encoder layers -> two-stage selection (900 queries)
+    -> 2 box decoder layers -> top-50 -> 50 x (1 box + 68 keypoint) queries through 4 keypoint decoder layers -> box / class /
+    keypoint heads; N images of 1024^2, [EMB] states of 1 object class + 17 keypoint classes (zero-padded to 100 slots each like
+    mv2.py:803-809).  Eager launches (the two top-k selections read indices on the host like the reference)."""
+    metric = "unipose_stage_images_per_sec_1024px"
+    N = 4
+
+    def setup(self):
+        import torch
+        from visionllm_b200.unipose import B200UniPose
+        from visionllm_b200.unipose_backbone import build_backbone
+        self.torch = torch
+        dev = self.device
+        torch.manual_seed(0)
+        bb = build_backbone("swin_T_224_1k", return_interm_indices=(1, 2, 3), hidden_dim=256)
+        m = B200UniPose(hidden_dim=256, l_hidden_size=4096, backbone_channels=tuple(bb.num_channels), num_feature_levels=4,
+                        num_queries=900, num_body_points=68, num_box_decoder_layers=2, nheads=8, backbone=bb,
+                        num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048, dropout=0.0,
+                        return_intermediate_dec=True, query_dim=4, deformable_encoder=True, deformable_decoder=True,
+                        enc_n_points=4, dec_n_points=4, learnable_tgt_init=True, two_stage_type="standard", embed_init_tgt=True,
+                        use_text_enhancer=True, use_fusion_layer=True, use_text_cross_attention=True, text_dropout=0.0,
+                        fusion_dropout=0.0, fusion_droppath=0.0, decoder_sa_type="sa")
+        self.model = m.to(dev, torch.bfloat16).eval()
+        g = torch.Generator(device=dev).manual_seed(7 + self.rank)
+        N = self.N
+        self.images = torch.randn(N, 3, 1024, 1024, device=dev, generator=g).bfloat16()
+        self.mask = torch.zeros(N, 1024, 1024, dtype=torch.bool, device=dev)
+        obj = torch.zeros(N, 100, 4, 4096, device=dev, dtype=torch.bfloat16)
+        kpt = torch.zeros(N, 100, 4, 4096, device=dev, dtype=torch.bfloat16)
+        obj[:, :1] = torch.randn(N, 1, 4, 4096, device=dev, generator=g).bfloat16()
+        kpt[:, :17] = torch.randn(N, 17, 4, 4096, device=dev, generator=g).bfloat16()
+        om = torch.zeros(N, 100, dtype=torch.bool, device=dev); om[:, :1] = True
+        km = torch.zeros(N, 100, dtype=torch.bool, device=dev); km[:, :17] = True
+        self.tq = dict(obj_querys=obj, obj_query_masks=om, kpt_querys=kpt, kpt_query_masks=km)
+        self.h_in = [t.cpu().pin_memory() for t in (self.images, obj, kpt)]
+        self.d_in = [torch.empty_like(t) for t in (self.images, obj, kpt)]
+        self.h_out = torch.empty((N, 50, 4 + 68 * 3), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(t.numel() * 2 for t in self.h_in)
+        self.d2h_bytes = self.h_out.numel() * 4
+
+    def _run(self, images, obj, kpt):
+        tq = dict(self.tq, obj_querys=obj, kpt_querys=kpt)
+        o = self.model.forward_samples(images, self.mask, tq)
+        return self.torch.cat((o.pred_boxes, o.pred_keypoints), -1)
+
+    def step_device(self):
+        self.out = self._run(self.images, self.tq["obj_querys"], self.tq["kpt_querys"])
+
+    def dominant_kernel_ms(self, steps):
+        from visionllm_b200 import ops
+        torch = self.torch
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        self.step_device()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for name, fl, by, e0, e1, *tag in prof:
+            a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl; a[3] += by
+        self.breakdown = {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / v[1] / 1e9 if v[1] else 0.0,
+                              "gbps": v[3] / v[1] / 1e6 if v[1] else 0.0} for k, v in agg.items()}
+        self.gemm_flops, self.gemm_ms = agg["gemm"][2], agg["gemm"][1]
+        return self.gemm_ms
+
+    def roofline(self, kern_ms, peaks):
+        pk = peaks["bf16_tflops_sustained"]
+        ach = self.gemm_flops / (kern_ms * 1e-3) / 1e12
+        return {"kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of one step, flop-weighted; short-K shapes, DESIGN 6.1)",
+                "bound": "tensor", "achieved": ach, "peak": pk, "peak_source": peaks["source"] + " (sustained)", "unit": "TFLOP/s",
+                "frac": ach / pk, "traffic": None, "kernel_ms_per_step": kern_ms, "algorithmic_flops_per_step": self.gemm_flops}
+
+    def config(self):
+        return {"workload": "UniPose whole stage from pixels (SURVEY 8f rank 4): N=4 images 1024^2, its Swin-T backbone, 6 enc + "
+                            "6 dec layers (2 box + 4 keypoint), 900 -> 50 x 69 queries, 1 object class + 17 keypoint [EMB] classes",
+                "l2_policy": "inputs_exceed_l2", "launch": "eager", "parallelism": f"dp{self.world}"}
+
+    def extra(self):
+        return {"kernel_breakdown": self.breakdown}
+
+
 class PairForwardGdinoWorkload(PairForwardWorkload):
     """BASELINE cfg 4: cfg 3 + the Grounding-DINO region decoder head -- 80 classes x 4 [EMB] super-link tokens
     after a [DET] tool token each (T = 1280 image + 256 text + 80 x 5 = 1936), text_query gathered from the LLM's
@@ -1345,7 +1428,7 @@ WORKLOADS = {"msda_encoder": MsdaEncoderWorkload, "msda_encoder_bf16": MsdaEncod
              "llm_tp": LlmTpWorkload, "llm_tp_plain": LlmTpPlainWorkload, "internimage_h": InternImageHWorkload, "cfg1_forward": Cfg1Workload,
              "llm_train": LlmTrainWorkload, "llm_tp_train": LlmTpTrainWorkload,
              "pair_forward_1tile": PairForward1TileWorkload, "pair_forward_clip7b": PairForwardClipWorkload,
-             "pair_forward_clip7b_1tile": PairForwardClip1TileWorkload}
+             "pair_forward_clip7b_1tile": PairForwardClip1TileWorkload, "unipose_stage": UniPoseStageWorkload}
 DEFAULT_WORKLOAD = "pair_forward"
 
 
@@ -1611,7 +1694,8 @@ _CPU = {"msda_encoder": _cpu_msda_encoder, "msda_encoder_bf16": _cpu_msda_encode
         "llm_tp_train": _cpu_llm_train,
         "pair_forward_1tile": lambda steps, warmup: _cpu_pair_forward(steps, warmup, tiles=1),
         "pair_forward_clip7b": _cpu_pair_forward_clip,
-        "pair_forward_clip7b_1tile": lambda steps, warmup: _cpu_pair_forward_clip(steps, warmup, tiles=1)}
+        "pair_forward_clip7b_1tile": lambda steps, warmup: _cpu_pair_forward_clip(steps, warmup, tiles=1),
+        "unipose_stage": _cpu_msda_encoder}
 
 
 def cpu_baseline(name):
