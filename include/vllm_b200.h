@@ -255,6 +255,12 @@ long long vllm_groupnorm_workspace_bytes(int batch, int groups);
 int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, int batch, long long hw,
                              int channels, int groups, float eps, int relu, void* workspace, long long workspace_bytes,
                              void* stream);
+/* The same over the valid [h, w] corner of a padded grid: pixel (r, c) of image n is read at pixel index
+ * n * x_image_pitch + r * x_w_pitch + c (what vllm_conv_rows_bf16 leaves for a 3x3 convolution); y is the contiguous
+ * [batch, h * w, channels] result.  Same statistics order, so the result equals copying the corner out first. */
+int vllm_groupnorm_nhwc_bf16_grid(const void* x, void* y, const void* gamma, const void* beta, int batch, long long h, long long w,
+                                  long long x_w_pitch, long long x_image_pitch, int channels, int groups, float eps, int relu,
+                                  void* workspace, long long workspace_bytes, void* stream);
 /* FPN top-down step of the Grounding-DINO mask-feature head (modeling_ov_grounding_dino_mask_dn.py:2486-2492):
  * out = lateral + F.interpolate(top, size=(out_h, out_w), mode="bilinear", align_corners=False) over channels-last bf16
  * maps top [batch, in_h, in_w, channels], lateral / out [batch, out_h, out_w, channels] in one pass (ATen's
@@ -262,6 +268,11 @@ int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const vo
  * channels % 8 == 0. */
 int vllm_upsample_add_nhwc_bf16(const void* top, const void* lateral, void* out, int batch, int in_h, int in_w, int out_h,
                                 int out_w, int channels, void* stream);
+/* _ex: `top` images top_image_pitch elements apart (a level slab of the flattened encoder output, read in place);
+ * out_pad > 0 writes the result into the interior of a caller-zeroed [batch, out_h + 2 pad, out_w + 2 pad, channels] map --
+ * the zero-padded input of the 3x3 output convolution that follows (:2493), without a pad copy. */
+int vllm_upsample_add_nhwc_bf16_ex(const void* top, long long top_image_pitch, const void* lateral, void* out, int batch, int in_h,
+                                   int in_w, int out_h, int out_w, int channels, int out_pad, void* stream);
 /* In-place rotate-half RoPE on x[tokens, heads, head_dim] rows with pitch ld; cos/sin
  * [tokens, head_dim] bf16 gathered per position (HF Llama apply_rotary_pos_emb;
  * internlm2/modeling_internlm2.py:218-232). */

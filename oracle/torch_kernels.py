@@ -91,14 +91,16 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
 
 
 def groupnorm_nhwc(x, w, b, groups, eps, relu=False):
+    if x.dim() == 4:                                       # a [B, H, W, C] (possibly strided) view -> rows [B, H*W, C]
+        x = x.reshape(x.shape[0], -1, x.shape[-1])
     y = F.group_norm(x.float().transpose(1, 2), groups, w.float(), b.float(), eps).transpose(1, 2)
     return torch.relu(y) if relu else y
 
 
-def conv2d_s1_rows(x, w_rows, bias, kernel, padding, act=None):
+def conv2d_s1_rows(x, w_rows, bias, kernel, padding, act=None, prepadded=False):
     Cout, C = w_rows.shape[0], x.shape[-1]
     w = w_rows.float().view(Cout, kernel, kernel, C).permute(0, 3, 1, 2)
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None if bias is None else bias.float(), padding=padding)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None if bias is None else bias.float(), padding=0 if prepadded else padding)
     return _ACT[act](y.permute(0, 2, 3, 1))
 
 
@@ -116,9 +118,10 @@ def ce_loss(logits, labels):
     return F.cross_entropy(logits.float(), labels.reshape(-1), ignore_index=-100)
 
 
-def upsample_add_nhwc(top, lateral):
+def upsample_add_nhwc(top, lateral, pad=0):
     up = F.interpolate(top.float().permute(0, 3, 1, 2), size=lateral.shape[1:3], mode="bilinear", align_corners=False)
-    return lateral.float() + up.permute(0, 2, 3, 1)
+    y = lateral.float() + up.permute(0, 2, 3, 1)
+    return F.pad(y, (0, 0, pad, pad, pad, pad)) if pad else y
 
 
 def msda_forward(value, shapes, lsi, loc, w, step=64, **kw):

@@ -49,23 +49,11 @@ def build_pair(seed=11, b200_backbone=False, **over):
 def gn_kernel(monkeypatch, torch_kernels):  # noqa: F811
     import visionllm_b200.ops as ops
 
-    def groupnorm_nhwc(x, w, b, groups, eps, relu=False):
-        y = F.group_norm(x.float().transpose(1, 2), groups, w.float(), b.float(), eps).transpose(1, 2)
-        return torch.relu(y) if relu else y
+    from oracle import torch_kernels as TK
 
-    def conv2d_s1_rows(x, w_rows, bias, kernel, padding, act=None):
-        Cout, C = w_rows.shape[0], x.shape[-1]
-        w = w_rows.float().view(Cout, kernel, kernel, C).permute(0, 3, 1, 2)
-        y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None if bias is None else bias.float(), padding=padding)
-        return y.permute(0, 2, 3, 1)
-
-    def upsample_add_nhwc(top, lateral):
-        up = F.interpolate(top.float().permute(0, 3, 1, 2), size=lateral.shape[1:3], mode="bilinear", align_corners=False)
-        return lateral.float() + up.permute(0, 2, 3, 1)
-
-    monkeypatch.setattr(ops, "groupnorm_nhwc", groupnorm_nhwc)
-    monkeypatch.setattr(ops, "conv2d_s1_rows", conv2d_s1_rows)
-    monkeypatch.setattr(ops, "upsample_add_nhwc", upsample_add_nhwc)
+    monkeypatch.setattr(ops, "groupnorm_nhwc", TK.groupnorm_nhwc)
+    monkeypatch.setattr(ops, "conv2d_s1_rows", TK.conv2d_s1_rows)
+    monkeypatch.setattr(ops, "upsample_add_nhwc", TK.upsample_add_nhwc)
 
 
 @pytest.mark.parametrize("ragged,b200_backbone", [(False, False), (True, False), (True, True)])

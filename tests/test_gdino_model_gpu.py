@@ -253,3 +253,34 @@ def test_sine_embed_kernel_matches_the_torch_chain():
         assert (got == ref).float().mean().item() >= 0.999, i
         assert (got.float() - ref.float()).abs().max().item() <= 2 ** -6, i
         off += n
+
+
+@pytest.mark.parametrize("B,H,W,C,k,p", [(2, 24, 32, 256, 3, 1), (1, 7, 5, 64, 3, 1), (2, 9, 11, 64, 5, 2)])
+def test_fpn_chain_without_copies_is_bit_identical(B, H, W, C, k, p):
+    """The mask-FPN chain in its copy-free form -- upsample_add written into the zero-bordered map (pad=), top read through a
+    batch pitch, the 3x3 convolution on the prepadded map, GroupNorm reading the convolution's corner of the padded grid in
+    place -- against the same kernels with the copies (F.pad, .contiguous()) in between: identical bits."""
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 10 + H)
+    S = (H // 2) * (W // 2) + 37
+    flat = torch.randn(B, S, C, device="cuda", generator=g).bfloat16()               # "encoder output": level slab + other levels
+    top = flat[:, :(H // 2) * (W // 2)].reshape(B, H // 2, W // 2, C)
+    assert not top.is_contiguous() or B == 1
+    lat = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(C, k * k * C, device="cuda", generator=g) / (C * k * k) ** 0.5).bfloat16()
+    gam = (1 + 0.1 * torch.randn(C, device="cuda", generator=g)).bfloat16()
+    bet = (0.1 * torch.randn(C, device="cuda", generator=g)).bfloat16()
+    # with copies
+    y0 = ops.upsample_add_nhwc(top.contiguous(), lat)
+    c0 = ops.conv2d_s1_rows(y0, wt, None, k, p)
+    n0 = ops.groupnorm_nhwc(c0.reshape(B, -1, C), gam, bet, 32 if C % 256 == 0 else 8, 1e-5, relu=True)
+    # copy-free
+    y1 = ops.upsample_add_nhwc(top, lat, pad=p)
+    assert y1.shape == (B, H + 2 * p, W + 2 * p, C)
+    assert torch.equal(y1[:, p:H + p, p:W + p], y0)
+    border = y1.clone(); border[:, p:H + p, p:W + p] = 0
+    assert not border.any()
+    c1 = ops.conv2d_s1_rows(y1, wt, None, k, p, prepadded=True)
+    assert torch.equal(c1, c0) and not c1.is_contiguous()
+    n1 = ops.groupnorm_nhwc(c1, gam, bet, 32 if C % 256 == 0 else 8, 1e-5, relu=True)
+    assert n1.is_contiguous() and torch.equal(n1, n0)

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "vllm_groupnorm_workspace_bytes": (cll, [ci, ci]),
     "vllm_groupnorm_nhwc_bf16": (ci, [vp, vp, vp, vp, ci, cll, ci, ci, cf, ci, vp, cll, vp]),
     "vllm_upsample_add_nhwc_bf16": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+    "vllm_upsample_add_nhwc_bf16_ex": (ci, [vp, cll, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
+    "vllm_groupnorm_nhwc_bf16_grid": (ci, [vp, vp, vp, vp, ci, cll, cll, cll, cll, ci, ci, cf, ci, vp, cll, vp]),
     "vllm_attention_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cll, cll, cll, cll, cll, cll, cll, cll,
                                  vp, vp, vp, vp, ci, ci, cf, vp, cll, vp]),
     "vllm_attention_set_variant": (ci, [ci]),

@@ -28,8 +28,18 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 
 // grid (chunks, n).  Thread t owns the channel octet (t % c8) of pixels t / c8, t / c8 + ppi, ...  Octets of one
 // group are reduced through shared memory; partial[n][chunk][g] = (sum, sumsq).
+// Source geometry (vllm_groupnorm_nhwc_bf16_grid): pixel p of image n is read at pixel index
+// n * img_pitch + (p / w_valid) * w_pitch + p % w_valid -- the valid [H, W] corner of a padded [Hp, Wp] grid, as the
+// implicit-GEMM 3x3 convolution leaves it.  w_valid == w_pitch is the plain contiguous case.
+__device__ __forceinline__ long long gn_src(long long p, long long w_valid, long long w_pitch) {
+  if (w_valid == w_pitch) return p;
+  const long long r = p / w_valid;
+  return r * w_pitch + (p - r * w_valid);
+}
+
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial,
-                                                              long long hw, int c, int groups, int chunks) {
+                                                              long long hw, int c, int groups, int chunks,
+                                                              long long w_valid, long long w_pitch, long long img_pitch) {
   extern __shared__ float2 sh[];  // [pixels-per-iteration][c8]
   const int c8 = c >> 3, cpg8 = (c / groups) >> 3;
   const int ppi = GN_THREADS / c8;  // pixels per iteration
@@ -39,10 +49,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat1
   const long long p0 = chunk * per, p1 = min(hw, p0 + per);
   float s = 0.f, ss = 0.f;
   if (prow < ppi) {
-    const uint4* base = reinterpret_cast<const uint4*>(x + (long long)n * hw * c) + oct;
+    const uint4* base = reinterpret_cast<const uint4*>(x + (long long)n * img_pitch * c) + oct;
     for (long long p = p0 + prow; p < p1; p += ppi) {
       float f[8];
-      unpack8(__ldg(base + p * c8), f);
+      unpack8(__ldg(base + gn_src(p, w_valid, w_pitch) * c8), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s += f[i];
@@ -69,7 +79,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __nv_bfloat1
                                                               const __nv_bfloat16* __restrict__ gamma,
                                                               const __nv_bfloat16* __restrict__ beta,
                                                               const float2* __restrict__ partial, long long hw, int c, int groups,
-                                                              int chunks, float eps, int relu) {
+                                                              int chunks, float eps, int relu, long long w_valid, long long w_pitch,
+                                                              long long img_pitch) {
   __shared__ float2 stat[256];
   const int n = blockIdx.y;
   const int c8 = c >> 3, cpg = c / groups;
@@ -92,11 +103,11 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __nv_bfloat1
   unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + oct), ga);
   unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + oct), be);
   const float2 st = stat[(oct * 8) / cpg];
-  const uint4* xin = reinterpret_cast<const uint4*>(x + (long long)n * hw * c) + oct;
+  const uint4* xin = reinterpret_cast<const uint4*>(x + (long long)n * img_pitch * c) + oct;
   uint4* yout = reinterpret_cast<uint4*>(y + (long long)n * hw * c) + oct;
   for (long long p = (long long)blockIdx.x * ppi + prow; p < hw; p += (long long)gridDim.x * ppi) {
     float f[8];
-    unpack8(__ldg(xin + p * c8), f);
+    unpack8(__ldg(xin + gn_src(p, w_valid, w_pitch) * c8), f);
     uint4 o;
     __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __nv_bfloat1
 __global__ void __launch_bounds__(256)
 upsample_add_nhwc_kernel(const __nv_bfloat16* __restrict__ top, const __nv_bfloat16* __restrict__ lat,
                          __nv_bfloat16* __restrict__ out, int Hi, int Wi, int Ho, int Wo, int C, long long n_vec,
-                         float scale_h, float scale_w) {
+                         float scale_h, float scale_w, long long top_pitch, int pad) {
   const int cv = C / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cv);
@@ -140,7 +151,7 @@ upsample_add_nhwc_kernel(const __nv_bfloat16* __restrict__ top, const __nv_bfloa
     const int y0 = (int)sy, x0 = (int)sx;
     const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
     const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-    const __nv_bfloat16* tb = top + ((size_t)b * Hi * Wi) * C + c8 * 8;
+    const __nv_bfloat16* tb = top + (size_t)b * top_pitch + c8 * 8;
     const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(tb + ((size_t)y0 * Wi + x0) * C));
     const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(tb + ((size_t)y0 * Wi + x1) * C));
     const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(tb + ((size_t)y1 * Wi + x0) * C));
@@ -163,7 +174,9 @@ upsample_add_nhwc_kernel(const __nv_bfloat16* __restrict__ top, const __nv_bfloa
       const float2 uf = __bfloat1622float2(ub);
       o2[k] = __floats2bfloat162_rn(fl.x + uf.x, fl.y + uf.y);               // lateral + up, one bf16 rounding
     }
-    *reinterpret_cast<uint4*>(out + (size_t)i * 8) = ov;
+    // pad > 0: the output is the interior of a zero-bordered [Ho + 2 pad, Wo + 2 pad] map (the next 3x3 convolution's input)
+    const size_t o = pad ? ((((size_t)b * (Ho + 2 * pad) + y + pad) * (Wo + 2 * pad) + x + pad) * cv + c8) : (size_t)i;
+    *reinterpret_cast<uint4*>(out + o * 8) = ov;
   }
 }
 
@@ -173,12 +186,14 @@ long long vllm_groupnorm_workspace_bytes(int batch, int groups) {
   return (long long)batch * GN_MAX_CHUNKS * groups * (long long)sizeof(float2);
 }
 
-int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, int batch, long long hw,
-                             int channels, int groups, float eps, int relu, void* workspace, long long workspace_bytes,
-                             void* stream) {
-  if (batch < 0 || hw < 0 || channels <= 0 || groups <= 0) return VLLM_EINVAL;
+int vllm_groupnorm_nhwc_bf16_grid(const void* x, void* y, const void* gamma, const void* beta, int batch, long long h, long long w,
+                                  long long x_w_pitch, long long x_image_pitch, int channels, int groups, float eps, int relu,
+                                  void* workspace, long long workspace_bytes, void* stream) {
+  if (batch < 0 || h < 0 || w < 0 || channels <= 0 || groups <= 0) return VLLM_EINVAL;
+  const long long hw = h * w;
   if (batch == 0 || hw == 0) return VLLM_OK;
   if (!x || !y || !gamma || !beta || !workspace) return VLLM_EINVAL;
+  if (x_w_pitch < w || x_image_pitch < (h - 1) * x_w_pitch + w) return VLLM_EINVAL;
   if (channels % groups) return VLLM_EINVAL;
   const int cpg = channels / groups;
   // one thread per 8-channel vector; a vector must not straddle two groups; a pixel row must fit one CTA pass
@@ -190,7 +205,7 @@ int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const vo
   if (workspace_bytes < (long long)batch * chunks * groups * (long long)sizeof(float2)) return VLLM_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   gn_stats_kernel<<<dim3(chunks, batch), GN_THREADS, (size_t)ppi * c8 * sizeof(float2), st>>>(
-      (const __nv_bfloat16*)x, (float2*)workspace, hw, channels, groups, chunks);
+      (const __nv_bfloat16*)x, (float2*)workspace, hw, channels, groups, chunks, w, x_w_pitch, x_image_pitch);
   VLLM_CHECK_LAUNCH();
   long long blocks = (hw + (long long)ppi * 4 - 1) / ((long long)ppi * 4);
   const long long cap = (long long)vllm_num_sms() * 8;
@@ -198,28 +213,42 @@ int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const vo
   if (blocks < 1) blocks = 1;
   gn_apply_kernel<<<dim3((unsigned)blocks, batch), GN_THREADS, 0, st>>>(
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-      (const float2*)workspace, hw, channels, groups, chunks, eps, relu);
+      (const float2*)workspace, hw, channels, groups, chunks, eps, relu, w, x_w_pitch, x_image_pitch);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
 }
 
+int vllm_groupnorm_nhwc_bf16(const void* x, void* y, const void* gamma, const void* beta, int batch, long long hw,
+                             int channels, int groups, float eps, int relu, void* workspace, long long workspace_bytes,
+                             void* stream) {
+  if (hw < 0) return VLLM_EINVAL;
+  return vllm_groupnorm_nhwc_bf16_grid(x, y, gamma, beta, batch, hw ? 1 : 0, hw, hw, hw, channels, groups, eps, relu, workspace,
+                                       workspace_bytes, stream);
+}
 
-int vllm_upsample_add_nhwc_bf16(const void* top, const void* lateral, void* out, int batch, int in_h, int in_w, int out_h,
-                                int out_w, int channels, void* stream) {
-  if (batch < 0 || in_h <= 0 || in_w <= 0 || out_h <= 0 || out_w <= 0 || channels <= 0) return VLLM_EINVAL;
+int vllm_upsample_add_nhwc_bf16_ex(const void* top, long long top_image_pitch, const void* lateral, void* out, int batch, int in_h,
+                                   int in_w, int out_h, int out_w, int channels, int out_pad, void* stream) {
+  if (batch < 0 || in_h <= 0 || in_w <= 0 || out_h <= 0 || out_w <= 0 || channels <= 0 || out_pad < 0) return VLLM_EINVAL;
+  if (top_image_pitch < (long long)in_h * in_w * channels) return VLLM_EINVAL;
   if (batch == 0) return VLLM_OK;
   if (!top || !lateral || !out) return VLLM_EINVAL;
   if (channels % 8) return VLLM_EUNSUPPORTED;
-  if (!vllm_aligned(top, 16) || !vllm_aligned(lateral, 16) || !vllm_aligned(out, 16)) return VLLM_EALIGN;
+  if (top_image_pitch % 8 || !vllm_aligned(top, 16) || !vllm_aligned(lateral, 16) || !vllm_aligned(out, 16)) return VLLM_EALIGN;
   const long long n_vec = (long long)batch * out_h * out_w * (channels / 8);
   long long blocks = (n_vec + 255) / 256;
   const long long cap = (long long)vllm_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   upsample_add_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)top, (const __nv_bfloat16*)lateral, (__nv_bfloat16*)out, in_h, in_w, out_h, out_w, channels, n_vec,
-      (float)in_h / (float)out_h, (float)in_w / (float)out_w);
+      (float)in_h / (float)out_h, (float)in_w / (float)out_w, top_image_pitch, out_pad);
   VLLM_CHECK_LAUNCH();
   return VLLM_OK;
+}
+
+int vllm_upsample_add_nhwc_bf16(const void* top, const void* lateral, void* out, int batch, int in_h, int in_w, int out_h,
+                                int out_w, int channels, void* stream) {
+  return vllm_upsample_add_nhwc_bf16_ex(top, (long long)in_h * in_w * channels, lateral, out, batch, in_h, in_w, out_h, out_w,
+                                        channels, 0, stream);
 }
 
 }  // extern "C"

@@ -122,8 +122,10 @@ def select_topk_proposals(enc_outputs_class, enc_outputs_coord_logits, object_qu
 
 
 @torch.no_grad()
-def forward_seg_heads(mask_embed_head, output, mask_features):
-    """einsum('bqc,bchw->bqhw', mask_embed(output), mask_features) as one [Q,C] x [HW,C]^T GEMM per image."""
+def forward_seg_heads(mask_embed_head, output, mask_features, out_dtype=None):
+    """einsum('bqc,bchw->bqhw', mask_embed(output), mask_features) as one [Q,C] x [HW,C]^T GEMM per image.
+    out_dtype=torch.float32: the fp32 accumulators are stored directly (the caller's `.float()` as the GEMM's store format,
+    like the LLM logits) instead of a bf16 store followed by a widening copy."""
     e = mask_embed_head(output)
     if isinstance(mask_features, tuple):                                  # (rows [B, H*W, C], H, W): the neck's own layout
         f, H, W = mask_features
@@ -133,7 +135,7 @@ def forward_seg_heads(mask_embed_head, output, mask_features):
         f = mask_features.permute(0, 2, 3, 1).reshape(B, H * W, C)      # free for channels_last features
         if not f.is_contiguous():
             f = f.contiguous()
-    out = torch.empty((B, e.shape[1], H * W), dtype=e.dtype, device=e.device)
+    out = torch.empty((B, e.shape[1], H * W), dtype=out_dtype or e.dtype, device=e.device)
     for b in range(B):
         ops.linear(e[b].contiguous(), f[b], out=out[b])
     return out.view(B, e.shape[1], H, W)

@@ -90,18 +90,23 @@ class GroundingDinoSinePositionEmbedding(nn.Module):
         return torch.cat((pos_y, pos_x), dim=3)
 
 
-def conv_rows(x, conv):
+def conv_rows(x, conv, prepadded=False, keep_grid=False):
     """Conv2d over a channels-last map x [B, H, W, Cin] as ONE GEMM on [B*Ho*Wo, kh*kw*Cin] rows (tap-major K, the
     weight repacked to match); returns ([B, Ho*Wo, Cout], Ho, Wo).  1x1 convs read the map in place."""
-    B, Hh, W, C = x.shape
     kh, kw = conv.kernel_size
     s, p = conv.stride[0], conv.padding[0]
+    implicit = s == 1 and kh == kw and kh > 1 and (kw * x.shape[3]) % 64 == 0 and conv.padding[0] == conv.padding[1]
+    if prepadded and not implicit:
+        x = x[:, p:x.shape[1] - p, p:x.shape[2] - p]                               # not the implicit-GEMM form: drop the border again
+    B, Hh, W, C = x.shape
     if (kh, kw, s, p) == (1, 1, 1, 0):
         rows, Ho, Wo = x.reshape(B, Hh * W, C), Hh, W
-    elif s == 1 and kh == kw and (kw * C) % 64 == 0 and conv.padding[0] == conv.padding[1]:
+    elif implicit:
         # implicit GEMM over the zero-padded map: no [B*Ho*Wo, kh*kw*C] im2col buffer
         w = conv.weight.permute(0, 2, 3, 1).reshape(conv.out_channels, -1).contiguous()
-        y = ops.conv2d_s1_rows(x, w, conv.bias, kh, p)
+        y = ops.conv2d_s1_rows(x, w, conv.bias, kh, p, prepadded=prepadded)
+        if keep_grid:                                                                # the valid corner of the padded grid, in place
+            return y, y.shape[1], y.shape[2]
         return y.reshape(B, y.shape[1] * y.shape[2], conv.out_channels), y.shape[1], y.shape[2]
     else:
         Ho, Wo = (Hh + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
@@ -124,8 +129,10 @@ class NormConv2d(nn.Conv2d):
         self.relu = relu
 
     @torch.no_grad()
-    def rows(self, x):
-        y, Ho, Wo = conv_rows(x, self)
+    def rows(self, x, prepadded=False):
+        """prepadded: x is the zero-bordered map `ops.upsample_add_nhwc(..., pad=)` wrote.  The GroupNorm reads the 3x3
+        convolution's output corner of the padded grid in place (no compaction copy)."""
+        y, Ho, Wo = conv_rows(x, self, prepadded=prepadded, keep_grid=True)
         return ops.groupnorm_nhwc(y, self.norm.weight, self.norm.bias, self.norm.num_groups, self.norm.eps, relu=self.relu), Ho, Wo
 
 
@@ -346,8 +353,12 @@ class B200GroundingDinoModel(nn.Module):
         top = enc_vision[:, :H0 * W0].reshape(B, H0, W0, -1)                              # level-0 slab, channels-last
         for idx in range(self.num_fpn_levels):
             cur, Hc, Wc = self.lateral_convs[idx].rows(feats[idx])
-            y = ops.upsample_add_nhwc(top.contiguous(), cur.view(B, Hc, Wc, -1).contiguous())   # lateral + bilinear(top), one pass
-            top, Hc, Wc = self.output_convs[idx].rows(y)
+            oc = self.output_convs[idx]
+            pad = oc.padding[0] if oc.padding[0] == oc.padding[1] and oc.stride[0] == 1 else 0
+            # lateral + bilinear(top) in one pass, written straight into the output convolution's zero-padded input; `top` (the
+            # level-0 slab of the flattened encoder output at idx 0) is read in place through its batch pitch
+            y = ops.upsample_add_nhwc(top, cur.view(B, Hc, Wc, -1), pad=pad)
+            top, Hc, Wc = oc.rows(y, prepadded=pad > 0)
             top = top.view(B, Hc, Wc, -1)
         mf, Hm, Wm = conv_rows(top, self.mask_features)
         return mf, Hm, Wm
@@ -448,7 +459,8 @@ class B200GroundingDinoForObjectDetection(nn.Module):
         for level in (range(n_levels) if all_levels else [n_levels - 1]):
             ref = out.init_reference_points if level == 0 else out.intermediate_reference_points[level - 1]
             hs = out.intermediate_hidden_states[level]
-            masks = H.forward_seg_heads(self.mask_embed[level], hs, out.mask_features)
+            masks = H.forward_seg_heads(self.mask_embed[level], hs, out.mask_features,
+                                        out_dtype=torch.float32 if hs.is_cuda and hs.dtype == torch.bfloat16 else None)
             logits = self.class_embed[level](hs, out.encoder_last_hidden_state_text, mask_bool)
             boxes = (self.bbox_embed[level](hs) + inverse_sigmoid(ref)).sigmoid()
             res.append((logits.to(torch.float32), boxes.to(torch.float32), masks.to(torch.float32)))

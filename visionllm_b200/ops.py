@@ -125,14 +125,20 @@ def gemm_tn(a, b, a_mn=False, b_mn=False, out_dtype=torch.bfloat16):
     return out
 
 
-def conv2d_s1_rows(x, weight_rows, bias, kernel, padding, act=None):
+def conv2d_s1_rows(x, weight_rows, bias, kernel, padding, act=None, prepadded=False):
     """Stride-1 KxK convolution of a channels-last map x [B, H, W, C] (bf16) with `weight_rows` [Cout, K*K*C] in
     (dy, dx, c) order -> [B, Ho, Wo, Cout] (a strided view of the kernel's padded-grid output).  One zero-pad copy of x,
-    then ONE implicit-GEMM launch (vllm_conv_rows_bf16) -- no im2col buffer (9x the activation for a 3x3)."""
+    then ONE implicit-GEMM launch (vllm_conv_rows_bf16) -- no im2col buffer (9x the activation for a 3x3).
+    prepadded: x already IS the zero-bordered [B, H + 2p, W + 2p, C] map (`upsample_add_nhwc(..., pad=p)`): no pad copy."""
     if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_cuda:
         raise RuntimeError("conv2d_s1_rows: x must be a CUDA bf16 [B, H, W, C] tensor")
-    B, Hh, W, C = x.shape
     k, p = int(kernel), int(padding)
+    if prepadded:
+        if not x.is_contiguous() or x.shape[1] <= 2 * p or x.shape[2] <= 2 * p:
+            raise RuntimeError("conv2d_s1_rows: a prepadded x must be a contiguous [B, H + 2p, W + 2p, C] map")
+        B, Hh, W, C = x.shape[0], x.shape[1] - 2 * p, x.shape[2] - 2 * p, x.shape[3]
+    else:
+        B, Hh, W, C = x.shape
     _bf16_2d(weight_rows, "weight_rows")
     if weight_rows.shape[1] != k * k * C:
         raise RuntimeError("conv2d_s1_rows: weight_rows must be [Cout, K*K*C]")
@@ -141,7 +147,7 @@ def conv2d_s1_rows(x, weight_rows, bias, kernel, padding, act=None):
         raise RuntimeError("conv2d_s1_rows: bias must be contiguous bf16 [Cout]")
     Hp, Wp = Hh + 2 * p, W + 2 * p
     Ho, Wo = Hp - k + 1, Wp - k + 1
-    xp = torch.nn.functional.pad(x, (0, 0, p, p, p, p)) if p else x.contiguous()
+    xp = x if prepadded else (torch.nn.functional.pad(x, (0, 0, p, p, p, p)) if p else x.contiguous())
     out = torch.empty((B, Hp, Wp, Cout), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device), _Prof("gemm", 2.0 * B * Hp * Wp * Cout * k * k * C,
                                             2.0 * (B * Hp * Wp * (C + Cout) + Cout * k * k * C)):
@@ -284,10 +290,22 @@ def _ws_key(device):
 
 def groupnorm_nhwc(x, weight, bias, groups, eps, relu=False):
     """GroupNorm of channels-last rows x [batch, pixels, channels] (bf16), optional fused ReLU -- nn.GroupNorm(32, 256)
-    of the Grounding-DINO neck (modeling_ov_grounding_dino_mask_dn.py:2085-2110) without leaving the GEMM's layout."""
-    if x.dim() != 3 or x.dtype != torch.bfloat16 or not x.is_contiguous() or not x.is_cuda:
-        raise RuntimeError("groupnorm_nhwc: x must be a contiguous CUDA bf16 [batch, pixels, channels] tensor")
-    n, hw, c = x.shape
+    of the Grounding-DINO neck (modeling_ov_grounding_dino_mask_dn.py:2085-2110) without leaving the GEMM's layout.
+    x may also be a 4-D [batch, H, W, channels] VIEW of a padded grid (unit channel stride, pixel stride == channels, any row /
+    image pitch: `conv2d_s1_rows`' output): the corner is read in place.  Returns contiguous [batch, pixels, channels]."""
+    if x.dtype != torch.bfloat16 or not x.is_cuda or x.dim() not in (3, 4):
+        raise RuntimeError("groupnorm_nhwc: x must be a CUDA bf16 [batch, pixels, channels] or [batch, H, W, channels] tensor")
+    c = x.shape[-1]
+    if x.dim() == 3:
+        if not x.is_contiguous():
+            raise RuntimeError("groupnorm_nhwc: 3-D x must be contiguous")
+        n, h, w = x.shape[0], 1 if x.shape[1] else 0, x.shape[1]
+        w_pitch = img_pitch = x.shape[1]
+    else:
+        n, h, w = x.shape[:3]
+        if x.stride(3) != 1 or x.stride(2) != c or x.stride(1) % c or x.stride(0) % c:
+            raise RuntimeError("groupnorm_nhwc: 4-D x must be a channels-last view with whole-pixel row / image pitches")
+        w_pitch, img_pitch = x.stride(1) // c, x.stride(0) // c
     if weight.dtype != torch.bfloat16 or bias.dtype != torch.bfloat16 or weight.numel() != c or bias.numel() != c:
         raise RuntimeError("groupnorm_nhwc: weight/bias must be bf16 [channels]")
     need = _lib.lib().vllm_groupnorm_workspace_bytes(n, groups)
@@ -295,29 +313,35 @@ def groupnorm_nhwc(x, weight, bias, groups, eps, relu=False):
     ws = _GN_WS.get(key)
     if ws is None or ws.numel() < need:
         ws = _GN_WS[key] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=x.device)
-    out = torch.empty_like(x)
-    with torch.cuda.device(x.device), _Prof("groupnorm", 0.0, 6.0 * n * hw * c):
-        rc = _lib.lib().vllm_groupnorm_nhwc_bf16(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(), n, hw, c,
-                                                 groups, float(eps), int(bool(relu)), ws.data_ptr(), ws.numel(), _stream())
-    _lib.check(rc, "vllm_groupnorm_nhwc_bf16")
+    out = torch.empty((n, h * w, c), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device), _Prof("groupnorm", 0.0, 6.0 * n * h * w * c):
+        rc = _lib.lib().vllm_groupnorm_nhwc_bf16_grid(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(), n, h, w,
+                                                      w_pitch, img_pitch, c, groups, float(eps), int(bool(relu)), ws.data_ptr(),
+                                                      ws.numel(), _stream())
+    _lib.check(rc, "vllm_groupnorm_nhwc_bf16_grid")
     return out
 
 
-def upsample_add_nhwc(top, lateral):
+def upsample_add_nhwc(top, lateral, pad=0):
     """lateral + F.interpolate(top, size=lateral's (H, W), mode='bilinear', align_corners=False) for channels-last bf16
-    maps top [B, Hi, Wi, C], lateral [B, Ho, Wo, C] (the FPN top-down step, gd.py:2486-2492) in one pass."""
+    maps top [B, Hi, Wi, C] (each image contiguous, any batch pitch), lateral [B, Ho, Wo, C] (the FPN top-down step,
+    gd.py:2486-2492) in one pass.  pad > 0: returns the zero-bordered [B, Ho + 2 pad, Wo + 2 pad, C] map with the sum in its
+    interior (the next 3x3 convolution's padded input, `conv2d_s1_rows(..., prepadded=True)`)."""
     for t, nm in ((top, "top"), (lateral, "lateral")):
-        if t.dim() != 4 or t.dtype != torch.bfloat16 or not t.is_cuda or not t.is_contiguous():
-            raise RuntimeError(f"upsample_add_nhwc: {nm} must be a contiguous CUDA bf16 [B, H, W, C] tensor")
+        if t.dim() != 4 or t.dtype != torch.bfloat16 or not t.is_cuda:
+            raise RuntimeError(f"upsample_add_nhwc: {nm} must be a CUDA bf16 [B, H, W, C] tensor")
     B, Hi, Wi, C = top.shape
+    if not lateral.is_contiguous() or not top[0].is_contiguous() or (B > 1 and top.stride(0) < Hi * Wi * C):
+        raise RuntimeError("upsample_add_nhwc: lateral must be contiguous, top contiguous per image")
     if lateral.shape[0] != B or lateral.shape[3] != C:
         raise RuntimeError("upsample_add_nhwc: batch / channel mismatch")
     Ho, Wo = lateral.shape[1], lateral.shape[2]
-    out = torch.empty_like(lateral)
+    pad = int(pad)
+    out = torch.zeros((B, Ho + 2 * pad, Wo + 2 * pad, C), dtype=torch.bfloat16, device=top.device) if pad else torch.empty_like(lateral)
     with torch.cuda.device(top.device), _Prof("upsample_add", 0.0, 2.0 * (top.numel() + 2 * lateral.numel())):
-        rc = _lib.lib().vllm_upsample_add_nhwc_bf16(top.data_ptr(), lateral.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C,
-                                                    _stream())
-    _lib.check(rc, "vllm_upsample_add_nhwc_bf16")
+        rc = _lib.lib().vllm_upsample_add_nhwc_bf16_ex(top.data_ptr(), top.stride(0) if B > 1 else Hi * Wi * C, lateral.data_ptr(),
+                                                       out.data_ptr(), B, Hi, Wi, Ho, Wo, C, pad, _stream())
+    _lib.check(rc, "vllm_upsample_add_nhwc_bf16_ex")
     return out
 
 

@@ -78,6 +78,9 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return self.forward_ffn(self.norm1(src + src2))
 
 
+_ATTEND_CACHE = {}          # single entry: the last self-attention mask in kernel format (see _attend_mask)
+
+
 class DeformableTransformerDecoderLayer(nn.Module):
     """modeling_unipose.py:3188-3323: self-attention, optional text cross-attention, deformable cross-attention, FFN;
     tensors are sequence-first ([nq, bs, d]) like the reference's nn.MultiheadAttention calls."""
@@ -125,10 +128,18 @@ class DeformableTransformerDecoderLayer(nn.Module):
             return None
         if self_attn_mask.dtype != torch.bool:
             raise NotImplementedError("float attn_mask")
+        # every keypoint layer receives the SAME mask tensor (tgt_mask2, 50 x 69 queries: 8 x 3450 x 3450 bytes per image):
+        # invert / expand / convert it once per forward, not once per layer.  The cache entry keeps the source tensor alive, so
+        # an `is` + version match cannot be a recycled allocation.
+        c = _ATTEND_CACHE
+        if c.get("src") is self_attn_mask and c.get("key") == (self_attn_mask._version, bs * self.n_heads, nq):
+            return c["mask"]
         m = ~self_attn_mask
         if m.dim() == 2:
             m = m[None].expand(bs * self.n_heads, nq, nq)
-        return m.contiguous()
+        m = m.to(torch.uint8).contiguous()                         # the kernel's mask format (ops.attention converts otherwise)
+        c.update(src=self_attn_mask, key=(self_attn_mask._version, bs * self.n_heads, nq), mask=m)
+        return m
 
     @torch.no_grad()
     def forward(self, tgt, tgt_query_pos=None, tgt_query_sine_embed=None, tgt_key_padding_mask=None,
