@@ -306,6 +306,21 @@ int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, in
                         long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
                         const unsigned char* attn_mask, const float* attn_bias, int bias_batches, int causal,
                         float scale, void* workspace, long long workspace_bytes, void* stream);
+/* Sparse attn_mask (UniPose's keypoint decoder: 50 groups of 1 + 68 queries attend within their group,
+ * unipose/modeling_unipose.py:887-917 -- 3450 x 3450 bytes per (image, head), > 95 % blocked): vllm_attention_mask_tiles lists, per
+ * (batch*heads, 64-row query block), the ascending ids of the 64-key tiles that hold at least one allowed pair
+ * (tile_counts int32 [n_batch_heads, ceil(Tq/64)], tile_lists int32 [n_batch_heads, ceil(Tq/64), ceil(Tk/64)]);
+ * vllm_attention_bf16_tiles is vllm_attention_bf16 (non-causal, head_dim 32 / 64 / 128, attn_mask required) walking only those
+ * tiles.  A fully blocked tile leaves the online softmax untouched, so the result is bit-identical to the dense walk. */
+int vllm_attention_mask_tiles(const unsigned char* attn_mask, long long n_batch_heads, int Tq, int Tk, int* tile_counts,
+                              int* tile_lists, void* stream);
+int vllm_attention_bf16_tiles(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
+                              int heads, int kv_heads, int head_dim, long long q_batch_pitch,
+                              long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
+                              long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
+                              long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
+                              const unsigned char* attn_mask, float scale, const int* tile_counts,
+                              const int* tile_lists, void* stream);
 /* Tuning knob (process-global), head_dim 128 without masks: 0 = tcgen05/TMEM kernel, schedule "tc2" (default),
  * 2 = tcgen05/TMEM ping-pong schedule, 1 = warp-MMA kernel always. */
 int vllm_attention_set_variant(int variant);

@@ -178,3 +178,41 @@ def test_attention_tcgen05_key_mask_and_split_kv(D, Tq, Tk):
         finally:
             _lib.lib().vllm_attention_set_variant(0)
         check(out, warp.float())
+
+
+@pytest.mark.parametrize("B,H,T,D,group", [(2, 8, 690, 32, 69), (1, 4, 200, 64, 40), (2, 2, 333, 128, 111), (1, 8, 3450, 32, 69)])
+def test_live_tile_lists_give_the_dense_result(B, H, T, D, group):
+    """vllm_attention_mask_tiles + vllm_attention_bf16_tiles (UniPose's keypoint decoder mask: groups of 1 + 68 queries that
+    attend within their group plus a few stripes): the tile lists match a torch evaluation of "any allowed pair per 64 x 64
+    tile", and walking only the live tiles reproduces the dense walk bit for bit -- including query rows that may attend
+    nothing (zero output) and query blocks with no live tile at all."""
+    from visionllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(T + D)
+    q, k, v = (torch.randn(B, T, H, D, device="cuda", generator=g).bfloat16() for _ in range(3))
+    idx = torch.arange(T, device="cuda")
+    allow = (idx[:, None] // group) == (idx[None, :] // group)                       # block diagonal
+    allow = allow[None].repeat(B * H, 1, 1)
+    allow[:, :, ::group] |= torch.rand(B * H, T, (T + group - 1) // group, device="cuda", generator=g) < 0.02   # sparse stripes
+    allow[0, 5] = False                                                                # a query row that attends nothing
+    if T > 128:
+        allow[-1, 64:128] = False                                                      # a whole query block without live tiles
+    dense = ops.attention(q, k, v, attn_mask=allow)
+    tiles = ops.attention_mask_tiles(allow)
+    nqb = nkt = (T + 63) // 64
+    pad = nqb * 64 - T
+    ap = torch.nn.functional.pad(allow, (0, pad, 0, pad))
+    any_t = ap.view(B * H, nqb, 64, nkt, 64).any(4).any(2)                             # [BH, nqb, nkt]
+    assert torch.equal(tiles.counts.long(), any_t.sum(-1))
+    for bh in range(0, B * H, max(1, B * H // 3)):
+        for qb in range(0, nqb, max(1, nqb // 4)):
+            n = int(tiles.counts[bh, qb])
+            assert tiles.lists[bh, qb, :n].tolist() == torch.nonzero(any_t[bh, qb]).flatten().tolist()
+    sparse = ops.attention(q, k, v, attn_mask=tiles)
+    assert torch.equal(sparse, dense)
+    assert not sparse[0, 5, :D].any()                                                  # head 0 of batch 0: the empty row
+    assert float(any_t.float().mean()) < 0.5                                           # the point: most tiles are skipped
+    ref_s = (q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 3, 1)) * D ** -0.5
+    ref_s = ref_s.masked_fill(~allow.view(B, H, T, T), float("-inf"))
+    p = torch.softmax(ref_s, -1).nan_to_num(0.0)
+    ref = (p @ v.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(B, T, H * D)
+    assert ((sparse.float() - ref).norm() / ref.norm()).item() < 6e-3

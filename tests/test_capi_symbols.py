@@ -53,6 +53,10 @@ def test_round2_entry_points_marshal_and_accept_empty_problems():
     assert L.vllm_groupnorm_nhwc_bf16_grid(None, None, None, None, 0, 8, 8, 10, 100, 256, 32, 1e-5, 0, None, 0, None) == 0
     assert L.vllm_groupnorm_nhwc_bf16_grid(None, None, None, None, 1, 8, 8, 10, 100, 256, 32, 1e-5, 0, None, 0, None) < 0   # null pointers
     assert L.vllm_upsample_add_nhwc_bf16_ex(None, 64 * 256, None, None, 0, 8, 8, 16, 16, 256, 1, None) == 0
+    assert L.vllm_attention_mask_tiles(None, 0, 100, 100, None, None, None) == 0
+    assert L.vllm_attention_mask_tiles(None, 4, 100, 100, None, None, None) < 0                                              # null pointers
+    args = [None] * 4 + [0, 64, 64, 8, 8, 32] + [0] * 8 + [None, None, None, 1.0]
+    assert L.vllm_attention_bf16_tiles(*args, None, None, None) < 0                                                          # no tile lists
     assert L.vllm_upsample_add_nhwc_bf16_ex(None, 10, None, None, 1, 8, 8, 16, 16, 256, 1, None) < 0                       # pitch < image
     assert L.vllm_sine_embed_f32(None, None, None, None, 1, 5, 0.0, None, 128, 0, None, 1024, 1, 0, 0, None, None) < 0    # > 4 features
     assert L.vllm_sine_embed_f32(None, None, None, None, 1, 2, 0.0, None, 100, 0, None, 256, 1, 0, 0, None, None) < 0     # nd % 8

@@ -80,6 +80,9 @@ _SIGNATURES = {
     "vllm_groupnorm_nhwc_bf16_grid": (ci, [vp, vp, vp, vp, ci, cll, cll, cll, cll, ci, ci, cf, ci, vp, cll, vp]),
     "vllm_attention_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cll, cll, cll, cll, cll, cll, cll, cll,
                                  vp, vp, vp, vp, ci, ci, cf, vp, cll, vp]),
+    "vllm_attention_bf16_tiles": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cll, cll, cll, cll, cll, cll, cll, cll,
+                                       vp, vp, vp, cf, vp, vp, vp]),
+    "vllm_attention_mask_tiles": (ci, [vp, cll, ci, ci, vp, vp, vp]),
     "vllm_attention_set_variant": (ci, [ci]),
     "vllm_peer_alloc": (ci, [ctypes.POINTER(vp), ctypes.c_size_t]),
     "vllm_peer_free": (ci, [vp]),

@@ -36,6 +36,12 @@ struct AttnArgs {
   float scale_log2;
   int n_splits;      // split-KV: CTAs along the key axis per query block (1 = off)
   float* ws;         // workspace [batch*heads*n_splits*Tq][D + 2] fp32 partials (unnormalised O, m, l)
+  // Live-tile lists of a sparse attn_mask (vllm_attention_mask_tiles): per (batch*heads, 64-row query block) the ascending
+  // ids of the 64-key tiles holding at least one allowed pair.  A fully blocked tile leaves the online softmax untouched
+  // (all scores -inf: corr = 1, p = 0), so walking only the live tiles gives bit-identical results.
+  const int* tile_counts;   // [batch*heads, q_blocks] or nullptr
+  const int* tile_lists;    // [batch*heads, q_blocks, k_tiles]
+  int q_blocks, k_tiles;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
@@ -112,13 +118,20 @@ flash_fwd_kernel(const AttnArgs a) {
   // split-KV: this CTA owns key tiles [t_begin, t_begin + n_tiles)
   const int per_split = (n_tiles_all + a.n_splits - 1) / a.n_splits;
   const int t_begin = split * per_split;
-  const int n_tiles = max(0, min(n_tiles_all, t_begin + per_split) - t_begin);
+  int n_tiles = max(0, min(n_tiles_all, t_begin + per_split) - t_begin);
+  const int* live = nullptr;                                    // live-tile list of this (batch, head, query block)
+  if (BN == 64 && a.tile_counts) {
+    const long long item = ((long long)b * a.heads + head) * a.q_blocks + mblk;
+    n_tiles = a.tile_counts[item];
+    live = a.tile_lists + item * a.k_tiles;
+  }
+  auto tile_id = [&](int t) { return live ? live[t] : t_begin + t; };
 
   load_tile<D, BM>(sQ, qb, a.q_ts, m0, a.Tq);
   cp_async_commit();
   if (n_tiles > 0) {
-    load_tile<D, BN>(sK0, kb, a.k_ts, t_begin * BN, len);
-    load_tile<D, BN>(sV0, vb, a.v_ts, t_begin * BN, len);
+    load_tile<D, BN>(sK0, kb, a.k_ts, tile_id(0) * BN, len);
+    load_tile<D, BN>(sV0, vb, a.v_ts, tile_id(0) * BN, len);
   }
   cp_async_commit();
 
@@ -146,8 +159,8 @@ flash_fwd_kernel(const AttnArgs a) {
     const int buf = t & 1;
     const uint32_t sK = sK0 + buf * KB, sV = sV0 + buf * KB;
     if (t + 1 < n_tiles) {
-      load_tile<D, BN>(sK0 + (buf ^ 1) * KB, kb, a.k_ts, (t_begin + t + 1) * BN, len);
-      load_tile<D, BN>(sV0 + (buf ^ 1) * KB, vb, a.v_ts, (t_begin + t + 1) * BN, len);
+      load_tile<D, BN>(sK0 + (buf ^ 1) * KB, kb, a.k_ts, tile_id(t + 1) * BN, len);
+      load_tile<D, BN>(sV0 + (buf ^ 1) * KB, vb, a.v_ts, tile_id(t + 1) * BN, len);
     }
     cp_async_commit();
     cp_async_wait<1>();
@@ -170,7 +183,7 @@ flash_fwd_kernel(const AttnArgs a) {
       }
     }
     // ---- mask + online softmax (scores scaled into log2 domain) ----
-    const int n0 = (t_begin + t) * BN;
+    const int n0 = tile_id(t) * BN;
     const unsigned char* km = a.key_mask ? a.key_mask + (long long)b * a.Tk : nullptr;
     const unsigned char* am = a.attn_mask ? a.attn_mask + ((long long)b * a.heads + head) * a.Tq * a.Tk : nullptr;
     const float* ab = a.attn_bias
@@ -277,6 +290,33 @@ flash_fwd_kernel(const AttnArgs a) {
       *reinterpret_cast<__nv_bfloat162*>(op + j * 8 + tq * 2) = __floats2bfloat162_rn(x, y);
     }
   }
+}
+
+// Live-tile lists of an attn_mask [n_bh, Tq, Tk] (1 = attend): one CTA per (bh, 64-row query block) walks the 64-key tiles,
+// ORs the 64 x 64 bytes of each block-wide and appends the ids of the non-empty ones.
+__global__ void __launch_bounds__(256)
+mask_tiles_kernel(const unsigned char* __restrict__ mask, int Tq, int Tk, int q_blocks, int k_tiles, int* __restrict__ counts,
+                  int* __restrict__ lists) {
+  const long long item = blockIdx.x;                            // bh * q_blocks + qb
+  const int qb = (int)(item % q_blocks);
+  const long long bh = item / q_blocks;
+  const unsigned char* m = mask + bh * (long long)Tq * Tk;
+  const int r = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16;  // thread: row r of the block, 16 consecutive keys
+  const int row = qb * 64 + r;
+  int n = 0;
+  for (int kt = 0; kt < k_tiles; ++kt) {
+    int any = 0;
+    if (row < Tq) {
+      const unsigned char* p = m + (long long)row * Tk + kt * 64 + c0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) any |= (kt * 64 + c0 + j < Tk) ? p[j] : 0;
+    }
+    if (__syncthreads_or(any)) {
+      if (threadIdx.x == 0) lists[item * k_tiles + n] = kt;
+      ++n;
+    }
+  }
+  if (threadIdx.x == 0) counts[item] = n;
 }
 
 // merge the split-KV partials of one query row: one warp per (batch, head, row), lanes over head_dim
@@ -497,7 +537,7 @@ int launch(AttnArgs a, int batch, cudaStream_t st, void* workspace, long long wo
   a.n_splits = 1; a.ws = nullptr;
   const long long ctas = (long long)m_blocks * a.heads * batch;
   const int n_tiles = (a.Tk + BN - 1) / BN;
-  if (workspace && !a.causal && ctas < 2LL * vllm_num_sms() && n_tiles >= 16) {
+  if (workspace && !a.causal && !a.tile_counts && ctas < 2LL * vllm_num_sms() && n_tiles >= 16) {
     // pick the split count that minimises (waves of resident CTAs) x (key tiles per split): a count that spills a
     // few CTAs into one more wave costs a whole extra pass (ncu: 640 CTAs on 296 slots = 2.16 waves ran as 3)
     static int per_sm = 0;
@@ -580,14 +620,17 @@ static int launch_tc2_split(const AttnArgs& a, int batch, float scale, cudaStrea
 static int g_attn_variant = 0;
 extern "C" int vllm_attention_set_variant(int v) { g_attn_variant = v; return VLLM_OK; }
 
-extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
-                                   int heads, int kv_heads, int head_dim, long long q_batch_pitch,
-                                   long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
-                                   long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
-                                   long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
-                                   const unsigned char* attn_mask, const float* attn_bias, int bias_batches,
-                                   int causal, float scale, void* workspace, long long workspace_bytes, void* stream) {
+static int attention_impl(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
+                          int heads, int kv_heads, int head_dim, long long q_batch_pitch,
+                          long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
+                          long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
+                          long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
+                          const unsigned char* attn_mask, const float* attn_bias, int bias_batches,
+                          int causal, float scale, void* workspace, long long workspace_bytes, const int* tile_counts,
+                          const int* tile_lists, void* stream) {
   if (batch < 0 || Tq < 0 || Tk < 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads) return VLLM_EINVAL;
+  if ((tile_counts == nullptr) != (tile_lists == nullptr)) return VLLM_EINVAL;
+  if (tile_counts && (!attn_mask || causal || (head_dim != 32 && head_dim != 64 && head_dim != 128))) return VLLM_EUNSUPPORTED;
   if (batch == 0 || Tq == 0) return VLLM_OK;
   if (!q || !k || !v || !o) return VLLM_EINVAL;
   if (attn_bias && bias_batches <= 0) return VLLM_EINVAL;
@@ -603,6 +646,7 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
   a.q_ts = q_token_pitch; a.k_ts = k_token_pitch; a.v_ts = v_token_pitch; a.o_ts = o_token_pitch;
   a.seqlens = seqlens; a.key_mask = key_mask; a.attn_mask = attn_mask; a.attn_bias = attn_bias; a.bias_batches = bias_batches; a.Tq = Tq; a.Tk = Tk; a.heads = heads; a.kv_heads = kv_heads; a.causal = causal;
   a.scale_log2 = scale * 1.4426950408889634f;
+  a.tile_counts = tile_counts; a.tile_lists = tile_lists; a.q_blocks = (Tq + 63) / 64; a.k_tiles = (Tk + 63) / 64;
   cudaStream_t st = (cudaStream_t)stream;
   if (head_dim == 128 && g_attn_variant == 0 && !key_mask && !attn_mask && !attn_bias) {
     const int rc = vllm_attention_tc2_d128(q, k, v, o, batch, Tq, Tk, heads, kv_heads, q_batch_pitch, q_token_pitch,
@@ -632,4 +676,42 @@ extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, 
     case 256: return launch<256, 32>(a, batch, st, workspace, workspace_bytes);
     default: return VLLM_EUNSUPPORTED;
   }
+}
+
+extern "C" int vllm_attention_bf16(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
+                                   int heads, int kv_heads, int head_dim, long long q_batch_pitch,
+                                   long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
+                                   long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
+                                   long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
+                                   const unsigned char* attn_mask, const float* attn_bias, int bias_batches,
+                                   int causal, float scale, void* workspace, long long workspace_bytes, void* stream) {
+  return attention_impl(q, k, v, o, batch, Tq, Tk, heads, kv_heads, head_dim, q_batch_pitch, q_token_pitch, k_batch_pitch,
+                        k_token_pitch, v_batch_pitch, v_token_pitch, o_batch_pitch, o_token_pitch, seqlens, key_mask, attn_mask,
+                        attn_bias, bias_batches, causal, scale, workspace, workspace_bytes, nullptr, nullptr, stream);
+}
+
+extern "C" int vllm_attention_bf16_tiles(const void* q, const void* k, const void* v, void* o, int batch, int Tq, int Tk,
+                                         int heads, int kv_heads, int head_dim, long long q_batch_pitch,
+                                         long long q_token_pitch, long long k_batch_pitch, long long k_token_pitch,
+                                         long long v_batch_pitch, long long v_token_pitch, long long o_batch_pitch,
+                                         long long o_token_pitch, const int* seqlens, const unsigned char* key_mask,
+                                         const unsigned char* attn_mask, float scale, const int* tile_counts,
+                                         const int* tile_lists, void* stream) {
+  if (!tile_counts || !tile_lists) return VLLM_EINVAL;
+  return attention_impl(q, k, v, o, batch, Tq, Tk, heads, kv_heads, head_dim, q_batch_pitch, q_token_pitch, k_batch_pitch,
+                        k_token_pitch, v_batch_pitch, v_token_pitch, o_batch_pitch, o_token_pitch, seqlens, key_mask, attn_mask,
+                        nullptr, 0, 0, scale, nullptr, 0, tile_counts, tile_lists, stream);
+}
+
+extern "C" int vllm_attention_mask_tiles(const unsigned char* attn_mask, long long n_batch_heads, int Tq, int Tk, int* tile_counts,
+                                         int* tile_lists, void* stream) {
+  if (n_batch_heads < 0 || Tq < 0 || Tk < 0) return VLLM_EINVAL;
+  if (n_batch_heads == 0 || Tq == 0) return VLLM_OK;
+  if (!attn_mask || !tile_counts || !tile_lists) return VLLM_EINVAL;
+  const int q_blocks = (Tq + 63) / 64, k_tiles = (Tk + 63) / 64;
+  const long long items = n_batch_heads * q_blocks;
+  if (items > 2147483647LL) return VLLM_EUNSUPPORTED;
+  mask_tiles_kernel<<<(unsigned)items, 256, 0, (cudaStream_t)stream>>>(attn_mask, Tq, Tk, q_blocks, k_tiles, tile_counts, tile_lists);
+  VLLM_CHECK_LAUNCH();
+  return VLLM_OK;
 }

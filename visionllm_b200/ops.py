@@ -373,6 +373,32 @@ def _attn_workspace(device, nbytes):
     return ws
 
 
+class MaskTiles:
+    """Live-tile lists of a sparse attention mask (`attention_mask_tiles`): the uint8 mask itself plus, per (batch*heads,
+    64-row query block), the 64-key tiles with at least one allowed pair."""
+    __slots__ = ("mask", "counts", "lists")
+
+    def __init__(self, mask, counts, lists):
+        self.mask, self.counts, self.lists = mask, counts, lists
+
+
+def attention_mask_tiles(attn_mask):
+    """attn_mask [B*H, Tq, Tk] bool / uint8, True = attend -> MaskTiles for `attention(..., attn_mask=<MaskTiles>)`: the dense
+    kernel then walks only the key tiles that are not fully blocked (bit-identical result; UniPose's 50 x 69-query group mask
+    is > 95 % blocked)."""
+    if attn_mask.dim() != 3 or not attn_mask.is_cuda:
+        raise RuntimeError("attention_mask_tiles: attn_mask must be a CUDA [B*H, Tq, Tk] tensor")
+    m = attn_mask.to(torch.uint8).contiguous()
+    BH, Tq, Tk = m.shape
+    nqb, nkt = (Tq + 63) // 64, (Tk + 63) // 64
+    counts = torch.empty((BH, nqb), dtype=torch.int32, device=m.device)
+    lists = torch.empty((BH, nqb, nkt), dtype=torch.int32, device=m.device)
+    with torch.cuda.device(m.device):
+        rc = _lib.lib().vllm_attention_mask_tiles(m.data_ptr(), BH, Tq, Tk, counts.data_ptr(), lists.data_ptr(), _stream())
+    _lib.check(rc, "vllm_attention_mask_tiles")
+    return MaskTiles(m, counts, lists)
+
+
 def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, attn_mask=None, attn_bias=None, out=None):
     """softmax(q k^T * scale) v.  q [B, Tq, H, D], k/v [B, Tk, Hkv, D] bf16 views whose last two dims are
     contiguous (any batch/token pitch, e.g. slices of a packed qkv tensor).  Returns [B, Tq, H*D].
@@ -403,7 +429,11 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
             raise RuntimeError("attention: key_mask must be CUDA [B, Tk]")
         key_mask = key_mask.to(torch.uint8).contiguous()
         km = key_mask.data_ptr()
-    amp = None
+    amp, tiles = None, None
+    if isinstance(attn_mask, MaskTiles):
+        tiles, attn_mask = attn_mask, attn_mask.mask
+        if causal or attn_bias is not None or D not in (32, 64, 128):
+            raise RuntimeError("attention: a MaskTiles mask needs a non-causal call without attn_bias, head_dim 32 / 64 / 128")
     if attn_mask is not None:
         if attn_mask.shape != (B * H, Tq, Tk) or not attn_mask.is_cuda:
             raise RuntimeError("attention: attn_mask must be CUDA [B*H, Tq, Tk]")
@@ -420,6 +450,14 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
         ws_bytes = min(B * H * 64 * Tq * (D + 2) * 4, 256 << 20)
         ws_ptr = _attn_workspace(q.device, ws_bytes).data_ptr()
     fl = 4.0 * B * H * Tq * Tk * D * (0.5 if causal and Tq == Tk else 1.0)
+    if tiles is not None:
+        with torch.cuda.device(q.device), _Prof("attention", fl, 2.0 * B * D * (2 * Tq * H + 2 * Tk * Hkv)):
+            rc = _lib.lib().vllm_attention_bf16_tiles(
+                q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Tq, Tk, H, Hkv, D,
+                q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                out.stride(0), out.stride(1), sl, km, amp, float(scale), tiles.counts.data_ptr(), tiles.lists.data_ptr(), _stream())
+        _lib.check(rc, "vllm_attention_bf16_tiles")
+        return out
     with torch.cuda.device(q.device), _Prof("attention", fl, 2.0 * B * D * (2 * Tq * H + 2 * Tk * Hkv)):
         rc = _lib.lib().vllm_attention_bf16(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Tq, Tk, H, Hkv, D,

@@ -138,6 +138,10 @@ class DeformableTransformerDecoderLayer(nn.Module):
         if m.dim() == 2:
             m = m[None].expand(bs * self.n_heads, nq, nq)
         m = m.to(torch.uint8).contiguous()                         # the kernel's mask format (ops.attention converts otherwise)
+        if m.is_cuda and nq >= 256 and self.self_attn is not None and (self.self_attn.embed_dim // self.n_heads) in (32, 64, 128):
+            # the keypoint layers' 50 x (1 + num_body_points) group mask is > 95 % blocked: list the live 64 x 64 tiles once and
+            # let the attention kernel walk only those (bit-identical to the dense walk)
+            m = ops.attention_mask_tiles(m)
         c.update(src=self_attn_mask, key=(self_attn_mask._version, bs * self.n_heads, nq), mask=m)
         return m
 
