@@ -39,6 +39,13 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _as_u8(t):
+    """A mask for the kernels (uint8, contiguous): a bool tensor is reinterpreted in place (same bytes, 0 / 1), not copied."""
+    if t.dtype == torch.bool:
+        return t.contiguous().view(torch.uint8)
+    return t.to(torch.uint8).contiguous()
+
+
 def _bf16_2d(t, name):
     if t.dtype != torch.bfloat16 or not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA bfloat16 tensor")
@@ -87,7 +94,7 @@ def linear(x, weight, bias=None, act=None, colscale=None, residual=None, out_dty
     if row_keep is not None:
         if row_keep.numel() != M or not row_keep.is_cuda or a == 4:
             raise RuntimeError("linear: row_keep must be a CUDA mask with one entry per row (not with swiglu)")
-        rk = row_keep.reshape(-1).to(torch.uint8).contiguous()
+        rk = _as_u8(row_keep.reshape(-1))
     with torch.cuda.device(x.device), _Prof("gemm", 2.0 * M * N * K,
                                             2.0 * (M * K + N * K) + out.element_size() * M * n_out, f"{M}x{N}x{K}"):
         args = (x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(), out.stride(0),
@@ -388,7 +395,7 @@ def attention_mask_tiles(attn_mask):
     is > 95 % blocked)."""
     if attn_mask.dim() != 3 or not attn_mask.is_cuda:
         raise RuntimeError("attention_mask_tiles: attn_mask must be a CUDA [B*H, Tq, Tk] tensor")
-    m = attn_mask.to(torch.uint8).contiguous()
+    m = _as_u8(attn_mask)
     BH, Tq, Tk = m.shape
     nqb, nkt = (Tq + 63) // 64, (Tk + 63) // 64
     counts = torch.empty((BH, nqb), dtype=torch.int32, device=m.device)
@@ -427,7 +434,7 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
     if key_mask is not None:
         if key_mask.shape != (B, Tk) or not key_mask.is_cuda:
             raise RuntimeError("attention: key_mask must be CUDA [B, Tk]")
-        key_mask = key_mask.to(torch.uint8).contiguous()
+        key_mask = _as_u8(key_mask)
         km = key_mask.data_ptr()
     amp, tiles = None, None
     if isinstance(attn_mask, MaskTiles):
@@ -437,7 +444,7 @@ def attention(q, k, v, causal=False, scale=None, seqlens=None, key_mask=None, at
     if attn_mask is not None:
         if attn_mask.shape != (B * H, Tq, Tk) or not attn_mask.is_cuda:
             raise RuntimeError("attention: attn_mask must be CUDA [B*H, Tq, Tk]")
-        attn_mask = attn_mask.to(torch.uint8).contiguous()
+        attn_mask = _as_u8(attn_mask)
         amp = attn_mask.data_ptr()
     abp, nb = None, 0
     if attn_bias is not None:

@@ -137,7 +137,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         m = ~self_attn_mask
         if m.dim() == 2:
             m = m[None].expand(bs * self.n_heads, nq, nq)
-        m = m.to(torch.uint8).contiguous()                         # the kernel's mask format (ops.attention converts otherwise)
+        m = m.contiguous().view(torch.uint8)                       # the kernel's mask format: the bool bytes (0 / 1) reinterpreted
         if m.is_cuda and nq >= 256 and self.self_attn is not None and (self.self_attn.embed_dim // self.n_heads) in (32, 64, 128):
             # the keypoint layers' 50 x (1 + num_body_points) group mask is > 95 % blocked: list the live 64 x 64 tiles once and
             # let the attention kernel walk only those (bit-identical to the dense walk)
