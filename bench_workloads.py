@@ -702,7 +702,7 @@ class UniPoseStageWorkload(GdinoHeadWorkload):
     1..3) -> input_proj (+ derived 4th level) -> 6 text-fused deformable encoder layers -> two-stage selection (900 queries)
     -> 2 box decoder layers -> top-50 -> 50 x (1 box + 68 keypoint) queries through 4 keypoint decoder layers -> box / class /
     keypoint heads; N images of 1024^2, [EMB] states of 1 object class + 17 keypoint classes (zero-padded to 100 slots each like
-    mv2.py:803-809).  Eager launches (the two top-k selections read indices on the host like the reference)."""
+    mv2.py:803-809).  One CUDA graph when the capture succeeds (the forward has no host sync), eager otherwise."""
     metric = "unipose_stage_images_per_sec_1024px"
     N = 4
 
@@ -738,11 +738,30 @@ class UniPoseStageWorkload(GdinoHeadWorkload):
         self.h_out = torch.empty((N, 50, 4 + 68 * 3), dtype=torch.float32).pin_memory()
         self.h2d_bytes = sum(t.numel() * 2 for t in self.h_in)
         self.d2h_bytes = self.h_out.numel() * 4
+        self.graphed, self.launch = None, "eager"
+        if os.environ.get("VLLM_BENCH_GRAPH", "1") != "0":
+            # ~1800 launches per step, host-bound when eager: try one CUDA graph (the forward has no host sync); keep eager if
+            # the capture is refused
+            from visionllm_b200.graphs import GraphedForward
+            gf = GraphedForward(lambda im, ob, kp: self._forward(im, ob, kp))
+            try:
+                gf(self.images, obj, kpt)
+                torch.cuda.synchronize()
+                self.graphed, self.launch = gf, "CUDA graph replay"
+            except Exception as e:                                    # noqa: BLE001
+                torch.cuda.synchronize()
+                self.launch = f"eager (graph capture refused: {type(e).__name__}: {str(e)[:120]})"
 
-    def _run(self, images, obj, kpt):
+    def _forward(self, images, obj, kpt):
         tq = dict(self.tq, obj_querys=obj, kpt_querys=kpt)
         o = self.model.forward_samples(images, self.mask, tq)
         return self.torch.cat((o.pred_boxes, o.pred_keypoints), -1)
+
+    def _run(self, images, obj, kpt):
+        from visionllm_b200 import ops
+        if self.graphed is not None and ops.PROFILE is None:
+            return self.graphed(images, obj, kpt)
+        return self._forward(images, obj, kpt)
 
     def step_device(self):
         self.out = self._run(self.images, self.tq["obj_querys"], self.tq["kpt_querys"])
@@ -774,7 +793,7 @@ class UniPoseStageWorkload(GdinoHeadWorkload):
     def config(self):
         return {"workload": "UniPose whole stage from pixels (SURVEY 8f rank 4): N=4 images 1024^2, its Swin-T backbone, 6 enc + "
                             "6 dec layers (2 box + 4 keypoint), 900 -> 50 x 69 queries, 1 object class + 17 keypoint [EMB] classes",
-                "l2_policy": "inputs_exceed_l2", "launch": "eager", "parallelism": f"dp{self.world}"}
+                "l2_policy": "inputs_exceed_l2", "launch": self.launch, "parallelism": f"dp{self.world}"}
 
     def extra(self):
         return {"kernel_breakdown": self.breakdown}

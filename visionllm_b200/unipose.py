@@ -79,6 +79,15 @@ class DeformableTransformerEncoderLayer(nn.Module):
 
 
 _ATTEND_CACHE = {}          # single entry: the last self-attention mask in kernel format (see _attend_mask)
+_CONST_CACHE = {}           # small constant index tensors per (values, device): built once, so a forward issues no H2D copy
+
+
+def _const_long(values, device, shape=None):
+    key = (tuple(values) if shape is None else tuple(tuple(v) for v in values), str(device))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = _CONST_CACHE[key] = torch.tensor(values, dtype=torch.long, device=device)
+    return t
 
 
 class DeformableTransformerDecoderLayer(nn.Module):
@@ -273,7 +282,7 @@ class TransformerDecoder(nn.Module):
         output = tgt
         reference_points = refpoints_unsigmoid.sigmoid()
         intermediate, ref_points = [], [reference_points]
-        kpt_index = torch.tensor(self.kpt_index, device=tgt.device)
+        kpt_index = _const_long(self.kpt_index, tgt.device)
         new_reference_points = None
         for layer_id, layer in enumerate(self.layers):
             if reference_points.shape[-1] == 4:
@@ -588,8 +597,9 @@ class DeformableTransformer(nn.Module):
             pos_l.append(pe)
         src_flatten, mask_flatten = torch.cat(src_l, 1).contiguous(), torch.cat(mask_l, 1)
         lvl_pos = torch.cat(pos_l, 1).contiguous()
-        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=src_flatten.device)
-        _msda.attach_host_shapes(spatial_shapes, shapes)
+        spatial_shapes = _const_long([tuple(int(v) for v in hw) for hw in shapes], src_flatten.device, shape=2)
+        if getattr(spatial_shapes, "_b200_host", None) is None:
+            _msda.attach_host_shapes(spatial_shapes, shapes)
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
 
@@ -787,7 +797,7 @@ class B200UniPose(nn.Module):
         text_dict = dict(text_dict)
         nbp, nb = self.num_body_points, self.num_box_decoder_layers
         coords, classes, keypoints = [], [], []
-        kpt_index = torch.tensor([x for x in range(50 * (nbp + 1)) if x % (nbp + 1) != 0], device=hs[0].device)
+        kpt_index = _const_long([x for x in range(50 * (nbp + 1)) if x % (nbp + 1) != 0], hs[0].device)
         text_dict['encoded_text'] = self.transformer.decoder_text if hasattr(self.transformer, "decoder_text") else text_dict['encoded_text']
         for lid, (ref_sig, bbox_embed, cls_embed, layer_hs) in enumerate(zip(reference[:-1], self.bbox_embed, self.class_embed, hs)):
             if lid < nb:
