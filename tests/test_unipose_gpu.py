@@ -179,3 +179,40 @@ def test_unipose_model_from_pixels_runs_on_gpu():
     assert torch.equal(a.pred_boxes, b.pred_boxes) and torch.equal(a.pred_keypoints, b.pred_keypoints)
     assert torch.isfinite(a.pred_boxes).all() and torch.isfinite(a.pred_keypoints).all()
     assert a.pred_boxes.dtype == torch.float32
+
+
+def test_unipose_from_pixels_replays_as_one_cuda_graph():
+    """The whole UniPose forward from pixels has no host synchronisation (constant index tensors are cached per device, shapes
+    stay on the host): captured into one CUDA graph it replays to exactly the eager result, also after the inputs change."""
+    from unipose_inputs import MODEL, TR, backbone_inputs, model_inputs, transformer_kwargs
+    from test_unipose_backbone_cpu import build_joiner
+    from weights_util import seeded_state_dict
+    from visionllm_b200.graphs import GraphedForward
+    from visionllm_b200.unipose import B200UniPose
+    j = build_joiner()
+    kw = transformer_kwargs()
+    for k in ("d_model", "nhead", "num_queries", "num_feature_levels"):
+        kw.pop(k)
+    m = B200UniPose(hidden_dim=TR["d_model"], l_hidden_size=MODEL["l_hidden"], backbone_channels=tuple(j.num_channels),
+                    num_feature_levels=4, num_queries=TR["num_queries"], num_body_points=TR["num_body_points"],
+                    num_box_decoder_layers=TR["num_box_decoder_layers"], nheads=TR["nhead"], backbone=j, **kw).eval()
+    m.load_state_dict(seeded_state_dict(m, 5))
+    m = m.to("cuda", torch.bfloat16)
+    x, mask = backbone_inputs()
+    x, mask = x.bfloat16().cuda(), mask.cuda()
+    cast = lambda t: (t.bfloat16() if t.is_floating_point() else t).cuda()  # noqa: E731
+    tq = {k: cast(v) for k, v in model_inputs()["text_query"].items()}
+
+    def fwd(images, obj, kpt):
+        o = m.forward_samples(images, mask, dict(tq, obj_querys=obj, kpt_querys=kpt))
+        return o.pred_boxes, o.pred_keypoints, o.pred_logits
+
+    gf = GraphedForward(fwd)
+    for trial in range(3):
+        xi = x if trial == 0 else (x * (1.0 + 0.2 * trial)).contiguous()
+        oq = tq["obj_querys"] if trial < 2 else (tq["obj_querys"] * 0.5).contiguous()
+        eager = [t.clone() for t in fwd(xi, oq, tq["kpt_querys"])]
+        got = gf(xi, oq, tq["kpt_querys"])
+        for a, b in zip(eager, got):
+            assert torch.equal(a, b), trial
+    assert len(gf._cache) == 1 and gf.launches_per_replay > 100
