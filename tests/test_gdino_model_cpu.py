@@ -188,3 +188,23 @@ def test_whole_stage_with_internimage_backbone_matches_reference(gn_kernel, monk
     assert (a.logits[finite] - b.logits[finite]).abs().max() < 2e-3
     assert (a.pred_boxes - b.pred_boxes).abs().max() < 1e-4
     assert (a.pred_masks - b.pred_masks).abs().max() < 2e-2 * a.pred_masks.abs().max().clamp(min=1)
+
+
+def test_conv_rows_prepadded_forms_agree(gn_kernel):
+    """conv_rows / NormConv2d.rows on the zero-bordered map `upsample_add_nhwc(..., pad=)` writes (the copy-free mask-FPN chain)
+    equal the plain call on the unpadded map -- for the implicit-GEMM 3x3 form (border consumed by the convolution) and for
+    shapes that take the general path (border dropped again)."""
+    import torch.nn as nn
+    from visionllm_b200.gdino_model import NormConv2d, conv_rows
+    g = torch.Generator().manual_seed(3)
+    for C, k, p in ((64, 3, 1), (24, 3, 1), (64, 1, 0)):                 # 3 * 64 % 64 == 0: implicit; 3 * 24: general; 1x1
+        x = torch.randn(2, 6, 7, C, generator=g)
+        conv = NormConv2d(C, 32, k, padding=p, relu=True).eval()
+        nn.init.normal_(conv.weight, std=0.1)
+        xp = torch.nn.functional.pad(x, (0, 0, p, p, p, p))
+        a, Ha, Wa = conv_rows(x, conv)
+        b, Hb, Wb = conv_rows(xp, conv, prepadded=p > 0)
+        assert (Ha, Wa) == (Hb, Wb) == (6, 7) and torch.allclose(a, b.reshape(a.shape), atol=1e-6)
+        ra, _, _ = conv.rows(x)
+        rb, _, _ = conv.rows(xp, prepadded=p > 0)
+        assert ra.shape == rb.shape == (2, 42, 32) and torch.allclose(ra, rb, atol=1e-5)
