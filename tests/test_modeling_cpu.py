@@ -228,15 +228,18 @@ def test_inject_emb_refuses_to_clobber_real_tokens():
     import pytest
     m = _tiny_composite()
     ids = torch.randint(0, 30, (1, 16))
-    ids[0, 3] = 50                                             # [DET] followed by ordinary tokens
-    with pytest.raises(NotImplementedError):
-        m(input_ids=ids)
+    ids[0, 3] = 50                                             # [DET] followed by ordinary tokens, no [EMB] id in row 0:
+    out = m(input_ids=ids)                                     # the reference's INSERT form (gap_len = 0), see the test below
+    assert out.input_ids.shape == (1, 20) and out.input_ids[0, 4:8].tolist() == [45, 46, 47, 48]
     ids[0, 4:8] = 45                                           # collator form: [EMB] x 4 placeholders after the tool
     out = m(input_ids=ids)
-    assert out.input_ids[0, 4:8].tolist() == [45, 46, 47, 48]
-    ids2 = ids.clone(); ids2[0, 15] = 50                       # tool token at the very end: slots run past the row
-    with pytest.raises(NotImplementedError):
+    assert out.input_ids.shape == (1, 16) and out.input_ids[0, 4:8].tolist() == [45, 46, 47, 48]
+    ids2 = ids.clone(); ids2[0, 15] = 50                       # [EMB] ids present (overwrite form) but a tool token at the very
+    with pytest.raises(NotImplementedError):                   # end has no slots: the reference would clobber / misalign
         m(input_ids=ids2)
+    ids3 = ids.clone(); ids3[0, 10] = 50                       # ... or is followed by ordinary tokens
+    with pytest.raises(NotImplementedError):
+        m(input_ids=ids3)
 
 
 def test_gdino_task_gate_follows_reference():
@@ -388,3 +391,62 @@ def test_pose_branch_routes_emb_states_to_unipose():
     assert m(input_ids=plain, images_aug=aug[:1], img_metas=metas[:1]).unipose_outputs is None and not seen
     # other tasks never reach it
     assert m(input_ids=ids, images_aug=aug, img_metas=[{"task": "det"}] * 3).unipose_outputs is None and not seen
+
+
+def _ref_insert_loop(input_ids, inputs_embeds, det_ids, pose_id, emb_token_id, num_embs, emb_det, emb_pose):
+    """mv2.py:436-527 with gap_len = 0, transcribed statement for statement (det / seg / grd positions concatenated, then pose;
+    positions taken from the ORIGINAL row)."""
+    emb_ids = torch.tensor(list(range(emb_token_id, emb_token_id + num_embs)), dtype=torch.long)
+    gap_len = 0
+    new_inputs_embeds, new_input_ids = [], []
+    for cur_input_ids, cur_input_embeds in zip(input_ids, inputs_embeds):
+        emb_start_pos_det = torch.cat([torch.where(cur_input_ids == t)[0] for t in det_ids], dim=0)
+        emb_start_pos_pose = torch.where(cur_input_ids == pose_id)[0]
+        cur_new_input_ids, cur_new_input_embeds = cur_input_ids, cur_input_embeds
+        for _start_pos in emb_start_pos_det:
+            cur_new_input_ids = torch.cat([cur_new_input_ids[: _start_pos + 1], emb_ids,
+                                           cur_new_input_ids[_start_pos + gap_len + 1:]], dim=0)
+            cur_new_input_embeds = torch.cat([cur_new_input_embeds[: _start_pos + 1], emb_det,
+                                              cur_new_input_embeds[_start_pos + gap_len + 1:]], dim=0)
+        for _start_pos in emb_start_pos_pose:
+            cur_new_input_ids = torch.cat([cur_new_input_ids[: _start_pos + 1], emb_ids,
+                                           cur_new_input_ids[_start_pos + gap_len + 1:]], dim=0)
+            cur_new_input_embeds = torch.cat([cur_new_input_embeds[: _start_pos + 1], emb_pose,
+                                              cur_new_input_embeds[_start_pos + gap_len + 1:]], dim=0)
+        new_input_ids.append(cur_new_input_ids)
+        new_inputs_embeds.append(cur_new_input_embeds)
+    return torch.stack(new_input_ids, dim=0), torch.stack(new_inputs_embeds, dim=0)
+
+
+def test_insert_form_matches_the_reference_loop():
+    """gap_len == 0 (mv2.py:428-429: a tool token in row 0 and no [EMB] id there -- generation, multi-round chat): [EMB] ids and
+    emb_embeddings are inserted after every tool token, with the reference's unshifted positions; the attention mask grows by
+    ones (mv2.py:539-545)."""
+    import pytest
+    m = _tiny_composite()
+    g = torch.Generator().manual_seed(5)
+    emb_det, emb_pose = m.emb_embeddings_det.weight.detach(), m.emb_embeddings_pose.weight.detach()
+    cases = []
+    a = torch.randint(0, 30, (1, 12), generator=g); a[0, 11] = 50                       # generation: [DET] is the last token
+    cases.append(a)
+    b = torch.randint(0, 30, (2, 14), generator=g); b[0, 3] = 50; b[0, 9] = 50; b[1, 2] = 50; b[1, 12] = 50   # two per row
+    cases.append(b)
+    c = torch.randint(0, 30, (2, 14), generator=g); c[0, 8] = 51; c[0, 2] = 50; c[1, 5] = 50; c[1, 6] = 51    # det + pose
+    cases.append(c)
+    for ids in cases:
+        emb = m.llm.get_input_embeddings()(ids).detach()
+        want_ids, want_emb = _ref_insert_loop(ids, emb, [50], 51, 45, 4, emb_det, emb_pose)
+        assert m.uses_insert_form(ids)
+        got_ids, got_emb = m.inject_emb(ids, emb)
+        assert torch.equal(got_ids, want_ids) and torch.equal(got_emb, want_emb)
+        am = torch.ones_like(ids); am[:, :2] = 0
+        out = m(input_ids=ids, attention_mask=am)
+        assert torch.equal(out.input_ids, want_ids) and torch.equal(out.last_hidden_state, want_emb)
+    ragged = torch.randint(0, 30, (2, 10), generator=g); ragged[0, 3] = 50; ragged[1, 3] = 50; ragged[1, 7] = 50
+    with pytest.raises(RuntimeError):
+        m(input_ids=ragged)
+    # row 0 decides (mv2.py:425-431): [EMB] ids in row 0 -> overwrite form -> a slot-less tool token elsewhere is refused
+    mixed = torch.randint(0, 30, (2, 12), generator=g); mixed[0, 2] = 50; mixed[0, 3:7] = 45; mixed[1, 4] = 50
+    assert not m.uses_insert_form(mixed)
+    with pytest.raises(NotImplementedError):
+        m(input_ids=mixed)

@@ -277,12 +277,49 @@ class B200VisionLLMv2Model(nn.Module):
             ok = bool(in_range.all()) and bool(((slots >= self.emb_token_id)
                                                 & (slots < self.emb_token_id + self.num_embs)).all())
             if not ok:
-                raise NotImplementedError("tool token without its pre-placed [EMB] slots: generation-time insertion "
-                                          "(mv2.py:428-429, gap_len == 0) is outside the forward hot path")
+                if self.uses_insert_form(input_ids):
+                    return self.inject_emb_insert(input_ids, inputs_embeds)
+                raise NotImplementedError("a tool token without its pre-placed [EMB] slots in a batch whose first row carries "
+                                          "[EMB] ids: the reference's overwrite form (mv2.py:430-431) would clobber real tokens")
             ids[b, p] = self.emb_token_id + j
             emb = emb.clone() if emb is inputs_embeds else emb
             emb[b, p] = table.weight.to(emb.dtype)[j]
         return ids, emb
+
+    def _tool_groups(self):
+        return (((self.det_tool_id, self.seg_tool_id, self.grd_tool_id), self.emb_embeddings_det),
+                ((self.pose_tool_id,), self.emb_embeddings_pose))
+
+    def uses_insert_form(self, input_ids):
+        """mv2.py:425-431: the reference inspects the FIRST row only -- a tool token there and no `emb_token_id` means
+        gap_len = 0 (the [EMB] ids / embeddings are INSERTED after every tool token: generation, multi-round chat history)."""
+        row = input_ids[0]
+        tools = [t for grp, _ in self._tool_groups() for t in grp if t is not None and t >= 0]
+        has_tool = any(bool((row == t).any()) for t in tools)
+        return has_tool and not bool((row == self.emb_token_id).any())
+
+    def inject_emb_insert(self, input_ids, inputs_embeds):
+        """The gap_len == 0 form of mv2.py:436-527: after every det / seg / grd (then pose) tool token the `num_embs` [EMB] ids
+        and the tool's emb_embeddings are inserted; the sequence grows.  Restated with the reference's own order of operations,
+        including its quirk: the insertion points are the positions found in the ORIGINAL row and are not shifted by earlier
+        insertions of the same row (so a second tool token's [EMB] block lands `num_embs` tokens early, exactly as in the
+        reference).  Rows must end up equally long (the reference `torch.stack`s them)."""
+        emb_ids = torch.arange(self.emb_token_id, self.emb_token_id + self.num_embs, dtype=torch.long, device=input_ids.device)
+        new_ids, new_emb = [], []
+        for row_ids, row_emb in zip(input_ids, inputs_embeds):
+            ids, emb = row_ids, row_emb
+            for tools, table in self._tool_groups():
+                pos = torch.cat([torch.where(row_ids == t)[0] for t in tools if t is not None and t >= 0] or
+                                [row_ids.new_zeros((0,))])
+                block = table.weight.to(row_emb.dtype)
+                for p0 in pos.tolist():
+                    ids = torch.cat((ids[:p0 + 1], emb_ids, ids[p0 + 1:]), 0)
+                    emb = torch.cat((emb[:p0 + 1], block, emb[p0 + 1:]), 0)
+            new_ids.append(ids)
+            new_emb.append(emb)
+        if len({t.shape[0] for t in new_ids}) != 1:
+            raise RuntimeError("rows carry different numbers of tool tokens: the reference cannot stack them either (mv2.py:526)")
+        return torch.stack(new_ids, 0), torch.stack(new_emb, 0)
 
     def encode_images(self, images):
         if isinstance(images, (list, tuple)):                      # 'anyres': bs x [1 + n_split, 3, h, w]
@@ -369,11 +406,13 @@ class B200VisionLLMv2Model(nn.Module):
                                  split_sizes if images is not None else False, feats.shape[1] if feats is not None else 0)
             status = int(plan.status.item())
             if status & 1:
-                raise NotImplementedError("tool token without its pre-placed [EMB] slots: generation-time insertion "
-                                          "(mv2.py:428-429, gap_len == 0) is outside the forward hot path")
-            if status & 2:
+                # no pre-placed [EMB] slots: the reference's insert form (mv2.py:428-429) changes the sequence length -- host
+                # logic of the torch path below (inject_emb decides between inserting and refusing)
+                fused, plan = False, None
+            elif status & 2:
                 raise RuntimeError("image token count mismatch between the <im_patch> slots and the ViT tokens (the "
                                    "reference tiles/trims and zeroes the loss here, mv2.py:591-604; this drop-in refuses)")
+        if fused:
             inputs_embeds = ops.assemble_embeds(
                 plan, embed_w, self.emb_embeddings_det.weight, self.emb_embeddings_pose.weight,
                 feats.reshape(-1, feats.shape[-1]).contiguous() if feats is not None else None, base_embeds=inputs_embeds)
@@ -385,6 +424,11 @@ class B200VisionLLMv2Model(nn.Module):
             if images is not None:
                 inputs_embeds = self.scatter_image_tokens(input_ids, inputs_embeds, feats.to(inputs_embeds.dtype),
                                                           split_sizes)
+        if attention_mask is not None and attention_mask.shape[1] != input_ids.shape[1]:    # mv2.py:539-545 (after an insertion)
+            add = input_ids.shape[1] - attention_mask.shape[1]
+            if add < 0:
+                raise ValueError("attention_mask is longer than the sequence")
+            attention_mask = torch.cat((attention_mask, attention_mask.new_ones((attention_mask.shape[0], add))), -1)
         if images is not None:
             if self.use_region_encoder and regions is not None:                              # mv2.py:607-698
                 ri, rm, rf = region_encoder_inputs(images, regions, vit_out.hidden_states, split_sizes, num_splits)
