@@ -13,6 +13,9 @@ packed q|k|v GEMM (+bias; already packed in the reference), window attention wit
 as fused residual, LayerNorm, fc1 GEMM + exact GELU, fc2 GEMM + residual; patch merging = 2x2 gather + LayerNorm(4C)
 in one pass + reduction GEMM.  The reference scales q before q k^T; we scale the scores (same value up to rounding).
 
+`build_backbone('internimage_h')` puts UniPose's copy of InternImage-H (:4675-4893, out indices (1, 2, 3)) behind the same
+interface (`B200UniPoseInternImage`, the module tree of `internimage.B200InternImage`).
+
 `B200Joiner(backbone)(tensors, mask)` returns what `Joiner.forward(NestedTensor)` returns: [(map NCHW, mask)] per
 out index -- masks by nearest `F.interpolate` of the padding mask (:1847-1850) -- and the `PositionEmbeddingSineHW` of every
 mask cast to the map dtype (:1223).
@@ -24,6 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .internimage import INTERNIMAGE_H, B200InternImage
 from .swin import _shift_mask, _window_reverse, _window_rows
 
 SWIN_PRESETS = {                                                     # build_swin_transformer (:4082-4120)
@@ -226,15 +230,49 @@ class B200Joiner(nn.Sequential):
         return out, pos
 
 
+class B200UniPoseInternImage(B200InternImage):
+    """UniPose's own copy of InternImage (modeling_unipose.py:4675-4864: the class of gd.py whose `forward(NestedTensor)` returns
+    {idx: NestedTensor(map NCHW, interpolated padding mask)}).  Same module tree as `internimage.B200InternImage`, so the
+    state-dict keys under the Joiner are the reference's (`0.patch_embed.*`, `0.levels.*`)."""
+
+    @torch.no_grad()
+    def forward(self, tensors, mask):
+        outs = B200InternImage.forward(self, tensors)                                       # channels-last [B, h, w, C] maps
+        res = {}
+        for i, o in enumerate(outs):
+            o = o.permute(0, 3, 1, 2)                                                        # NCHW view of the channels-last storage
+            res[i] = (o, F.interpolate(mask[None].float(), size=o.shape[-2:]).to(torch.bool)[0])
+        return res
+
+
+def build_internimage_h(**overrides):
+    """modeling_unipose.py:4866-4893: the InternImage-H preset with out_indices (1, 2, 3); `num_features` pinned to the H widths."""
+    cfg = dict(INTERNIMAGE_H)
+    cfg.update(out_indices=(1, 2, 3), channels_last_out=True)
+    cfg.update(overrides)
+    m = B200UniPoseInternImage(**cfg)
+    if not overrides:
+        m.num_features = [320, 640, 1280, 2560]
+    return m
+
+
 def build_backbone(backbone="swin_T_224_1k", return_interm_indices=(1, 2, 3), hidden_dim=256, pe_temperatureH=20,
                    pe_temperatureW=20, **swin_overrides):
-    """`build_backbone(args)` (:4162-4222) for the Swin presets + `build_position_encoding` ('sine', :4224-4233)."""
+    """`build_backbone(args)` (:4162-4222) for the Swin presets and 'internimage_h' + `build_position_encoding` ('sine',
+    :4224-4233).  Keyword overrides (tests) replace preset fields of the chosen backbone."""
     from .unipose import PositionEmbeddingSineHW
     if list(return_interm_indices) not in ([0, 1, 2, 3], [1, 2, 3], [3]):
         raise ValueError("return_interm_indices must be [0, 1, 2, 3], [1, 2, 3] or [3]")
+    if backbone == "internimage_h":                                                        # :4203-4205
+        body = build_internimage_h(**swin_overrides)
+        joiner = B200Joiner(body, PositionEmbeddingSineHW(hidden_dim // 2, pe_temperatureH, pe_temperatureW, normalize=True))
+        joiner.num_channels = list(body.num_features[4 - len(return_interm_indices):])
+        if len(joiner.num_channels) != len(body.out_indices):                              # the reference's assert (:4209-4211)
+            raise ValueError(f"internimage_h returns levels {body.out_indices}: return_interm_indices must have as many entries")
+        return joiner
     if backbone not in SWIN_PRESETS:
-        raise NotImplementedError(f"backbone {backbone!r}: the Swin presets are built here; 'internimage_h' is "
-                                  "visionllm_b200.internimage.build_internimage_h")
+        raise NotImplementedError(f"backbone {backbone!r}: the Swin presets and 'internimage_h' are built here (the ResNet "
+                                  "backbones of :4187-4195 are torchvision models outside this path)")
     kw = dict(SWIN_PRESETS[backbone])
     kw.update(swin_overrides)
     swin = B200UniPoseSwin(pretrain_img_size=int(backbone.split("_")[-2]), out_indices=tuple(return_interm_indices),
