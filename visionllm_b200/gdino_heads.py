@@ -274,3 +274,33 @@ def post_process_instseg_gdino(logits, pred_boxes, pred_masks, target_sizes, ima
         res.append({"scores": scores, "labels": labels, "boxes": boxes, "masks": m.sigmoid() > 0.5,
                     "topk_indexes": idx, "topk_boxes": box_idx})
     return res
+
+
+@torch.no_grad()
+def post_process_sem_seg(logits, pred_masks, target_sizes, image_sizes, num_classes=150, sem_seg_postprocess_before_inference=True):
+    """eval_semseg.py:16-62 (task 'seg'): per image, class probabilities [nq, K] and mask probabilities [nq, h/4, w/4] ->
+    4x bilinear -> crop of the padding -> bilinear to the original size -> einsum('qc,qhw->chw') -> argmax over the classes.
+    `sem_seg_postprocess_before_inference=False` contracts with the classes first and resizes the K class maps instead
+    (the reference's low-memory order).  Returns a list of int64 [H, W] class maps (the reference returns their `.cpu().numpy()`).
+    Host-side torch primitives in the reference's order (no fused kernel yet: one image per call at eval time)."""
+    if target_sizes is not None and len(logits) != len(target_sizes):
+        raise ValueError("Make sure that you pass in as many target sizes as the batch dimension of the logits")
+    res = []
+    for cls, mask, image_size, target_size in zip(logits, pred_masks, image_sizes, target_sizes):
+        prob = cls[..., :num_classes].sigmoid()
+        m = mask.sigmoid()
+        H, W = m.shape[-2:]
+        size = tuple(int(v) for v in target_size[:2])
+        if sem_seg_postprocess_before_inference:
+            m = F.interpolate(m[:, None], size=(H * 4, W * 4), mode="bilinear", align_corners=False)
+            m = m[:, :, :image_size[0], :image_size[1]]
+            m = F.interpolate(m, size=size, mode="bilinear", align_corners=False)[:, 0]
+            res.append(torch.einsum("qc,qhw->chw", prob, m).argmax(dim=0))
+        else:
+            m = torch.einsum("qc,qhw->chw", prob, m)
+            m = F.interpolate(m[:, None], size=(H * 4, W * 4), mode="bilinear", align_corners=False)
+            m = m[:, :, :image_size[0], :image_size[1]]
+            m = F.interpolate(m, size=size, mode="bilinear", align_corners=False)[:, 0]
+            res.append(m.argmax(dim=0))
+    return res
+

@@ -815,3 +815,43 @@ class B200UniPose(nn.Module):
                 keypoints.append(keypoint_xyzxyz_to_xyxyzz(xyv.reshape((bs, 50, nbp, 3)).flatten(2, 3)).to(torch.float32))
         return SimpleNamespace(loss=None, loss_dict=None, pred_logits=classes[-1], pred_boxes=coords[-1], pred_keypoints=keypoints[-1],
                                aux=dict(classes=classes, coords=coords, keypoints=keypoints, hs_enc=hs_enc, ref_enc=ref_enc))
+
+
+@torch.no_grad()
+def post_process_pose(pred_logits, pred_boxes, pred_keypoints, target_sizes, num_classes=1, topk=100, num_body_points=17,
+                      id_mapping=None, threshold=0.):
+    """eval_pose.py:19-86, the caller right after the UniPose path: sigmoid -> top-k over (query, class) -> `//`, `%` -> labels
+    through `id_mapping` (continuous -> dataset category id) -> boxes cxcywh -> xyxy scaled to the image -> the selected
+    queries' keypoints (x, y of the first `num_body_points`, scaled; visibility 1) re-interleaved xyxy..zz -> xyzxyz ->
+    score threshold.  target_sizes: [bs, 2] tensor or list of (h, w).  The id mapping is one table lookup instead of the
+    reference's per-element `.item()` loop (same integers)."""
+    if id_mapping is None:
+        raise ValueError("id_mapping is required (the reference asserts it, eval_pose.py:42)")
+    if target_sizes is not None and len(pred_logits) != len(target_sizes):
+        raise ValueError("Make sure that you pass in as many target sizes as the batch dimension of the logits")
+    logits = pred_logits[:, :, :num_classes]
+    bs, K = logits.shape[0], logits.shape[2]
+    prob = logits.sigmoid().view(bs, -1)
+    scores, idx = torch.topk(prob, min(topk, prob.size(1)), dim=1)
+    q_idx = torch.div(idx, K, rounding_mode="floor")
+    labels = idx % K
+    keys = sorted(id_mapping)
+    table = torch.zeros(max(keys) + 1, dtype=labels.dtype, device=labels.device)
+    table[torch.tensor(keys, device=labels.device)] = torch.tensor([id_mapping[k] for k in keys], dtype=labels.dtype,
+                                                                    device=labels.device)
+    labels = table[labels]
+    if not torch.is_tensor(target_sizes):
+        target_sizes = torch.stack([torch.as_tensor(t) for t in target_sizes])
+    img_h, img_w = target_sizes.to(pred_boxes.device).unbind(1)
+    boxes = torch.gather(_H.box_cxcywh_to_xyxy(pred_boxes), 1, q_idx.unsqueeze(-1).repeat(1, 1, 4))
+    boxes = boxes * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :]
+    kp = torch.gather(pred_keypoints, 1, q_idx.unsqueeze(-1).repeat(1, 1, pred_keypoints.shape[-1]))
+    z = kp[:, :, :num_body_points * 2] * torch.stack([img_w, img_h], dim=1).repeat(1, num_body_points)[:, None, :]
+    out = torch.zeros((bs, z.shape[1], num_body_points * 3), dtype=z.dtype, device=z.device)
+    out[..., 0::3], out[..., 1::3], out[..., 2::3] = z[..., 0::2], z[..., 1::2], 1.0
+    res = []
+    for s_, l_, b_, k_ in zip(scores, labels, boxes, out):
+        keep = s_ > threshold
+        res.append({"scores": s_[keep], "labels": l_[keep], "boxes": b_[keep], "keypoints": k_[keep]})
+    return res
+
