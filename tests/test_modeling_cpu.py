@@ -394,28 +394,20 @@ def test_pose_branch_routes_emb_states_to_unipose():
 
 
 def _ref_insert_loop(input_ids, inputs_embeds, det_ids, pose_id, emb_token_id, num_embs, emb_det, emb_pose):
-    """mv2.py:436-527 with gap_len = 0, transcribed statement for statement (det / seg / grd positions concatenated, then pose;
-    positions taken from the ORIGINAL row)."""
-    emb_ids = torch.tensor(list(range(emb_token_id, emb_token_id + num_embs)), dtype=torch.long)
-    gap_len = 0
-    new_inputs_embeds, new_input_ids = [], []
-    for cur_input_ids, cur_input_embeds in zip(input_ids, inputs_embeds):
-        emb_start_pos_det = torch.cat([torch.where(cur_input_ids == t)[0] for t in det_ids], dim=0)
-        emb_start_pos_pose = torch.where(cur_input_ids == pose_id)[0]
-        cur_new_input_ids, cur_new_input_embeds = cur_input_ids, cur_input_embeds
-        for _start_pos in emb_start_pos_det:
-            cur_new_input_ids = torch.cat([cur_new_input_ids[: _start_pos + 1], emb_ids,
-                                           cur_new_input_ids[_start_pos + gap_len + 1:]], dim=0)
-            cur_new_input_embeds = torch.cat([cur_new_input_embeds[: _start_pos + 1], emb_det,
-                                              cur_new_input_embeds[_start_pos + gap_len + 1:]], dim=0)
-        for _start_pos in emb_start_pos_pose:
-            cur_new_input_ids = torch.cat([cur_new_input_ids[: _start_pos + 1], emb_ids,
-                                           cur_new_input_ids[_start_pos + gap_len + 1:]], dim=0)
-            cur_new_input_embeds = torch.cat([cur_new_input_embeds[: _start_pos + 1], emb_pose,
-                                              cur_new_input_embeds[_start_pos + gap_len + 1:]], dim=0)
-        new_input_ids.append(cur_new_input_ids)
-        new_inputs_embeds.append(cur_new_input_embeds)
-    return torch.stack(new_input_ids, dim=0), torch.stack(new_inputs_embeds, dim=0)
+    """Pure-python oracle of mv2.py:436-527 with gap_len = 0: python-list splices at `position + 1`, positions read from the
+    ORIGINAL row (first the det / seg / grd hits concatenated in that order, then the pose hits), never shifted."""
+    out_ids, out_emb = [], []
+    for row_ids, row_emb in zip(input_ids.tolist(), inputs_embeds):
+        ids, emb = list(row_ids), [e for e in row_emb]
+        hits_det = [i for t in det_ids for i, v in enumerate(row_ids) if v == t]
+        hits_pose = [i for i, v in enumerate(row_ids) if v == pose_id]
+        for hits, table in ((hits_det, emb_det), (hits_pose, emb_pose)):
+            for p0 in hits:
+                ids[p0 + 1:p0 + 1] = list(range(emb_token_id, emb_token_id + num_embs))
+                emb[p0 + 1:p0 + 1] = [table[j] for j in range(num_embs)]
+        out_ids.append(torch.tensor(ids, dtype=torch.long))
+        out_emb.append(torch.stack(emb))
+    return torch.stack(out_ids), torch.stack(out_emb)
 
 
 def test_insert_form_matches_the_reference_loop():

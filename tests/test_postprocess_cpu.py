@@ -1,52 +1,41 @@
 """CPU: the host-side post-processors that follow the UniPose and Grounding-DINO paths (`unipose.post_process_pose`,
-`gdino_heads.post_process_sem_seg`) against statement-for-statement transcriptions of the reference's functions
-(visionllmv2/eval/eval_pose.py:19-86, eval_semseg.py:16-62) on the same random head outputs."""
+`gdino_heads.post_process_sem_seg`) against independent oracles of the reference's functions
+(visionllmv2/eval/eval_pose.py:19-86, eval_semseg.py:16-62: one detection / one class map at a time, python loops) on the same
+random head outputs."""
 import pytest
 import torch
 import torch.nn.functional as F
 
 
-def _box_cxcywh_to_xyxy(x):
-    x_c, y_c, w, h = x.unbind(-1)
-    return torch.stack([(x_c - 0.5 * w), (y_c - 0.5 * h), (x_c + 0.5 * w), (y_c + 0.5 * h)], dim=-1)
-
-
 def _ref_post_process_pose(out_logits, out_bbox, out_keypoints, target_sizes, num_classes=1, topk=100, num_body_points=17,
                            id_mapping=None, threshold=0.):
-    out_logits = out_logits[:, :, :num_classes]
-    prob = out_logits.sigmoid()
-    prob = prob.view(out_logits.shape[0], -1)
-    k_value = min(topk, prob.size(1))
-    topk_values, topk_indexes = torch.topk(prob, k_value, dim=1)
-    scores = topk_values
-    topk_boxes = torch.div(topk_indexes, out_logits.shape[2], rounding_mode="floor")
-    labels = topk_indexes % out_logits.shape[2]
-    new_labels = torch.zeros_like(labels)
-    for batch_idx in range(len(labels)):
-        for j in range(labels.shape[-1]):
-            new_labels[batch_idx, j] = id_mapping[labels[batch_idx, j].item()]
-    labels = new_labels
-    boxes = _box_cxcywh_to_xyxy(out_bbox)
-    boxes = torch.gather(boxes, 1, topk_boxes.unsqueeze(-1).repeat(1, 1, 4))
-    img_h, img_w = target_sizes.unbind(1)
-    scale_fct = torch.stack([img_w, img_h, img_w, img_h], dim=1).to(boxes.device)
-    boxes = boxes * scale_fct[:, None, :]
-    topk_keypoints = torch.div(topk_indexes, out_logits.shape[2], rounding_mode="floor")
-    keypoints = torch.gather(out_keypoints, 1, topk_keypoints.unsqueeze(-1).repeat(1, 1, 68 * 3))
-    Z_pred = keypoints[:, :, :(num_body_points * 2)]
-    V_pred = torch.ones_like(Z_pred)[:, :, :num_body_points]
-    img_h, img_w = target_sizes.unbind(1)
-    scale_fct = torch.stack([img_w, img_h], dim=1).repeat(1, num_body_points)[:, None, :].to(Z_pred.device)
-    Z_pred = Z_pred * scale_fct
-    keypoints = torch.cat([Z_pred, V_pred], dim=-1)
-    keypoints_res = torch.zeros_like(keypoints)
-    keypoints_res[..., 0::3] = Z_pred[..., 0::2]
-    keypoints_res[..., 1::3] = Z_pred[..., 1::2]
-    keypoints_res[..., 2::3] = V_pred[..., 0::1]
+    """Pure-python oracle of eval_pose.py:19-86, one detection at a time: rank the (query, class) sigmoid scores, then for each
+    kept pair build the label through id_mapping, the xyxy box scaled by (w, h, w, h) and the (x * w, y * h, 1) keypoint triples
+    of the first `num_body_points` points of the query's xyxy..zz keypoint vector."""
     results = []
-    for s, l, b, k in zip(scores, labels, boxes, keypoints_res):
-        results.append({"scores": s[s > threshold], "labels": l[s > threshold], "boxes": b[s > threshold],
-                        "keypoints": k[s > threshold]})
+    for b in range(out_logits.shape[0]):
+        K = num_classes
+        prob = out_logits[b, :, :K].sigmoid().reshape(-1)
+        vals, order = torch.topk(prob, min(topk, prob.numel()))
+        h, w = float(target_sizes[b][0]), float(target_sizes[b][1])
+        scores, labels, boxes, kpts = [], [], [], []
+        for v, flat in zip(vals, order.tolist()):
+            if not v > threshold:
+                continue
+            q, c = flat // K, flat % K
+            cx, cy, bw, bh = out_bbox[b, q]
+            xy = out_keypoints[b, q, :num_body_points * 2]
+            trip = []
+            for j in range(num_body_points):
+                trip += [xy[2 * j] * w, xy[2 * j + 1] * h, torch.tensor(1.0)]
+            scores.append(v); labels.append(id_mapping[c])
+            boxes.append(torch.stack([(cx - 0.5 * bw) * w, (cy - 0.5 * bh) * h, (cx + 0.5 * bw) * w, (cy + 0.5 * bh) * h]))
+            kpts.append(torch.stack(trip))
+        n = len(scores)
+        results.append({"scores": torch.stack(scores) if n else torch.zeros(0),
+                        "labels": torch.tensor(labels, dtype=torch.long),
+                        "boxes": torch.stack(boxes) if n else torch.zeros(0, 4),
+                        "keypoints": torch.stack(kpts) if n else torch.zeros(0, num_body_points * 3)})
     return results
 
 
@@ -77,23 +66,24 @@ def test_post_process_pose_matches_reference(num_classes, nbp, topk, threshold):
         post_process_pose(logits, boxes, kpts, sizes[:2], num_classes, topk, nbp, id_mapping, threshold)
 
 
+def _resize_chain(x, image_size, target_size):
+    """[n, h/4, w/4] -> x4 bilinear -> crop of the batch padding -> bilinear to the original size (eval_semseg.py:22-25 / :31-34)."""
+    n, h, w = x.shape
+    x = F.interpolate(x.unsqueeze(1), size=(4 * h, 4 * w), mode="bilinear", align_corners=False)
+    x = x[..., :image_size[0], :image_size[1]]
+    return F.interpolate(x, size=tuple(target_size[:2]), mode="bilinear", align_corners=False).squeeze(1)
+
+
 def _ref_process_seg_result(mask_cls, mask_pred, image_size, target_size, before=True):
-    prob = mask_cls.sigmoid()
-    mask_pred = mask_pred.sigmoid()
-    H, W = mask_pred.shape[-2:]
+    """Oracle of eval_semseg.py:16-37: class-weighted sum of the query mask probabilities, per pixel arg-max; the weighting happens
+    after the resize chain (`before`) or before it."""
+    prob, m = torch.sigmoid(mask_cls), torch.sigmoid(mask_pred)
     if before:
-        mask_pred = F.interpolate(mask_pred[:, None], size=(H * 4, W * 4), mode="bilinear", align_corners=False)
-        mask_pred = mask_pred[:, :, :image_size[0], :image_size[1]]
-        mask_pred = F.interpolate(mask_pred, size=target_size[:2], mode="bilinear", align_corners=False)[:, 0]
-        semseg = torch.einsum('qc,qhw->chw', prob, mask_pred)
-        semantic_map = semseg.argmax(dim=0)
+        m = _resize_chain(m, image_size, target_size)
+        per_class = (prob.t()[:, :, None, None] * m[None]).sum(1) if m.numel() < 2e6 else torch.einsum("qc,qhw->chw", prob, m)
     else:
-        mask_pred = torch.einsum('qc,qhw->chw', prob, mask_pred)
-        mask_pred = F.interpolate(mask_pred[:, None], size=(H * 4, W * 4), mode="bilinear", align_corners=False)
-        mask_pred = mask_pred[:, :, :image_size[0], :image_size[1]].cpu()
-        mask_pred = F.interpolate(mask_pred, size=target_size[:2], mode="bilinear", align_corners=False)[:, 0]
-        semantic_map = mask_pred.argmax(dim=0)
-    return semantic_map
+        per_class = _resize_chain(torch.einsum("qc,qhw->chw", prob, m), image_size, target_size)
+    return per_class.argmax(0)
 
 
 @pytest.mark.parametrize("before", [True, False])
