@@ -89,3 +89,84 @@ def test_unipose_model_runs_from_pixels(torch_kernels, monkeypatch):  # noqa: F8
     assert torch.equal(a.pred_boxes, b.pred_boxes) and torch.equal(a.pred_keypoints, b.pred_keypoints)
     assert a.pred_boxes.shape == (2, 50, 4) or a.pred_boxes.shape[0] == 2
     assert torch.isfinite(a.pred_boxes).all()
+
+
+def test_composite_pose_branch_runs_the_real_unipose(torch_kernels, monkeypatch):  # noqa: F811
+    """The composite forward's 'pose' branch (mv2.py:795-836) with the REAL B200UniPose behind it (backbone from pixels,
+    transformer, heads; stand-in kernels): the [EMB] hidden states of the LLM reach UniPose as object / keypoint queries and
+    the result equals calling UniPose directly on the queries the reference's loop would build."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from types import SimpleNamespace
+    import visionllm_b200.ops as ops
+    from unipose_inputs import TR, transformer_kwargs
+    from visionllm_b200.modeling import B200VisionLLMv2Model, pad_images_aug
+    from visionllm_b200.unipose import B200UniPose
+
+    def groupnorm_nhwc(x, w, b, groups, eps, relu=False):
+        y = F.group_norm(x.float().transpose(1, 2), groups, w.float(), b.float(), eps).transpose(1, 2)
+        return torch.relu(y) if relu else y
+
+    monkeypatch.setattr(ops, "groupnorm_nhwc", groupnorm_nhwc)
+    C, V = 16, 64
+
+    class FakeViT(nn.Module):
+        config = SimpleNamespace(hidden_size=C, patch_size=2)
+
+        def forward(self, x, output_hidden_states=True):
+            t = torch.zeros(x.shape[0], 5, C)
+            return SimpleNamespace(hidden_states=(t, t, t))
+
+    class FakeLLM(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.config = SimpleNamespace(hidden_size=C, vocab_size=V)
+            self.emb = nn.Embedding(V, C)
+            self.dtype = torch.float32
+
+        def get_input_embeddings(self):
+            return self.emb
+
+        def forward(self, attention_mask=None, inputs_embeds=None, output_hidden_states=True):
+            h = torch.tanh(inputs_embeds) * 2.0
+            return SimpleNamespace(hidden_states=(inputs_embeds, h), logits=None)
+
+    j = build_joiner()
+    kw = transformer_kwargs()
+    for k in ("d_model", "nhead", "num_queries", "num_feature_levels"):
+        kw.pop(k)
+    torch.manual_seed(11)
+    pose = B200UniPose(hidden_dim=TR["d_model"], l_hidden_size=C, backbone_channels=tuple(j.num_channels), num_feature_levels=4,
+                       num_queries=TR["num_queries"], num_body_points=TR["num_body_points"],
+                       num_box_decoder_layers=TR["num_box_decoder_layers"], nheads=TR["nhead"], backbone=j, **kw).eval()
+    pose.load_state_dict(seeded_state_dict(pose, 5))
+    cfg = SimpleNamespace(use_pixelshuffle=False, vl_bridge_type="linear", vis_output_layer=-1, num_embs=4, imp_token_id=40,
+                          emb_token_id=45, det_tool_id=-1, seg_tool_id=-1, grd_tool_id=-1, pose_tool_id=51)
+    m = B200VisionLLMv2Model(cfg, FakeViT(), FakeLLM(), unipose=pose).eval()
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(0, 30, (2, 48), generator=g)
+    n_patch, n_obj = [4, 3], [1, 1]                                   # 1 object class + 3 / 2 keypoint classes
+    for b, n in enumerate(n_patch):
+        for q in range(n):
+            p = 2 + 5 * q
+            ids[b, p] = 51
+            ids[b, p + 1:p + 5] = 45
+    aug = [torch.randn(3, 100, 138, generator=g), torch.randn(3, 80, 110, generator=g)]
+    metas = [{"task": "pose", "id2index": {0: 0}} for _ in n_obj]
+    out = m(input_ids=ids, images_aug=aug, img_metas=metas)
+    up = out.unipose_outputs
+    assert up.pred_boxes.shape[0] == 2 and up.pred_keypoints.shape[-1] == TR["num_body_points"] * 3
+    assert torch.isfinite(up.pred_boxes).all() and torch.isfinite(up.pred_keypoints).all()
+    # the reference's query construction (mv2.py:803-823) on the same hidden states, then UniPose called directly
+    h, new_ids = out.last_hidden_state, out.input_ids
+    sel = (new_ids >= 45) & (new_ids <= 48)
+    obj, kpt = torch.zeros(2, 100, 4, C), torch.zeros(2, 100, 4, C)
+    objm, kptm = torch.zeros(2, 100, dtype=torch.bool), torch.zeros(2, 100, dtype=torch.bool)
+    for b in range(2):
+        tq_i = h[b, sel[b]].reshape(-1, 4, C)
+        no, nk = n_obj[b], tq_i.shape[0] - n_obj[b]
+        obj[b, :no], objm[b, :no], kpt[b, :nk], kptm[b, :nk] = tq_i[:no], True, tq_i[no:], True
+    tensors, mask = pad_images_aug(aug, 32, return_mask=True)
+    direct = pose.forward_samples(tensors, mask, dict(obj_querys=obj, obj_query_masks=objm, kpt_querys=kpt, kpt_query_masks=kptm))
+    assert torch.equal(direct.pred_boxes, up.pred_boxes) and torch.equal(direct.pred_keypoints, up.pred_keypoints)
+    assert torch.equal(torch.isfinite(direct.pred_logits), torch.isfinite(up.pred_logits))
